@@ -1,0 +1,3 @@
+"""B200-native tensor-network engine behind the qibotn plugin surface."""
+__version__ = "0.1.0"
+
