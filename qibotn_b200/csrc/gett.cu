@@ -1,0 +1,412 @@
+// Pairwise contraction of bit tensors (every extent 2) with the permutation
+// fused into the loads and stores: a GETT-style kernel driven by bit-deposit
+// address algebra instead of a separate transpose pass.
+//
+// Address model: each label of a tensor owns one *address bit*.  A CTA works on
+// a tile whose labels (m_lo, n_lo, k_lo) were chosen on the host so that they
+// cover the low address bits of A, B and C; the remaining labels index tiles
+// (m_hi, n_hi, batch) or loop iterations (k_hi).  Inside a tile, elements are
+// enumerated in ascending *address* order of the operand being moved, so global
+// traffic is coalesced whatever the logical (GEMM) order of the labels is.
+//
+// Arithmetic: complex FMA on the FP32 / FP64 pipes (4 real FMA per complex MAC),
+// 4x4 complex outputs per thread, 256 threads -> 4096 outputs per CTA.
+#include <cstdint>
+#include <type_traits>
+
+#include "qtn_internal.h"
+
+namespace {
+
+template <typename R> struct cx_of;
+template <> struct cx_of<float> { using type = float2; };
+template <> struct cx_of<double> { using type = double2; };
+template <typename R> using cx = typename cx_of<R>::type;
+
+template <typename R> __device__ __forceinline__ cx<R> cx_zero() { cx<R> z; z.x = 0; z.y = 0; return z; }
+
+template <typename R>
+__device__ __forceinline__ void cfma(cx<R> &acc, const cx<R> &a, const cx<R> &b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+
+__device__ __forceinline__ long long deposit(unsigned long long idx, const uint8_t *pos, int n) {
+  long long off = 0;
+  for (int i = 0; i < n; ++i) off |= (long long)((idx >> i) & 1ull) << pos[i];
+  return off;
+}
+
+__device__ __forceinline__ long long slice_offset(const int32_t *slice_id, int n, const uint8_t *bit,
+                                                  const uint8_t *pos) {
+  if (n == 0) return 0;
+  const unsigned sid = (unsigned)(*slice_id);
+  long long off = 0;
+  for (int i = 0; i < n; ++i) off |= (long long)((sid >> bit[i]) & 1u) << pos[i];
+  return off;
+}
+
+// --------------------------------------------------------------------------
+// Tiled kernel
+// --------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256)
+gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restrict__ A,
+                 const cx<R> *__restrict__ B, cx<R> *__restrict__ C, cx<R> *__restrict__ ws,
+                 const int32_t *__restrict__ slice_id) {
+  using T = cx<R>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *sA = reinterpret_cast<T *>(smem_raw);
+  T *sB = sA + (P.sa_stride << P.tkb);
+  T *sC = reinterpret_cast<T *>(smem_raw);
+  // per-iteration parts of the tile enumerations (bits 8.. of the element index)
+  __shared__ long long a_it_g[16], b_it_g[16], c_it_g[16];
+  __shared__ int a_it_s[16], b_it_s[16];
+
+  const int t = threadIdx.x;
+  const int TK = 1 << P.tkb;
+
+  // ---- which tile ----------------------------------------------------------
+  unsigned long long id = blockIdx.x;
+  const unsigned split = (unsigned)(id & ((1ull << P.split_bits) - 1));
+  id >>= P.split_bits;
+  const unsigned long long mh = id & ((1ull << P.n_mhi) - 1);
+  id >>= P.n_mhi;
+  const unsigned long long nh = id & ((1ull << P.n_nhi) - 1);
+  id >>= P.n_nhi;
+  const unsigned long long bt = id;
+
+  const long long a_base = deposit(mh, P.a_mhi, P.n_mhi) | deposit(bt, P.a_bat, P.n_batch) |
+                           slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
+  const long long b_base = deposit(nh, P.b_nhi, P.n_nhi) | deposit(bt, P.b_bat, P.n_batch) |
+                           slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
+  const long long c_base = deposit(mh, P.c_mhi, P.n_mhi) | deposit(nh, P.c_nhi, P.n_nhi) |
+                           deposit(bt, P.c_bat, P.n_batch);
+
+  // ---- enumeration tables ---------------------------------------------------
+  if (t < 16) {
+    long long g = 0; int s = 0;
+    for (int j = 8; j < P.na_lo; ++j)
+      if ((t >> (j - 8)) & 1) {
+        if (P.a_lo_pos[j] == 255) g = -1; else if (g >= 0) g |= 1ll << P.a_lo_pos[j];
+        s += P.a_lo_sstr[j];
+      }
+    a_it_g[t] = g; a_it_s[t] = s;
+    g = 0; s = 0;
+    for (int j = 8; j < P.nb_lo; ++j)
+      if ((t >> (j - 8)) & 1) {
+        if (P.b_lo_pos[j] == 255) g = -1; else if (g >= 0) g |= 1ll << P.b_lo_pos[j];
+        s += P.b_lo_sstr[j];
+      }
+    b_it_g[t] = g; b_it_s[t] = s;
+    g = 0;
+    for (int j = 8; j < P.nc_lo; ++j)
+      if ((t >> (j - 8)) & 1) g |= 1ll << P.c_lo_pos[j];
+    c_it_g[t] = g;
+  }
+  long long a_t_g = 0, b_t_g = 0, c_t_g = 0;
+  int a_t_s = 0, b_t_s = 0;
+  for (int j = 0; j < 8; ++j) {
+    if (!((t >> j) & 1)) continue;
+    if (j < P.na_lo) {
+      if (P.a_lo_pos[j] == 255) a_t_g = -1; else if (a_t_g >= 0) a_t_g |= 1ll << P.a_lo_pos[j];
+      a_t_s += P.a_lo_sstr[j];
+    }
+    if (j < P.nb_lo) {
+      if (P.b_lo_pos[j] == 255) b_t_g = -1; else if (b_t_g >= 0) b_t_g |= 1ll << P.b_lo_pos[j];
+      b_t_s += P.b_lo_sstr[j];
+    }
+    if (j < P.nc_lo) c_t_g |= 1ll << P.c_lo_pos[j];
+  }
+  const bool a_act = P.na_lo >= 8 || t < (1 << P.na_lo);
+  const bool b_act = P.nb_lo >= 8 || t < (1 << P.nb_lo);
+  const int a_nit = P.na_lo > 8 ? 1 << (P.na_lo - 8) : 1;
+  const int b_nit = P.nb_lo > 8 ? 1 << (P.nb_lo - 8) : 1;
+
+  // ---- thread's 4x4 outputs --------------------------------------------------
+  const int tn = t & ((1 << (P.tnb - 2)) - 1);
+  const int tm = t >> (P.tnb - 2);
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = cx_zero<R>();
+
+  // ---- K loop -----------------------------------------------------------------
+  const int k_iters_bits = P.n_khi - P.split_bits;
+  const unsigned long long k_iters = 1ull << k_iters_bits;
+  const unsigned long long kh0 = (unsigned long long)split << k_iters_bits;
+  long long a_k = deposit(kh0, P.a_khi, P.n_khi);
+  long long b_k = deposit(kh0, P.b_khi, P.n_khi);
+  __syncthreads();
+
+  for (unsigned long long kk = 0; kk < k_iters; ++kk) {
+    // global -> shared, ascending address order of each operand
+    if (a_act) {
+      for (int it = 0; it < a_nit; ++it) {
+        const long long g = a_it_g[it];
+        T v = cx_zero<R>();
+        if (a_t_g >= 0 && g >= 0) {
+          v = A[a_base + a_k + (a_t_g | g)];
+          if (P.conj_a) v.y = -v.y;
+        }
+        sA[a_t_s + a_it_s[it]] = v;
+      }
+    }
+    if (b_act) {
+      for (int it = 0; it < b_nit; ++it) {
+        const long long g = b_it_g[it];
+        T v = cx_zero<R>();
+        if (b_t_g >= 0 && g >= 0) {
+          v = B[b_base + b_k + (b_t_g | g)];
+          if (P.conj_b) v.y = -v.y;
+        }
+        sB[b_t_s + b_it_s[it]] = v;
+      }
+    }
+    __syncthreads();
+    const T *pa = sA + tm * 4;
+    const T *pb = sB + tn * 4;
+#pragma unroll 4
+    for (int k = 0; k < TK; ++k) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = pa[i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = pb[j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cfma<R>(acc[i][j], a[i], b[j]);
+      pa += P.sa_stride;
+      pb += P.sb_stride;
+    }
+    __syncthreads();
+    // next k_hi: flip the trailing bits that change between kk and kk+1
+    const unsigned long long flip = kk ^ (kk + 1);
+    const int nflip = 64 - __clzll(flip);
+    for (int i = 0; i < nflip && i < k_iters_bits; ++i) {
+      a_k ^= 1ll << P.a_khi[i];
+      b_k ^= 1ll << P.b_khi[i];
+    }
+  }
+
+  // ---- epilogue: registers -> staging (C address order) -> global ---------------
+  int mi[4], nj[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = tm * 4 + i, n = tn * 4 + i;
+    int sm = 0, sn = 0;
+    for (int b = 0; b < P.tmb; ++b) if ((m >> b) & 1) sm += P.c_m_sidx[b];
+    for (int b = 0; b < P.tnb; ++b) if ((n >> b) & 1) sn += P.c_n_sidx[b];
+    mi[i] = sm; nj[i] = sn;
+  }
+  const int c_count = 1 << P.nc_lo;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = mi[i] + nj[j];
+      if (idx < c_count) sC[idx] = acc[i][j];
+    }
+  __syncthreads();
+  T *out = C;
+  long long out_off = c_base;
+  if (P.split_bits) { out = ws; out_off += (long long)split * P.c_elems; }
+  for (int e = t, it = 0; e < c_count; e += 256, ++it) {
+    const long long g = out_off + (c_t_g | c_it_g[it]);
+    T v = sC[e];
+    if (P.accumulate && !P.split_bits) { const T o = out[g]; v.x += o.x; v.y += o.y; }
+    out[g] = v;
+  }
+}
+
+// C (+)= sum over split-K partials, elementwise (C dense: c_elems contiguous elements)
+template <typename R>
+__global__ void __launch_bounds__(256)
+splitk_sum_kernel(cx<R> *__restrict__ C, const cx<R> *__restrict__ ws, long long c_elems, int nsplit,
+                  int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c_elems) return;
+  cx<R> s = cx_zero<R>();
+  for (int k = 0; k < nsplit; ++k) { const cx<R> v = ws[k * c_elems + i]; s.x += v.x; s.y += v.y; }
+  if (accumulate) { const cx<R> o = C[i]; s.x += o.x; s.y += o.y; }
+  C[i] = s;
+}
+
+// --------------------------------------------------------------------------
+// K-parallel reduction kernel: outputs <= 16, long contracted extent.
+// Each thread walks k = base + t + 256*it (logical k order = ascending
+// min(address bit in A, address bit in B)), accumulating all M*N outputs.
+// --------------------------------------------------------------------------
+template <typename R, int MB, int NB>
+__global__ void __launch_bounds__(256)
+gett_reduce_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restrict__ A,
+                   const cx<R> *__restrict__ B, cx<R> *__restrict__ ws,
+                   const int32_t *__restrict__ slice_id) {
+  using T = cx<R>;
+  constexpr int M = 1 << MB, N = 1 << NB;
+  __shared__ T red[8][M * N];
+  const int t = threadIdx.x;
+  const int chunk = P.red_chunk_bits;
+  long long a_m[M], b_n[N];
+#pragma unroll
+  for (int m = 0; m < M; ++m) a_m[m] = deposit(m, P.a_mhi, MB);
+#pragma unroll
+  for (int n = 0; n < N; ++n) b_n[n] = deposit(n, P.b_nhi, NB);
+  const long long a_base = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
+  const long long b_base = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
+  const int tb = chunk < 8 ? chunk : 8;   // bits of k carried by the thread id
+  const unsigned long long k0 = ((unsigned long long)blockIdx.x << chunk) | (unsigned)t;
+  long long a_k = a_base | deposit(k0, P.a_khi, P.n_khi);
+  long long b_k = b_base | deposit(k0, P.b_khi, P.n_khi);
+  T acc[M * N];
+#pragma unroll
+  for (int i = 0; i < M * N; ++i) acc[i] = cx_zero<R>();
+  const int it_bits = chunk - tb;
+  const unsigned iters = (t < (1 << tb)) ? (1u << it_bits) : 0u;
+  for (unsigned it = 0; it < iters; ++it) {
+    T a[M], b[N];
+#pragma unroll
+    for (int m = 0; m < M; ++m) { a[m] = A[a_k | a_m[m]]; if (P.conj_a) a[m].y = -a[m].y; }
+#pragma unroll
+    for (int n = 0; n < N; ++n) { b[n] = B[b_k | b_n[n]]; if (P.conj_b) b[n].y = -b[n].y; }
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+      for (int n = 0; n < N; ++n) cfma<R>(acc[m * N + n], a[m], b[n]);
+    const unsigned flip = it ^ (it + 1);
+    const int nflip = 32 - __clz(flip);
+    for (int i = 0; i < nflip && i < it_bits; ++i) {
+      a_k ^= 1ll << P.a_khi[tb + i];
+      b_k ^= 1ll << P.b_khi[tb + i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < M * N; ++i) {
+    R x = acc[i].x, y = acc[i].y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      x += __shfl_xor_sync(0xffffffffu, x, o);
+      y += __shfl_xor_sync(0xffffffffu, y, o);
+    }
+    if ((t & 31) == 0) { red[t >> 5][i].x = x; red[t >> 5][i].y = y; }
+  }
+  __syncthreads();
+  if (t < M * N) {
+    T s = cx_zero<R>();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { s.x += red[w][t].x; s.y += red[w][t].y; }
+    ws[(long long)blockIdx.x * 16 + t] = s;
+  }
+}
+
+// second stage: one CTA sums the per-CTA partials and writes the (<=16) outputs
+template <typename R>
+__global__ void __launch_bounds__(256)
+reduce_final_kernel(const __grid_constant__ qtn_pair_plan_t P, cx<R> *__restrict__ C,
+                    const cx<R> *__restrict__ ws, long long nparts) {
+  using T = cx<R>;
+  __shared__ T red[8][16];
+  const int t = threadIdx.x;
+  const int MN = 1 << (P.n_mhi + P.n_nhi);
+  T s[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s[i] = cx_zero<R>();
+  for (long long p = t; p < nparts; p += 256)
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < MN) { const T v = ws[p * 16 + i]; s[i].x += v.x; s[i].y += v.y; }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    R x = s[i].x, y = s[i].y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      x += __shfl_xor_sync(0xffffffffu, x, o);
+      y += __shfl_xor_sync(0xffffffffu, y, o);
+    }
+    if ((t & 31) == 0) { red[t >> 5][i].x = x; red[t >> 5][i].y = y; }
+  }
+  __syncthreads();
+  if (t < MN) {
+    T v = cx_zero<R>();
+    for (int w = 0; w < 8; ++w) { v.x += red[w][t].x; v.y += red[w][t].y; }
+    // acc index = m * N + n
+    const int n = t & ((1 << P.n_nhi) - 1), m = t >> P.n_nhi;
+    const long long g = deposit(m, P.c_mhi, P.n_mhi) | deposit(n, P.c_nhi, P.n_nhi);
+    if (P.accumulate) { const T o = C[g]; v.x += o.x; v.y += o.y; }
+    C[g] = v;
+  }
+}
+
+template <typename R>
+int launch_tile(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
+                const int32_t *slice_id, cudaStream_t st) {
+  using T = cx<R>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tile_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        4096 * (int)sizeof(T)));
+    attr_set = true;
+  }
+  if (P.grid <= 0 || P.grid > 0x7fffffffLL) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_run: grid too large");
+  gett_tile_kernel<R><<<(unsigned)P.grid, 256, P.smem_bytes, st>>>(
+      P, (const T *)a, (const T *)b, (T *)c, (T *)ws, slice_id);
+  QTN_LAUNCH_CHECK();
+  if (P.split_bits) {
+    const long long n = P.c_elems;
+    splitk_sum_kernel<R><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((T *)c, (const T *)ws, n,
+                                                                     1 << P.split_bits, P.accumulate);
+    QTN_LAUNCH_CHECK();
+  }
+  return QTN_OK;
+}
+
+template <typename R, int MB, int NB>
+int launch_reduce_mn(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
+                     const int32_t *slice_id, cudaStream_t st) {
+  using T = cx<R>;
+  gett_reduce_kernel<R, MB, NB><<<(unsigned)P.grid, 256, 0, st>>>(P, (const T *)a, (const T *)b,
+                                                                  (T *)ws, slice_id);
+  QTN_LAUNCH_CHECK();
+  reduce_final_kernel<R><<<1, 256, 0, st>>>(P, (T *)c, (const T *)ws, P.grid);
+  QTN_LAUNCH_CHECK();
+  return QTN_OK;
+}
+
+template <typename R>
+int launch_reduce(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
+                  const int32_t *slice_id, cudaStream_t st) {
+  const int key = P.n_mhi * 8 + P.n_nhi;
+  switch (key) {
+#define QTN_CASE(MB, NB) \
+  case MB * 8 + NB: return launch_reduce_mn<R, MB, NB>(P, a, b, c, ws, slice_id, st);
+    QTN_CASE(0, 0) QTN_CASE(1, 0) QTN_CASE(2, 0) QTN_CASE(3, 0) QTN_CASE(4, 0)
+    QTN_CASE(1, 1) QTN_CASE(2, 1) QTN_CASE(3, 1) QTN_CASE(2, 2)
+#undef QTN_CASE
+    default: return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_run: reduce kernel needs m >= n, m + n <= 4");
+  }
+}
+
+}  // namespace
+
+extern "C" int qtn_pair_run(const qtn_pair_plan_t *plan, const void *a, const void *b, void *c,
+                            void *workspace, const int32_t *slice_id, void *stream) {
+  if (!plan || !a || !b || !c) return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: null argument");
+  if (plan->workspace_bytes > 0 && !workspace)
+    return qtn_fail(QTN_ERR_WORKSPACE, "qtn_pair_run: plan needs a workspace");
+  if ((plan->n_slice_a || plan->n_slice_b) && !slice_id)
+    return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: plan has sliced labels but slice_id is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->swapped) { const void *tmp = a; a = b; b = tmp; }
+  const bool f32 = plan->dtype == QTN_C64;
+  if (plan->kernel == QTN_KERNEL_TILE)
+    return f32 ? launch_tile<float>(*plan, a, b, c, workspace, slice_id, st)
+               : launch_tile<double>(*plan, a, b, c, workspace, slice_id, st);
+  if (plan->kernel == QTN_KERNEL_REDUCE)
+    return f32 ? launch_reduce<float>(*plan, a, b, c, workspace, slice_id, st)
+               : launch_reduce<double>(*plan, a, b, c, workspace, slice_id, st);
+  return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: unknown kernel id");
+}

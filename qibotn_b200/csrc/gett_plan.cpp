@@ -1,0 +1,253 @@
+// Host-side planning of one pairwise bit-tensor contraction: label roles,
+// tile shape, which labels live inside a tile (chosen so that global loads and
+// stores walk contiguous addresses), C's layout when the caller leaves it free,
+// split-K, launch geometry.  Pure function of the descriptor: no CUDA calls,
+// so it is unit-tested on CPU-only machines.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "qtn_internal.h"
+
+namespace {
+
+struct Lab {
+  int label;
+  int pa = -1, pb = -1, pc = -1;  // address bit positions (-1: absent)
+};
+
+int find_label(const int32_t *labels, int n, int label) {
+  for (int i = 0; i < n; ++i)
+    if (labels[i] == label) return i;
+  return -1;
+}
+
+constexpr int kPhantom = 255;
+
+}  // namespace
+
+extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p) {
+  if (!d || !p) return qtn_fail(QTN_ERR_ARG, "qtn_pair_plan: null argument");
+  if (d->dtype != QTN_C64 && d->dtype != QTN_C128)
+    return qtn_fail(QTN_ERR_ARG, "qtn_pair_plan: dtype must be QTN_C64 or QTN_C128");
+  if (d->rank_a < 0 || d->rank_b < 0 || d->rank_c < 0 || d->rank_a > QTN_MAX_RANK ||
+      d->rank_b > QTN_MAX_RANK || d->rank_c > QTN_MAX_RANK)
+    return qtn_fail(QTN_ERR_ARG, "qtn_pair_plan: rank out of range");
+  if (d->n_slice_a < 0 || d->n_slice_b < 0 || d->n_slice_a > QTN_MAX_SLICE ||
+      d->n_slice_b > QTN_MAX_SLICE)
+    return qtn_fail(QTN_ERR_ARG, "qtn_pair_plan: too many sliced labels on one operand");
+  if (sm_count <= 0) sm_count = 148;
+  std::memset(p, 0, sizeof(*p));
+
+  // ---- swap so that the left free extent is the larger one -----------------
+  int free_a = 0, free_b = 0;
+  for (int i = 0; i < d->rank_a; ++i)
+    if (find_label(d->label_b, d->rank_b, d->label_a[i]) < 0) ++free_a;
+  for (int i = 0; i < d->rank_b; ++i)
+    if (find_label(d->label_a, d->rank_a, d->label_b[i]) < 0) ++free_b;
+  const bool swap = free_b > free_a;
+  const int32_t *la = swap ? d->label_b : d->label_a;
+  const uint8_t *pa = swap ? d->pos_b : d->pos_a;
+  const int ra = swap ? d->rank_b : d->rank_a;
+  const int32_t *lb = swap ? d->label_a : d->label_b;
+  const uint8_t *pb = swap ? d->pos_a : d->pos_b;
+  const int rb = swap ? d->rank_a : d->rank_b;
+  p->swapped = swap;
+  p->dtype = d->dtype;
+  p->conj_a = swap ? d->conj_b : d->conj_a;
+  p->conj_b = swap ? d->conj_a : d->conj_b;
+  p->accumulate = d->accumulate;
+  p->n_slice_a = swap ? d->n_slice_b : d->n_slice_a;
+  p->n_slice_b = swap ? d->n_slice_a : d->n_slice_b;
+  std::memcpy(p->slice_bit_a, swap ? d->slice_bit_b : d->slice_bit_a, QTN_MAX_SLICE);
+  std::memcpy(p->slice_pos_a, swap ? d->slice_pos_b : d->slice_pos_a, QTN_MAX_SLICE);
+  std::memcpy(p->slice_bit_b, swap ? d->slice_bit_a : d->slice_bit_b, QTN_MAX_SLICE);
+  std::memcpy(p->slice_pos_b, swap ? d->slice_pos_a : d->slice_pos_b, QTN_MAX_SLICE);
+
+  // ---- classify labels ------------------------------------------------------
+  std::vector<Lab> M, N, K, Bt;
+  for (int i = 0; i < ra; ++i) {
+    Lab l;
+    l.label = la[i];
+    l.pa = pa[i];
+    for (int j = 0; j < i; ++j)
+      if (la[j] == la[i]) return qtn_fail(QTN_ERR_ARG, "qtn_pair_plan: repeated label in an operand");
+    int jb = find_label(lb, rb, l.label);
+    int jc = find_label(d->label_c, d->rank_c, l.label);
+    if (jb >= 0) l.pb = pb[jb];
+    if (jc >= 0) l.pc = d->c_layout_free ? -1 : d->pos_c[jc];
+    if (jb >= 0 && jc >= 0) Bt.push_back(l);
+    else if (jb >= 0) K.push_back(l);
+    else if (jc >= 0) M.push_back(l);
+    else return qtn_fail(QTN_ERR_ARG, "qtn_pair_plan: label of A is neither in B nor in C");
+  }
+  for (int i = 0; i < rb; ++i) {
+    if (find_label(la, ra, lb[i]) >= 0) continue;
+    Lab l;
+    l.label = lb[i];
+    l.pb = pb[i];
+    int jc = find_label(d->label_c, d->rank_c, l.label);
+    if (jc < 0) return qtn_fail(QTN_ERR_ARG, "qtn_pair_plan: label of B is neither in A nor in C");
+    l.pc = d->c_layout_free ? -1 : d->pos_c[jc];
+    N.push_back(l);
+  }
+  if ((int)(M.size() + N.size() + Bt.size()) != d->rank_c)
+    return qtn_fail(QTN_ERR_ARG, "qtn_pair_plan: C has labels found in neither operand");
+  const int mbits = (int)M.size(), nbits = (int)N.size(), kbits = (int)K.size(),
+            bbits = (int)Bt.size();
+  const int esz = d->dtype == QTN_C64 ? 8 : 16;
+  p->flops = 8.0 * std::ldexp(1.0, mbits + nbits + kbits + bbits);
+  p->bytes = esz * (std::ldexp(1.0, ra) + std::ldexp(1.0, rb) + std::ldexp(1.0, d->rank_c));
+  p->c_elems = (int64_t)1 << d->rank_c;
+  p->block = 256;
+
+  std::vector<std::pair<int, int>> assigned;   // (label, chosen C position) when C is free
+  // positions below this many bits are "forced" into a tile for coalescing
+  const int cforce = d->dtype == QTN_C64 ? 4 : 3;
+
+  // ---- K-parallel reduction for tiny outputs --------------------------------
+  if (bbits == 0 && mbits + nbits <= 4 && kbits >= 10) {
+    p->kernel = QTN_KERNEL_REDUCE;
+    std::sort(K.begin(), K.end(), [](const Lab &x, const Lab &y) {
+      return std::min(x.pa, x.pb) != std::min(y.pa, y.pb) ? std::min(x.pa, x.pb) < std::min(y.pa, y.pb)
+                                                          : x.label < y.label;
+    });
+    std::sort(M.begin(), M.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
+    std::sort(N.begin(), N.end(), [](const Lab &x, const Lab &y) { return x.pb < y.pb; });
+    int next_c = 0;
+    // C layout when free: n bits lowest, then m bits
+    for (auto &l : N) if (d->c_layout_free) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
+    for (auto &l : M) if (d->c_layout_free) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
+    p->n_mhi = mbits; p->n_nhi = nbits; p->n_khi = kbits;
+    for (int i = 0; i < mbits; ++i) { p->a_mhi[i] = M[i].pa; p->c_mhi[i] = M[i].pc; }
+    for (int i = 0; i < nbits; ++i) { p->b_nhi[i] = N[i].pb; p->c_nhi[i] = N[i].pc; }
+    for (int i = 0; i < kbits; ++i) { p->a_khi[i] = K[i].pa; p->b_khi[i] = K[i].pb; }
+    p->m_real = mbits; p->n_real = nbits; p->k_real = kbits;
+    // 2^chunk k values per CTA; aim for >= 4 CTAs per SM but at least 2^11 per CTA
+    int chunk = std::max(11, kbits - (int)std::ceil(std::log2((double)sm_count * 8)));
+    chunk = std::min(chunk, kbits);
+    p->red_chunk_bits = chunk;
+    p->grid = (int64_t)1 << (kbits - chunk);
+    p->smem_bytes = 0;
+    p->workspace_bytes = p->grid * 16 * esz;
+  } else {
+    // ---- shared-memory tiled kernel -----------------------------------------
+    p->kernel = QTN_KERNEL_TILE;
+    int tmb, tnb;
+    if (nbits >= 6 && mbits >= 6) { tmb = 6; tnb = 6; }
+    else if (nbits < 6) { tnb = std::max(nbits, 2); tmb = 12 - tnb; }
+    else { tmb = std::max(mbits, 2); tnb = 12 - tmb; }   // unreachable after swap, kept for safety
+    const int TM = 1 << tmb, TN = 1 << tnb;
+    int tkb = 4;
+    while (tkb > 0 && (1 << tkb) * (TM + TN + 4) > 4096) --tkb;
+    tkb = std::min(tkb, kbits);
+    p->tmb = tmb; p->tnb = tnb; p->tkb = tkb;
+    p->sa_stride = TM + 2; p->sb_stride = TN + 2;
+
+    // pick which labels sit inside the tile
+    auto pick = [&](std::vector<Lab> &v, int want, auto key, auto forced) {
+      std::stable_sort(v.begin(), v.end(), [&](const Lab &x, const Lab &y) {
+        bool fx = forced(x), fy = forced(y);
+        if (fx != fy) return fx;
+        if (key(x) != key(y)) return key(x) < key(y);
+        return x.label < y.label;
+      });
+      int take = std::min<int>(want, (int)v.size());
+      std::vector<Lab> lo(v.begin(), v.begin() + take), hi(v.begin() + take, v.end());
+      return std::make_pair(lo, hi);
+    };
+    auto m_sel = pick(M, tmb, [](const Lab &l) { return l.pa; },
+                      [&](const Lab &l) { return l.pa < cforce || (l.pc >= 0 && l.pc < cforce); });
+    auto n_sel = pick(N, tnb, [](const Lab &l) { return l.pb; },
+                      [&](const Lab &l) { return l.pb < cforce || (l.pc >= 0 && l.pc < cforce); });
+    auto k_sel = pick(K, tkb, [](const Lab &l) { return std::min(l.pa, l.pb); },
+                      [&](const Lab &l) { return l.pa < cforce || l.pb < cforce; });
+    std::vector<Lab> &mlo = m_sel.first, &mhi = m_sel.second;
+    std::vector<Lab> &nlo = n_sel.first, &nhi = n_sel.second;
+    std::vector<Lab> &klo = k_sel.first, &khi = k_sel.second;
+    // logical bit order inside the tile = ascending address bit of the operand read
+    std::sort(mlo.begin(), mlo.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
+    std::sort(nlo.begin(), nlo.end(), [](const Lab &x, const Lab &y) { return x.pb < y.pb; });
+    std::sort(klo.begin(), klo.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
+    std::sort(mhi.begin(), mhi.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
+    std::sort(nhi.begin(), nhi.end(), [](const Lab &x, const Lab &y) { return x.pb < y.pb; });
+    std::sort(khi.begin(), khi.end(), [](const Lab &x, const Lab &y) {
+      return std::max(x.pa, x.pb) < std::max(y.pa, y.pb);
+    });
+    std::sort(Bt.begin(), Bt.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
+    p->m_real = (int)mlo.size(); p->n_real = (int)nlo.size(); p->k_real = (int)klo.size();
+    p->n_mhi = (int)mhi.size(); p->n_nhi = (int)nhi.size(); p->n_khi = (int)khi.size();
+    p->n_batch = bbits;
+    if (bbits > QTN_LO_MAX) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_plan: too many batch labels");
+
+    // C layout when free: tile bits lowest (n then m), then n-hi, m-hi, batch
+    if (d->c_layout_free) {
+      int next_c = 0;
+      for (auto *v : {&nlo, &mlo, &nhi, &mhi, &Bt})
+        for (auto &l : *v) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
+    }
+
+    // A tile enumeration: (m_lo, k_lo) labels sorted by A position; phantoms last
+    struct E { int pos; int sstr; };
+    std::vector<E> ea, eb;
+    for (int i = 0; i < tmb; ++i)
+      ea.push_back({i < (int)mlo.size() ? mlo[i].pa : kPhantom, 1 << i});
+    for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, p->sa_stride << i});
+    for (int i = 0; i < tnb; ++i)
+      eb.push_back({i < (int)nlo.size() ? nlo[i].pb : kPhantom, 1 << i});
+    for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, p->sb_stride << i});
+    auto by_pos = [](const E &x, const E &y) { return x.pos < y.pos; };
+    std::stable_sort(ea.begin(), ea.end(), by_pos);
+    std::stable_sort(eb.begin(), eb.end(), by_pos);
+    p->na_lo = (int)ea.size(); p->nb_lo = (int)eb.size();
+    for (int i = 0; i < p->na_lo; ++i) { p->a_lo_pos[i] = (uint8_t)ea[i].pos; p->a_lo_sstr[i] = (uint16_t)ea[i].sstr; }
+    for (int i = 0; i < p->nb_lo; ++i) { p->b_lo_pos[i] = (uint8_t)eb[i].pos; p->b_lo_sstr[i] = (uint16_t)eb[i].sstr; }
+
+    // epilogue: real tile labels of C sorted by C position; staging index = rank in that order
+    struct CE { int pos; bool is_m; int bit; };
+    std::vector<CE> ec;
+    for (int i = 0; i < (int)mlo.size(); ++i) ec.push_back({mlo[i].pc, true, i});
+    for (int i = 0; i < (int)nlo.size(); ++i) ec.push_back({nlo[i].pc, false, i});
+    std::sort(ec.begin(), ec.end(), [](const CE &x, const CE &y) { return x.pos < y.pos; });
+    p->nc_lo = (int)ec.size();
+    for (int r = 0; r < p->nc_lo; ++r) {
+      p->c_lo_pos[r] = (uint8_t)ec[r].pos;
+      if (ec[r].is_m) p->c_m_sidx[ec[r].bit] = (uint16_t)(1 << r);
+      else p->c_n_sidx[ec[r].bit] = (uint16_t)(1 << r);
+    }
+    // phantom m/n bits: staging index beyond the real range (never stored)
+    {
+      int r = p->nc_lo;
+      for (int i = (int)mlo.size(); i < tmb; ++i) p->c_m_sidx[i] = (uint16_t)(1 << r++);
+      for (int i = (int)nlo.size(); i < tnb; ++i) p->c_n_sidx[i] = (uint16_t)(1 << r++);
+    }
+    if ((int)mhi.size() > QTN_HI_MAX || (int)nhi.size() > QTN_HI_MAX || (int)khi.size() > QTN_HI_MAX)
+      return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_plan: rank too large");
+    for (int i = 0; i < (int)mhi.size(); ++i) { p->a_mhi[i] = mhi[i].pa; p->c_mhi[i] = mhi[i].pc; }
+    for (int i = 0; i < (int)nhi.size(); ++i) { p->b_nhi[i] = nhi[i].pb; p->c_nhi[i] = nhi[i].pc; }
+    for (int i = 0; i < (int)khi.size(); ++i) { p->a_khi[i] = khi[i].pa; p->b_khi[i] = khi[i].pb; }
+    for (int i = 0; i < bbits; ++i) { p->a_bat[i] = Bt[i].pa; p->b_bat[i] = Bt[i].pb; p->c_bat[i] = Bt[i].pc; }
+
+    // split-K when the tile grid cannot fill the machine
+    const double tiles = std::ldexp(1.0, p->n_mhi + p->n_nhi + p->n_batch);
+    int split = 0;
+    while (split < p->n_khi - 1 && tiles * (1 << split) < 2.0 * sm_count) ++split;
+    p->split_bits = split;
+    int64_t grid_tiles = (int64_t)1 << (p->n_mhi + p->n_nhi + p->n_batch);
+    p->grid = grid_tiles << split;
+    p->workspace_bytes = split ? ((int64_t)esz << (d->rank_c + split)) : 0;
+    int tile_bytes = ((1 << tkb) * (p->sa_stride + p->sb_stride)) * esz;
+    int stage_bytes = 4096 * esz;
+    p->smem_bytes = std::max(tile_bytes, stage_bytes);
+  }
+
+  // write the chosen layout of C back to the descriptor
+  for (const auto &lp : assigned) {
+    int jc = find_label(d->label_c, d->rank_c, lp.first);
+    d->pos_c[jc] = (uint8_t)lp.second;
+  }
+  return QTN_OK;
+}

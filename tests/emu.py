@@ -1,0 +1,141 @@
+"""Numpy emulation of the *address algebra* of the GETT kernels, driven by the
+launch-ready ``qtn_pair_plan_t`` the C library produces.
+
+Test infrastructure only: it lets CPU-only runs check that the host planner's
+tables (tile membership, enumeration orders, staging indices, split-K, slices)
+describe the right contraction, without a GPU.  It mirrors the kernel loop
+structure on purpose (tile -> k_hi loop -> staged epilogue) but computes the
+tile product with numpy.
+"""
+
+import numpy as np
+
+
+def dep(idx, pos, n):
+    off = 0
+    for i in range(n):
+        if (idx >> i) & 1:
+            off |= 1 << pos[i]
+    return off
+
+
+def slice_off(slice_id, n, bits, pos):
+    off = 0
+    for i in range(n):
+        if (slice_id >> bits[i]) & 1:
+            off |= 1 << pos[i]
+    return off
+
+
+def flat_from_dense(arr, labels, pos):
+    """Dense numpy array with axes ``labels`` -> flat address-indexed vector for layout ``pos``."""
+    r = len(labels)
+    size = 1 << (max(pos) + 1) if r else 1
+    flat = np.zeros(size, dtype=arr.dtype)
+    it = np.ndindex(*arr.shape) if r else [()]
+    for idx in it:
+        off = sum(v << p for v, p in zip(idx, pos))
+        flat[off] = arr[idx]
+    return flat
+
+
+def dense_from_flat(flat, labels, pos):
+    r = len(labels)
+    out = np.zeros((2,) * r, dtype=flat.dtype)
+    it = np.ndindex(*out.shape) if r else [()]
+    for idx in it:
+        off = sum(v << p for v, p in zip(idx, pos))
+        out[idx] = flat[off]
+    return out
+
+
+def run_plan(P, a, b, c, slice_id=0):
+    """Emulate qtn_pair_run on flat address-indexed numpy vectors (c is updated in place)."""
+    if P.swapped:
+        a, b = b, a
+    if P.conj_a:
+        a = a.conj()
+    if P.conj_b:
+        b = b.conj()
+    sa = slice_off(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a)
+    sb = slice_off(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b)
+    if P.kernel == 1:
+        return _run_reduce(P, a, b, c, sa, sb)
+    TM, TN, TK = 1 << P.tmb, 1 << P.tnb, 1 << P.tkb
+    nsplit = 1 << P.split_bits
+    ws = np.zeros((nsplit, P.c_elems), dtype=c.dtype)
+    kbits = P.n_khi - P.split_bits
+    for cta in range(P.grid):
+        split = cta & (nsplit - 1)
+        rest = cta >> P.split_bits
+        mh = rest & ((1 << P.n_mhi) - 1)
+        rest >>= P.n_mhi
+        nh = rest & ((1 << P.n_nhi) - 1)
+        bt = rest >> P.n_nhi
+        a_base = dep(mh, P.a_mhi, P.n_mhi) | dep(bt, P.a_bat, P.n_batch) | sa
+        b_base = dep(nh, P.b_nhi, P.n_nhi) | dep(bt, P.b_bat, P.n_batch) | sb
+        c_base = dep(mh, P.c_mhi, P.n_mhi) | dep(nh, P.c_nhi, P.n_nhi) | dep(bt, P.c_bat, P.n_batch)
+        acc = np.zeros((TM, TN), dtype=c.dtype)
+        for kk in range(1 << kbits):
+            kh = (split << kbits) | kk
+            a_k, b_k = dep(kh, P.a_khi, P.n_khi), dep(kh, P.b_khi, P.n_khi)
+            s_a = np.zeros(TK * P.sa_stride, dtype=c.dtype)
+            s_b = np.zeros(TK * P.sb_stride, dtype=c.dtype)
+            for (n_lo, lo_pos, lo_sstr, smem, src, base) in (
+                    (P.na_lo, P.a_lo_pos, P.a_lo_sstr, s_a, a, a_base + a_k),
+                    (P.nb_lo, P.b_lo_pos, P.b_lo_sstr, s_b, b, b_base + b_k)):
+                for e in range(1 << n_lo):
+                    g, s, ph = 0, 0, False
+                    for j in range(n_lo):
+                        if (e >> j) & 1:
+                            if lo_pos[j] == 255:
+                                ph = True
+                            else:
+                                g |= 1 << lo_pos[j]
+                            s += lo_sstr[j]
+                    smem[s] = 0 if ph else src[base + g]
+            am = s_a.reshape(TK, P.sa_stride)[:, :TM]
+            bm = s_b.reshape(TK, P.sb_stride)[:, :TN]
+            acc += am.T @ bm
+        count = 1 << P.nc_lo
+        stage = np.zeros(4096, dtype=c.dtype)
+        for m in range(TM):
+            sm = sum(P.c_m_sidx[bb] for bb in range(P.tmb) if (m >> bb) & 1)
+            for n in range(TN):
+                sn = sum(P.c_n_sidx[bb] for bb in range(P.tnb) if (n >> bb) & 1)
+                if sm + sn < count:
+                    stage[sm + sn] = acc[m, n]
+        for e in range(count):
+            g = c_base + dep(e, P.c_lo_pos, P.nc_lo)
+            if P.split_bits:
+                ws[split, g] = stage[e]
+            elif P.accumulate:
+                c[g] += stage[e]
+            else:
+                c[g] = stage[e]
+    if P.split_bits:
+        tot = ws.sum(0)
+        if P.accumulate:
+            c[: P.c_elems] += tot
+        else:
+            c[: P.c_elems] = tot
+    return c
+
+
+def _run_reduce(P, a, b, c, sa, sb):
+    M, N = 1 << P.n_mhi, 1 << P.n_nhi
+    acc = np.zeros((M, N), dtype=c.dtype)
+    for k in range(1 << P.n_khi):
+        a_k = sa | dep(k, P.a_khi, P.n_khi)
+        b_k = sb | dep(k, P.b_khi, P.n_khi)
+        av = np.array([a[a_k | dep(m, P.a_mhi, P.n_mhi)] for m in range(M)])
+        bv = np.array([b[b_k | dep(n, P.b_nhi, P.n_nhi)] for n in range(N)])
+        acc += np.outer(av, bv)
+    for m in range(M):
+        for n in range(N):
+            g = dep(m, P.c_mhi, P.n_mhi) | dep(n, P.c_nhi, P.n_nhi)
+            if P.accumulate:
+                c[g] += acc[m, n]
+            else:
+                c[g] = acc[m, n]
+    return c

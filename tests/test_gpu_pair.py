@@ -1,0 +1,133 @@
+"""GPU parity of the pairwise contraction and permute kernels through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from qibotn_b200 import lib
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _dense(flat, labels, pos, off=0):
+    idx = np.zeros((2,) * len(labels), dtype=np.int64) + off
+    for ax, p in enumerate(pos):
+        shape = [1] * len(labels)
+        shape[ax] = 2
+        idx = idx + (np.arange(2).reshape(shape) << p)
+    return flat[idx]
+
+
+def run_pair(dtype, la, pa, lb, pb, lc, pc, a, b, c0=None, slice_a=(), slice_b=(), slice_id=0,
+             accumulate=False):
+    h = lib.load()
+    tdt = torch.complex64 if dtype == "complex64" else torch.complex128
+    free = pc is None
+    desc = lib.make_pair_desc(dtype, list(zip(la, pa)), list(zip(lb, pb)),
+                              list(lc) if free else list(zip(lc, pc)),
+                              accumulate=accumulate, slice_a=slice_a, slice_b=slice_b)
+    plan = lib.pair_plan(desc)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    dc = torch.zeros(1 << len(lc), dtype=tdt, device="cuda") if c0 is None else torch.from_numpy(c0).cuda()
+    ws = torch.empty(max(int(plan.workspace_bytes), 16), dtype=torch.uint8, device="cuda")
+    sid = torch.tensor([slice_id], dtype=torch.int32, device="cuda")
+    lib.check(h.qtn_pair_run(C.byref(plan), da.data_ptr(), db.data_ptr(), dc.data_ptr(),
+                             ws.data_ptr(), sid.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    lc_used = [desc.label_c[i] for i in range(len(lc))]
+    pc_used = [desc.pos_c[i] for i in range(len(lc))]
+    return _dense(dc.cpu().numpy(), lc_used, pc_used), lc_used, plan
+
+
+CASES = [
+    (6, 6, 3, 0), (7, 7, 5, 0), (12, 2, 2, 0), (3, 13, 2, 0), (1, 1, 1, 0), (0, 0, 3, 0),
+    (2, 0, 1, 0), (9, 8, 6, 0), (4, 4, 2, 2), (7, 3, 2, 1), (1, 1, 14, 0), (2, 2, 16, 0),
+    (0, 0, 20, 0), (16, 0, 1, 0), (6, 7, 0, 0), (3, 3, 12, 0), (10, 10, 4, 0), (14, 3, 3, 0),
+    (5, 5, 10, 0), (8, 8, 8, 0),
+]
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("case", CASES)
+def test_pair_contraction_matches_einsum(case, dtype):
+    m, n, k, batch = case
+    rng = np.random.default_rng(1000 * m + 100 * n + 10 * k + batch)
+    labels = list(range(m + n + k + batch))
+    M, N, K, Bt = labels[:m], labels[m:m + n], labels[m + n:m + n + k], labels[m + n + k:]
+    la, lb, lc = M + K + Bt, K + N + Bt, M + N + Bt
+    rng.shuffle(la); rng.shuffle(lb); rng.shuffle(lc)
+    pa = [int(x) for x in rng.permutation(len(la))]
+    pb = [int(x) for x in rng.permutation(len(lb))]
+    pc = [int(x) for x in rng.permutation(len(lc))]
+    a = (rng.normal(size=1 << len(la)) + 1j * rng.normal(size=1 << len(la))).astype(dtype)
+    b = (rng.normal(size=1 << len(lb)) + 1j * rng.normal(size=1 << len(lb))).astype(dtype)
+    A = _dense(a.astype(np.complex128), la, pa)
+    B = _dense(b.astype(np.complex128), lb, pb)
+    tol = 2e-6 if dtype == "complex64" else 1e-13
+    for prescribed in (False, True):
+        got, lc_used, plan = run_pair(dtype, la, pa, lb, pb, lc, pc if prescribed else None, a, b)
+        want = np.einsum(A, la, B, lb, lc_used)
+        scale = np.abs(want).max() + 1e-30
+        assert np.abs(got - want).max() / scale < tol * max(1, k), (case, prescribed, plan.kernel)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_slices_and_accumulate(dtype):
+    rng = np.random.default_rng(5)
+    # A stored with 2 extra (sliced) bits, B with 1; C accumulates over 8 slice ids
+    la, pa, sa = [0, 1, 2, 3, 4, 5, 6], [8, 0, 3, 4, 6, 1, 7], [(0, 2), (2, 5)]
+    lb, pb, sb = [4, 5, 6, 7, 8], [0, 5, 2, 3, 1], [(1, 4)]
+    lc, pc = [0, 1, 2, 3, 7, 8], [5, 0, 1, 4, 3, 2]
+    a = (rng.normal(size=1 << 9) + 1j * rng.normal(size=1 << 9)).astype(dtype)
+    b = (rng.normal(size=1 << 6) + 1j * rng.normal(size=1 << 6)).astype(dtype)
+    c = np.zeros(1 << 6, dtype=dtype)
+    want = np.zeros((2,) * 6, dtype=np.complex128)
+    for sid in range(8):
+        offa = sum(((sid >> bt) & 1) << p for bt, p in sa)
+        offb = sum(((sid >> bt) & 1) << p for bt, p in sb)
+        want += np.einsum(_dense(a.astype(np.complex128), la, pa, offa), la,
+                          _dense(b.astype(np.complex128), lb, pb, offb), lb, lc)
+        got, _, _ = run_pair(dtype, la, pa, lb, pb, lc, pc, a, b, c0=c, slice_a=sa, slice_b=sb,
+                             slice_id=sid, accumulate=True)
+        c = np.zeros(1 << 6, dtype=dtype)
+        idx = np.zeros((2,) * 6, dtype=np.int64)
+        for ax, p in enumerate(pc):
+            shape = [1] * 6; shape[ax] = 2
+            idx = idx + (np.arange(2).reshape(shape) << p)
+        c[idx] = got
+    tol = 1e-5 if dtype == "complex64" else 1e-12
+    assert np.abs(got - want).max() < tol * np.abs(want).max()
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("rank", [0, 1, 5, 12, 13, 20, 24])
+def test_permute_bits(rank, dtype):
+    h = lib.load()
+    rng = np.random.default_rng(rank)
+    x = (rng.normal(size=1 << rank) + 1j * rng.normal(size=1 << rank)).astype(dtype)
+    pin = [int(v) for v in rng.permutation(rank)]
+    pout = [int(v) for v in rng.permutation(rank)]
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros_like(dx)
+    lib.check(h.qtn_permute_bits(lib.dtype_code(dtype), rank, lib.u8(pin), lib.u8(pout),
+                                 dx.data_ptr(), dy.data_ptr(), 0,
+                                 torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    labels = list(range(rank))
+    assert np.array_equal(_dense(dy.cpu().numpy(), labels, pout), _dense(x, labels, pin))
+
+
+def test_general_permute():
+    h = lib.load()
+    rng = np.random.default_rng(0)
+    x = (rng.normal(size=(3, 2, 5, 4)) + 1j * rng.normal(size=(3, 2, 5, 4))).astype(np.complex128)
+    perm = [2, 0, 3, 1]
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(5, 3, 4, 2, dtype=torch.complex128, device="cuda")
+    ext = (C.c_int64 * 4)(*x.shape)
+    pm = (C.c_int32 * 4)(*perm)
+    lib.check(h.qtn_permute(lib.QTN_C128, 4, ext, pm, dx.data_ptr(), dy.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(dy.cpu().numpy(), x.transpose(perm))

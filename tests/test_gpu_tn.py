@@ -1,0 +1,119 @@
+"""GPU parity of the tensor-network path through the backend surface, against the
+closed forms the reference's own tests pin and against the CPU oracle."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import contract as ocontract
+from oracle import statevector as osv
+from qibotn_b200 import MetaBackend, circuits, engine
+from qibotn_b200 import eval as ev
+from qibotn_b200.network import QiboCircuitToEinsum
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = {"complex64": 1e-5, "complex128": 1e-10}
+
+
+def _backend(dtype):
+    b = MetaBackend.load("cutensornet")
+    b.set_precision("single" if dtype == "complex64" else "double")
+    return b
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("nqubits", [1, 2, 5, 10])
+def test_eval_qft_uniform(nqubits, dtype):
+    """reference tests/test_cuquantum_cutensor_backend.py:46-85: QFT|0..0> = uniform vector."""
+    circ = circuits.qft(nqubits, True)
+    b = _backend(dtype)
+    got = b.execute_circuit(circuit=circ).statevector.flatten().get()
+    want = np.full(1 << nqubits, 2.0 ** (-nqubits / 2))
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-8 if dtype == "complex128" else 1e-6)
+    b.configure_tn_simulation({"MPI_enabled": False, "MPS_enabled": False, "NCCL_enabled": False,
+                               "expectation_enabled": False})
+    got = b.execute_circuit(circuit=circ, return_array=True).statevector.get()
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-8 if dtype == "complex128" else 1e-6)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("nqubits,layers", [(2, 2), (5, 2), (7, 2), (12, 3), (16, 4), (20, 3)])
+def test_random_circuit_state_vs_oracle(nqubits, layers, dtype):
+    circ = circuits.ry_rz_cnot_ring(nqubits, layers, seed=42)
+    want = osv.simulate(circ)
+    got = ev.dense_vector_tn(circ, dtype).flatten().get()
+    assert np.abs(got - want).max() < TOL[dtype] * max(1.0, np.abs(want).max()) * 4
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("nqubits", [2, 5, 10])
+def test_expectation_three_runcard_forms(nqubits, dtype):
+    """reference tests/test_cuquantum_cutensor_backend.py:145-199 (value is 0 on QFT|0>) and a
+    discriminating random circuit (value is not 0)."""
+    from qibotn_b200.observables import build_observable
+    terms = {"terms": [{"coefficient": 0.5, "operators": [("X", i), ("Z", (i + 1) % nqubits)]}
+                       for i in range(nqubits)]}
+    for circ in (circuits.qft(nqubits, True), circuits.ry_rz_cnot_ring(nqubits, 2, seed=42)):
+        psi = osv.simulate(circ)
+        want = osv.pauli_expectation(
+            psi, [(0.5, [("X", i), ("Z", (i + 1) % nqubits)]) for i in range(nqubits)], nqubits).real
+        b = _backend(dtype)
+        for value in (True, build_observable(nqubits), terms):
+            b.configure_tn_simulation({"MPI_enabled": False, "MPS_enabled": False,
+                                       "NCCL_enabled": False, "expectation_enabled": value})
+            res = b.execute_circuit(circuit=circ)
+            assert math.isclose(want, res.real.get().item(), abs_tol=1e-7 if dtype == "complex128" else 2e-5)
+            assert math.isclose(want, float(res[0]), abs_tol=1e-7 if dtype == "complex128" else 2e-5)
+
+
+def test_pauli_string_pattern_runcard():
+    n = 6
+    circ = circuits.brickwork(n, 4, seed=1)
+    psi = osv.simulate(circ)
+    want = osv.pauli_expectation(psi, [(1.0, [("XZ"[q % 2], q) for q in range(n)])], n).real
+    b = _backend("complex128")
+    b.configure_tn_simulation({"MPI_enabled": False, "MPS_enabled": False, "NCCL_enabled": False,
+                               "expectation_enabled": {"pauli_string_pattern": "XZ"}})
+    assert math.isclose(want, float(b.execute_circuit(circ)[0]), abs_tol=1e-9)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_amplitude_sliced_equals_unsliced_and_oracle(dtype):
+    circ = circuits.brickwork(14, 8, seed=2)
+    psi = osv.simulate(circ)
+    bits = "01101001110100"
+    want = psi[int(bits, 2)]
+    conv = QiboCircuitToEinsum(circ, dtype)
+    net = conv.amplitude_network(bits)
+    vals = []
+    for min_slices, graph in ((1, True), (8, True), (8, False), (64, True)):
+        engine.clear_caches()
+        out = engine.contract(net, dtype, samples=4, min_slices=min_slices, use_graph=graph)
+        vals.append(complex(out.cpu().numpy().reshape(-1)[0]))
+    for v in vals:
+        assert abs(v - want) < TOL[dtype] * max(abs(want), 1e-3) * 10
+    # partial slice ranges add up (what each rank of a multi-GPU run computes)
+    engine.clear_caches()
+    info, low = engine.plan(net, dtype, samples=4, min_slices=8)
+    parts = [engine.contract(net, dtype, info=info, slice_ids=ev.compute_slices(info.num_slices, r, 3))
+             .cpu().numpy().reshape(-1)[0] for r in range(3)]
+    assert abs(sum(parts) - want) < TOL[dtype] * max(abs(want), 1e-3) * 10
+    # and each partial equals the oracle's sum over the same slice ids on the same path
+    r1 = ev.compute_slices(info.num_slices, 1, 3)
+    o = ocontract.contract_sliced(net.interleaved(), info.path, info.sliced_labels, r1,
+                                  dtype=np.complex128)
+    assert abs(parts[1] - o) < TOL[dtype] * max(abs(o), 1e-3) * 10
+
+
+def test_dense_output_drops_inactive_qubits_and_initial_state_rejected():
+    from qibotn_b200.qibo_compat import Circuit, H, CNOT
+    c = Circuit(5)
+    c.add(H(1)); c.add(CNOT(1, 3))
+    b = _backend("complex128")
+    res = b.execute_circuit(c)
+    assert res.statevector.shape == (2, 2)          # only qubits 1 and 3 are active
+    assert np.allclose(res.statevector.flatten().get(), [2 ** -0.5, 0, 0, 2 ** -0.5])
+    with pytest.raises(NotImplementedError):
+        b.execute_circuit(c, initial_state=np.ones(32))

@@ -1,0 +1,97 @@
+"""CPU checks of the host-side pair planner (C library) through a numpy emulation
+of the kernel's address algebra: the tables it emits must describe the einsum."""
+import numpy as np
+import pytest
+
+import emu
+from qibotn_b200 import lib
+
+
+def random_case(rng, m, n, k, batch=0, nslice_a=0, nslice_b=0):
+    labels = list(range(m + n + k + batch))
+    M, N, K, Bt = labels[:m], labels[m:m + n], labels[m + n:m + n + k], labels[m + n + k:]
+    la, lb, lc = M + K + Bt, K + N + Bt, M + N + Bt
+    rng.shuffle(la); rng.shuffle(lb); rng.shuffle(lc)
+    # sliced labels occupy extra address bits of the stored operand
+    ra, rb = len(la) + nslice_a, len(lb) + nslice_b
+    pa_all = list(rng.permutation(ra)); pb_all = list(rng.permutation(rb))
+    pa, sa = pa_all[:len(la)], pa_all[len(la):]
+    pb, sb = pb_all[:len(lb)], pb_all[len(lb):]
+    pc = list(rng.permutation(len(lc)))
+    return la, [int(x) for x in pa], [int(x) for x in sa], lb, [int(x) for x in pb], \
+        [int(x) for x in sb], lc, [int(x) for x in pc]
+
+
+def reference(a_flat, la, pa, sa_pos, b_flat, lb, pb, sb_pos, lc, slice_id, bits_a, bits_b):
+    off_a = sum(((slice_id >> bt) & 1) << p for bt, p in zip(bits_a, sa_pos))
+    off_b = sum(((slice_id >> bt) & 1) << p for bt, p in zip(bits_b, sb_pos))
+    def dense(flat, labels, pos, off):
+        out = np.zeros((2,) * len(labels), dtype=flat.dtype)
+        for idx in (np.ndindex(*out.shape) if labels else [()]):
+            out[idx] = flat[off + sum(v << p for v, p in zip(idx, pos))]
+        return out
+    A = dense(a_flat, la, pa, off_a)
+    B = dense(b_flat, lb, pb, off_b)
+    return np.einsum(A, la, B, lb, lc)
+
+
+CASES = [
+    # m, n, k, batch, slices a/b, C free?
+    (6, 6, 3, 0, 0, 0, True), (7, 7, 5, 0, 0, 0, False), (8, 2, 2, 0, 0, 0, True),
+    (3, 9, 2, 0, 0, 0, True), (1, 1, 1, 0, 0, 0, True), (0, 0, 3, 0, 0, 0, True),
+    (2, 0, 1, 0, 0, 0, False), (5, 4, 6, 0, 0, 0, True), (4, 4, 2, 2, 0, 0, False),
+    (7, 3, 2, 1, 2, 1, True), (1, 1, 11, 0, 0, 0, True), (2, 2, 10, 0, 1, 1, False),
+    (0, 0, 12, 0, 2, 0, True), (13, 0, 1, 0, 0, 0, True), (6, 7, 0, 0, 0, 0, True),
+    (3, 3, 8, 0, 0, 0, True),
+]
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("case", CASES)
+def test_plan_tables_describe_the_einsum(case, dtype):
+    m, n, k, batch, nsa, nsb, free = case
+    rng = np.random.default_rng(hash(case) % 2**32)
+    la, pa, sa_pos, lb, pb, sb_pos, lc, pc = random_case(rng, m, n, k, batch, nsa, nsb)
+    ra, rb = len(la) + nsa, len(lb) + nsb
+    a = (rng.normal(size=1 << ra) + 1j * rng.normal(size=1 << ra)).astype(dtype)
+    b = (rng.normal(size=1 << rb) + 1j * rng.normal(size=1 << rb)).astype(dtype)
+    bits_a = list(range(nsa)); bits_b = list(range(1, 1 + nsb))
+    desc = lib.make_pair_desc(dtype, list(zip(la, pa)), list(zip(lb, pb)),
+                              lc if free else list(zip(lc, pc)),
+                              slice_a=list(zip(bits_a, sa_pos)), slice_b=list(zip(bits_b, sb_pos)))
+    plan = lib.pair_plan(desc)
+    pc_used = [desc.pos_c[i] for i in range(len(lc))]
+    lc_used = [desc.label_c[i] for i in range(len(lc))]
+    assert sorted(pc_used) == list(range(len(lc)))
+    for slice_id in ([0] if nsa + nsb == 0 else [0, 3, 5]):
+        c = np.zeros(1 << len(lc), dtype=dtype)
+        emu.run_plan(plan, a, b, c, slice_id)
+        got = emu.dense_from_flat(c, lc_used, pc_used)
+        want = reference(a, la, pa, sa_pos, b, lb, pb, sb_pos, lc_used, slice_id, bits_a, bits_b)
+        tol = 1e-4 if dtype == "complex64" else 1e-11
+        assert np.allclose(got, want, rtol=tol, atol=tol * (1 << (k // 2)))
+    assert plan.flops == 8.0 * 2 ** (m + n + k + batch)
+
+
+def test_accumulate_and_conj_flags():
+    rng = np.random.default_rng(1)
+    la, pa, _, lb, pb, _, lc, pc = random_case(rng, 3, 3, 2)
+    a = rng.normal(size=32) + 1j * rng.normal(size=32)
+    b = rng.normal(size=32) + 1j * rng.normal(size=32)
+    desc = lib.make_pair_desc("complex128", list(zip(la, pa)), list(zip(lb, pb)), list(zip(lc, pc)),
+                              accumulate=True, conj_a=True)
+    plan = lib.pair_plan(desc)
+    c0 = rng.normal(size=64) + 0j
+    c = c0.copy()
+    emu.run_plan(plan, a, b, c)
+    want = reference(a.conj(), la, pa, [], b, lb, pb, [], lc, 0, [], [])
+    assert np.allclose(emu.dense_from_flat(c - c0, lc, pc), want)
+
+
+def test_bad_descriptors_are_rejected():
+    d = lib.make_pair_desc("complex64", [(0, 0), (1, 1)], [(1, 0), (2, 1)], [(0, 0), (3, 1)])
+    with pytest.raises(lib.QtnError):
+        lib.pair_plan(d)
+    d = lib.make_pair_desc("complex64", [(0, 0), (0, 1)], [(1, 0)], [1])
+    with pytest.raises(lib.QtnError):
+        lib.pair_plan(d)
