@@ -143,27 +143,46 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   __syncthreads();
 
   for (unsigned long long kk = 0; kk < k_iters; ++kk) {
-    // global -> shared, ascending address order of each operand
+    // global -> shared, ascending address order of each operand; loads are issued in
+    // batches of 8 before any shared-memory store so that many requests are in flight
     if (a_act) {
-      for (int it = 0; it < a_nit; ++it) {
-        const long long g = a_it_g[it];
-        T v = cx_zero<R>();
-        if (a_t_g >= 0 && g >= 0) {
-          v = A[a_base + a_k + (a_t_g | g)];
-          if (P.conj_a) v.y = -v.y;
+#pragma unroll 1
+      for (int it0 = 0; it0 < a_nit; it0 += 8) {
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          v[u] = cx_zero<R>();
+          if (it0 + u < a_nit) {
+            const long long g = a_it_g[it0 + u];
+            if (a_t_g >= 0 && g >= 0) v[u] = A[a_base + a_k + (a_t_g | g)];
+          }
         }
-        sA[a_t_s + a_it_s[it]] = v;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (it0 + u < a_nit) {
+            if (P.conj_a) v[u].y = -v[u].y;
+            sA[a_t_s + a_it_s[it0 + u]] = v[u];
+          }
       }
     }
     if (b_act) {
-      for (int it = 0; it < b_nit; ++it) {
-        const long long g = b_it_g[it];
-        T v = cx_zero<R>();
-        if (b_t_g >= 0 && g >= 0) {
-          v = B[b_base + b_k + (b_t_g | g)];
-          if (P.conj_b) v.y = -v.y;
+#pragma unroll 1
+      for (int it0 = 0; it0 < b_nit; it0 += 4) {
+        T v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = cx_zero<R>();
+          if (it0 + u < b_nit) {
+            const long long g = b_it_g[it0 + u];
+            if (b_t_g >= 0 && g >= 0) v[u] = B[b_base + b_k + (b_t_g | g)];
+          }
         }
-        sB[b_t_s + b_it_s[it]] = v;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (it0 + u < b_nit) {
+            if (P.conj_b) v[u].y = -v[u].y;
+            sB[b_t_s + b_it_s[it0 + u]] = v[u];
+          }
       }
     }
     __syncthreads();
@@ -215,10 +234,12 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   T *out = C;
   long long out_off = c_base;
   if (P.split_bits) { out = ws; out_off += (long long)split * P.c_elems; }
+  const bool acc_out = P.accumulate && !P.split_bits;
+#pragma unroll 4
   for (int e = t, it = 0; e < c_count; e += 256, ++it) {
     const long long g = out_off + (c_t_g | c_it_g[it]);
     T v = sC[e];
-    if (P.accumulate && !P.split_bits) { const T o = out[g]; v.x += o.x; v.y += o.y; }
+    if (acc_out) { const T o = out[g]; v.x += o.x; v.y += o.y; }
     out[g] = v;
   }
 }
@@ -348,7 +369,7 @@ int launch_tile(const qtn_pair_plan_t &P, const void *a, const void *b, void *c,
   static bool attr_set = false;
   if (!attr_set) {
     QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tile_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        4096 * (int)sizeof(T)));
+                                        4608 * (int)sizeof(T)));
     attr_set = true;
   }
   if (P.grid <= 0 || P.grid > 0x7fffffffLL) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_run: grid too large");

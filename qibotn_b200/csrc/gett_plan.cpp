@@ -142,7 +142,7 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     else { tmb = std::max(mbits, 2); tnb = 12 - tmb; }   // unreachable after swap, kept for safety
     const int TM = 1 << tmb, TN = 1 << tnb;
     int tkb = 4;
-    while (tkb > 0 && (1 << tkb) * (TM + TN + 4) > 4096) --tkb;
+    while (tkb > 0 && (1 << tkb) * (TM + TN + 4) > 4224) --tkb;
     tkb = std::min(tkb, kbits);
     p->tmb = tmb; p->tnb = tnb; p->tkb = tkb;
     p->sa_stride = TM + 2; p->sb_stride = TN + 2;

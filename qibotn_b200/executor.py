@@ -86,6 +86,7 @@ class _Arena:
     def __init__(self):
         self.free = []          # sorted list of (offset, size)
         self.top = 0
+        self.peak = 0           # high-water mark: the buffer size to allocate
 
     def alloc(self, size):
         size = (size + 255) & ~255
@@ -98,6 +99,7 @@ class _Arena:
                 return off
         off = self.top
         self.top += size
+        self.peak = max(self.peak, self.top)
         return off
 
     def release(self, off, size):
@@ -209,10 +211,7 @@ def lower(modes, out, info: PathInfo, dtype="complex64", sm_count=148) -> Lowere
 
 
 def _peak(arena):
-    top = arena.top
-    for off, sz in arena.free:
-        top = max(top, off + sz)
-    return top
+    return arena.peak
 
 
 class ContractionRunner:
@@ -239,6 +238,7 @@ class ContractionRunner:
         self.slice_id = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.use_graph = use_graph
         self._graph = None
+        self._copied = None
         self.launches = 0
 
     def _live_out_rank(self):
@@ -251,12 +251,16 @@ class ContractionRunner:
     def upload(self, leaves):
         """Pack every leaf into pinned host memory and ship it with one async copy."""
         low = self.low
+        if self._copied is not None:
+            self._copied.synchronize()      # previous async copy still reads the staging buffer
         host = self.host_buf.numpy()
         for i, arr in enumerate(leaves):
             t = low.tensors[i]
             a = np.ascontiguousarray(np.asarray(arr), dtype=self.np_dtype).reshape(-1)
             host[t.offset:t.offset + a.nbytes] = a.view(np.uint8)
         self.leaf_buf.copy_(self.host_buf, non_blocking=True)
+        self._copied = self.torch.cuda.Event()
+        self._copied.record()
         return low.leaf_bytes
 
     def _ptr(self, tid):

@@ -96,6 +96,24 @@ class PathInfo:
     def slices(self):
         return self.sliced_labels
 
+    def to_json(self):
+        import json
+
+        return json.dumps({
+            "path": [list(p) for p in self.path], "sliced_labels": list(self.sliced_labels),
+            "num_slices": self.num_slices, "opt_cost": self.opt_cost, "flops": self.flops,
+            "log2_width": self.log2_width, "per_slice_cost": self.per_slice_cost,
+            "hoisted_cost": self.hoisted_cost, "seed": self.seed, "method": self.method,
+            "extra": self.extra})
+
+    @classmethod
+    def from_json(cls, text):
+        import json
+
+        d = json.loads(text)
+        d["path"] = [tuple(p) for p in d["path"]]
+        return cls(**d)
+
 
 # ------------------------------------------------------------------ cost model
 def _walk(net: SymbolicNetwork, path, sliced_mask=0):
@@ -452,45 +470,83 @@ def _slice(net: SymbolicNetwork, path, target_log2_width, min_slices, max_sliced
 
 # ------------------------------------------------------------------ front door
 def find_path(modes, out, samples=32, seed=0, target_log2_width=30, min_slices=1,
-              methods=("greedy", "partition"), time_budget_s=None):
+              methods=("greedy", "partition"), time_budget_s=None, refine=3, reconf_rounds=6,
+              subtree_size=8):
     """Search a contraction path and slicing for the network ``(modes, out)``.
 
     ``samples`` and ``seed`` play the role of cuTensorNet's ``samples`` hyper-
     optimiser knob (the reference passes 32 from the backend,
     ``backends/cutensornet.py:110,119,136,147``); ranks may search with
     different seeds and vote on ``opt_cost`` (``eval.py:191-194``).
+
+    Stages: rank-<=2 absorption; ``samples`` x ``methods`` candidate trees; the
+    ``refine`` cheapest are polished by subtree reconfiguration, sliced down to
+    ``2^target_log2_width`` elements (and >= ``min_slices`` slices) with the tree
+    re-polished as labels are removed; the cheapest sliced plan wins.
     """
     import time
+
+    from .treeopt import Tree
 
     net = SymbolicNetwork(modes, out)
     pre, live, nxt = _absorb_small(net)
     rng = random.Random(seed)
-    best = None
     t0 = time.time()
-    trials = []
+    deadline = None if time_budget_s is None else t0 + time_budget_s
+    cands = []
     if len(live) <= 1:
-        trials.append(("trivial", None))
+        cands.append((0.0, "trivial", []))
     else:
         for s in range(max(1, samples)):
             for meth in methods:
-                trials.append((meth, s))
-    for meth, s in trials:
-        if meth == "trivial":
-            tail = []
-        elif meth == "greedy":
-            temp = 0.0 if s == 0 else rng.choice([0.01, 0.03, 0.1, 0.3])
-            alpha = 1.0 if s == 0 else rng.choice([0.0, 0.5, 1.0, 1.0, 2.0])
-            tail = _greedy(live, net.out_mask, net.hyper_mask, nxt, rng, alpha, temp)
+                if meth == "greedy":
+                    temp = 0.0 if s == 0 else rng.choice([0.01, 0.03, 0.1, 0.3])
+                    alpha = 1.0 if s == 0 else rng.choice([0.0, 0.5, 1.0, 1.0, 2.0])
+                    tail = _greedy(live, net.out_mask, net.hyper_mask, nxt, rng, alpha, temp)
+                else:
+                    imb = rng.choice([0.02, 0.05, 0.1, 0.15, 0.2, 0.3, 0.4])
+                    leaf = rng.choice([4, 6, 8, 12])
+                    tail = _partition_path(live, net.out_mask, net.hyper_mask, nxt, rng, imb, leaf)
+                cost, width, _, _ = path_cost(net, pre + tail, 0)
+                cands.append((cost * (1.0 + 2.0 ** max(0, width - target_log2_width)) ** 0.5, meth, tail))
+            if deadline is not None and time.time() > t0 + 0.4 * time_budget_s:
+                break
+    # every candidate gets a cheap polish (small subtrees); ranking happens after it
+    polished = []
+    can_refine = not net.hyper_mask and len(live) >= 3
+    for score, meth, tail in cands:
+        if can_refine and meth != "trivial":
+            tree = Tree(live, tail, nxt, net.out_mask)
+            tree.reconfigure(rounds=reconf_rounds, k=min(8, subtree_size), deadline=deadline)
+            w = tree.width()
+            score = tree.total_cost() * (1.0 + 2.0 ** max(0, w - target_log2_width)) ** 0.5
+            polished.append((score, meth, tail, tree))
         else:
-            imb = rng.choice([0.02, 0.05, 0.1, 0.15, 0.2, 0.3, 0.4])
-            leaf = rng.choice([4, 6, 8, 12])
-            tail = _partition_path(live, net.out_mask, net.hyper_mask, nxt, rng, imb, leaf)
-        path = pre + tail
-        sliced, order = _slice(net, path, target_log2_width, min_slices)
+            polished.append((score, meth, tail, None))
+        if deadline is not None and time.time() > t0 + 0.7 * time_budget_s:
+            break
+    polished.sort(key=lambda c: c[0])
+    best = None
+    for _score, meth, tail, tree in polished[:max(1, refine)]:
+        if tree is None:
+            path = pre + tail
+            sliced, order = _slice(net, path, target_log2_width, min_slices)
+        else:
+            if subtree_size > 8:
+                tree.reconfigure(rounds=3, k=subtree_size, deadline=deadline)
+            order, sliced = tree.slice_greedy(target_log2_width, min_slices, k=min(8, subtree_size),
+                                              deadline=deadline)
+            if order:
+                tree.reconfigure(rounds=3, k=subtree_size, removed=sliced, deadline=deadline)
+                # re-polishing may have widened a node again: slice further if so
+                more, sliced = tree.slice_greedy(target_log2_width, 1, removed=sliced,
+                                                 reconf_every=0)
+                order += more
+            path = pre + tree.ssa_pairs(nxt)
         cost, width, per_slice, hoisted = path_cost(net, path, sliced)
         if best is None or cost < best[0]:
             best = (cost, width, per_slice, hoisted, path, order, meth)
-        if time_budget_s is not None and time.time() - t0 > time_budget_s:
+        if deadline is not None and time.time() > deadline:
             break
     cost, width, per_slice, hoisted, path, order, meth = best
     labels = [net.bit_label[low.bit_length() - 1] for low in order]

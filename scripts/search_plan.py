@@ -1,0 +1,51 @@
+"""Offline, process-parallel plan search for a named workload; keeps the cheapest plan in plans/.
+Usage: python scripts/search_plan.py <workload> [--procs 8] [--rounds 4] [--width 31] [--min-slices 32]"""
+import argparse
+import math
+import multiprocessing as mp
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from qibotn_b200 import plans, workloads  # noqa: E402
+from qibotn_b200.planner import find_path  # noqa: E402
+
+
+def _one(args):
+    name, seed, width, min_slices, samples, k = args
+    wl = workloads.build(name)
+    net = wl.network()
+    info = find_path(net.modes, net.out, samples=samples, seed=seed, target_log2_width=width,
+                     min_slices=min_slices, refine=6, subtree_size=k)
+    return info
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("workload")
+    ap.add_argument("--procs", type=int, default=os.cpu_count() or 4)
+    ap.add_argument("--rounds", type=int, default=2)
+    ap.add_argument("--width", type=int, default=31)
+    ap.add_argument("--min-slices", type=int, default=1)
+    ap.add_argument("--samples", type=int, default=16)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--name", default=None)
+    a = ap.parse_args()
+    wl = workloads.build(a.workload)
+    net = wl.network()
+    name = a.name or a.workload
+    best = plans.load_plan(name, net.modes, net.out)
+    print("start:", None if best is None else "log10 flops %.2f" % math.log10(best.flops), flush=True)
+    t0 = time.time()
+    with mp.Pool(a.procs) as pool:
+        for r in range(a.rounds):
+            jobs = [(a.workload, 1000 * r + p, a.width, a.min_slices, a.samples, a.k) for p in range(a.procs)]
+            for info in pool.imap_unordered(_one, jobs):
+                if best is None or info.opt_cost < best.opt_cost:
+                    best = info
+                    plans.save_plan(name, best, net.modes, net.out)
+                    print("%.0fs: new best seed %d %s log10 flops %.2f W %d slices %d" % (
+                        time.time() - t0, info.seed, info.method, math.log10(info.flops),
+                        info.log2_width, info.num_slices), flush=True)
+    print("done: log10 flops %.2f W %d slices %d" % (math.log10(best.flops), best.log2_width, best.num_slices))

@@ -19,12 +19,23 @@ def emulate(low, leaves, slice_ids):
         bufs[i] = np.ascontiguousarray(arr, dtype=dt).reshape(-1)
     root = low.tensors[low.root]
     out = np.zeros(1 << len(root.labels), dtype=dt)
+    esz = np.dtype(dt).itemsize
+    # intermediates live at their planned offsets inside shared arenas, filled with NaN,
+    # so that aliasing or an undersized arena shows up as a wrong result
+    arenas = {"hoist": np.full(low.hoist_bytes // esz + 1, np.nan, dtype=dt),
+              "slice": np.full(low.slice_bytes // esz + 1, np.nan, dtype=dt)}
     def run(depends, sid):
         for node in low.nodes:
             if node.depends != depends:
                 continue
             tc = low.tensors[node.c]
-            c = out if tc.where == "out" else np.zeros(1 << len(tc.labels), dtype=dt)
+            if tc.where == "out":
+                c = out
+            else:
+                n = 1 << len(tc.labels)
+                assert tc.offset % esz == 0 and tc.offset + n * esz <= getattr(low, tc.where + "_bytes")
+                c = arenas[tc.where][tc.offset // esz: tc.offset // esz + n]
+                c[:] = 0
             emu.run_plan(node.plan, bufs[node.a], bufs[node.b], c, sid)
             bufs[node.c] = c
     run(False, 0)
