@@ -80,6 +80,7 @@ typedef struct {
 
 #define QTN_KERNEL_TILE 0   /* shared-memory tiled FFMA/DFMA kernel */
 #define QTN_KERNEL_REDUCE 1 /* tiny output, long contracted extent: K-parallel reduction */
+#define QTN_KERNEL_TC 2     /* complex64, large tiles: tcgen05 TF32x3 MMAs, accumulators in TMEM */
 
 #define QTN_LO_MAX 16
 #define QTN_HI_MAX 40
@@ -127,7 +128,19 @@ typedef struct {
   /* accounting (SURVEY.md section 8d conventions) */
   double flops;                  /* 8 * 2^(m+n+k+batch) */
   double bytes;                  /* elem * (|A| + |B| + |C|) */
+  /* QTN_KERNEL_TC only: shared-memory pipeline depth and the byte sizes of one A / one B
+   * operand plane (a stage holds 4 A planes then 4 B planes: re_hi, re_lo, im_hi, im_lo) */
+  int32_t tc_stages;
+  int32_t tc_plane_a, tc_plane_b;
+  int32_t tc_reserved;
 } qtn_pair_plan_t;
+
+/* Library-wide switches (thread-unsafe, meant for tests and A/B measurements):
+ *   "tc_enable"    1 (default) lets qtn_pair_plan choose QTN_KERNEL_TC, 0 forbids it;
+ *   "tc_min_log2"  smallest m+n+k (log2 of the MAC count) for which TC is chosen (default 18).
+ * Returns QTN_ERR_ARG for an unknown name. */
+int qtn_set_option(const char *name, int value);
+int qtn_get_option(const char *name, int *value);
 
 /* Host-only: derive roles, tile shape, coalescing-driven label placement and,
  * when desc->c_layout_free, C's layout (written back to desc->pos_c).
@@ -162,6 +175,69 @@ int qtn_axpy(int dtype, int64_t n, double alpha_re, double alpha_im, const void 
              int accumulate, void *stream);
 int qtn_set_i32(int32_t *dst, int32_t value, void *stream);
 int qtn_add_i32(int32_t *dst, int32_t delta, void *stream);
+
+
+/* ------------------------------------------------------------------------
+ * MPS path (arbitrary extents, dense row-major tensors).
+ * Site tensors are (chi_l, 2, chi_r) as in mps_utils.py:48-50; a two-site block
+ * theta is the (2*chi_l) x (2*chi_r) matrix with rows (i,p) and columns (q,k).
+ * ------------------------------------------------------------------------ */
+
+/* C[m x n] = opA(A) * opB(B) (+ C).  op bit 0 = conjugate, bit 1 = the stored matrix is the
+ * transpose of the operand (so 0 = N, 1 = conj, 2 = T, 3 = H).  lda/ldb/ldc in elements.
+ * Takes over the contraction half of contract_decompose (mps_utils.py:78-84: A.B), the chain
+ * contractions of mps_contraction_helper.py:115-118 and the transfer-matrix sweeps of :32-51,73-113. */
+#define QTN_OP_N 0
+#define QTN_OP_C 1
+#define QTN_OP_T 2
+#define QTN_OP_H 3
+int qtn_gemm(int dtype, int opa, int opb, int64_t m, int64_t n, int64_t k, const void *a, int64_t lda,
+             const void *b, int64_t ldb, void *c, int64_t ldc, int accumulate, void *stream);
+
+/* site[i][q][j] = sum_p gate[q][p] site[i][p][j] in place; gate = 4 device elements.
+ * Takes over contract("ipj,qp->iqj") (mps_utils.py:64-69). */
+int qtn_mps_apply_1q(int dtype, int64_t chi_l, int64_t chi_r, void *site, const void *gate, void *stream);
+
+/* theta[(i,r),(s,k)] = sum_pq gate[r][s][p][q] theta[(i,p),(q,k)] in place; gate = 16 device
+ * elements.  With the SWAP matrix this is the leg exchange "ipj,jqk->iqj,jpk" (mps_utils.py:32-37). */
+int qtn_mps_apply_2q(int dtype, int64_t chi_l, int64_t chi_r, void *theta, const void *gate, void *stream);
+
+/* Batched one-sided Jacobi SVD with truncation: the decompose half of contract_decompose
+ * (mps_utils.py:32,78; cuTensorNet SVDMethod semantics: abs_cutoff, rel_cutoff,
+ * discarded_weight_cutoff, max_extent, normalization, partition). */
+typedef struct {
+  void *w;                /* device, n x m row-major, n <= m advised; rows orthogonalised IN PLACE */
+  int32_t n, m;
+  int32_t block, nblocks; /* out: blocking chosen by the library */
+} qtn_svd_item;
+
+typedef struct {
+  double abs_cutoff, rel_cutoff, discarded_weight_cutoff;
+  int32_t max_extent;     /* 0 = unlimited */
+  int32_t normalization;  /* 0 none, 1 L1, 2 L2, 3 LInf (applied to the kept singular values) */
+} qtn_svd_trunc;
+
+int64_t qtn_svd_workspace_bytes(int batch, int64_t ld);
+/* On return every W holds J*W_in with mutually orthogonal rows; sigma[i*ld + c] is the c-th
+ * largest row norm (= singular value) of matrix i and perm[i*ld + c] the row that carries it;
+ * rank_host[i] = number of singular values kept, scale_host[i] = factor the kept values are
+ * multiplied by (normalization).  `items` is a HOST array (its block fields are filled in);
+ * sigma/perm/workspace are device buffers.  Synchronises `stream` (one read-back per sweep). */
+int qtn_svd_rows(int dtype, int batch, qtn_svd_item *items, double tol, int max_sweeps,
+                 const qtn_svd_trunc *trunc, double *sigma, int32_t *perm, int64_t ld,
+                 int32_t *rank_host, double *scale_host, int32_t *sweeps_host, void *workspace,
+                 int64_t workspace_bytes, void *stream);
+/* Scaled copies of the k leading rows (sorted order) of an orthogonalised W (m columns):
+ * with s = sigma[c], sn = s*scale and (fa, fb) the share of sn absorbed by the left / right factor
+ * (partition 0 none: (1,1); 1 "U": (sn,1); 2 "V": (1,sn); 3 "UV": (sqrt sn, sqrt sn)):
+ *   transposed == 0 (W_in = theta):    out1 = fb/s * row   (the right factor, k x m)
+ *                                      out2 = fa/s^2 * row (left factor = theta * out2^H)
+ *   transposed == 1 (W_in = theta^T):  out1 = fa/s * row   (left factor transposed, k x m)
+ *                                      out2 = fb/s^2 * row (right factor = conj(out2) * theta)
+ * sigma/perm point at this matrix's row of the arrays qtn_svd_rows filled. */
+int qtn_svd_emit(int dtype, const void *w, int32_t m, const int32_t *perm, const double *sigma,
+                 double scale, int32_t k, int32_t partition, int32_t transposed, void *out1, void *out2,
+                 void *stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,28 @@ extern "C" int qtn_fail(int code, const char *msg) {
 
 extern "C" const char *qtn_last_error(void) { return g_last_error.c_str(); }
 
+namespace {
+int g_tc_enable = 1;
+int g_tc_min_log2 = 18;
+}  // namespace
+
+extern "C" int qtn_option_tc_enable(void) { return g_tc_enable; }
+extern "C" int qtn_option_tc_min_log2(void) { return g_tc_min_log2; }
+
+extern "C" int qtn_set_option(const char *name, int value) {
+  if (!name) return qtn_fail(QTN_ERR_ARG, "qtn_set_option: null name");
+  if (!std::strcmp(name, "tc_enable")) { g_tc_enable = value != 0; return QTN_OK; }
+  if (!std::strcmp(name, "tc_min_log2")) { g_tc_min_log2 = value; return QTN_OK; }
+  return qtn_fail(QTN_ERR_ARG, "qtn_set_option: unknown option");
+}
+
+extern "C" int qtn_get_option(const char *name, int *value) {
+  if (!name || !value) return qtn_fail(QTN_ERR_ARG, "qtn_get_option: null argument");
+  if (!std::strcmp(name, "tc_enable")) { *value = g_tc_enable; return QTN_OK; }
+  if (!std::strcmp(name, "tc_min_log2")) { *value = g_tc_min_log2; return QTN_OK; }
+  return qtn_fail(QTN_ERR_ARG, "qtn_get_option: unknown option");
+}
+
 extern "C" const char *qtn_version(void) { return "qibotn_b200 0.1.0 (sm_100a)"; }
 
 extern "C" int qtn_device_info(int device, int *sm_count, int *max_smem_optin, int *cc_major,

@@ -413,6 +413,17 @@ int launch_reduce(const qtn_pair_plan_t &P, const void *a, const void *b, void *
 
 }  // namespace
 
+int qtn_launch_splitk_sum(int dtype, void *c, const void *ws, long long n, int nsplit, int accumulate,
+                          cudaStream_t st) {
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (dtype == QTN_C64)
+    splitk_sum_kernel<float><<<grid, 256, 0, st>>>((float2 *)c, (const float2 *)ws, n, nsplit, accumulate);
+  else
+    splitk_sum_kernel<double><<<grid, 256, 0, st>>>((double2 *)c, (const double2 *)ws, n, nsplit, accumulate);
+  QTN_LAUNCH_CHECK();
+  return QTN_OK;
+}
+
 extern "C" int qtn_pair_run(const qtn_pair_plan_t *plan, const void *a, const void *b, void *c,
                             void *workspace, const int32_t *slice_id, void *stream) {
   if (!plan || !a || !b || !c) return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: null argument");
@@ -423,6 +434,8 @@ extern "C" int qtn_pair_run(const qtn_pair_plan_t *plan, const void *a, const vo
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->swapped) { const void *tmp = a; a = b; b = tmp; }
   const bool f32 = plan->dtype == QTN_C64;
+  if (plan->kernel == QTN_KERNEL_TC)
+    return qtn_launch_tc(*plan, a, b, c, workspace, slice_id, st);
   if (plan->kernel == QTN_KERNEL_TILE)
     return f32 ? launch_tile<float>(*plan, a, b, c, workspace, slice_id, st)
                : launch_tile<double>(*plan, a, b, c, workspace, slice_id, st);

@@ -133,6 +133,93 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     p->grid = (int64_t)1 << (kbits - chunk);
     p->smem_bytes = 0;
     p->workspace_bytes = p->grid * 16 * esz;
+  } else if (d->dtype == QTN_C64 && d->c_layout_free && bbits == 0 && mbits >= 7 && nbits >= 4 &&
+             kbits >= 3 && mbits + nbits + kbits >= qtn_option_tc_min_log2() && qtn_option_tc_enable()) {
+    // ---- tensor-core kernel (gett_tc.cu) ----------------------------------------
+    // Tile = 128 rows of A x 2^tnb rows of B, 2^tkb contracted values per pipeline stage.
+    p->kernel = QTN_KERNEL_TC;
+    const int tmb = 7, tnb = std::min(nbits, 8), tkb = std::min(kbits, 4);
+    const int KT = 1 << tkb, TN = 1 << tnb;
+    p->tmb = tmb; p->tnb = tnb; p->tkb = tkb;
+    p->block = 288;
+    auto pick = [&](std::vector<Lab> &v, int want, auto key, auto forced) {
+      std::stable_sort(v.begin(), v.end(), [&](const Lab &x, const Lab &y) {
+        bool fx = forced(x), fy = forced(y);
+        if (fx != fy) return fx;
+        if (key(x) != key(y)) return key(x) < key(y);
+        return x.label < y.label;
+      });
+      std::vector<Lab> lo(v.begin(), v.begin() + want), hi(v.begin() + want, v.end());
+      return std::make_pair(lo, hi);
+    };
+    auto m_sel = pick(M, tmb, [](const Lab &l) { return l.pa; }, [&](const Lab &l) { return l.pa < cforce; });
+    auto n_sel = pick(N, tnb, [](const Lab &l) { return l.pb; }, [&](const Lab &l) { return l.pb < cforce; });
+    auto k_sel = pick(K, tkb, [](const Lab &l) { return std::min(l.pa, l.pb); },
+                      [&](const Lab &l) { return l.pa < cforce || l.pb < cforce; });
+    std::vector<Lab> &mlo = m_sel.first, &mhi = m_sel.second;
+    std::vector<Lab> &nlo = n_sel.first, &nhi = n_sel.second;
+    std::vector<Lab> &klo = k_sel.first, &khi = k_sel.second;
+    // logical bit j of the row / k index inside the tile = j-th label in ascending address order
+    // of the operand it is read from: the lowest-address labels then land on the 8 rows x 4
+    // values of one core matrix, which spreads a warp's shared-memory stores over the banks
+    std::sort(mlo.begin(), mlo.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
+    std::sort(nlo.begin(), nlo.end(), [](const Lab &x, const Lab &y) { return x.pb < y.pb; });
+    std::sort(klo.begin(), klo.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
+    std::sort(mhi.begin(), mhi.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
+    std::sort(nhi.begin(), nhi.end(), [](const Lab &x, const Lab &y) { return x.pb < y.pb; });
+    std::sort(khi.begin(), khi.end(), [](const Lab &x, const Lab &y) {
+      return std::max(x.pa, x.pb) < std::max(y.pa, y.pb);
+    });
+    p->m_real = tmb; p->n_real = tnb; p->k_real = tkb;
+    p->n_mhi = (int)mhi.size(); p->n_nhi = (int)nhi.size(); p->n_khi = (int)khi.size();
+    p->n_batch = 0;
+    if (p->n_mhi > QTN_HI_MAX || p->n_nhi > QTN_HI_MAX || p->n_khi > QTN_HI_MAX)
+      return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_plan: rank too large");
+    // C: m bits 0-4 | n bits | m bits 5-6 | n-hi | m-hi  (the epilogue's store order)
+    {
+      int next_c = 0;
+      auto give = [&](Lab &l) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); };
+      for (int j = 0; j < 5; ++j) give(mlo[j]);
+      for (auto &l : nlo) give(l);
+      for (int j = 5; j < tmb; ++j) give(mlo[j]);
+      for (auto &l : nhi) give(l);
+      for (auto &l : mhi) give(l);
+    }
+    // offset (in floats inside one operand plane) of row bit j / k bit i in the canonical
+    // K-major no-swizzle layout: (r&7)*4 + (k&3) + (r>>3)*(KT*8) + (k>>2)*32
+    auto row_off = [&](int j) { return j < 3 ? 4 << j : (KT * 8) << (j - 3); };
+    auto k_off = [&](int i) { return i < 2 ? 1 << i : 32 << (i - 2); };
+    struct E { int pos; int sstr; };
+    std::vector<E> ea, eb;
+    for (int j = 0; j < tmb; ++j) ea.push_back({mlo[j].pa, row_off(j)});
+    for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, k_off(i)});
+    for (int j = 0; j < tnb; ++j) eb.push_back({nlo[j].pb, row_off(j)});
+    for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, k_off(i)});
+    auto by_pos = [](const E &x, const E &y) { return x.pos < y.pos; };
+    std::sort(ea.begin(), ea.end(), by_pos);
+    std::sort(eb.begin(), eb.end(), by_pos);
+    p->na_lo = (int)ea.size(); p->nb_lo = (int)eb.size();
+    for (int i = 0; i < p->na_lo; ++i) { p->a_lo_pos[i] = (uint8_t)ea[i].pos; p->a_lo_sstr[i] = (uint16_t)ea[i].sstr; }
+    for (int i = 0; i < p->nb_lo; ++i) { p->b_lo_pos[i] = (uint8_t)eb[i].pos; p->b_lo_sstr[i] = (uint16_t)eb[i].sstr; }
+    p->nc_lo = tmb + tnb;
+    for (int j = 0; j < tmb; ++j) p->c_lo_pos[j] = (uint8_t)mlo[j].pc;          // m bits, then n bits
+    for (int j = 0; j < tnb; ++j) p->c_lo_pos[tmb + j] = (uint8_t)nlo[j].pc;
+    for (int i = 0; i < p->n_mhi; ++i) { p->a_mhi[i] = mhi[i].pa; p->c_mhi[i] = mhi[i].pc; }
+    for (int i = 0; i < p->n_nhi; ++i) { p->b_nhi[i] = nhi[i].pb; p->c_nhi[i] = nhi[i].pc; }
+    for (int i = 0; i < p->n_khi; ++i) { p->a_khi[i] = khi[i].pa; p->b_khi[i] = khi[i].pb; }
+    // split-K when there are fewer tiles than SMs (one CTA owns a whole SM here)
+    const double tiles = std::ldexp(1.0, p->n_mhi + p->n_nhi);
+    int split = 0;
+    while (split < p->n_khi - 1 && tiles * (1 << split) < (double)sm_count) ++split;
+    p->split_bits = split;
+    p->grid = ((int64_t)1 << (p->n_mhi + p->n_nhi)) << split;
+    p->workspace_bytes = split ? ((int64_t)esz << (d->rank_c + split)) : 0;
+    p->tc_plane_a = 128 * KT * 4;
+    p->tc_plane_b = TN * KT * 4;
+    const int stage_bytes = 4 * (p->tc_plane_a + p->tc_plane_b);
+    p->tc_stages = std::max(2, std::min(4, (200 * 1024) / stage_bytes));
+    p->smem_bytes = p->tc_stages * stage_bytes + 256;
+    p->sa_stride = 0; p->sb_stride = 0;
   } else {
     // ---- shared-memory tiled kernel -----------------------------------------
     p->kernel = QTN_KERNEL_TILE;

@@ -1,0 +1,410 @@
+// Pairwise contraction of complex64 bit tensors on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, accumulators in TMEM), permutation fused into the loads
+// and stores exactly as in gett.cu.
+//
+// Arithmetic.  A complex GEMM C = A * B is four real GEMMs on separate re/im planes
+//     Cr = Ar*Br - Ai*Bi        Ci = Ar*Bi + Ai*Br
+// (the minus sign is the MMA's negate-A bit), and every fp32 operand x is split as
+// x = hi + lo with hi = tf32_round_nearest(x), lo = x - hi (exact in fp32), keeping
+// hi*hi + hi*lo + lo*hi: the classic error-compensated "3xTF32" product, whose
+// relative error per term is ~2^-21 (dropped lo*lo and the truncation of lo to tf32).
+// So one complex MAC costs 12 tf32 MACs; the 8 real flops it is credited with
+//  do not depend on that.
+//
+// Structure of a CTA (288 threads):
+//   warps 0-7  producers: gather one K-chunk of the A and B tiles from global memory in
+//              ascending *address* order (coalesced whatever the label order), split to
+//              the 4+4 planes and scatter them into shared memory in the tensor core's
+//              canonical K-major no-swizzle layout (8-row x 16-byte core matrices);
+//              fence.proxy.async + mbarrier arrive per stage;  afterwards the same
+//              warps are the epilogue: tcgen05.ld of Cr/Ci, interleave, coalesced stores;
+//   warp 8     allocates TMEM; lane 0 issues the tcgen05.mma's of each stage and
+//              releases the stage with tcgen05.commit.
+// C's layout is chosen by the planner (m bits 0-4 | n bits | m bits 5-6 | tile index),
+// which makes the epilogue's stores contiguous straight out of the TMEM registers.
+#include <cstdint>
+
+#include "qtn_internal.h"
+
+namespace {
+
+constexpr int kProducerThreads = 256;
+constexpr int kThreads = 288;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug must surface as a launch error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS)
+               : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes,
+// stored as 128 contiguous bytes; LBO = byte step between core matrices along K,
+// SBO = byte step between 8-row groups.  (PTX ISA "tcgen05 shared memory descriptor";
+// bit 46 = descriptor version 1 of sm_100.)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) |
+         ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+// kind::tf32 instruction descriptor: D fp32, A/B tf32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n, int neg_a) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)neg_a << 13) | ((uint32_t)(n >> 3) << 17) |
+         ((128u >> 4) << 24);
+}
+
+template <int N> struct tmem_ld;
+template <> struct tmem_ld<16> {
+  __device__ static __forceinline__ void run(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+  }
+};
+template <> struct tmem_ld<8> {
+  __device__ static __forceinline__ void run(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7])
+        : "r"(taddr));
+  }
+};
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// x = hi + lo, hi representable in tf32 (round to nearest, ties away), lo = x - hi exact
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  hi = __uint_as_float(u);
+  lo = x - hi;
+}
+
+__device__ __forceinline__ long long deposit(unsigned long long idx, const uint8_t *pos, int n) {
+  long long off = 0;
+  for (int i = 0; i < n; ++i) off |= (long long)((idx >> i) & 1ull) << pos[i];
+  return off;
+}
+
+__device__ __forceinline__ long long slice_offset(const int32_t *slice_id, int n, const uint8_t *bit,
+                                                  const uint8_t *pos) {
+  if (n == 0) return 0;
+  const unsigned sid = (unsigned)(*slice_id);
+  long long off = 0;
+  for (int i = 0; i < n; ++i) off |= (long long)((sid >> bit[i]) & 1u) << pos[i];
+  return off;
+}
+
+template <int TNB, int TKB>
+__global__ void __launch_bounds__(kThreads, 1)
+gett_tc_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ A,
+               const float2 *__restrict__ B, float2 *__restrict__ C, float2 *__restrict__ ws,
+               const int32_t *__restrict__ slice_id) {
+  constexpr int TN = 1 << TNB, KT = 1 << TKB;
+  constexpr int PLANE_A = 128 * KT;                 // floats per A plane
+  constexpr int PLANE_B = TN * KT;                  // floats per B plane
+  constexpr int STAGE = 4 * (PLANE_A + PLANE_B);    // floats per stage
+  constexpr int NA = PLANE_A / kProducerThreads;    // A elements per producer thread and stage
+  constexpr int NB = (PLANE_B + kProducerThreads - 1) / kProducerThreads;
+  constexpr int TMEM_COLS = 2 * TN < 32 ? 32 : 2 * TN;
+  constexpr uint32_t LBO = 128, SBO = KT * 32;      // bytes
+  constexpr uint32_t IDESC = umma_idesc_tf32(TN, 0), IDESC_NEG = umma_idesc_tf32(TN, 1);
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float *stages = reinterpret_cast<float *>(smem_raw);
+  const int S = P.tc_stages;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * STAGE * sizeof(float));
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 1);
+  __shared__ long long a_it_g[8], b_it_g[16];
+  __shared__ int a_it_s[8], b_it_s[16];
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  const uint32_t accum_bar = bar0 + 8u * (2 * S);
+
+  // ---- which tile ----------------------------------------------------------------
+  unsigned long long id = blockIdx.x;
+  const unsigned split = (unsigned)(id & ((1ull << P.split_bits) - 1));
+  id >>= P.split_bits;
+  const unsigned long long mh = id & ((1ull << P.n_mhi) - 1);
+  id >>= P.n_mhi;
+  const unsigned long long nh = id;
+  const long long a_base = deposit(mh, P.a_mhi, P.n_mhi) |
+                           slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
+  const long long b_base = deposit(nh, P.b_nhi, P.n_nhi) |
+                           slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
+  const long long c_base = deposit(mh, P.c_mhi, P.n_mhi) | deposit(nh, P.c_nhi, P.n_nhi);
+  const int k_iters_bits = P.n_khi - P.split_bits;
+  const unsigned long long k_iters = 1ull << k_iters_bits;
+  const unsigned long long kh0 = (unsigned long long)split << k_iters_bits;
+
+  // ---- one-time setup ----------------------------------------------------------------
+  if (t < 16) {
+    long long g = 0;
+    int s = 0;
+    if (t < 8) {
+      for (int j = 8; j < P.na_lo; ++j)
+        if ((t >> (j - 8)) & 1) { g |= 1ll << P.a_lo_pos[j]; s += P.a_lo_sstr[j]; }
+      a_it_g[t] = g; a_it_s[t] = s;
+    }
+    g = 0; s = 0;
+    for (int j = 8; j < P.nb_lo; ++j)
+      if ((t >> (j - 8)) & 1) { g |= 1ll << P.b_lo_pos[j]; s += P.b_lo_sstr[j]; }
+    b_it_g[t] = g; b_it_s[t] = s;
+  }
+  if (t == 32) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), kProducerThreads);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_proxy_async_smem();
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ================= producers =================
+    long long a_t_g = 0, b_t_g = 0;
+    int a_t_s = 0, b_t_s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!((t >> j) & 1)) continue;
+      if (j < P.na_lo) { a_t_g |= 1ll << P.a_lo_pos[j]; a_t_s += P.a_lo_sstr[j]; }
+      if (j < P.nb_lo) { b_t_g |= 1ll << P.b_lo_pos[j]; b_t_s += P.b_lo_sstr[j]; }
+    }
+    const bool b_act = P.nb_lo >= 8 || t < (1 << P.nb_lo);
+    const float sgn_a = P.conj_a ? -1.f : 1.f, sgn_b = P.conj_b ? -1.f : 1.f;
+    long long a_k = a_base | deposit(kh0, P.a_khi, P.n_khi);
+    long long b_k = b_base | deposit(kh0, P.b_khi, P.n_khi);
+    int s = 0;
+    uint32_t ph = 0;
+    for (unsigned long long kk = 0; kk < k_iters; ++kk) {
+      // all global loads of this stage are in flight before the slot is even free
+      float2 va[NA], vb[NB];
+#pragma unroll
+      for (int i = 0; i < NA; ++i) va[i] = __ldg(A + (a_k | a_t_g | a_it_g[i]));
+#pragma unroll
+      for (int i = 0; i < NB; ++i)
+        vb[i] = b_act ? __ldg(B + (b_k | b_t_g | b_it_g[i])) : make_float2(0.f, 0.f);
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      float *sA = stages + (size_t)s * STAGE;
+      float *sB = sA + 4 * PLANE_A;
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        const int o = a_t_s + a_it_s[i];
+        float h, l;
+        split_tf32(va[i].x, h, l);
+        sA[o] = h; sA[PLANE_A + o] = l;
+        split_tf32(va[i].y * sgn_a, h, l);
+        sA[2 * PLANE_A + o] = h; sA[3 * PLANE_A + o] = l;
+      }
+      if (b_act) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          const int o = b_t_s + b_it_s[i];
+          float h, l;
+          split_tf32(vb[i].x, h, l);
+          sB[o] = h; sB[PLANE_B + o] = l;
+          split_tf32(vb[i].y * sgn_b, h, l);
+          sB[2 * PLANE_B + o] = h; sB[3 * PLANE_B + o] = l;
+        }
+      }
+      fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core
+      mbar_arrive(full_bar(s));
+      if (++s == S) { s = 0; ph ^= 1u; }
+      const unsigned long long flip = kk ^ (kk + 1);
+      const int nflip = 64 - __clzll(flip);
+      for (int i = 0; i < nflip && i < k_iters_bits; ++i) {
+        a_k ^= 1ll << P.a_khi[i];
+        b_k ^= 1ll << P.b_khi[i];
+      }
+    }
+
+    // ================= epilogue =================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;                     // tile row = TMEM lane
+    float2 *out = P.split_bits ? ws + (long long)split * P.c_elems : C;
+    out += c_base + (r & 31) + ((long long)(r >> 5) << (5 + TNB));
+    constexpr int HALF = TN / 2;
+    constexpr int CH = HALF < 16 ? HALF : 16;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += CH) {
+      uint32_t re[CH], im[CH];
+      tmem_ld<CH>::run(trow + (uint32_t)c0, re);
+      tmem_ld<CH>::run(trow + (uint32_t)(TN + c0), im);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        out[(long long)(c0 + j) << 5] = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+    }
+  } else if (lane == 0) {
+    // ================= MMA issuer (one thread) =================
+    int s = 0;
+    uint32_t ph = 0;
+    for (unsigned long long kk = 0; kk < k_iters; ++kk) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(stages + (size_t)s * STAGE);
+      const uint32_t sb = sa + 16u * PLANE_A;
+#pragma unroll
+      for (int ks = 0; ks < KT / 8; ++ks) {
+        const uint32_t ko = (uint32_t)ks * 2u * LBO;
+        const uint64_t arh = umma_desc(sa + ko, LBO, SBO);
+        const uint64_t arl = umma_desc(sa + 4u * PLANE_A + ko, LBO, SBO);
+        const uint64_t aih = umma_desc(sa + 8u * PLANE_A + ko, LBO, SBO);
+        const uint64_t ail = umma_desc(sa + 12u * PLANE_A + ko, LBO, SBO);
+        const uint64_t brh = umma_desc(sb + ko, LBO, SBO);
+        const uint64_t brl = umma_desc(sb + 4u * PLANE_B + ko, LBO, SBO);
+        const uint64_t bih = umma_desc(sb + 8u * PLANE_B + ko, LBO, SBO);
+        const uint64_t bil = umma_desc(sb + 12u * PLANE_B + ko, LBO, SBO);
+        const uint32_t first = (kk | (unsigned)ks) ? 1u : 0u;
+        const uint32_t cr = tmem_base, ci = tmem_base + TN;
+        // small cross terms first, the hi*hi products last
+        umma_tf32(cr, arl, brh, IDESC, first);
+        umma_tf32(cr, arh, brl, IDESC, 1u);
+        umma_tf32(cr, ail, bih, IDESC_NEG, 1u);
+        umma_tf32(cr, aih, bil, IDESC_NEG, 1u);
+        umma_tf32(cr, arh, brh, IDESC, 1u);
+        umma_tf32(cr, aih, bih, IDESC_NEG, 1u);
+        umma_tf32(ci, arl, bih, IDESC, first);
+        umma_tf32(ci, arh, bil, IDESC, 1u);
+        umma_tf32(ci, ail, brh, IDESC, 1u);
+        umma_tf32(ci, aih, brl, IDESC, 1u);
+        umma_tf32(ci, arh, bih, IDESC, 1u);
+        umma_tf32(ci, aih, brh, IDESC, 1u);
+      }
+      umma_commit(empty_bar(s));            // frees the stage once these MMAs have read it
+      if (++s == S) { s = 0; ph ^= 1u; }
+    }
+    umma_commit(accum_bar);                 // accumulators complete
+  }
+
+  // ---- teardown ------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int TNB, int TKB>
+int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
+                   const int32_t *slice_id, cudaStream_t st) {
+  static int smem_set = 0;
+  if (smem_set < P.smem_bytes) {
+    QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tc_kernel<TNB, TKB>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+    smem_set = P.smem_bytes;
+  }
+  gett_tc_kernel<TNB, TKB><<<(unsigned)P.grid, kThreads, P.smem_bytes, st>>>(
+      P, (const float2 *)a, (const float2 *)b, (float2 *)c, (float2 *)ws, slice_id);
+  QTN_LAUNCH_CHECK();
+  return QTN_OK;
+}
+
+}  // namespace
+
+int qtn_launch_tc(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
+                  const int32_t *slice_id, cudaStream_t st) {
+  if (P.dtype != QTN_C64) return qtn_fail(QTN_ERR_UNSUPPORTED, "tensor-core kernel is complex64 only");
+  if (P.grid <= 0 || P.grid > 0x7fffffffLL) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_run: grid too large");
+  if (P.tmb != 7 || P.tc_stages < 2 || P.tc_stages > 8)
+    return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: malformed tensor-core plan");
+  int rc;
+  switch (P.tnb * 8 + P.tkb) {
+#define QTN_TC_CASE(NB, KB) \
+  case NB * 8 + KB: rc = launch_tc_inst<NB, KB>(P, a, b, c, ws, slice_id, st); break;
+    QTN_TC_CASE(4, 3) QTN_TC_CASE(4, 4) QTN_TC_CASE(5, 3) QTN_TC_CASE(5, 4) QTN_TC_CASE(6, 3)
+    QTN_TC_CASE(6, 4) QTN_TC_CASE(7, 3) QTN_TC_CASE(7, 4) QTN_TC_CASE(8, 3) QTN_TC_CASE(8, 4)
+#undef QTN_TC_CASE
+    default: return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: unsupported tensor-core tile");
+  }
+  if (rc != QTN_OK) return rc;
+  if (P.split_bits)
+    return qtn_launch_splitk_sum(QTN_C64, c, ws, P.c_elems, 1 << P.split_bits, P.accumulate, st);
+  return QTN_OK;
+}

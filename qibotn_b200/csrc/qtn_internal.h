@@ -7,6 +7,9 @@ extern "C" {
 #endif
 // Records `msg` as the thread-local last error and returns `code`.
 int qtn_fail(int code, const char *msg);
+// Library-wide switches (api.cu); read by the host planner.
+int qtn_option_tc_enable(void);
+int qtn_option_tc_min_log2(void);
 #ifdef __cplusplus
 }
 #endif
@@ -18,6 +21,12 @@ int qtn_fail(int code, const char *msg);
     cudaError_t _e = (expr);                                                        \
     if (_e != cudaSuccess) return qtn_fail(QTN_ERR_CUDA, cudaGetErrorString(_e));   \
   } while (0)
+// gett_tc.cu: tcgen05 kernel launch (plan->kernel == QTN_KERNEL_TC)
+int qtn_launch_tc(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
+                  const int32_t *slice_id, cudaStream_t st);
+// gett.cu: C (+)= sum of `nsplit` split-K partials of `n` elements each
+int qtn_launch_splitk_sum(int dtype, void *c, const void *ws, long long n, int nsplit, int accumulate,
+                          cudaStream_t st);
 #define QTN_LAUNCH_CHECK()                                                          \
   do {                                                                              \
     cudaError_t _e = cudaGetLastError();                                            \

@@ -1,0 +1,359 @@
+// Batched one-sided Jacobi SVD with truncation, the "decompose" half of
+// cuquantum.tensornet.experimental.contract_decompose as the reference uses it for MPS
+// gates (mps_utils.py:32-37, 78-84; SVDMethod semantics in SURVEY.md Appendix B).
+//
+// Formulation.  For W (n x m, n <= m, row-major) plane rotations from the left make the ROWS
+// mutually orthogonal:  J W = diag(sigma) V^H  (up to order), so sigma_i = |row_i| and
+// V^H_i = row_i / sigma_i.  No left factor is accumulated: the caller recovers
+// U diag(f(sigma)) = W_in (row_i)^H f(sigma_i) / sigma_i^2 with one GEMM, which is exact
+// for the product of the two emitted factors whatever the conditioning
+// (A B = W_in V V^H).  A matrix with more rows than columns is handed in transposed.
+//
+// Blocking.  Rows are grouped in blocks of `block` rows; a CTA loads one PAIR of blocks into
+// shared memory, runs a full round-robin over the 2*block rows there (one warp per row pair:
+// three dot products by warp-shuffle reduction, then the rotation) and writes them back.
+// A sweep = round-robin over block pairs (one launch per step, all matrices of the batch
+// in the same launch).  Matrices that fit one block pair run to convergence inside a
+// single launch.  Sweeps stop when no rotation above `tol` happened (host reads one
+// counter per matrix per sweep).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "qtn_internal.h"
+
+namespace {
+
+template <typename R> struct cx_of;
+template <> struct cx_of<float> { using type = float2; };
+template <> struct cx_of<double> { using type = double2; };
+template <typename R> using cx = typename cx_of<R>::type;
+
+constexpr int kWarps = 8;
+constexpr int kSmemBudget = 160 * 1024;
+
+// Round-robin tournament ("circle method") on n players, n even: step in [0, n-1), p in [0, n/2).
+__host__ __device__ inline void circle(int step, int p, int n, int &a, int &b) {
+  const int m = n - 1;
+  if (p == 0) { a = step % m; b = m; }
+  else { a = (step + p) % m; b = (step - p + m) % m; }
+}
+
+template <typename R>
+__device__ __forceinline__ R warp_sum(R v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+fro2_kernel(const qtn_svd_item *__restrict__ items, double *__restrict__ fro2) {
+  using T = cx<R>;
+  __shared__ double red[kWarps];
+  const qtn_svd_item it = items[blockIdx.x];
+  const T *w = (const T *)it.w;
+  const long long total = (long long)it.n * it.m;
+  double s = 0;
+  for (long long e = threadIdx.x; e < total; e += 256) { const T v = w[e]; s += (double)v.x * v.x + (double)v.y * v.y; }
+  s = warp_sum<double>(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { double tsum = 0; for (int i = 0; i < kWarps; ++i) tsum += red[i]; fro2[blockIdx.x] = tsum; }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, int max_inner, R tol,
+                   double tiny_rel, const double *__restrict__ fro2, const int *__restrict__ rot_prev,
+                   int *__restrict__ rot_cur) {
+  using T = cx<R>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *rows = reinterpret_cast<T *>(smem_raw);
+  const int item_id = blockIdx.y;
+  if (sweep > 0 && rot_prev[item_id] == 0) return;          // this matrix has converged
+  const qtn_svd_item it = items[item_id];
+  const int n = it.n, m = it.m, b = it.block, nb = it.nblocks;
+  if (n < 2) return;
+  const int nbe = nb + (nb & 1);
+  const int nsteps = nb == 1 ? 1 : nbe - 1;
+  if (step >= nsteps) return;
+  int I = 0, J = -1;
+  if (nb == 1) {
+    if (blockIdx.x > 0) return;
+  } else {
+    if ((int)blockIdx.x >= nbe / 2) return;
+    circle(step, blockIdx.x, nbe, I, J);
+    if (I >= nb || J >= nb) return;                           // paired with the dummy block: idle
+  }
+  const int nr = J < 0 ? b : 2 * b;                            // rows held by this CTA (even)
+  T *W = (T *)it.w;
+  auto grow = [&](int lr) { return lr < b ? I * b + lr : J * b + (lr - b); };
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int lr = warp; lr < nr; lr += kWarps) {
+    const int g = grow(lr);
+    T *dst = rows + (size_t)lr * m;
+    if (g < n) { const T *src = W + (size_t)g * m; for (int c = lane; c < m; c += 32) dst[c] = src[c]; }
+    else { T z; z.x = 0; z.y = 0; for (int c = lane; c < m; c += 32) dst[c] = z; }
+  }
+  __syncthreads();
+  const R tiny = (R)(tiny_rel * fro2[item_id]);
+  const int inner_max = nb == 1 ? max_inner : 1;
+  int rotated_any = 0;
+  for (int inner = 0; inner < inner_max; ++inner) {
+    int rotated = 0;
+    for (int round = 0; round < nr - 1; ++round) {
+      for (int q = warp; q < nr / 2; q += kWarps) {
+        int x, y;
+        circle(round, q, nr, x, y);
+        if (grow(x) >= n || grow(y) >= n) continue;
+        T *X = rows + (size_t)x * m, *Y = rows + (size_t)y * m;
+        R a = 0, bb = 0, gr = 0, gi = 0;
+        for (int c = lane; c < m; c += 32) {
+          const T u = X[c], v = Y[c];
+          a = fma(u.x, u.x, fma(u.y, u.y, a));
+          bb = fma(v.x, v.x, fma(v.y, v.y, bb));
+          gr = fma(u.x, v.x, fma(u.y, v.y, gr));               // g = sum u * conj(v)
+          gi = fma(u.y, v.x, fma(-u.x, v.y, gi));
+        }
+        a = warp_sum<R>(a); bb = warp_sum<R>(bb); gr = warp_sum<R>(gr); gi = warp_sum<R>(gi);
+        const R g2 = gr * gr + gi * gi;
+        if (!(g2 > tol * tol * a * bb) || !(fmin(a, bb) > tiny)) continue;
+        rotated = 1;
+        const double gabs = sqrt((double)g2);
+        const double zeta = ((double)bb - (double)a) / (2.0 * gabs);
+        const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double cd = 1.0 / sqrt(1.0 + tt * tt), sd = cd * tt;
+        const R c = (R)cd;
+        const R spr = (R)(sd * gr / gabs), spi = (R)(sd * gi / gabs);   // s * e^{i phi}
+        for (int col = lane; col < m; col += 32) {
+          const T u = X[col], v = Y[col];
+          T xn, yn;
+          // x' = c x - s e^{i phi} y ;  y' = s e^{-i phi} x + c y
+          xn.x = c * u.x - (spr * v.x - spi * v.y);
+          xn.y = c * u.y - (spr * v.y + spi * v.x);
+          yn.x = c * v.x + (spr * u.x + spi * u.y);
+          yn.y = c * v.y + (spr * u.y - spi * u.x);
+          X[col] = xn; Y[col] = yn;
+        }
+      }
+      __syncthreads();
+    }
+    rotated = __syncthreads_or(rotated);
+    rotated_any = rotated;
+    if (!rotated) break;
+  }
+  for (int lr = warp; lr < nr; lr += kWarps) {
+    const int g = grow(lr);
+    if (g >= n) continue;
+    const T *src = rows + (size_t)lr * m;
+    T *dst = W + (size_t)g * m;
+    for (int c = lane; c < m; c += 32) dst[c] = src[c];
+  }
+  if (t == 0 && rotated_any) atomicAdd(&rot_cur[item_id], 1);
+}
+
+// Row norms -> singular values sorted descending (+ permutation), truncation rank, S normalisation.
+template <typename R>
+__global__ void __launch_bounds__(256)
+finalize_kernel(const qtn_svd_item *__restrict__ items, qtn_svd_trunc tr, double *__restrict__ scratch,
+                double *__restrict__ sigma, int32_t *__restrict__ perm, long long ld,
+                int32_t *__restrict__ rank, double *__restrict__ scale) {
+  using T = cx<R>;
+  const qtn_svd_item it = items[blockIdx.x];
+  const int n = it.n, m = it.m;
+  const T *W = (const T *)it.w;
+  double *raw = scratch + (long long)blockIdx.x * ld;
+  double *sg = sigma + (long long)blockIdx.x * ld;
+  int32_t *pm = perm + (long long)blockIdx.x * ld;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int r = warp; r < n; r += kWarps) {
+    double s = 0;
+    for (int c = lane; c < m; c += 32) { const T v = W[(size_t)r * m + c]; s += (double)v.x * v.x + (double)v.y * v.y; }
+    s = warp_sum<double>(s);
+    if (lane == 0) raw[r] = sqrt(s);
+  }
+  __syncthreads();
+  for (int i = t; i < n; i += 256) {
+    const double si = raw[i];
+    int rk = 0;
+    for (int j = 0; j < n; ++j) { const double sj = raw[j]; rk += (sj > si) || (sj == si && j < i); }
+    sg[rk] = si; pm[rk] = i;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int keep = n;
+    const double thr = fmax(tr.abs_cutoff, tr.rel_cutoff * sg[0]);
+    if (thr > 0) { keep = 0; while (keep < n && sg[keep] > thr) ++keep; }
+    if (tr.discarded_weight_cutoff > 0) {
+      double total = 0;
+      for (int i = 0; i < n; ++i) total += sg[i] * sg[i];
+      double tail = 0;                                          // weight of sg[keep-1:] kept so far
+      while (keep > 1) {
+        tail += sg[keep - 1] * sg[keep - 1];
+        if (tail / total < tr.discarded_weight_cutoff) --keep; else break;
+      }
+    }
+    if (tr.max_extent > 0 && keep > tr.max_extent) keep = tr.max_extent;
+    if (keep < 1) keep = 1;
+    double sc = 1.0;
+    if (tr.normalization == 1) { double s1 = 0; for (int i = 0; i < keep; ++i) s1 += sg[i]; sc = s1 > 0 ? 1.0 / s1 : 1.0; }
+    else if (tr.normalization == 2) { double s2 = 0; for (int i = 0; i < keep; ++i) s2 += sg[i] * sg[i]; sc = s2 > 0 ? 1.0 / sqrt(s2) : 1.0; }
+    else if (tr.normalization == 3) { sc = sg[0] > 0 ? 1.0 / sg[0] : 1.0; }
+    rank[blockIdx.x] = keep;
+    scale[blockIdx.x] = sc;
+  }
+}
+
+// out1[c][:] = f1_c * W[perm[c]][:],  out2[c][:] = f2_c * W[perm[c]][:]   for c < k
+template <typename R>
+__global__ void __launch_bounds__(256)
+emit_kernel(const cx<R> *__restrict__ W, int m, const int32_t *__restrict__ perm,
+            const double *__restrict__ sigma, double scale, int partition, int transposed,
+            cx<R> *__restrict__ out1, cx<R> *__restrict__ out2) {
+  using T = cx<R>;
+  const int c = blockIdx.x;
+  const double s = sigma[c], sn = s * scale;
+  double fa = 1, fb = 1;                 // what the left / right factor absorbs
+  if (partition == 1) fa = sn;
+  else if (partition == 2) fb = sn;
+  else if (partition == 3) { fa = sqrt(sn); fb = fa; }
+  double f1 = 0, f2 = 0;
+  if (s > 0) {
+    if (!transposed) { f1 = fb / s; f2 = fa / (s * s); }
+    else { f1 = fa / s; f2 = fb / (s * s); }
+  }
+  const T *src = W + (size_t)perm[c] * m;
+  for (int col = threadIdx.x; col < m; col += 256) {
+    const T v = src[col];
+    T o1, o2;
+    o1.x = (R)(f1 * v.x); o1.y = (R)(f1 * v.y);
+    o2.x = (R)(f2 * v.x); o2.y = (R)(f2 * v.y);
+    out1[(size_t)c * m + col] = o1;
+    out2[(size_t)c * m + col] = o2;
+  }
+}
+
+int choose_block(int n, int m, int esz, int *block, int *nblocks) {
+  int b = 32;
+  while (b >= 1 && (long long)2 * b * m * esz > kSmemBudget) b >>= 1;
+  if (b < 1) return -1;
+  if (n <= 2 * b) {                       // the whole matrix is one resident block
+    int p = 2;
+    while (p < n) p <<= 1;
+    *block = p; *nblocks = 1;
+    return 0;
+  }
+  *block = b; *nblocks = (n + b - 1) / b;
+  return 0;
+}
+
+template <typename R>
+int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, const qtn_svd_trunc *trunc,
+                  double *sigma, int32_t *perm, int64_t ld, int32_t *rank_host, double *scale_host,
+                  int32_t *sweeps_host, unsigned char *ws, cudaStream_t st) {
+  const int esz = (int)sizeof(cx<R>);
+  int max_steps = 1, max_pairs = 1;
+  size_t smem = 0;
+  for (int i = 0; i < batch; ++i) {
+    qtn_svd_item &it = items[i];
+    if (it.n < 1 || it.m < 1 || !it.w) return qtn_fail(QTN_ERR_ARG, "qtn_svd_rows: bad item");
+    if (it.n > ld) return qtn_fail(QTN_ERR_ARG, "qtn_svd_rows: ld smaller than a row count");
+    if (choose_block(it.n, it.m, esz, &it.block, &it.nblocks))
+      return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_svd_rows: rows too long for shared memory");
+    const int nbe = it.nblocks + (it.nblocks & 1);
+    max_steps = std::max(max_steps, it.nblocks == 1 ? 1 : nbe - 1);
+    max_pairs = std::max(max_pairs, it.nblocks == 1 ? 1 : nbe / 2);
+    const int nr = it.nblocks == 1 ? it.block : 2 * it.block;
+    smem = std::max(smem, (size_t)nr * it.m * esz);
+  }
+  // workspace: items | fro2 | rot[2] | rank | scale | scratch sigma
+  qtn_svd_item *d_items = (qtn_svd_item *)ws;
+  size_t off = ((size_t)batch * sizeof(qtn_svd_item) + 255) & ~(size_t)255;
+  double *d_fro2 = (double *)(ws + off); off += ((size_t)batch * 8 + 255) & ~(size_t)255;
+  int *d_rot = (int *)(ws + off); off += ((size_t)batch * 8 + 255) & ~(size_t)255;
+  int32_t *d_rank = (int32_t *)(ws + off); off += ((size_t)batch * 4 + 255) & ~(size_t)255;
+  double *d_scale = (double *)(ws + off); off += ((size_t)batch * 8 + 255) & ~(size_t)255;
+  double *d_scratch = (double *)(ws + off);
+  QTN_CUDA_CHECK(cudaMemcpyAsync(d_items, items, (size_t)batch * sizeof(qtn_svd_item), cudaMemcpyHostToDevice, st));
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    QTN_CUDA_CHECK(cudaFuncSetAttribute(jacobi_step_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)std::max(smem, (size_t)kSmemBudget)));
+    smem_set = std::max(smem, (size_t)kSmemBudget);
+  }
+  fro2_kernel<R><<<batch, 256, 0, st>>>(d_items, d_fro2);
+  QTN_LAUNCH_CHECK();
+  const double tiny_rel = sizeof(R) == 8 ? 1e-30 : 1e-14;
+  std::vector<int> rot(batch);
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    int *rot_cur = d_rot + (sweep & 1) * batch, *rot_prev = d_rot + ((sweep & 1) ^ 1) * batch;
+    QTN_CUDA_CHECK(cudaMemsetAsync(rot_cur, 0, (size_t)batch * sizeof(int), st));
+    dim3 grid((unsigned)max_pairs, (unsigned)batch);
+    for (int step = 0; step < max_steps; ++step) {
+      jacobi_step_kernel<R><<<grid, 256, smem, st>>>(d_items, step, sweep, max_sweeps, (R)tol, tiny_rel, d_fro2,
+                                                    rot_prev, rot_cur);
+      QTN_LAUNCH_CHECK();
+    }
+    QTN_CUDA_CHECK(cudaMemcpyAsync(rot.data(), rot_cur, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+    QTN_CUDA_CHECK(cudaStreamSynchronize(st));
+    bool any = false;
+    for (int i = 0; i < batch; ++i) any = any || rot[i] != 0;
+    if (!any) { ++sweep; break; }
+  }
+  if (sweeps_host) *sweeps_host = sweep;
+  finalize_kernel<R><<<batch, 256, 0, st>>>(d_items, *trunc, d_scratch, sigma, perm, ld, d_rank, d_scale);
+  QTN_LAUNCH_CHECK();
+  QTN_CUDA_CHECK(cudaMemcpyAsync(rank_host, d_rank, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  QTN_CUDA_CHECK(cudaMemcpyAsync(scale_host, d_scale, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, st));
+  QTN_CUDA_CHECK(cudaStreamSynchronize(st));
+  return QTN_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t qtn_svd_workspace_bytes(int batch, int64_t ld) {
+  if (batch < 1 || ld < 1) return 0;
+  int64_t off = ((int64_t)batch * (int64_t)sizeof(qtn_svd_item) + 255) & ~(int64_t)255;
+  off += 4 * (((int64_t)batch * 8 + 255) & ~(int64_t)255);
+  off += (int64_t)batch * ld * 8 + 256;
+  return off;
+}
+
+extern "C" int qtn_svd_rows(int dtype, int batch, qtn_svd_item *items, double tol, int max_sweeps,
+                            const qtn_svd_trunc *trunc, double *sigma, int32_t *perm, int64_t ld,
+                            int32_t *rank_host, double *scale_host, int32_t *sweeps_host, void *workspace,
+                            int64_t workspace_bytes, void *stream) {
+  if (dtype != QTN_C64 && dtype != QTN_C128) return qtn_fail(QTN_ERR_ARG, "qtn_svd_rows: bad dtype");
+  if (batch < 1 || !items || !trunc || !sigma || !perm || !rank_host || !scale_host || !workspace)
+    return qtn_fail(QTN_ERR_ARG, "qtn_svd_rows: null argument");
+  if (workspace_bytes < qtn_svd_workspace_bytes(batch, ld))
+    return qtn_fail(QTN_ERR_WORKSPACE, "qtn_svd_rows: workspace too small (qtn_svd_workspace_bytes)");
+  if (max_sweeps < 1) max_sweeps = 30;
+  if (!(tol > 0)) tol = dtype == QTN_C64 ? 1e-6 : 1e-14;
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == QTN_C64
+             ? svd_rows_impl<float>(batch, items, tol, max_sweeps, trunc, sigma, perm, ld, rank_host, scale_host,
+                                    sweeps_host, (unsigned char *)workspace, st)
+             : svd_rows_impl<double>(batch, items, tol, max_sweeps, trunc, sigma, perm, ld, rank_host, scale_host,
+                                     sweeps_host, (unsigned char *)workspace, st);
+}
+
+extern "C" int qtn_svd_emit(int dtype, const void *w, int32_t m, const int32_t *perm, const double *sigma,
+                            double scale, int32_t k, int32_t partition, int32_t transposed, void *out1,
+                            void *out2, void *stream) {
+  if (dtype != QTN_C64 && dtype != QTN_C128) return qtn_fail(QTN_ERR_ARG, "qtn_svd_emit: bad dtype");
+  if (!w || !perm || !sigma || !out1 || !out2 || m < 1 || k < 1 || partition < 0 || partition > 3)
+    return qtn_fail(QTN_ERR_ARG, "qtn_svd_emit: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == QTN_C64)
+    emit_kernel<float><<<k, 256, 0, st>>>((const float2 *)w, m, perm, sigma, scale, partition, transposed,
+                                          (float2 *)out1, (float2 *)out2);
+  else
+    emit_kernel<double><<<k, 256, 0, st>>>((const double2 *)w, m, perm, sigma, scale, partition, transposed,
+                                           (double2 *)out1, (double2 *)out2);
+  QTN_LAUNCH_CHECK();
+  return QTN_OK;
+}

@@ -12,7 +12,7 @@ from functools import lru_cache
 
 QTN_C64, QTN_C128 = 0, 1
 QTN_MAX_RANK, QTN_MAX_SLICE, QTN_LO_MAX, QTN_HI_MAX = 48, 24, 16, 40
-KERNEL_TILE, KERNEL_REDUCE = 0, 1
+KERNEL_TILE, KERNEL_REDUCE, KERNEL_TC = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqibotn_b200.so")
@@ -61,6 +61,8 @@ class PairPlan(C.Structure):
         ("grid", C.c_int64), ("block", C.c_int32), ("smem_bytes", C.c_int32),
         ("workspace_bytes", C.c_int64), ("c_elems", C.c_int64),
         ("flops", C.c_double), ("bytes", C.c_double),
+        ("tc_stages", C.c_int32), ("tc_plane_a", C.c_int32), ("tc_plane_b", C.c_int32),
+        ("tc_reserved", C.c_int32),
     ]
 
 
@@ -81,6 +83,8 @@ _SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "qtn_axpy": (C.c_int, [C.c_int, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                            C.c_int, C.c_void_p]),
+    "qtn_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "qtn_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "qtn_set_i32": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "qtn_add_i32": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
 }
@@ -107,6 +111,17 @@ def exported_symbols():
 def check(status):
     if status != 0:
         raise QtnError(f"qibotn_b200 error {status}: {load().qtn_last_error().decode()}")
+
+
+def set_option(name, value):
+    """Library-wide switch (``tc_enable``, ``tc_min_log2``); see include/qibotn_b200.h."""
+    check(load().qtn_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    v = C.c_int(0)
+    check(load().qtn_get_option(name.encode(), C.byref(v)))
+    return v.value
 
 
 def dtype_code(dtype) -> int:

@@ -61,6 +61,8 @@ def run_plan(P, a, b, c, slice_id=0):
     sb = slice_off(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b)
     if P.kernel == 1:
         return _run_reduce(P, a, b, c, sa, sb)
+    if P.kernel == 2:
+        return _run_tc(P, a, b, c, sa, sb)
     TM, TN, TK = 1 << P.tmb, 1 << P.tnb, 1 << P.tkb
     nsplit = 1 << P.split_bits
     ws = np.zeros((nsplit, P.c_elems), dtype=c.dtype)
@@ -138,4 +140,65 @@ def _run_reduce(P, a, b, c, sa, sb):
                 c[g] += acc[m, n]
             else:
                 c[g] = acc[m, n]
+    return c
+
+
+def _canonical_kmajor(plane, rows, kt):
+    """Read a ``rows x kt`` operand out of the tensor core's K-major no-swizzle layout
+    (8-row x 4-value core matrices of 32 floats; K-neighbours 32 floats apart, 8-row groups
+    ``kt * 8`` floats apart) -- written independently of the planner's stride tables."""
+    out = np.zeros((rows, kt), dtype=plane.dtype)
+    for r in range(rows):
+        for k in range(kt):
+            out[r, k] = plane[(r & 7) * 4 + (k & 3) + (r >> 3) * (kt * 8) + (k >> 2) * 32]
+    return out
+
+
+def _run_tc(P, a, b, c, sa, sb):
+    """Emulate gett_tc.cu: gather into canonical-layout planes, tile product, fixed C tile layout."""
+    TN, KT = 1 << P.tnb, 1 << P.tkb
+    assert P.tmb == 7 and P.n_batch == 0 and not P.accumulate
+    assert P.tc_plane_a == 128 * KT * 4 and P.tc_plane_b == TN * KT * 4
+    assert P.smem_bytes >= P.tc_stages * 4 * (P.tc_plane_a + P.tc_plane_b) + 8 * (2 * P.tc_stages + 2)
+    assert P.smem_bytes <= 227 * 1024 and 2 <= P.tc_stages <= 8
+    # the epilogue hard-codes C's tile layout: m bits 0-4 | n bits | m bits 5-6
+    want = list(range(5)) + [5 + P.tnb, 6 + P.tnb] + [5 + j for j in range(P.tnb)]
+    assert [P.c_lo_pos[i] for i in range(7 + P.tnb)] == want
+    nsplit = 1 << P.split_bits
+    ws = np.zeros((nsplit, P.c_elems), dtype=c.dtype)
+    kbits = P.n_khi - P.split_bits
+    for cta in range(P.grid):
+        split = cta & (nsplit - 1)
+        rest = cta >> P.split_bits
+        mh = rest & ((1 << P.n_mhi) - 1)
+        nh = rest >> P.n_mhi
+        a_base = dep(mh, P.a_mhi, P.n_mhi) | sa
+        b_base = dep(nh, P.b_nhi, P.n_nhi) | sb
+        c_base = dep(mh, P.c_mhi, P.n_mhi) | dep(nh, P.c_nhi, P.n_nhi)
+        acc = np.zeros((128, TN), dtype=np.complex128)
+        for kk in range(1 << kbits):
+            kh = (split << kbits) | kk
+            a_k, b_k = dep(kh, P.a_khi, P.n_khi), dep(kh, P.b_khi, P.n_khi)
+            planes = []
+            for (n_lo, lo_pos, lo_sstr, size, src, base) in (
+                    (P.na_lo, P.a_lo_pos, P.a_lo_sstr, 128 * KT, a, a_base | a_k),
+                    (P.nb_lo, P.b_lo_pos, P.b_lo_sstr, TN * KT, b, b_base | b_k)):
+                assert (1 << n_lo) == size
+                plane = np.full(size, np.nan, dtype=np.complex128)
+                for e in range(size):
+                    g = s = 0
+                    for j in range(n_lo):
+                        if (e >> j) & 1:
+                            g |= 1 << lo_pos[j]
+                            s += lo_sstr[j]
+                    assert np.isnan(plane[s])           # every slot written exactly once
+                    plane[s] = src[base | g]
+                planes.append(plane)
+            acc += _canonical_kmajor(planes[0], 128, KT) @ _canonical_kmajor(planes[1], TN, KT).T
+        out = ws[split] if P.split_bits else c
+        for r in range(128):
+            for n in range(TN):
+                out[c_base + (r & 31) + (n << 5) + ((r >> 5) << (5 + P.tnb))] = acc[r, n]
+    if P.split_bits:
+        c[: P.c_elems] = ws.sum(0)
     return c

@@ -95,3 +95,52 @@ def test_bad_descriptors_are_rejected():
     d = lib.make_pair_desc("complex64", [(0, 0), (0, 1)], [(1, 0)], [1])
     with pytest.raises(lib.QtnError):
         lib.pair_plan(d)
+
+
+TC_CASES = [
+    # m, n, k, slices a/b  (complex64, C free: the tensor-core kernel's domain)
+    (7, 4, 3, 0, 0), (8, 5, 4, 0, 0), (7, 8, 5, 0, 0), (9, 9, 3, 1, 1), (7, 6, 9, 0, 0),
+    (10, 4, 6, 2, 0), (8, 7, 4, 0, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_tensor_core_plan_tables(case):
+    m, n, k, nsa, nsb = case
+    lib.set_option("tc_min_log2", 0)
+    try:
+        rng = np.random.default_rng(hash(case) % 2**32)
+        la, pa, sa_pos, lb, pb, sb_pos, lc, _ = random_case(rng, m, n, k, 0, nsa, nsb)
+        ra, rb = len(la) + nsa, len(lb) + nsb
+        a = (rng.normal(size=1 << ra) + 1j * rng.normal(size=1 << ra)).astype(np.complex64)
+        b = (rng.normal(size=1 << rb) + 1j * rng.normal(size=1 << rb)).astype(np.complex64)
+        bits_a = list(range(nsa)); bits_b = list(range(1, 1 + nsb))
+        desc = lib.make_pair_desc("complex64", list(zip(la, pa)), list(zip(lb, pb)), lc,
+                                  slice_a=list(zip(bits_a, sa_pos)), slice_b=list(zip(bits_b, sb_pos)))
+        plan = lib.pair_plan(desc, 4)
+    finally:
+        lib.set_option("tc_min_log2", 18)
+    assert plan.kernel == lib.KERNEL_TC
+    pc_used = [desc.pos_c[i] for i in range(len(lc))]
+    lc_used = [desc.label_c[i] for i in range(len(lc))]
+    assert sorted(pc_used) == list(range(len(lc)))
+    for slice_id in ([0] if nsa + nsb == 0 else [0, 3]):
+        c = np.zeros(1 << len(lc), dtype=np.complex64)
+        emu.run_plan(plan, a, b, c, slice_id)
+        got = emu.dense_from_flat(c, lc_used, pc_used)
+        want = reference(a, la, pa, sa_pos, b, lb, pb, sb_pos, lc_used, slice_id, bits_a, bits_b)
+        assert np.allclose(got, want, rtol=1e-4, atol=1e-4 * (1 << (k // 2)))
+
+
+def test_tensor_core_kernel_is_optional():
+    la = [(i, i) for i in range(12)]          # m = 8 labels, k = 4 labels
+    lb = [(8 + i, i) for i in range(10)]      # k = 4, n = 6
+    lib.set_option("tc_min_log2", 0)
+    try:
+        assert lib.pair_plan(lib.make_pair_desc("complex64", la, lb)).kernel == lib.KERNEL_TC
+        assert lib.pair_plan(lib.make_pair_desc("complex128", la, lb)).kernel == lib.KERNEL_TILE
+        lib.set_option("tc_enable", 0)
+        assert lib.pair_plan(lib.make_pair_desc("complex64", la, lb)).kernel == lib.KERNEL_TILE
+    finally:
+        lib.set_option("tc_enable", 1)
+        lib.set_option("tc_min_log2", 18)
