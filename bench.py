@@ -300,21 +300,40 @@ def run_b200(a):
     k_ms = float(np.mean(ts[1:]))
     k_tfs = node.plan.flops / (k_ms * 1e-3) / 1e12
     intensity = node.plan.flops / node.plan.bytes
-    fp32_peak = measure_fp32_peak(torch)
-    hbm_bound = intensity < fp32_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)
-    if hbm_bound:
-        roof = {"bound": "hbm", "achieved": node.plan.bytes / (k_ms * 1e-3) / 1e9,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s"}
-    else:
+    names = {0: "gett_tile_kernel<float>", 1: "gett_reduce_kernel<float>", 2: "gett_tc_kernel"}
+    if node.plan.kernel == lib.KERNEL_TC:
+        # tcgen05 kind::tf32, 3 MMAs per product (hi*hi + hi*lo + lo*hi): the tensor pipe does 3x
+        # the algorithmic flops at the tf32 rate (half the bf16 rate measured in MEASURED_PEAKS.json)
         roof = {"bound": "tensor", "achieved": k_tfs, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s"}
+        extra = {"mma": "tcgen05.mma kind::tf32, 3xTF32 split, complex as 4 real GEMMs",
+                 "tensor_flops_per_algorithmic_flop": 3.0,
+                 "tf32_peak_assumed_tflops": peaks["bf16_tflops"] / 2,
+                 "tensor_pipe_frac_tf32": 3.0 * k_tfs / (peaks["bf16_tflops"] / 2),
+                 "hbm_gbs_at_this_speed": node.plan.bytes / (k_ms * 1e-3) / 1e9,
+                 "note": "frac is algorithmic complex64 flops over the measured bf16 cuBLAS burst; "
+                         "tensor_pipe_frac_tf32 is the share of the tf32 pipe the 3x split keeps busy"}
+    else:
+        fp32_peak = measure_fp32_peak(torch)
+        hbm_bound = intensity < fp32_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)
+        if hbm_bound:
+            roof = {"bound": "hbm", "achieved": node.plan.bytes / (k_ms * 1e-3) / 1e9,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+        else:
+            roof = {"bound": "tensor", "achieved": k_tfs, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s"}
+        extra = {"fp32_pipe_tflops_measured": fp32_peak, "fp32_pipe_frac": k_tfs / fp32_peak,
+                 "note": "complex64 FFMA kernel on the FP32 pipe; tensor peak is the bf16 cuBLAS burst"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof.update({"traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json bf16 burst)",
-                 "kernel": "gett_tile_kernel<float>" if node.plan.kernel == 0 else "gett_reduce_kernel",
+    roof.update({"traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json, burst)",
+                 "kernel": names.get(node.plan.kernel, "?"),
                  "kernel_ms": k_ms, "kernel_flops": node.plan.flops, "kernel_bytes": node.plan.bytes,
                  "tile_log2": [node.plan.tmb, node.plan.tnb, node.plan.tkb],
-                 "share_of_step_flops": node.plan.flops * (batch if node.depends else 1) / flops_step,
-                 "fp32_pipe_tflops_measured": fp32_peak, "fp32_pipe_frac": k_tfs / fp32_peak,
-                 "note": "complex64 FFMA kernel on the FP32 pipe; tensor peak is the bf16 cuBLAS burst"})
+                 "share_of_step_flops": node.plan.flops * (batch if node.depends else 1) / flops_step})
+    roof.update(extra)
+    kinds = {}
+    for nd in low.nodes:
+        if nd.depends or info.num_slices == 1:
+            kinds[names.get(nd.plan.kernel, "?")] = kinds.get(names.get(nd.plan.kernel, "?"), 0.0) + nd.plan.flops
+    roof["flops_share_by_kernel"] = {k: v / sum(kinds.values()) for k, v in kinds.items()}
 
     line = {
         "metric": "tn_contraction_tflops", "value": tfs, "unit": "TFLOP/s", "n_gpus": size,

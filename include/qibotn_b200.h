@@ -141,6 +141,9 @@ typedef struct {
  * Returns QTN_ERR_ARG for an unknown name. */
 int qtn_set_option(const char *name, int value);
 int qtn_get_option(const char *name, int *value);
+/* sizeof() of a public struct by name ("qtn_pair_desc", "qtn_pair_plan_t", "qtn_svd_item",
+ * "qtn_svd_trunc"), -1 if unknown: lets a foreign-language binding verify its mirror. */
+int64_t qtn_sizeof(const char *struct_name);
 
 /* Host-only: derive roles, tile shape, coalescing-driven label placement and,
  * when desc->c_layout_free, C's layout (written back to desc->pos_c).

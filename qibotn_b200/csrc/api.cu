@@ -37,6 +37,15 @@ extern "C" int qtn_get_option(const char *name, int *value) {
   return qtn_fail(QTN_ERR_ARG, "qtn_get_option: unknown option");
 }
 
+extern "C" int64_t qtn_sizeof(const char *name) {
+  if (!name) return -1;
+  if (!std::strcmp(name, "qtn_pair_desc")) return (int64_t)sizeof(qtn_pair_desc);
+  if (!std::strcmp(name, "qtn_pair_plan_t")) return (int64_t)sizeof(qtn_pair_plan_t);
+  if (!std::strcmp(name, "qtn_svd_item")) return (int64_t)sizeof(qtn_svd_item);
+  if (!std::strcmp(name, "qtn_svd_trunc")) return (int64_t)sizeof(qtn_svd_trunc);
+  return -1;
+}
+
 extern "C" const char *qtn_version(void) { return "qibotn_b200 0.1.0 (sm_100a)"; }
 
 extern "C" int qtn_device_info(int device, int *sm_count, int *max_smem_optin, int *cc_major,

@@ -195,9 +195,20 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, k_off(i)});
     for (int j = 0; j < tnb; ++j) eb.push_back({nlo[j].pb, row_off(j)});
     for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, k_off(i)});
-    auto by_pos = [](const E &x, const E &y) { return x.pos < y.pos; };
-    std::sort(ea.begin(), ea.end(), by_pos);
-    std::sort(eb.begin(), eb.end(), by_pos);
+    // Enumeration order = which label each bit of (lane, warp, iteration) walks.  The five lane
+    // bits are the labels that own the five bank-selecting offsets of a core matrix (row bits
+    // 0-2 -> 4, 8, 16 floats; k bits 0-1 -> 1, 2 floats): a warp's 32 stores then hit 32
+    // different banks.  Those labels are the lowest-address ones of their kind, so the two
+    // lowest address bits are always among them and global loads keep >= 32-byte runs.
+    auto lane_first = [](std::vector<E> &v) {
+      auto is_lane = [](const E &x) { return x.sstr < 32; };
+      std::stable_sort(v.begin(), v.end(), [&](const E &x, const E &y) {
+        if (is_lane(x) != is_lane(y)) return is_lane(x);
+        return x.pos < y.pos;
+      });
+    };
+    lane_first(ea);
+    lane_first(eb);
     p->na_lo = (int)ea.size(); p->nb_lo = (int)eb.size();
     for (int i = 0; i < p->na_lo; ++i) { p->a_lo_pos[i] = (uint8_t)ea[i].pos; p->a_lo_sstr[i] = (uint16_t)ea[i].sstr; }
     for (int i = 0; i < p->nb_lo; ++i) { p->b_lo_pos[i] = (uint8_t)eb[i].pos; p->b_lo_sstr[i] = (uint16_t)eb[i].sstr; }
@@ -217,8 +228,14 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     p->tc_plane_a = 128 * KT * 4;
     p->tc_plane_b = TN * KT * 4;
     const int stage_bytes = 4 * (p->tc_plane_a + p->tc_plane_b);
-    p->tc_stages = std::max(2, std::min(4, (200 * 1024) / stage_bytes));
-    p->smem_bytes = p->tc_stages * stage_bytes + 256;
+    // pipeline depth: never deeper than the k loop; small tiles leave room for 2 CTAs per SM
+    // (110 KB each) so that one CTA's epilogue overlaps the other's loads
+    const int64_t k_iters = (int64_t)1 << (p->n_khi - split);
+    const int budget = (tnb <= 6 && 2 * stage_bytes <= 110 * 1024) ? 110 * 1024 : 200 * 1024;
+    int stages = std::max(1, std::min(4, budget / stage_bytes));
+    if ((int64_t)stages > k_iters) stages = (int)k_iters;
+    p->tc_stages = stages;
+    p->smem_bytes = stages * stage_bytes + 256;
     p->sa_stride = 0; p->sb_stride = 0;
   } else {
     // ---- shared-memory tiled kernel -----------------------------------------

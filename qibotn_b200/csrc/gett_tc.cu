@@ -167,7 +167,7 @@ __device__ __forceinline__ long long slice_offset(const int32_t *slice_id, int n
 }
 
 template <int TNB, int TKB>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, (TNB <= 6 ? 2 : 1))
 gett_tc_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ A,
                const float2 *__restrict__ B, float2 *__restrict__ C, float2 *__restrict__ ws,
                const int32_t *__restrict__ slice_id) {
@@ -200,9 +200,10 @@ gett_tc_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restri
   unsigned long long id = blockIdx.x;
   const unsigned split = (unsigned)(id & ((1ull << P.split_bits) - 1));
   id >>= P.split_bits;
-  const unsigned long long mh = id & ((1ull << P.n_mhi) - 1);
-  id >>= P.n_mhi;
-  const unsigned long long nh = id;
+  // n tiles vary fastest: CTAs that share an A tile run together and the second read hits L2
+  const unsigned long long nh = id & ((1ull << P.n_nhi) - 1);
+  id >>= P.n_nhi;
+  const unsigned long long mh = id;
   const long long a_base = deposit(mh, P.a_mhi, P.n_mhi) |
                            slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
   const long long b_base = deposit(nh, P.b_nhi, P.n_nhi) |
@@ -257,14 +258,22 @@ gett_tc_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restri
     long long b_k = b_base | deposit(kh0, P.b_khi, P.n_khi);
     int s = 0;
     uint32_t ph = 0;
-    for (unsigned long long kk = 0; kk < k_iters; ++kk) {
-      // all global loads of this stage are in flight before the slot is even free
-      float2 va[NA], vb[NB];
+    auto load = [&](float2(&va)[NA], float2(&vb)[NB]) {
 #pragma unroll
       for (int i = 0; i < NA; ++i) va[i] = __ldg(A + (a_k | a_t_g | a_it_g[i]));
 #pragma unroll
       for (int i = 0; i < NB; ++i)
         vb[i] = b_act ? __ldg(B + (b_k | b_t_g | b_it_g[i])) : make_float2(0.f, 0.f);
+    };
+    auto advance = [&](unsigned long long kk) {          // offsets of k chunk kk -> kk + 1
+      const unsigned long long flip = kk ^ (kk + 1);
+      const int nflip = 64 - __clzll(flip);
+      for (int i = 0; i < nflip && i < k_iters_bits; ++i) {
+        a_k ^= 1ll << P.a_khi[i];
+        b_k ^= 1ll << P.b_khi[i];
+      }
+    };
+    auto store = [&](const float2(&va)[NA], const float2(&vb)[NB]) {
       mbar_wait(empty_bar(s), ph ^ 1u);
       float *sA = stages + (size_t)s * STAGE;
       float *sB = sA + 4 * PLANE_A;
@@ -291,11 +300,19 @@ gett_tc_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restri
       fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core
       mbar_arrive(full_bar(s));
       if (++s == S) { s = 0; ph ^= 1u; }
-      const unsigned long long flip = kk ^ (kk + 1);
-      const int nflip = 64 - __clzll(flip);
-      for (int i = 0; i < nflip && i < k_iters_bits; ++i) {
-        a_k ^= 1ll << P.a_khi[i];
-        b_k ^= 1ll << P.b_khi[i];
+    };
+    // register double buffering: the loads of chunk kk+1 are in flight while chunk kk is split
+    // and stored (and before its pipeline slot is even free)
+    float2 va0[NA], vb0[NB], va1[NA], vb1[NB];
+    load(va0, vb0);
+    advance(0);
+    for (unsigned long long kk = 0; kk < k_iters; kk += 2) {
+      const bool more1 = kk + 1 < k_iters;
+      if (more1) { load(va1, vb1); advance(kk + 1); }
+      store(va0, vb0);
+      if (more1) {
+        if (kk + 2 < k_iters) { load(va0, vb0); advance(kk + 2); }
+        store(va1, vb1);
       }
     }
 
@@ -392,7 +409,7 @@ int qtn_launch_tc(const qtn_pair_plan_t &P, const void *a, const void *b, void *
                   const int32_t *slice_id, cudaStream_t st) {
   if (P.dtype != QTN_C64) return qtn_fail(QTN_ERR_UNSUPPORTED, "tensor-core kernel is complex64 only");
   if (P.grid <= 0 || P.grid > 0x7fffffffLL) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_run: grid too large");
-  if (P.tmb != 7 || P.tc_stages < 2 || P.tc_stages > 8)
+  if (P.tmb != 7 || P.tc_stages < 1 || P.tc_stages > 8)
     return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: malformed tensor-core plan");
   int rc;
   switch (P.tnb * 8 + P.tkb) {

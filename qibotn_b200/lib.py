@@ -66,6 +66,20 @@ class PairPlan(C.Structure):
     ]
 
 
+class SvdItem(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("n", C.c_int32), ("m", C.c_int32),
+                ("block", C.c_int32), ("nblocks", C.c_int32)]
+
+
+class SvdTrunc(C.Structure):
+    _fields_ = [("abs_cutoff", C.c_double), ("rel_cutoff", C.c_double),
+                ("discarded_weight_cutoff", C.c_double), ("max_extent", C.c_int32),
+                ("normalization", C.c_int32)]
+
+
+OP_N, OP_C, OP_T, OP_H = 0, 1, 2, 3
+
+
 class QtnError(RuntimeError):
     pass
 
@@ -83,6 +97,18 @@ _SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "qtn_axpy": (C.c_int, [C.c_int, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                            C.c_int, C.c_void_p]),
+    "qtn_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                           C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "qtn_mps_apply_1q": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qtn_mps_apply_2q": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qtn_svd_workspace_bytes": (C.c_int64, [C.c_int, C.c_int64]),
+    "qtn_svd_rows": (C.c_int, [C.c_int, C.c_int, C.POINTER(SvdItem), C.c_double, C.c_int,
+                               C.POINTER(SvdTrunc), C.c_void_p, C.c_void_p, C.c_int64,
+                               C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                               C.c_void_p, C.c_int64, C.c_void_p]),
+    "qtn_svd_emit": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double,
+                               C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qtn_sizeof": (C.c_int64, [C.c_char_p]),
     "qtn_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "qtn_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "qtn_set_i32": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),

@@ -1,0 +1,387 @@
+"""MPS evolution on the GPU: circuit -> MPS gate loop, truncation, read-out.
+
+Drop-in for three reference modules, same names and call conventions:
+
+* ``QiboCircuitToMPS(circ, gate_algo, dtype)`` -- ``/root/reference/src/qibotn/circuit_to_mps.py:9-47``;
+* ``initial`` / ``apply_gate`` / ``mps_site_right_swap`` -- ``mps_utils.py:6-95`` (1-site update,
+  adjacent 2-site contract+decompose, swap-in/swap-out recursion for distant pairs, reversed
+  pairs by ``transpose(1,0,3,2)``, ``NotImplementedError`` beyond two qubits);
+* ``MPSContractionHelper`` -- ``mps_contraction_helper.py:6-118`` (norm, dense vector,
+  local-operator expectation).
+
+What replaces cuQuantum's ``contract`` / ``contract_decompose``: ``qtn_gemm`` (A.B),
+``qtn_mps_apply_1q/2q`` (gate legs) and the batched one-sided Jacobi SVD
+``qtn_svd_rows`` + ``qtn_svd_emit`` with cuTensorNet's ``SVDMethod`` truncation rules
+(SURVEY.md Appendix B).  No canonical form is kept, exactly like the reference: truncation is
+local to the two-site block.
+
+Scheduling differs from the reference (results do not): consecutive two-site updates on
+disjoint site pairs -- a brickwork layer -- are decomposed as ONE batch, so the Jacobi
+kernels see tens of matrices per launch instead of one library call per gate.
+There is no CPU path; without the CUDA library or a GPU this module raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib
+from .network import QiboCircuitToEinsum, np_dtype
+
+_SWAP = np.zeros((2, 2, 2, 2))
+for _p in range(2):
+    for _q in range(2):
+        _SWAP[_q, _p, _p, _q] = 1.0          # out (r,s) = in (q,p)
+
+_PARTITION = {None: 0, "U": 1, "V": 2, "UV": 3}
+_NORMALIZATION = {None: 0, "L1": 1, "L2": 2, "LInf": 3}
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise lib.QtnError("qibotn_b200 MPS needs a CUDA device; there is no CPU fallback")
+    return torch
+
+
+def parse_algorithm(algorithm):
+    """``gate_algo`` dict -> (SvdTrunc, partition code).  Keys as cuQuantum's
+    ``ContractDecomposeAlgorithm`` (``qr_method``, ``svd_method{...}``).  ``svd_method: False``
+    (pure QR) is served by the same Jacobi kernel as an untruncated orthogonal factorisation
+    theta = Q R' with Q^H Q = 1 (R' is not triangular: the MPS gauge differs, the state does not)."""
+    algorithm = algorithm or {}
+    svd = algorithm.get("svd_method", {})
+    tr = lib.SvdTrunc(0.0, 0.0, 0.0, 0, 0)
+    if svd is False:
+        return tr, _PARTITION["V"], True
+    svd = svd or {}
+    unknown = set(svd) - {"abs_cutoff", "rel_cutoff", "discarded_weight_cutoff", "max_extent", "partition",
+                          "normalization", "algorithm", "gesvdj_tol", "gesvdj_max_sweeps",
+                          "gesvdr_oversampling", "gesvdr_niters"}
+    if unknown:
+        raise ValueError(f"unknown svd_method option(s): {sorted(unknown)}")
+    tr.abs_cutoff = float(svd.get("abs_cutoff") or 0.0)
+    tr.rel_cutoff = float(svd.get("rel_cutoff") or 0.0)
+    tr.discarded_weight_cutoff = float(svd.get("discarded_weight_cutoff") or 0.0)
+    tr.max_extent = int(svd.get("max_extent") or 0)
+    try:
+        tr.normalization = _NORMALIZATION[svd.get("normalization")]
+        part = _PARTITION[svd.get("partition")]
+    except KeyError as exc:
+        raise ValueError(f"unknown svd_method value {exc}") from None
+    return tr, part, False
+
+
+class MPSEngine:
+    """Owns the site tensors (torch, on the GPU) and applies gates to them."""
+
+    def __init__(self, num_qubits, dtype="complex128", algorithm=None, tol=None, max_sweeps=30):
+        torch = _torch()
+        self.torch = torch
+        self.lib = lib.load()
+        self.n = int(num_qubits)
+        self.np_dtype = np_dtype(dtype)
+        self.dtype = "complex64" if self.np_dtype is np.complex64 else "complex128"
+        self.code = lib.dtype_code(self.dtype)
+        self.cdtype = torch.complex64 if self.dtype == "complex64" else torch.complex128
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.trunc, self.partition, self.qr_only = parse_algorithm(algorithm)
+        self.tol = float(tol) if tol else 0.0
+        self.max_sweeps = int(max_sweeps)
+        zero = torch.zeros(1, 2, 1, dtype=self.cdtype, device=self.device)
+        zero[0, 0, 0] = 1
+        self.sites = [zero.clone() for _ in range(self.n)]
+        self._batch = []               # pending two-site updates on disjoint pairs: (i, gate 2x2x2x2)
+        self._busy = set()
+        self.stats = {"two_site": 0, "one_site": 0, "swaps": 0, "svd_batches": 0, "svd_sweeps": 0,
+                      "max_bond": 1, "launches": 0}
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def _dev(self, host_array):
+        t = self.torch.from_numpy(np.ascontiguousarray(host_array, dtype=self.np_dtype))
+        return t.to(self.device, non_blocking=False)
+
+    def _gemm(self, opa, opb, m, n, k, a, lda, b, ldb, c, ldc, accumulate=0):
+        lib.check(self.lib.qtn_gemm(self.code, opa, opb, m, n, k, a.data_ptr(), lda, b.data_ptr(), ldb,
+                                    c.data_ptr(), ldc, accumulate, self._stream()))
+        self.stats["launches"] += 1
+
+    def _transpose(self, src, rows, cols):
+        """(rows x cols) row-major -> (cols x rows) row-major, through qtn_permute."""
+        dst = self.torch.empty(cols * rows, dtype=self.cdtype, device=self.device)
+        ext = (C.c_int64 * 2)(rows, cols)
+        perm = (C.c_int32 * 2)(1, 0)
+        lib.check(self.lib.qtn_permute(self.code, 2, ext, perm, src.data_ptr(), dst.data_ptr(), self._stream()))
+        self.stats["launches"] += 1
+        return dst
+
+    # ------------------------------------------------------------------ gates
+    def apply_gate(self, gate, qubits):
+        """Reference ``apply_gate`` (mps_utils.py:42-95)."""
+        qubits = tuple(int(q) for q in qubits)
+        if len(qubits) == 1:
+            self._one_site(qubits[0], np.asarray(gate).reshape(2, 2))
+        elif len(qubits) == 2:
+            i, j = qubits
+            gate = np.asarray(gate).reshape(2, 2, 2, 2)
+            if i > j:
+                return self.apply_gate(gate.transpose(1, 0, 3, 2), (j, i))
+            if i == j:
+                raise ValueError("two-qubit gate needs two different qubits")
+            if i + 1 == j:
+                self._queue_two_site(i, gate)
+                self.stats["two_site"] += 1
+            else:
+                self.right_swap(i)
+                self.apply_gate(gate, (i + 1, j))
+                self.right_swap(i)
+        else:
+            raise NotImplementedError("Only one- and two-qubit gates supported")
+
+    def right_swap(self, i):
+        """Reference ``mps_site_right_swap`` (mps_utils.py:21-39): exchange the physical legs of
+        sites i, i+1 and split again with the same algorithm."""
+        self._queue_two_site(i, _SWAP)
+        self.stats["swaps"] += 1
+
+    def _one_site(self, i, gate):
+        if i in self._busy:
+            self.flush()
+        site = self.sites[i]
+        g = self._dev(gate)
+        lib.check(self.lib.qtn_mps_apply_1q(self.code, site.shape[0], site.shape[2], site.data_ptr(),
+                                            g.data_ptr(), self._stream()))
+        self.stats["one_site"] += 1
+        self.stats["launches"] += 1
+
+    def _queue_two_site(self, i, gate):
+        if i in self._busy or (i + 1) in self._busy:
+            self.flush()
+        self._batch.append((i, np.asarray(gate, dtype=self.np_dtype)))
+        self._busy.update((i, i + 1))
+
+    # ------------------------------------------------------------------ batched two-site update
+    def flush(self):
+        """Run the pending two-site updates: theta = gate(A.B) for each, then ONE batched SVD."""
+        if not self._batch:
+            return
+        torch = self.torch
+        batch, self._batch, self._busy = self._batch, [], set()
+        gates = self._dev(np.stack([g.reshape(16) for _, g in batch]))
+        work = []
+        for k, (i, _) in enumerate(batch):
+            a, b = self.sites[i], self.sites[i + 1]
+            l, m, r = a.shape[0], a.shape[2], b.shape[2]
+            p, q = 2 * l, 2 * r
+            theta = torch.empty(p * q, dtype=self.cdtype, device=self.device)
+            self._gemm(lib.OP_N, lib.OP_N, p, q, m, a, m, b, q, theta, q)
+            lib.check(self.lib.qtn_mps_apply_2q(self.code, l, r, theta.data_ptr(), gates[k].data_ptr(),
+                                                self._stream()))
+            self.stats["launches"] += 1
+            transposed = p > q
+            w = self._transpose(theta, p, q) if transposed else theta.clone()
+            work.append((i, l, r, p, q, theta, w, transposed))
+        nb = len(work)
+        items = (lib.SvdItem * nb)()
+        ld = 1
+        for k, (_, _, _, p, q, _, w, transposed) in enumerate(work):
+            items[k].w = w.data_ptr()
+            items[k].n, items[k].m = (q, p) if transposed else (p, q)
+            ld = max(ld, items[k].n)
+        sigma = torch.empty(nb * ld, dtype=torch.float64, device=self.device)
+        perm = torch.empty(nb * ld, dtype=torch.int32, device=self.device)
+        ws_bytes = int(self.lib.qtn_svd_workspace_bytes(nb, ld))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        ranks = (C.c_int32 * nb)()
+        scales = (C.c_double * nb)()
+        sweeps = C.c_int32(0)
+        lib.check(self.lib.qtn_svd_rows(self.code, nb, items, self.tol, self.max_sweeps, C.byref(self.trunc),
+                                        sigma.data_ptr(), perm.data_ptr(), ld, ranks, scales,
+                                        C.byref(sweeps), ws.data_ptr(), ws_bytes, self._stream()))
+        self.stats["svd_batches"] += 1
+        self.stats["svd_sweeps"] += int(sweeps.value)
+        esz = 8
+        for k, (i, l, r, p, q, theta, w, transposed) in enumerate(work):
+            kk = int(ranks[k])
+            mcols = p if transposed else q
+            out1 = torch.empty(kk * mcols, dtype=self.cdtype, device=self.device)
+            out2 = torch.empty(kk * mcols, dtype=self.cdtype, device=self.device)
+            lib.check(self.lib.qtn_svd_emit(self.code, w.data_ptr(), mcols, perm.data_ptr() + 4 * k * ld,
+                                            sigma.data_ptr() + esz * k * ld, float(scales[k]), kk,
+                                            self.partition, int(transposed), out1.data_ptr(),
+                                            out2.data_ptr(), self._stream()))
+            self.stats["launches"] += 1
+            if not transposed:
+                right = out1                                             # (kk x q)
+                left = torch.empty(p * kk, dtype=self.cdtype, device=self.device)
+                self._gemm(lib.OP_N, lib.OP_H, p, kk, q, theta, q, out2, q, left, kk)   # theta * out2^H
+            else:
+                left = self._transpose(out1, kk, p)                      # (p x kk)
+                right = torch.empty(kk * q, dtype=self.cdtype, device=self.device)
+                self._gemm(lib.OP_C, lib.OP_N, kk, q, p, out2, p, theta, q, right, q)   # conj(out2) * theta
+            self.sites[i] = left.view(l, 2, kk)
+            self.sites[i + 1] = right.view(kk, 2, r)
+            self.stats["max_bond"] = max(self.stats["max_bond"], kk)
+
+    def bond_dimensions(self):
+        self.flush()
+        return [int(t.shape[2]) for t in self.sites[:-1]]
+
+
+# ----------------------------------------------------------------------------- reference surface
+def initial(num_qubits, dtype):
+    """|0...0> as ``num_qubits`` tensors of shape (1,2,1) on the GPU (mps_utils.py:6-18)."""
+    return MPSEngine(num_qubits, dtype).sites
+
+
+def _engine_from(mps_tensors, algorithm):
+    torch = _torch()
+    dt = "complex64" if mps_tensors[0].dtype == torch.complex64 else "complex128"
+    eng = MPSEngine(len(mps_tensors), dt, algorithm)
+    eng.sites = [t.contiguous() for t in mps_tensors]
+    return eng
+
+
+def apply_gate(mps_tensors, gate, qubits, **kwargs):
+    """In-place gate application on a list of site tensors (mps_utils.py:42-95)."""
+    eng = _engine_from(mps_tensors, kwargs.get("algorithm"))
+    gate = gate.detach().cpu().numpy() if hasattr(gate, "detach") else np.asarray(gate)
+    eng.apply_gate(gate, qubits)
+    eng.flush()
+    mps_tensors[:] = eng.sites
+    return mps_tensors
+
+
+def mps_site_right_swap(mps_tensors, i, **kwargs):
+    """Swap sites i and i+1 (mps_utils.py:21-39)."""
+    eng = _engine_from(mps_tensors, kwargs.get("algorithm"))
+    eng.right_swap(i)
+    eng.flush()
+    mps_tensors[:] = eng.sites
+    return mps_tensors
+
+
+class QiboCircuitToMPS:
+    """Circuit -> MPS (circuit_to_mps.py:9-47): |0..0>, then every gate in queue order."""
+
+    def __init__(self, circ_qibo, gate_algo, dtype="complex128", rand_seed=0):
+        np.random.seed(rand_seed)
+        self.num_qubits = circ_qibo.nqubits
+        self.dtype = dtype
+        self.handle = None                      # the reference keeps a cutensornet handle here
+        conv = QiboCircuitToEinsum(circ_qibo, dtype=dtype)
+        self.engine = MPSEngine(self.num_qubits, dtype, gate_algo)
+        for gate, qubits in conv.gate_tensors:
+            self.engine.apply_gate(gate, qubits)
+        self.engine.flush()
+        self.mps_tensors = self.engine.sites
+        self.stats = self.engine.stats
+
+
+class MPSContractionHelper:
+    """Norm, dense vector and local expectation of an MPS (mps_contraction_helper.py:6-118),
+    computed as GEMM sweeps on the GPU instead of cuTensorNet network contractions."""
+
+    def __init__(self, num_qubits):
+        self.num_qubits = num_qubits
+        self.lib = lib.load()
+
+    @staticmethod
+    def _setup(mps_tensors):
+        torch = _torch()
+        t0 = mps_tensors[0]
+        dt = "complex64" if t0.dtype == torch.complex64 else "complex128"
+        return torch, dt, lib.dtype_code(dt), t0.dtype, t0.device
+
+    def _gemm(self, code, opa, opb, m, n, k, a, lda, b, ldb, c, ldc, torch):
+        lib.check(self.lib.qtn_gemm(code, opa, opb, m, n, k, a.data_ptr(), lda, b.data_ptr(), ldb,
+                                    c.data_ptr(), ldc, 0, torch.cuda.current_stream().cuda_stream))
+
+    def contract_state_vector(self, mps_tensors, options=None):
+        """Dense (2,)*n state; refuses what cannot fit (the reference has no such guard)."""
+        torch, dt, code, cdtype, dev = self._setup(mps_tensors)
+        n = len(mps_tensors)
+        if n > 33:
+            raise ValueError(f"dense read-out of {n} qubits does not fit on one GPU; use "
+                             "contract_norm / contract_expectation")
+        psi = mps_tensors[0].contiguous().reshape(-1)          # (1*2) x chi
+        rows = 2 * mps_tensors[0].shape[0]
+        for t in mps_tensors[1:]:
+            chi, cols = t.shape[0], 2 * t.shape[2]
+            nxt = torch.empty(rows * cols, dtype=cdtype, device=dev)
+            self._gemm(code, lib.OP_N, lib.OP_N, rows, cols, chi, psi, chi, t.contiguous(), cols, nxt, cols, torch)
+            psi, rows = nxt, rows * 2
+        return psi.reshape((2,) * n)
+
+    def _transfer(self, env, ket, bra, torch, code):
+        """env'[c,d] = sum_{a,b,p} env[a,b] ket[a,p,c] conj(bra[b,p,d])."""
+        a, _, c = ket.shape
+        b, _, d = bra.shape
+        x = torch.empty(b * 2 * c, dtype=ket.dtype, device=ket.device)              # x[b,(p,c)]
+        self._gemm(code, lib.OP_T, lib.OP_N, b, 2 * c, a, env, b, ket, 2 * c, x, 2 * c, torch)
+        out = torch.empty(c * d, dtype=ket.dtype, device=ket.device)
+        self._gemm(code, lib.OP_T, lib.OP_C, c, d, 2 * b, x, c, bra, d, out, d, torch)  # x^T conj(bra)
+        return out.view(c, d)
+
+    def contract_norm(self, mps_tensors, options=None):
+        """<psi|psi> (mps_contraction_helper.py:32-51); real device scalar."""
+        torch, dt, code, cdtype, dev = self._setup(mps_tensors)
+        env = torch.ones(1, 1, dtype=cdtype, device=dev)
+        for t in mps_tensors:
+            t = t.contiguous()
+            env = self._transfer(env, t, t, torch, code)
+        return env.reshape(()).real
+
+    def contract_expectation(self, mps_tensors, operator, qubits, options=None, normalize=False):
+        """<psi| O |psi> for an operator on ``qubits`` given as a (2,)*2k tensor or 2^k x 2^k
+        matrix, modes = outputs then inputs (mps_contraction_helper.py:73-113).  The operator is
+        expanded in Pauli products; each product is one transfer-matrix sweep."""
+        torch, dt, code, cdtype, dev = self._setup(mps_tensors)
+        from .observables import PAULI
+
+        qubits = [int(q) for q in qubits]
+        k = len(qubits)
+        op = operator.detach().cpu().numpy() if hasattr(operator, "detach") else np.asarray(operator)
+        op = op.reshape(1 << k, 1 << k).astype(np.complex128)
+        letters = "IXYZ"
+        total = None
+        for idx in np.ndindex(*(4,) * k):
+            mats = [PAULI[letters[x]] for x in idx]
+            full = mats[0]
+            for mt in mats[1:]:
+                full = np.kron(full, mt)
+            coeff = np.trace(full.conj().T @ op) / (1 << k)
+            if abs(coeff) < 1e-15:
+                continue
+            val = self.pauli_expectation(mps_tensors, {q: letters[x] for q, x in zip(qubits, idx)})
+            total = coeff * val if total is None else total + coeff * val
+        if total is None:
+            total = torch.zeros((), dtype=cdtype, device=dev)
+        if normalize:
+            total = total / self.contract_norm(mps_tensors)
+        return total
+
+    def pauli_expectation(self, mps_tensors, pauli_map):
+        """<psi| prod_q sigma_q |psi> for ``{qubit: 'X'|'Y'|'Z'|'I'}``: one left-to-right sweep."""
+        torch, dt, code, cdtype, dev = self._setup(mps_tensors)
+        from .observables import PAULI
+
+        npdt = np.complex64 if dt == "complex64" else np.complex128
+        env = torch.ones(1, 1, dtype=cdtype, device=dev)
+        for q, t in enumerate(mps_tensors):
+            t = t.contiguous()
+            ket = t
+            letter = pauli_map.get(q, "I")
+            if letter != "I":
+                ket = t.clone()
+                g = torch.from_numpy(PAULI[letter].astype(npdt)).to(dev)
+                lib.check(self.lib.qtn_mps_apply_1q(code, t.shape[0], t.shape[2], ket.data_ptr(), g.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream))
+            env = self._transfer(env, ket, t, torch, code)
+        return env.reshape(())

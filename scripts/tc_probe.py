@@ -124,6 +124,9 @@ def case(m, n, k, seed=0, layout="random", structured=False, time_it=False, chec
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which == "one":        # python scripts/tc_probe.py one m n k [layout]  (short run for ncu)
+    mm, nn, kk = (int(x) for x in sys.argv[2:5])
+    case(mm, nn, kk, layout=sys.argv[5] if len(sys.argv) > 5 else "random", seed=8, time_it=True, check=False)
 if which in ("probe", "all"):
     case(7, 4, 3, layout="gemm", structured=True)
     case(7, 4, 3, layout="gemm")
@@ -143,6 +146,8 @@ if which in ("time", "all"):
     case(20, 9, 7, layout="gemm", seed=8, time_it=True, check=False)
     case(19, 8, 8, layout="random", seed=9, time_it=True, check=False)
     case(24, 5, 5, layout="random", seed=10, time_it=True, check=False)
+    case(23, 4, 6, layout="random", seed=15, time_it=True, check=False)
+    case(24, 5, 5, layout="gemm", seed=10, time_it=True, check=False)
     case(20, 6, 8, layout="random", seed=11, time_it=True, check=False)
     case(7, 6, 20, layout="random", seed=12, time_it=True, check=False)
     case(13, 13, 6, layout="random", seed=13, time_it=True, check=False)

@@ -160,7 +160,7 @@ def _run_tc(P, a, b, c, sa, sb):
     assert P.tmb == 7 and P.n_batch == 0 and not P.accumulate
     assert P.tc_plane_a == 128 * KT * 4 and P.tc_plane_b == TN * KT * 4
     assert P.smem_bytes >= P.tc_stages * 4 * (P.tc_plane_a + P.tc_plane_b) + 8 * (2 * P.tc_stages + 2)
-    assert P.smem_bytes <= 227 * 1024 and 2 <= P.tc_stages <= 8
+    assert P.smem_bytes <= 227 * 1024 and 1 <= P.tc_stages <= 8
     # the epilogue hard-codes C's tile layout: m bits 0-4 | n bits | m bits 5-6
     want = list(range(5)) + [5 + P.tnb, 6 + P.tnb] + [5 + j for j in range(P.tnb)]
     assert [P.c_lo_pos[i] for i in range(7 + P.tnb)] == want
@@ -170,8 +170,8 @@ def _run_tc(P, a, b, c, sa, sb):
     for cta in range(P.grid):
         split = cta & (nsplit - 1)
         rest = cta >> P.split_bits
-        mh = rest & ((1 << P.n_mhi) - 1)
-        nh = rest >> P.n_mhi
+        nh = rest & ((1 << P.n_nhi) - 1)
+        mh = rest >> P.n_nhi
         a_base = dep(mh, P.a_mhi, P.n_mhi) | sa
         b_base = dep(nh, P.b_nhi, P.n_nhi) | sb
         c_base = dep(mh, P.c_mhi, P.n_mhi) | dep(nh, P.c_nhi, P.n_nhi)
@@ -184,6 +184,8 @@ def _run_tc(P, a, b, c, sa, sb):
                     (P.na_lo, P.a_lo_pos, P.a_lo_sstr, 128 * KT, a, a_base | a_k),
                     (P.nb_lo, P.b_lo_pos, P.b_lo_sstr, TN * KT, b, b_base | b_k)):
                 assert (1 << n_lo) == size
+                # the five lane bits own the five bank-selecting offsets (1, 2, 4, 8, 16 floats)
+                assert sorted(lo_sstr[j] for j in range(5)) == [1, 2, 4, 8, 16]
                 plane = np.full(size, np.nan, dtype=np.complex128)
                 for e in range(size):
                     g = s = 0

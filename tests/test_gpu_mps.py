@@ -1,0 +1,228 @@
+"""GPU parity of the MPS path: general GEMM, site kernels, batched Jacobi SVD with truncation,
+the gate loop of mps_utils.py and the read-outs of mps_contraction_helper.py, against the CPU
+oracle (oracle/mps.py, oracle/statevector.py) and LAPACK singular values."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import mps as omps
+from oracle import statevector as osv
+from oracle.network import gate_tensors
+from qibotn_b200 import MetaBackend, circuits, lib
+from qibotn_b200 import mps as gmps
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = {"complex64": 2e-5, "complex128": 1e-10}
+
+
+def _rand(rng, *shape, dtype="complex128"):
+    return (rng.normal(size=shape) + 1j * rng.normal(size=shape)).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 7, 3), (64, 64, 16), (130, 70, 33), (2, 300, 129)])
+@pytest.mark.parametrize("ops", [(0, 0), (2, 0), (0, 3), (3, 1), (1, 2)])
+def test_gemm_all_ops(shape, ops, dtype):
+    m, n, k = shape
+    opa, opb = ops
+    rng = np.random.default_rng(m * 1000 + n * 10 + k + opa * 7 + opb)
+    a = _rand(rng, *((k, m) if opa & 2 else (m, k)), dtype=dtype)
+    b = _rand(rng, *((n, k) if opb & 2 else (k, n)), dtype=dtype)
+    A = a.T if opa & 2 else a
+    A = A.conj() if opa & 1 else A
+    B = b.T if opb & 2 else b
+    B = B.conj() if opb & 1 else B
+    want = A.astype(np.complex128) @ B.astype(np.complex128)
+    h = lib.load()
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    dc = torch.zeros(m, n, dtype=da.dtype, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    lib.check(h.qtn_gemm(lib.dtype_code(dtype), opa, opb, m, n, k, da.data_ptr(), a.shape[1],
+                         db.data_ptr(), b.shape[1], dc.data_ptr(), n, 0, st))
+    got = dc.cpu().numpy()
+    tol = 1e-5 if dtype == "complex64" else 1e-12
+    assert np.abs(got - want).max() <= tol * (np.abs(want).max() + 1)
+    lib.check(h.qtn_gemm(lib.dtype_code(dtype), opa, opb, m, n, k, da.data_ptr(), a.shape[1],
+                         db.data_ptr(), b.shape[1], dc.data_ptr(), n, 1, st))
+    assert np.abs(dc.cpu().numpy() - 2 * want).max() <= 2 * tol * (np.abs(want).max() + 1)
+
+
+def _svd_split(theta, dtype, algorithm):
+    """theta (p x q numpy) -> (left p x k, right k x q, sigma) through the C ABI, the way
+    MPSEngine.flush drives it."""
+    eng = gmps.MPSEngine(2, dtype, algorithm)
+    p, q = theta.shape
+    t = torch.from_numpy(theta.astype(dtype)).cuda().reshape(-1)
+    transposed = p > q
+    w = eng._transpose(t, p, q) if transposed else t.clone()
+    items = (lib.SvdItem * 1)()
+    items[0].w, items[0].n, items[0].m = w.data_ptr(), (q if transposed else p), (p if transposed else q)
+    ld = items[0].n
+    sigma = torch.empty(ld, dtype=torch.float64, device="cuda")
+    perm = torch.empty(ld, dtype=torch.int32, device="cuda")
+    nbytes = int(eng.lib.qtn_svd_workspace_bytes(1, ld))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    rank, scale, sweeps = (C.c_int32 * 1)(), (C.c_double * 1)(), C.c_int32(0)
+    st = torch.cuda.current_stream().cuda_stream
+    lib.check(eng.lib.qtn_svd_rows(eng.code, 1, items, 0.0, 40, C.byref(eng.trunc), sigma.data_ptr(),
+                                   perm.data_ptr(), ld, rank, scale, C.byref(sweeps), ws.data_ptr(), nbytes, st))
+    k = int(rank[0])
+    mcols = items[0].m
+    o1 = torch.empty(k * mcols, dtype=t.dtype, device="cuda")
+    o2 = torch.empty(k * mcols, dtype=t.dtype, device="cuda")
+    lib.check(eng.lib.qtn_svd_emit(eng.code, w.data_ptr(), mcols, perm.data_ptr(), sigma.data_ptr(),
+                                   float(scale[0]), k, eng.partition, int(transposed), o1.data_ptr(),
+                                   o2.data_ptr(), st))
+    if not transposed:
+        right = o1.view(k, q)
+        left = torch.empty(p * k, dtype=t.dtype, device="cuda")
+        eng._gemm(lib.OP_N, lib.OP_H, p, k, q, t, q, o2, q, left, k)
+        left = left.view(p, k)
+    else:
+        left = eng._transpose(o1, k, p).view(p, k)
+        right = torch.empty(k * q, dtype=t.dtype, device="cuda")
+        eng._gemm(lib.OP_C, lib.OP_N, k, q, p, o2, p, t, q, right, q)
+        right = right.view(k, q)
+    return left.cpu().numpy(), right.cpu().numpy(), sigma.cpu().numpy()[:k] * scale[0], int(sweeps.value)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("shape", [(2, 2), (4, 4), (6, 10), (10, 6), (32, 32), (64, 48), (70, 200), (160, 160),
+                                   (257, 130)])
+def test_jacobi_svd_matches_lapack(shape, dtype):
+    rng = np.random.default_rng(shape[0] * 31 + shape[1])
+    theta = _rand(rng, *shape)
+    s_ref = np.linalg.svd(theta.astype(dtype).astype(np.complex128), compute_uv=False)
+    tol = 3e-5 if dtype == "complex64" else 1e-11
+    for part in (None, "U", "V", "UV"):
+        left, right, sig, sweeps = _svd_split(theta, dtype, {"svd_method": {"partition": part}})
+        assert sweeps < 40
+        assert sig.shape == s_ref.shape
+        assert np.abs(sig - s_ref).max() <= tol * s_ref[0]
+        if part is None:
+            rec = (left * sig) @ right
+            # isometries: left^H left = 1, right right^H = 1
+            assert np.abs(left.conj().T @ left - np.eye(len(sig))).max() < tol * 50
+            assert np.abs(right @ right.conj().T - np.eye(len(sig))).max() < tol * 50
+        else:
+            rec = left @ right
+        assert np.abs(rec - theta).max() <= tol * 20 * s_ref[0]
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_truncation_rules(dtype):
+    rng = np.random.default_rng(7)
+    u, _ = np.linalg.qr(_rand(rng, 24, 24))
+    v, _ = np.linalg.qr(_rand(rng, 40, 40))
+    s = np.array([3.0, 2.0, 1.0, 0.5, 0.2, 1e-3, 1e-4] + [1e-9] * 5 + [0.0] * 12)
+    theta = (u * s) @ v[:24]
+    cases = [({"abs_cutoff": 1e-6}, 7), ({"abs_cutoff": 0.3}, 4), ({"rel_cutoff": 0.1}, 4),
+             ({"max_extent": 3}, 3), ({"abs_cutoff": 1e-6, "max_extent": 5}, 5),
+             ({"discarded_weight_cutoff": 0.01}, 4), ({"abs_cutoff": 10.0}, 1)]
+    for method, keep in cases:
+        algo = {"svd_method": dict(method, partition="UV")}
+        left, right, sig, _ = _svd_split(theta, dtype, algo)
+        assert omps.truncation_rank(s, algo["svd_method"]) == keep
+        assert len(sig) == keep, (method, len(sig))
+        want = (u[:, :keep] * s[:keep]) @ v[:keep]
+        tol = 2e-5 if dtype == "complex64" else 1e-10
+        assert np.abs(left @ right - want).max() < tol * 10
+    for norm, f in (("L1", lambda x: x / x.sum()), ("L2", lambda x: x / np.sqrt((x ** 2).sum())),
+                    ("LInf", lambda x: x / x[0])):
+        _, _, sig, _ = _svd_split(theta, dtype, {"svd_method": {"max_extent": 4, "normalization": norm}})
+        assert np.allclose(sig, f(s[:4]), rtol=1e-4 if dtype == "complex64" else 1e-10)
+
+
+def _mps_state(circ, dtype, algorithm):
+    conv = gmps.QiboCircuitToMPS(circ, algorithm, dtype=dtype)
+    dense = gmps.MPSContractionHelper(circ.nqubits).contract_state_vector(conv.mps_tensors)
+    return dense.reshape(-1).cpu().numpy(), conv
+
+
+DEFAULT_ALGO = {"qr_method": False, "svd_method": {"partition": "UV", "abs_cutoff": 1e-12}}
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("nqubits", [2, 5, 10])
+def test_mps_qft_uniform(nqubits, dtype):
+    """reference tests/test_cuquantum_cutensor_backend.py:88-142 (bond dimension stays 1)."""
+    b = MetaBackend.load("cutensornet")
+    b.set_precision("single" if dtype == "complex64" else "double")
+    want = np.full(1 << nqubits, 2.0 ** (-nqubits / 2))
+    for runcard_value in (True, DEFAULT_ALGO):
+        b.configure_tn_simulation({"MPI_enabled": False, "MPS_enabled": runcard_value, "NCCL_enabled": False,
+                                   "expectation_enabled": False})
+        got = b.execute_circuit(circuit=circuits.qft(nqubits, True)).statevector.flatten().get()
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-8 if dtype == "complex128" else 1e-6)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("builder", ["ring", "brick", "tfim", "distant"])
+def test_mps_state_vs_dense_simulator(builder, dtype):
+    if builder == "ring":
+        circ = circuits.ry_rz_cnot_ring(8, 3, seed=42)          # has the (7,0) CNOT: swaps + reversed pair
+    elif builder == "brick":
+        circ = circuits.brickwork(10, 6, seed=3)
+    elif builder == "tfim":
+        circ = circuits.tfim_trotter(12, 4)
+    else:
+        circ = circuits.Circuit(7)
+        rng = np.random.default_rng(5)
+        for q in range(7):
+            circ.add(circuits.gates.U3(q, *rng.uniform(-3, 3, 3)))
+        for a, b in [(6, 2), (0, 5), (3, 1), (2, 6), (4, 0)]:
+            circ.add(circuits.gates.CNOT(a, b))
+            circ.add(circuits.gates.RY(b, theta=float(rng.uniform(-3, 3))))
+    want = osv.simulate(circ)
+    got, conv = _mps_state(circ, dtype, DEFAULT_ALGO)
+    assert np.abs(got - want).max() < TOL[dtype] * 10
+    # the oracle MPS (numpy.linalg.svd, same truncation rule) has the same bond profile
+    ref = omps.evolve(circ, DEFAULT_ALGO)
+    if dtype == "complex128":
+        assert [t.shape[2] for t in ref[:-1]] == [int(t.shape[2]) for t in conv.mps_tensors[:-1]]
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_mps_truncated_matches_oracle(dtype):
+    circ = circuits.brickwork(10, 8, seed=11)
+    algo = {"qr_method": False, "svd_method": {"partition": "UV", "abs_cutoff": 1e-12, "max_extent": 6}}
+    ref = omps.to_dense(omps.evolve(circ, algo)).reshape(-1)
+    got, conv = _mps_state(circ, dtype, algo)
+    assert max(int(t.shape[2]) for t in conv.mps_tensors[:-1]) == 6
+    # same local truncation => same (unnormalised) state up to rounding
+    assert np.abs(got - ref).max() < (2e-4 if dtype == "complex64" else 1e-8)
+    exact = osv.simulate(circ)
+    assert np.abs(got - exact).max() > 1e-4            # the truncation really happened
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_norm_and_expectation_sweeps(dtype):
+    circ = circuits.tfim_trotter(10, 3)
+    psi = osv.simulate(circ)
+    conv = gmps.QiboCircuitToMPS(circ, DEFAULT_ALGO, dtype=dtype)
+    helper = gmps.MPSContractionHelper(10)
+    tol = TOL[dtype] * 10
+    assert abs(float(helper.contract_norm(conv.mps_tensors).cpu()) - 1.0) < tol
+    zz = np.kron(np.diag([1.0, -1.0]), np.diag([1.0, -1.0]))
+    for qubits, op in (((3,), np.array([[0, 1], [1, 0]])), ((2, 3), zz), ((1, 7), zz),
+                       ((4, 5), np.array([[0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0], [1, 0, 0, 0]]))):
+        got = complex(helper.contract_expectation(conv.mps_tensors, op, qubits).cpu())
+        phi = osv.apply_matrix(psi.copy(), np.asarray(op, dtype=complex), list(qubits), 10)
+        assert abs(got - np.vdot(psi, phi)) < tol
+    ref = omps.evolve(circ, DEFAULT_ALGO)
+    assert abs(omps.norm(ref) - 1.0) < 1e-10
+
+
+def test_mps_rejects_three_qubit_gates_and_pure_qr_keeps_the_state():
+    circ = circuits.ry_rz_cnot_ring(6, 2, seed=1)
+    want = osv.simulate(circ)
+    got, _ = _mps_state(circ, "complex128", {"qr_method": {}, "svd_method": False})
+    assert np.abs(got - want).max() < 1e-10
+    eng = gmps.MPSEngine(4, "complex128", DEFAULT_ALGO)
+    with pytest.raises(NotImplementedError):
+        eng.apply_gate(np.eye(8).reshape((2,) * 6), (0, 1, 2))
+    gts, _ = gate_tensors(circ, np.complex128)
+    assert len(gts) > 0

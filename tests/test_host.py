@@ -1,0 +1,156 @@
+"""Host-side logic that needs no GPU: the plugin boundary (runcard type rules, dispatch errors,
+result container), observable normalisation, the C-ABI surface (every symbol the header declares
+is exported; ctypes mirrors match the C structs), and that compute paths fail loudly without CUDA."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from qibotn_b200 import MetaBackend, circuits, lib
+from qibotn_b200 import eval as ev
+from qibotn_b200 import observables as obs
+from qibotn_b200.network import QiboCircuitToEinsum
+from qibotn_b200.result import TensorNetworkResult
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_plugin_alias_and_platforms():
+    import qibotn
+    assert qibotn.MetaBackend is MetaBackend
+    b = MetaBackend.load("cutensornet")
+    assert (b.name, b.platform, b.supports_multigpu) == ("qibotn", "cutensornet", True)
+    assert MetaBackend.load("qutensornet").platform == "cutensornet"        # README's spelling
+    with pytest.raises(NotImplementedError):
+        MetaBackend.load("qmatchatea")
+    assert MetaBackend().list_available() == {"cutensornet": True, "qutensornet": True}
+
+
+def test_runcard_type_rules():
+    """reference backends/cutensornet.py:24-69."""
+    b = MetaBackend.load("cutensornet")
+    assert not (b.MPI_enabled or b.NCCL_enabled or b.MPS_enabled or b.expectation_enabled)
+    b.configure_tn_simulation({"MPI_enabled": False, "NCCL_enabled": True, "MPS_enabled": False,
+                               "expectation_enabled": True})
+    assert b.NCCL_enabled and b.expectation_enabled and b.observable is None
+    b.configure_tn_simulation({"MPS_enabled": True, "expectation_enabled": False})
+    assert b.gate_algo == {"qr_method": False, "svd_method": {"partition": "UV", "abs_cutoff": 1e-12}}
+    custom = {"qr_method": False, "svd_method": {"partition": "UV", "abs_cutoff": 1e-6, "max_extent": 8}}
+    b.configure_tn_simulation({"MPS_enabled": custom, "expectation_enabled": False})
+    assert b.gate_algo is custom
+    b.configure_tn_simulation({"MPS_enabled": False, "expectation_enabled": {"pauli_string_pattern": "IXZ"}})
+    assert b.expectation_enabled and b.observable == {"pauli_string_pattern": "IXZ"}
+    with pytest.raises(TypeError):
+        b.configure_tn_simulation({"MPS_enabled": False})                      # expectation_enabled missing
+    with pytest.raises(TypeError):
+        b.configure_tn_simulation({"MPS_enabled": "yes", "expectation_enabled": False})
+    with pytest.raises(TypeError):
+        b.configure_tn_simulation({"MPS_enabled": False, "expectation_enabled": 3})
+
+
+def test_dispatch_errors():
+    """reference backends/cutensornet.py:87-88,151-152."""
+    b = MetaBackend.load("cutensornet")
+    circ = circuits.qft(3, True)
+    with pytest.raises(NotImplementedError):
+        b.execute_circuit(circ, initial_state=np.ones(8))
+    b.configure_tn_simulation({"MPI_enabled": True, "NCCL_enabled": False, "MPS_enabled": True,
+                               "expectation_enabled": False})
+    with pytest.raises(NotImplementedError):
+        b.execute_circuit(circ)
+    for meth in ("apply_gate", "apply_gate_density_matrix"):
+        with pytest.raises(NotImplementedError):
+            getattr(b, meth)(None, None, 3)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    b = MetaBackend.load("cutensornet")
+    with pytest.raises(lib.QtnError):
+        b.execute_circuit(circuits.qft(3, True))
+    b.configure_tn_simulation({"MPS_enabled": True, "expectation_enabled": False})
+    with pytest.raises(lib.QtnError):
+        b.execute_circuit(circuits.qft(3, True))
+
+
+def test_result_container():
+    """reference result.py:12-66."""
+    r = TensorNetworkResult(nqubits=3, backend=None, measures=None, measured_probabilities=None,
+                            prob_type=None, statevector=np.arange(8))
+    assert (r.state() == np.arange(8)).all()
+    with pytest.raises(ValueError):
+        r.frequencies()
+    big = TensorNetworkResult(nqubits=20, backend=None, measures={"00": 3}, measured_probabilities={"U": {"0": (0.1, 0.4)}},
+                              prob_type="U", statevector=None)
+    with pytest.raises(NotImplementedError):
+        big.state()
+    assert big.frequencies() == {"00": 3}
+    assert abs(big.probabilities()["0"] - 0.3) < 1e-15
+
+
+def test_observable_helpers():
+    """reference eval.py:15-150."""
+    ham = obs.check_observable(None, 3)
+    terms = obs.extract_gates_and_qubits(ham)
+    assert terms == [[(0, "X", 0.5), (1, "Z", 1.0)], [(1, "X", 0.5), (2, "Z", 1.0)], [(2, "X", 0.5), (0, "Z", 1.0)]] \
+        or sorted(map(sorted, terms)) == sorted(map(sorted, [[(0, "X", 0.5), (1, "Z", 1.0)], [(1, "X", 0.5), (2, "Z", 1.0)],
+                                                             [(0, "Z", 0.5), (2, "X", 1.0)]]))
+    d = {"terms": [{"coefficient": 1.5, "operators": [("Y", 2)]}]}
+    t = obs.extract_gates_and_qubits(obs.check_observable(d, 3))
+    assert len(t) == 1 and [(q, l) for q, l, _ in t[0]] == [(0, "I"), (1, "I"), (2, "Y")]
+    assert abs(np.prod([c for _, _, c in t[0]]) - 1.5) < 1e-15
+    gates = obs.get_ham_gates(t[0], "complex64")
+    assert gates[2][0].dtype == np.complex64 and gates[2][1] == (2,)
+    with pytest.raises(ValueError):
+        obs.get_ham_gates([(0, "Q", 1.0)])
+    with pytest.raises(ValueError):
+        obs.create_hamiltonian_from_dict({"terms": []}, 3)
+    with pytest.raises(TypeError):
+        obs.check_observable(1.0, 3)
+    p = obs.extract_gates_and_qubits(obs.check_observable({"pauli_string_pattern": "XZ"}, 5))
+    assert [(q, l) for q, l, _ in p[0]] == [(0, "X"), (1, "Z"), (2, "X"), (3, "Z"), (4, "X")]
+
+
+def test_converter_operand_conventions():
+    """reference circuit_convertor.py:28-58 (active qubits only) and :198-246 (all qubits)."""
+    c = circuits.Circuit(4)
+    c.add(circuits.gates.H(1)); c.add(circuits.gates.CNOT(1, 3)); c.add(circuits.gates.M(0, 1, 2, 3))
+    conv = QiboCircuitToEinsum(c, "complex64")
+    assert list(conv.active_qubits) == [1, 3] and len(conv.gate_tensors) == 2
+    inter = conv.state_vector_operands()
+    assert len(inter) == 2 * 4 + 1 and len(inter[-1]) == 2 and inter[0].dtype == np.complex64
+    assert conv.gate_tensors[1][0].shape == (2, 2, 2, 2) and conv.gate_tensors[1][1] == (1, 3)
+    exp = conv.expectation_operands(obs.get_ham_gates([(0, "Z", 1.0)], "complex64"))
+    assert len(exp) == 2 * (4 + 2 + 1 + 2 + 4)
+    with pytest.raises(ValueError):
+        conv.amplitude_operands("012")
+
+
+def test_compute_slices_matches_reference_formula():
+    """reference eval.py:197-205."""
+    for ns, size in ((32, 1), (32, 3), (33, 4), (5, 8), (512, 8)):
+        got = [ev.compute_slices(ns, r, size) for r in range(size)]
+        assert [x for p in got for x in p] == list(range(ns))
+        chunk, extra = divmod(ns, size)
+        assert [len(p) for p in got] == [chunk + (1 if r < extra else 0) for r in range(size)]
+
+
+def test_header_symbols_are_exported_and_structs_match():
+    text = open(os.path.join(ROOT, "include", "qibotn_b200.h")).read()
+    declared = set(re.findall(r"\b(qtn_[a-z0-9_]+)\s*\(", text))
+    h = lib.load()
+    for name in declared:
+        assert hasattr(h, name), f"{name} declared in the header but not exported"
+    assert declared == set(lib.exported_symbols()) | {"qtn_sizeof"} or declared >= set(lib.exported_symbols())
+    h.qtn_sizeof.restype, h.qtn_sizeof.argtypes = C.c_int64, [C.c_char_p]
+    for cname, ctype in (("qtn_pair_desc", lib.PairDesc), ("qtn_pair_plan_t", lib.PairPlan),
+                         ("qtn_svd_item", lib.SvdItem), ("qtn_svd_trunc", lib.SvdTrunc)):
+        assert h.qtn_sizeof(cname.encode()) == C.sizeof(ctype), cname
+    assert h.qtn_sizeof(b"nonsense") == -1
+    assert b"sm_100a" in h.qtn_version()
+    with pytest.raises(lib.QtnError):
+        lib.set_option("no_such_option", 1)
