@@ -132,12 +132,14 @@ typedef struct {
    * operand plane (a stage holds 4 A planes then 4 B planes: re_hi, re_lo, im_hi, im_lo) */
   int32_t tc_stages;
   int32_t tc_plane_a, tc_plane_b;
-  int32_t tc_reserved;
+  int32_t tc_reserved;           /* > 0: persistent variant, number of CTAs to launch */
 } qtn_pair_plan_t;
 
 /* Library-wide switches (thread-unsafe, meant for tests and A/B measurements):
  *   "tc_enable"    1 (default) lets qtn_pair_plan choose QTN_KERNEL_TC, 0 forbids it;
- *   "tc_min_log2"  smallest m+n+k (log2 of the MAC count) for which TC is chosen (default 18).
+ *   "tc_min_log2"  smallest m+n+k (log2 of the MAC count) for which TC is chosen (default 18);
+ *   "tc_persistent" 1 (default): one CTA per SM streams over the tiles with loads, MMAs and
+ *                  epilogue of neighbouring tiles overlapped; 0: one CTA per tile.
  * Returns QTN_ERR_ARG for an unknown name. */
 int qtn_set_option(const char *name, int value);
 int qtn_get_option(const char *name, int *value);

@@ -234,6 +234,13 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     const int budget = (tnb <= 6 && 2 * stage_bytes <= 110 * 1024) ? 110 * 1024 : 200 * 1024;
     int stages = std::max(1, std::min(4, budget / stage_bytes));
     if ((int64_t)stages > k_iters) stages = (int)k_iters;
+    p->tc_reserved = 0;
+    if (qtn_option_tc_persistent()) {
+      // persistent kernel: one CTA per SM streams over tiles, so the pipeline may be deeper than
+      // one tile's k loop; tc_reserved carries the number of CTAs to launch
+      stages = std::max(2, std::min(6, (200 * 1024) / stage_bytes));
+      p->tc_reserved = sm_count;
+    }
     p->tc_stages = stages;
     p->smem_bytes = stages * stage_bytes + 256;
     p->sa_stride = 0; p->sb_stride = 0;

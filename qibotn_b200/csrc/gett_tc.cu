@@ -56,7 +56,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) __trap();
+    if (++spins > (1u << 24)) __trap();
   }
 }
 
@@ -388,9 +388,271 @@ gett_tc_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restri
   }
 }
 
+
+// --------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+// Roles are fully decoupled so that every phase of tile i overlaps another phase of tile i+1:
+//   warps 0-7   producers  (global gathers -> split -> shared memory), a flat stream over
+//               (tile, k chunk) that runs ahead across tile boundaries;
+//   warps 8-11  epilogue   (TMEM -> registers -> global), one TMEM lane quarter each;
+//   warp 12     MMA issuer (+ TMEM allocation).
+// Accumulators are double-buffered in TMEM when two fit (2^TNB <= 128).
+// --------------------------------------------------------------------------------------------
+constexpr int kThreadsP = 416;
+constexpr int kEpilogueThreads = 128;
+
+template <int TNB, int TKB>
+__global__ void __launch_bounds__(kThreadsP, 1)
+gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ A,
+                          const float2 *__restrict__ B, float2 *__restrict__ C,
+                          float2 *__restrict__ ws, const int32_t *__restrict__ slice_id) {
+  constexpr int TN = 1 << TNB, KT = 1 << TKB;
+  constexpr int PLANE_A = 128 * KT, PLANE_B = TN * KT;
+  constexpr int STAGE = 4 * (PLANE_A + PLANE_B);
+  constexpr int NA = PLANE_A / kProducerThreads;
+  constexpr int NB = (PLANE_B + kProducerThreads - 1) / kProducerThreads;
+  constexpr int NBUF = 4 * TN <= 512 ? 2 : 1;
+  constexpr int TMEM_COLS = NBUF * 2 * TN < 32 ? 32 : NBUF * 2 * TN;
+  constexpr uint32_t LBO = 128, SBO = KT * 32;
+  constexpr uint32_t IDESC = umma_idesc_tf32(TN, 0), IDESC_NEG = umma_idesc_tf32(TN, 1);
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float *stages = reinterpret_cast<float *>(smem_raw);
+  const int S = P.tc_stages;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * STAGE * sizeof(float));
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 2 * NBUF);
+  __shared__ long long a_it_g[8], b_it_g[16];
+  __shared__ int a_it_s[8], b_it_s[16];
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * S + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * S + NBUF + b); };
+
+  const unsigned long long ntiles = (unsigned long long)P.grid;     // tiles incl. split-K parts
+  const int k_iters_bits = P.n_khi - P.split_bits;
+  const unsigned long long k_iters = 1ull << k_iters_bits;
+  const long long a_slice = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
+  const long long b_slice = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
+
+  if (t < 16) {
+    long long g = 0;
+    int s = 0;
+    if (t < 8) {
+      for (int j = 8; j < P.na_lo; ++j)
+        if ((t >> (j - 8)) & 1) { g |= 1ll << P.a_lo_pos[j]; s += P.a_lo_sstr[j]; }
+      a_it_g[t] = g; a_it_s[t] = s;
+    }
+    g = 0; s = 0;
+    for (int j = 8; j < P.nb_lo; ++j)
+      if ((t >> (j - 8)) & 1) { g |= 1ll << P.b_lo_pos[j]; s += P.b_lo_sstr[j]; }
+    b_it_g[t] = g; b_it_s[t] = s;
+  }
+  if (t == 32) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), kProducerThreads); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpilogueThreads); }
+    fence_proxy_async_smem();
+    fence_mbar_init();
+  }
+  if (warp == 12) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ================= producers: flat stream over (tile, k chunk) =================
+    long long a_t_g = 0, b_t_g = 0;
+    int a_t_s = 0, b_t_s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!((t >> j) & 1)) continue;
+      if (j < P.na_lo) { a_t_g |= 1ll << P.a_lo_pos[j]; a_t_s += P.a_lo_sstr[j]; }
+      if (j < P.nb_lo) { b_t_g |= 1ll << P.b_lo_pos[j]; b_t_s += P.b_lo_sstr[j]; }
+    }
+    const bool b_act = P.nb_lo >= 8 || t < (1 << P.nb_lo);
+    const float sgn_a = P.conj_a ? -1.f : 1.f, sgn_b = P.conj_b ? -1.f : 1.f;
+    unsigned long long tile = blockIdx.x, kk = 0;
+    long long a_k = 0, b_k = 0;
+    auto enter_tile = [&]() {
+      unsigned long long id = tile;
+      const unsigned split = (unsigned)(id & ((1ull << P.split_bits) - 1));
+      id >>= P.split_bits;
+      const unsigned long long nh = id & ((1ull << P.n_nhi) - 1);
+      const unsigned long long mh = id >> P.n_nhi;
+      const unsigned long long kh0 = (unsigned long long)split << k_iters_bits;
+      a_k = a_slice | deposit(mh, P.a_mhi, P.n_mhi) | deposit(kh0, P.a_khi, P.n_khi);
+      b_k = b_slice | deposit(nh, P.b_nhi, P.n_nhi) | deposit(kh0, P.b_khi, P.n_khi);
+      kk = 0;
+    };
+    auto advance = [&]() {                        // next k chunk, or the first one of the next tile
+      if (kk + 1 == k_iters) { tile += gridDim.x; if (tile < ntiles) enter_tile(); return; }
+      const unsigned long long flip = kk ^ (kk + 1);
+      const int nflip = 64 - __clzll(flip);
+      for (int i = 0; i < nflip && i < k_iters_bits; ++i) {
+        a_k ^= 1ll << P.a_khi[i];
+        b_k ^= 1ll << P.b_khi[i];
+      }
+      ++kk;
+    };
+    auto load = [&](float2(&va)[NA], float2(&vb)[NB]) {
+#pragma unroll
+      for (int i = 0; i < NA; ++i) va[i] = __ldg(A + (a_k | a_t_g | a_it_g[i]));
+#pragma unroll
+      for (int i = 0; i < NB; ++i)
+        vb[i] = b_act ? __ldg(B + (b_k | b_t_g | b_it_g[i])) : make_float2(0.f, 0.f);
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    auto store = [&](const float2(&va)[NA], const float2(&vb)[NB]) {
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      float *sA = stages + (size_t)s * STAGE;
+      float *sB = sA + 4 * PLANE_A;
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        const int o = a_t_s + a_it_s[i];
+        float h, l;
+        split_tf32(va[i].x, h, l);
+        sA[o] = h; sA[PLANE_A + o] = l;
+        split_tf32(va[i].y * sgn_a, h, l);
+        sA[2 * PLANE_A + o] = h; sA[3 * PLANE_A + o] = l;
+      }
+      if (b_act) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          const int o = b_t_s + b_it_s[i];
+          float h, l;
+          split_tf32(vb[i].x, h, l);
+          sB[o] = h; sB[PLANE_B + o] = l;
+          split_tf32(vb[i].y * sgn_b, h, l);
+          sB[2 * PLANE_B + o] = h; sB[3 * PLANE_B + o] = l;
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(full_bar(s));
+      if (++s == S) { s = 0; ph ^= 1u; }
+    };
+    float2 va0[NA], vb0[NB], va1[NA], vb1[NB];
+    bool have0 = tile < ntiles;
+    if (have0) { enter_tile(); load(va0, vb0); advance(); }
+    while (have0) {
+      const bool have1 = tile < ntiles;
+      if (have1) { load(va1, vb1); advance(); }
+      store(va0, vb0);
+      if (!have1) break;
+      have0 = tile < ntiles;
+      if (have0) { load(va0, vb0); advance(); }
+      store(va1, vb1);
+    }
+  } else if (warp < 12) {
+    // ================= epilogue: TMEM -> global, tile after tile =================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const long long row_off = (r & 31) + ((long long)(r >> 5) << (5 + TNB));
+    constexpr int CH = TN < 16 ? TN : 16;
+    unsigned long long it = 0;
+    for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int buf = (int)(it % NBUF);
+      const uint32_t tph = (uint32_t)((it / NBUF) & 1);
+      unsigned long long id = tile;
+      const unsigned split = (unsigned)(id & ((1ull << P.split_bits) - 1));
+      id >>= P.split_bits;
+      const unsigned long long nh = id & ((1ull << P.n_nhi) - 1);
+      const unsigned long long mh = id >> P.n_nhi;
+      const long long c_base = deposit(mh, P.c_mhi, P.n_mhi) | deposit(nh, P.c_nhi, P.n_nhi);
+      float2 *out = (P.split_bits ? ws + (long long)split * P.c_elems : C) + c_base + row_off;
+      mbar_wait(tfull_bar(buf), tph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * TN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += CH) {
+        uint32_t re[CH], im[CH];
+        tmem_ld<CH>::run(trow + (uint32_t)c0, re);
+        tmem_ld<CH>::run(trow + (uint32_t)(TN + c0), im);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          out[(long long)(c0 + j) << 5] = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));                 // accumulator buffer may be overwritten
+    }
+  } else if (lane == 0) {
+    // ================= MMA issuer =================
+    int s = 0;
+    uint32_t ph = 0;
+    unsigned long long it = 0;
+    for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int buf = (int)(it % NBUF);
+      const uint32_t tph = (uint32_t)((it / NBUF) & 1);
+      mbar_wait(tempty_bar(buf), tph ^ 1u);         // epilogue has drained this buffer
+      tc_fence_after();
+      const uint32_t cr = tmem_base + (uint32_t)(buf * 2 * TN), ci = cr + TN;
+      for (unsigned long long kk = 0; kk < k_iters; ++kk) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(stages + (size_t)s * STAGE);
+        const uint32_t sb = sa + 16u * PLANE_A;
+#pragma unroll
+        for (int ks = 0; ks < KT / 8; ++ks) {
+          const uint32_t ko = (uint32_t)ks * 2u * LBO;
+          const uint64_t arh = umma_desc(sa + ko, LBO, SBO);
+          const uint64_t arl = umma_desc(sa + 4u * PLANE_A + ko, LBO, SBO);
+          const uint64_t aih = umma_desc(sa + 8u * PLANE_A + ko, LBO, SBO);
+          const uint64_t ail = umma_desc(sa + 12u * PLANE_A + ko, LBO, SBO);
+          const uint64_t brh = umma_desc(sb + ko, LBO, SBO);
+          const uint64_t brl = umma_desc(sb + 4u * PLANE_B + ko, LBO, SBO);
+          const uint64_t bih = umma_desc(sb + 8u * PLANE_B + ko, LBO, SBO);
+          const uint64_t bil = umma_desc(sb + 12u * PLANE_B + ko, LBO, SBO);
+          const uint32_t acc = (kk | (unsigned)ks) ? 1u : 0u;
+          umma_tf32(cr, arl, brh, IDESC, acc);
+          umma_tf32(cr, arh, brl, IDESC, 1u);
+          umma_tf32(cr, ail, bih, IDESC_NEG, 1u);
+          umma_tf32(cr, aih, bil, IDESC_NEG, 1u);
+          umma_tf32(cr, arh, brh, IDESC, 1u);
+          umma_tf32(cr, aih, bih, IDESC_NEG, 1u);
+          umma_tf32(ci, arl, bih, IDESC, acc);
+          umma_tf32(ci, arh, bil, IDESC, 1u);
+          umma_tf32(ci, ail, brh, IDESC, 1u);
+          umma_tf32(ci, aih, brl, IDESC, 1u);
+          umma_tf32(ci, arh, bih, IDESC, 1u);
+          umma_tf32(ci, aih, brh, IDESC, 1u);
+        }
+        umma_commit(empty_bar(s));
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(tfull_bar(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
 template <int TNB, int TKB>
 int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
                    const int32_t *slice_id, cudaStream_t st) {
+  if (P.tc_reserved > 0) {                      // persistent variant: tc_reserved = CTAs to launch
+    static int smem_set_p = 0;
+    if (smem_set_p < P.smem_bytes) {
+      QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tc_persistent_kernel<TNB, TKB>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+      smem_set_p = P.smem_bytes;
+    }
+    const long long ctas = P.grid < P.tc_reserved ? P.grid : P.tc_reserved;
+    gett_tc_persistent_kernel<TNB, TKB><<<(unsigned)ctas, kThreadsP, P.smem_bytes, st>>>(
+        P, (const float2 *)a, (const float2 *)b, (float2 *)c, (float2 *)ws, slice_id);
+    QTN_LAUNCH_CHECK();
+    return QTN_OK;
+  }
   static int smem_set = 0;
   if (smem_set < P.smem_bytes) {
     QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tc_kernel<TNB, TKB>,

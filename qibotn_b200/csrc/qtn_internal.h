@@ -10,6 +10,7 @@ int qtn_fail(int code, const char *msg);
 // Library-wide switches (api.cu); read by the host planner.
 int qtn_option_tc_enable(void);
 int qtn_option_tc_min_log2(void);
+int qtn_option_tc_persistent(void);
 #ifdef __cplusplus
 }
 #endif

@@ -98,7 +98,7 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
     else { T z; z.x = 0; z.y = 0; for (int c = lane; c < m; c += 32) dst[c] = z; }
   }
   __syncthreads();
-  const R tiny = (R)(tiny_rel * fro2[item_id]);
+  (void)tiny_rel; (void)fro2;
   const int inner_max = nb == 1 ? max_inner : 1;
   int rotated_any = 0;
   for (int inner = 0; inner < inner_max; ++inner) {
@@ -119,7 +119,9 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
         }
         a = warp_sum<R>(a); bb = warp_sum<R>(bb); gr = warp_sum<R>(gr); gi = warp_sum<R>(gi);
         const R g2 = gr * gr + gi * gi;
-        if (!(g2 > tol * tol * a * bb) || !(fmin(a, bb) > tiny)) continue;
+        // relative criterion at every scale (rows far below sigma_max are orthogonalised as
+        // accurately as the leading ones); a row whose squared norm underflowed is left alone
+        if (!(g2 > tol * tol * a * bb) || !(fmin(a, bb) > (R)0)) continue;
         rotated = 1;
         const double gabs = sqrt((double)g2);
         const double zeta = ((double)bb - (double)a) / (2.0 * gabs);
@@ -183,9 +185,14 @@ finalize_kernel(const qtn_svd_item *__restrict__ items, qtn_svd_trunc tr, double
   }
   __syncthreads();
   if (t == 0) {
-    int keep = n;
-    const double thr = fmax(tr.abs_cutoff, tr.rel_cutoff * sg[0]);
-    if (thr > 0) { keep = 0; while (keep < n && sg[keep] > thr) ++keep; }
+    // Noise floor: the left factor is recovered as theta * V / sigma, which is only meaningful for
+    // sigma well above the rounding level of the working precision; directions below
+    // 16 eps sigma_max are numerical noise of the input and are dropped whatever the cutoffs say
+    // (their total weight is below the precision of the state itself).
+    const double eps = sizeof(R) == 8 ? 1.1e-16 : 6.0e-8;
+    int keep = 0;
+    const double thr = fmax(fmax(tr.abs_cutoff, tr.rel_cutoff * sg[0]), 16.0 * eps * sg[0]);
+    while (keep < n && sg[keep] > thr) ++keep;
     if (tr.discarded_weight_cutoff > 0) {
       double total = 0;
       for (int i = 0; i < n; ++i) total += sg[i] * sg[i];
@@ -332,7 +339,11 @@ extern "C" int qtn_svd_rows(int dtype, int batch, qtn_svd_item *items, double to
   if (workspace_bytes < qtn_svd_workspace_bytes(batch, ld))
     return qtn_fail(QTN_ERR_WORKSPACE, "qtn_svd_rows: workspace too small (qtn_svd_workspace_bytes)");
   if (max_sweeps < 1) max_sweeps = 30;
-  if (!(tol > 0)) tol = dtype == QTN_C64 ? 1e-6 : 1e-14;
+  if (!(tol > 0)) {            // LAPACK xGESVJ-style: sqrt(row length) * machine epsilon (x8)
+    int max_m = 1;
+    for (int i = 0; i < batch; ++i) max_m = std::max(max_m, (int)items[i].m);
+    tol = 8.0 * std::sqrt((double)max_m) * (dtype == QTN_C64 ? 6.0e-8 : 1.1e-16);
+  }
   cudaStream_t st = (cudaStream_t)stream;
   return dtype == QTN_C64
              ? svd_rows_impl<float>(batch, items, tol, max_sweeps, trunc, sigma, perm, ld, rank_host, scale_host,

@@ -1,0 +1,63 @@
+"""MPS evolution benchmark (BASELINE config 3 and reduced variants).
+
+    python scripts/mps_bench.py [--n 64] [--steps 20] [--chi 256] [--dtype complex128] [--cpu-seconds 0]
+
+Prints one JSON line: wall time of the gate loop (CUDA-synchronised), gates/s (circuit gates, swaps
+excluded), bond profile, <psi|psi>, SVD sweep statistics; with --cpu-seconds > 0 also times the CPU
+oracle (numpy.linalg.svd gate loop) for that many seconds and reports its gate rate."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from qibotn_b200 import circuits, mps as gmps  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=64)
+ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--chi", type=int, default=256)
+ap.add_argument("--dtype", default="complex128")
+ap.add_argument("--cpu-seconds", type=float, default=0.0)
+ap.add_argument("--repeat", type=int, default=1)
+a = ap.parse_args()
+
+circ = circuits.tfim_trotter(a.n, a.steps)
+algo = {"qr_method": False, "svd_method": {"partition": "UV", "abs_cutoff": 1e-12, "max_extent": a.chi}}
+ngates = sum(1 for g in circ.queue)
+best = None
+for _ in range(a.repeat + 1):          # first pass warms up (module load, allocator)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    conv = gmps.QiboCircuitToMPS(circ, algo, dtype=a.dtype)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    best = dt if best is None else min(best, dt)
+helper = gmps.MPSContractionHelper(a.n)
+norm = float(helper.contract_norm(conv.mps_tensors).cpu())
+zz = complex(helper.pauli_expectation(conv.mps_tensors, {a.n // 2: "Z", a.n // 2 + 1: "Z"}).cpu())
+bonds = [int(t.shape[2]) for t in conv.mps_tensors[:-1]]
+line = {"workload": f"{a.n}-site TFIM Trotter, {a.steps} steps, chi<={a.chi}, {a.dtype}", "gates": ngates,
+        "seconds": best, "gates_per_s": ngates / best, "max_bond": max(bonds), "bonds": bonds, "norm": norm,
+        "zz_mid": [zz.real, zz.imag], "stats": conv.stats}
+if a.cpu_seconds > 0:
+    from oracle import mps as omps
+    from oracle.network import gate_tensors
+    gts, _ = gate_tensors(circ, np.complex128 if a.dtype == "complex128" else np.complex64)
+    sites = omps.initial(a.n, np.complex128 if a.dtype == "complex128" else np.complex64)
+    t0 = time.perf_counter()
+    done = 0
+    for g, qs in gts:
+        omps.apply_gate(sites, g, tuple(qs), algo)
+        done += 1
+        if time.perf_counter() - t0 > a.cpu_seconds:
+            break
+    wall = time.perf_counter() - t0
+    line["cpu"] = {"gates_done": done, "seconds": wall, "gates_per_s": done / wall,
+                   "max_bond_reached": max(t.shape[2] for t in sites), "cores": len(os.sched_getaffinity(0)),
+                   "note": "oracle gate loop (numpy.linalg.svd), first gates only: bonds are still small early on"}
+print(json.dumps(line), flush=True)

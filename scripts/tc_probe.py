@@ -29,13 +29,15 @@ def dense(flat, labels, pos):
     return flat[idx]
 
 
-def run(la, pa, lb, pb, lc, a, b, tc=True, time_it=False):
+def run(la, pa, lb, pb, lc, a, b, tc=True, time_it=False, persistent=True):
+    lib.set_option("tc_persistent", 1 if persistent else 0)
     lib.set_option("tc_enable", 1 if tc else 0)
     lib.set_option("tc_min_log2", 0)
     desc = lib.make_pair_desc("complex64", list(zip(la, pa)), list(zip(lb, pb)), list(lc))
     plan = lib.pair_plan(desc)
     lib.set_option("tc_enable", 1)
     lib.set_option("tc_min_log2", 18)
+    lib.set_option("tc_persistent", 1)
     da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     dc = torch.zeros(1 << len(lc), dtype=torch.complex64, device="cuda")
     ws = torch.empty(max(int(plan.workspace_bytes), 16), dtype=torch.uint8, device="cuda")
@@ -96,11 +98,11 @@ def case(m, n, k, seed=0, layout="random", structured=False, time_it=False, chec
         A64 = dense(a.astype(np.complex128), la, pa)
         B64 = dense(b.astype(np.complex128), lb, pb)
     res = {"m": m, "n": n, "k": k, "layout": layout, "structured": structured}
-    for tc in (True, False):
+    for tag, tc, pers in (("tc", True, True), ("tc_np", True, False), ("ffma", False, False)):
         try:
-            got, lcu, plan, ms = run(la, pa, lb, pb, lc, a, b, tc=tc, time_it=time_it)
+            got, lcu, plan, ms = run(la, pa, lb, pb, lc, a, b, tc=tc, time_it=time_it, persistent=pers)
         except Exception as e:  # noqa: BLE001
-            res["tc" if tc else "ffma"] = {"error": str(e)}
+            res[tag] = {"error": str(e)}
             continue
         if check:
             want = np.tensordot(A64, B64, axes=(list(range(m, m + k)), list(range(n, n + k))))
@@ -108,13 +110,12 @@ def case(m, n, k, seed=0, layout="random", structured=False, time_it=False, chec
             err = float(np.abs(got - want).max() / (np.abs(want).max() + 1e-30))
         else:
             want, err = None, -1.0
-        tag = "tc" if tc else "ffma"
         res[tag] = {"kernel": plan.kernel, "tile": [plan.tmb, plan.tnb, plan.tkb], "split": plan.split_bits,
                     "stages": plan.tc_stages, "rel_err": err, "ms": ms}
         if ms:
             res[tag]["TFs"] = plan.flops / ms / 1e9
             res[tag]["GBs"] = plan.bytes / ms / 1e6
-        if tc and (err > 1e-4 or structured):
+        if tag == "tc" and (err > 1e-4 or structured):
             name = f"gpurun_out/tc_probe_m{m}n{n}k{k}_{layout}{'_s' if structured else ''}"
             np.save(name + "_got.npy", got.reshape(1 << m, 1 << n) if lcu == lc else got)
             np.save(name + "_want.npy", want.reshape(1 << m, 1 << n) if lcu == lc else want)
