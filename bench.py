@@ -5,7 +5,7 @@ Sycamore-like random circuit (BASELINE.json configs[3], the config the metric is
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c4]
 
 One *step* = the hot path over one batch of slices: ``--slices-per-step`` slices of the
-plan (default 8, fixed for every N: strong scaling), split over the N ranks as
+plan (default 16, fixed for every N: strong scaling), split over the N ranks as
 ``compute_slices`` does, each rank running its slices through the fused
 permute+contract kernels, followed by the single NCCL all-reduce of the partials.
 ``value`` = algorithmic TFLOP/s (8 flops per complex MAC) of the
@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4")
-    ap.add_argument("--slices-per-step", type=int, default=8)
+    ap.add_argument("--slices-per-step", type=int, default=16)
+    ap.add_argument("--no-mps", action="store_true", help="skip the MPS gates/s measurement (N=1 only)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--plan-seconds", type=float, default=60.0)
@@ -209,6 +210,28 @@ def measure_fp32_peak(torch):
     return 3 * 2 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
 
+def mps_metric(n=64, steps=20, chi=256):
+    """The second half of BASELINE.json's metric: MPS gates/s on config 3 (64-site TFIM Trotter
+    brickwork, 20 steps, bond <= 256, QR off, SVD abs_cutoff 1e-12, complex128), one GPU."""
+    import torch
+
+    from qibotn_b200 import circuits, mps as gmps
+
+    algo = {"qr_method": False, "svd_method": {"partition": "UV", "abs_cutoff": 1e-12, "max_extent": chi}}
+    gmps.QiboCircuitToMPS(circuits.tfim_trotter(n, 2), algo, dtype="complex128")          # warm-up
+    circ = circuits.tfim_trotter(n, steps)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    conv = gmps.QiboCircuitToMPS(circ, algo, dtype="complex128")
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    gates = len(circ.queue)
+    return {"workload": f"{n}-site TFIM Trotter, {steps} steps, bond<={chi}, complex128", "gates": gates,
+            "seconds": dt, "gates_per_s": gates / dt, "max_bond": conv.stats["max_bond"],
+            "two_site_updates": conv.stats["two_site"], "svd_batches": conv.stats["svd_batches"],
+            "svd_sweeps": conv.stats["svd_sweeps"]}
+
+
 def run_b200(a):
     import ctypes as C
 
@@ -352,6 +375,8 @@ def run_b200(a):
                 "h2d_bytes_per_step": low.leaf_bytes, "d2h_bytes_per_step": 8 if wl.dtype == "complex64" else 16},
         "gpu_launches": launches, "lower_s": lower_s, "clocks": clocks, "roofline": roof,
     }
+    if size == 1 and not a.no_mps:
+        line["mps"] = mps_metric()
     if size == 1 and not a.no_cpu_baseline:
         cinfo = cpu_plan(wl, net, a.workload, a.plan_seconds)
         r, done, wall, _ = cpu_sample(wl, net, cinfo, a.cpu_seconds)

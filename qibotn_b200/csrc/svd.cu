@@ -10,10 +10,10 @@
 // (A B = W_in V V^H).  A matrix with more rows than columns is handed in transposed.
 //
 // Blocking.  Rows are grouped in blocks of `block` rows; a CTA loads one PAIR of blocks into
-// shared memory, runs a full round-robin over the 2*block rows there (one warp per row pair:
-// three dot products by warp-shuffle reduction, then the rotation) and writes them back.
-// A sweep = round-robin over block pairs (one launch per step, all matrices of the batch
-// in the same launch).  Matrices that fit one block pair run to convergence inside a
+// shared memory, rotates the block x block cross pairs there (one warp per row pair: three dot
+// products by warp-shuffle reduction, then the rotation) and writes them back.
+// A sweep = round-robin over block pairs plus one step for the pairs inside each block (one
+// launch per step, all matrices of the batch in the same launch).  Matrices that fit one block pair run to convergence inside a
 // single launch.  Sweeps stop when no rotation above `tol` happened (host reads one
 // counter per matrix per sweep).
 #include <algorithm>
@@ -77,11 +77,16 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
   const int n = it.n, m = it.m, b = it.block, nb = it.nblocks;
   if (n < 2) return;
   const int nbe = nb + (nb & 1);
-  const int nsteps = nb == 1 ? 1 : nbe - 1;
+  // steps 0 .. nbe-2: block PAIRS (I, J), only the b*b cross pairs are rotated;
+  // step nbe-1: every block alone, its b(b-1)/2 internal pairs.  One sweep = all of them.
+  const int nsteps = nb == 1 ? 1 : nbe;
   if (step >= nsteps) return;
   int I = 0, J = -1;
   if (nb == 1) {
     if (blockIdx.x > 0) return;
+  } else if (step == nbe - 1) {
+    if ((int)blockIdx.x >= nb) return;
+    I = blockIdx.x;
   } else {
     if ((int)blockIdx.x >= nbe / 2) return;
     circle(step, blockIdx.x, nbe, I, J);
@@ -103,10 +108,13 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
   int rotated_any = 0;
   for (int inner = 0; inner < inner_max; ++inner) {
     int rotated = 0;
-    for (int round = 0; round < nr - 1; ++round) {
-      for (int q = warp; q < nr / 2; q += kWarps) {
+    const int nrounds = J < 0 ? nr - 1 : b;
+    const int npairs = J < 0 ? nr / 2 : b;
+    for (int round = 0; round < nrounds; ++round) {
+      for (int q = warp; q < npairs; q += kWarps) {
         int x, y;
-        circle(round, q, nr, x, y);
+        if (J < 0) circle(round, q, nr, x, y);                  // all pairs inside one block
+        else { x = q; y = b + ((q + round) & (b - 1)); }        // row q of I with row (q+round)%b of J
         if (grow(x) >= n || grow(y) >= n) continue;
         T *X = rows + (size_t)x * m, *Y = rows + (size_t)y * m;
         R a = 0, bb = 0, gr = 0, gi = 0;
@@ -270,8 +278,8 @@ int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, co
     if (choose_block(it.n, it.m, esz, &it.block, &it.nblocks))
       return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_svd_rows: rows too long for shared memory");
     const int nbe = it.nblocks + (it.nblocks & 1);
-    max_steps = std::max(max_steps, it.nblocks == 1 ? 1 : nbe - 1);
-    max_pairs = std::max(max_pairs, it.nblocks == 1 ? 1 : nbe / 2);
+    max_steps = std::max(max_steps, it.nblocks == 1 ? 1 : nbe);
+    max_pairs = std::max(max_pairs, it.nblocks == 1 ? 1 : std::max(nbe / 2, it.nblocks));
     const int nr = it.nblocks == 1 ? it.block : 2 * it.block;
     smem = std::max(smem, (size_t)nr * it.m * esz);
   }

@@ -238,6 +238,7 @@ class ContractionRunner:
         self.slice_id = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.use_graph = use_graph
         self._graph = None
+        self._graph_hoist = None
         self._copied = None
         self.launches = 0
 
@@ -300,7 +301,7 @@ class ContractionRunner:
         any_dep = any(n.depends for n in low.nodes)
         if any_dep:
             self.out.zero_()
-        launches += self._run_nodes(False)
+        launches += self._run_hoisted()
         if any_dep and slice_ids:
             contiguous = slice_ids == list(range(slice_ids[0], slice_ids[0] + len(slice_ids)))
             if self.use_graph and contiguous and len(slice_ids) > 1:
@@ -316,6 +317,23 @@ class ContractionRunner:
                     launches += 1 + self._run_nodes(True)
         self.launches = launches
         return self.out.reshape((2,) * self._live_out_rank())
+
+    def _run_hoisted(self):
+        """Slice-independent nodes (mostly tiny gate-against-gate products): hundreds of
+        launches, replayed as one CUDA graph after the first call."""
+        n = self.low.launches_hoisted
+        if not self.use_graph or n < 8:
+            return self._run_nodes(False)
+        torch = self.torch
+        if self._graph_hoist is None:
+            self._run_nodes(False)                      # warm-up outside capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_nodes(False)
+            self._graph_hoist = g
+        self._graph_hoist.replay()
+        return n
 
     def _capture(self):
         torch = self.torch

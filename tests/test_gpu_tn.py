@@ -117,3 +117,63 @@ def test_dense_output_drops_inactive_qubits_and_initial_state_rejected():
     assert np.allclose(res.statevector.flatten().get(), [2 ** -0.5, 0, 0, 2 ** -0.5])
     with pytest.raises(NotImplementedError):
         b.execute_circuit(c, initial_state=np.ones(32))
+
+
+# ----------------------------------------------------------------------------- golden fixtures
+import os
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_vectors.npz"))
+CLOSED = np.load(os.path.join(os.path.dirname(__file__), "golden", "closed_forms.npz"))
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_against_committed_golden_vectors(dtype):
+    for n, layers in ((5, 2), (8, 3), (12, 3)):
+        circ = circuits.ry_rz_cnot_ring(n, layers, seed=42)
+        got = ev.dense_vector_tn(circ, dtype).flatten().get()
+        assert np.abs(got - GOLD[f"ring_state_{n}_{layers}"]).max() < TOL[dtype] * 4
+        exp = float(ev.expectation_tn(circ, dtype, None)[0])
+        assert abs(exp - float(GOLD[f"ring_xz_{n}_{layers}"])) < TOL[dtype] * 10
+    circ = circuits.brickwork(12, 6, seed=0)
+    z = float(ev.expectation_tn(circ, dtype, {"pauli_string_pattern": "Z"})[0])
+    assert abs(z - float(GOLD["brick12x6_zall"])) < TOL[dtype] * 10
+    # 53-qubit Sycamore-like circuit, 4 cycles: single amplitudes (the C4 code path at reduced depth)
+    circ = circuits.sycamore_rqc(4, seed=0)
+    for bits in ("0" * 53, "01" * 26 + "1"):
+        want = complex(GOLD[f"syc53_d4_amp_{bits[:4]}"])
+        got = complex(ev.amplitude_tn(circ, dtype, bits, n_samples=4).get().reshape(-1)[0])
+        assert abs(got - want) <= TOL[dtype] * abs(want) + 1e-30
+
+
+def test_qft_on_zero_state_is_uniform_at_reference_sizes():
+    """reference tests: allclose(rtol 1e-5, atol 1e-8) against the uniform vector."""
+    for n in (1, 2, 5, 10):
+        got = ev.dense_vector_tn(circuits.qft(n, True), "complex128").flatten().get()
+        assert np.allclose(got, CLOSED[f"qft_zero_{n}"], rtol=1e-5, atol=1e-8)
+
+
+def test_c4_amplitude_properties_at_depth_8():
+    """Full-width properties the domain offers (no dense oracle at 53 qubits): the same amplitude
+    from two different contraction trees, from the tensor-core and the FFMA kernels, in complex64
+    and complex128, and as a sum of slice partials."""
+    from qibotn_b200 import lib
+    circ = circuits.sycamore_rqc(8, seed=0)
+    bits = "0" * 53
+    net64 = QiboCircuitToEinsum(circ, "complex64").amplitude_network(bits)
+    net128 = QiboCircuitToEinsum(circ, "complex128").amplitude_network(bits)
+    engine.clear_caches()
+    ref = complex(engine.contract(net128, "complex128", samples=4, seed=0).cpu().numpy().reshape(-1)[0])
+    assert abs(ref) > 0
+    vals = {}
+    for seed in (0, 1):
+        engine.clear_caches()
+        vals[f"tc{seed}"] = complex(engine.contract(net64, "complex64", samples=4, seed=seed, min_slices=4)
+                                    .cpu().numpy().reshape(-1)[0])
+    lib.set_option("tc_enable", 0)
+    try:
+        engine.clear_caches()
+        vals["ffma"] = complex(engine.contract(net64, "complex64", samples=4, seed=0).cpu().numpy().reshape(-1)[0])
+    finally:
+        lib.set_option("tc_enable", 1)
+    for k, v in vals.items():
+        assert abs(v - ref) <= 1e-5 * abs(ref), (k, v, ref)
