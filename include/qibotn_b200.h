@@ -244,6 +244,16 @@ int qtn_svd_emit(int dtype, const void *w, int32_t m, const int32_t *perm, const
                  double scale, int32_t k, int32_t partition, int32_t transposed, void *out1, void *out2,
                  void *stream);
 
+/* ------------------------------------------------------------------------
+ * Fused Pauli-string expectation on a dense state (qubit 0 = most significant address bit):
+ * out[t] = <psi| P_t |psi> (complex128 pairs, device) for nterms strings given as bit masks over
+ * the ADDRESS bits: xmask = qubits with X or Y, zmask = qubits with Z or Y, ny = number of Y.
+ * One streaming pass over psi per term, P|psi> is never stored.  Serves the per-term loop of
+ * expectation_tn (eval.py:473-476) when the dense state fits in memory.
+ * ------------------------------------------------------------------------ */
+int qtn_pauli_expectation(int dtype, int nqubits, const void *state, int nterms, const uint64_t *xmask,
+                          const uint64_t *zmask, const int32_t *ny, void *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

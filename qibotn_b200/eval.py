@@ -33,7 +33,7 @@ from .result import DeviceArray
 
 __all__ = [
     "dense_vector_tn", "dense_vector_tn_MPI", "dense_vector_tn_nccl", "expectation_tn",
-    "expectation_tn_MPI", "expectation_tn_nccl", "dense_vector_mps", "amplitude_tn",
+    "expectation_tn_MPI", "expectation_tn_nccl", "dense_vector_mps", "amplitude_tn", "expectation_from_state",
     "check_observable", "build_observable", "create_hamiltonian_from_dict", "get_ham_gates",
     "extract_gates_and_qubits", "compute_slices", "initialize_mpi", "initialize_nccl",
     "compute_optimal_path", "reduce_result",
@@ -114,9 +114,79 @@ def _term_networks(qibo_circ, datatype, observable):
         yield conv.expectation_network(get_ham_gates(term, dtype=datatype))
 
 
-def expectation_tn(qibo_circ, datatype, observable):
-    """sum over Hamiltonian terms of <0|U^dag P U|0>, one contraction per term (eval.py:455-477)."""
+# How expectation_tn evaluates a Hamiltonian: "network" = one closed <0|U^dag P U|0> contraction
+# per term, as the reference does; "state" = contract U|0> once to a dense vector and run the fused
+# Pauli kernel (one streaming pass per term); "auto" = "state" when the active qubits fit easily
+# and there are at least two terms.  Same value either way (tests/test_gpu_tn.py).
+EXPECTATION_ROUTE = "auto"
+_STATE_ROUTE_AUTO_QUBITS = 26
+_STATE_ROUTE_MAX_QUBITS = 31
+
+
+def expectation_from_state(qibo_circ, datatype, terms):
+    """sum_t coeff_t <psi|P_t|psi> with |psi> = U|0..0> dense over the active qubits and
+    ``qtn_pauli_expectation`` doing every term in one pass each.  ``terms`` as produced by
+    ``extract_gates_and_qubits``.  Inactive qubits stay |0>: I and Z act as 1, X and Y give 0."""
+    import ctypes as C
+
     import torch
+
+    from . import lib
+
+    conv = QiboCircuitToEinsum(qibo_circ, dtype=datatype)
+    active = [int(q) for q in conv.active_qubits]
+    n = len(active)
+    if n == 0 or n > _STATE_ROUTE_MAX_QUBITS:
+        raise ValueError("state route needs between 1 and %d active qubits" % _STATE_ROUTE_MAX_QUBITS)
+    bit = {q: n - 1 - k for k, q in enumerate(active)}          # qubit -> address bit of the dense state
+    state = engine.contract(conv.state_vector_network(), datatype).reshape(-1)
+    xm, zm, ny, coeffs = [], [], [], []
+    for term in terms:
+        coeff, fx, fz, cy, dead = 1.0, 0, 0, 0, False
+        for qubit, letter, c in term:
+            coeff = coeff * c
+            if letter not in ("I", "X", "Y", "Z"):
+                raise ValueError("pauli string character must be one of I/X/Y/Z")
+            if qubit not in bit:
+                dead = dead or letter in ("X", "Y")
+                continue
+            if letter in ("X", "Y"):
+                fx |= 1 << bit[qubit]
+            if letter in ("Z", "Y"):
+                fz |= 1 << bit[qubit]
+            cy += letter == "Y"
+        if dead:
+            continue
+        xm.append(fx); zm.append(fz); ny.append(cy); coeffs.append(complex(coeff))
+    cdtype = torch.complex64 if str(datatype) == "complex64" else torch.complex128
+    if not coeffs:
+        return DeviceArray(torch.zeros(1, dtype=cdtype, device=state.device))
+    dev = state.device
+    d_x = torch.tensor(xm, dtype=torch.int64, device=dev)
+    d_z = torch.tensor(zm, dtype=torch.int64, device=dev)
+    d_y = torch.tensor(ny, dtype=torch.int32, device=dev)
+    out = torch.empty(len(coeffs), dtype=torch.complex128, device=dev)
+    lib.check(lib.load().qtn_pauli_expectation(lib.dtype_code(str(datatype)), n, state.data_ptr(), len(coeffs),
+                                               d_x.data_ptr(), d_z.data_ptr(), d_y.data_ptr(), out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream))
+    total = (out * torch.tensor(coeffs, dtype=torch.complex128, device=dev)).sum().reshape(1)
+    return DeviceArray(total.to(cdtype))
+
+
+def expectation_tn(qibo_circ, datatype, observable):
+    """sum over Hamiltonian terms of <0|U^dag P U|0> (eval.py:455-477): one contraction per term,
+    or -- see EXPECTATION_ROUTE -- one dense contraction plus the fused Pauli kernel."""
+    import torch
+
+    if EXPECTATION_ROUTE in ("auto", "state"):
+        ham = check_observable(observable, qibo_circ.nqubits)
+        terms = extract_gates_and_qubits(ham)
+        if not terms:
+            raise ValueError("No valid Hamiltonian terms were added.")
+        n_active = len(QiboCircuitToEinsum(qibo_circ, dtype=datatype).active_qubits)
+        limit = _STATE_ROUTE_MAX_QUBITS if EXPECTATION_ROUTE == "state" else _STATE_ROUTE_AUTO_QUBITS
+        if 1 <= n_active <= limit and (EXPECTATION_ROUTE == "state" or len(terms) >= 2):
+            return expectation_from_state(qibo_circ, datatype, terms)
 
     total = None
     for net in _term_networks(qibo_circ, datatype, observable):

@@ -177,3 +177,38 @@ def test_c4_amplitude_properties_at_depth_8():
         lib.set_option("tc_enable", 1)
     for k, v in vals.items():
         assert abs(v - ref) <= 1e-5 * abs(ref), (k, v, ref)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_fused_pauli_kernel_route_equals_network_route(dtype):
+    """north_star (d): dense state + one-pass Pauli kernel vs one sandwich contraction per term."""
+    n = 9
+    circ = circuits.brickwork(n, 5, seed=4)
+    psi = osv.simulate(circ)
+    terms = [(0.7, [("X", 0), ("Y", 3), ("Z", 8)]), (-1.3, [("Y", 1), ("Y", 2)]), (0.4, [("Z", 4)]),
+             (2.0, [("X", 5), ("X", 6), ("Z", 7), ("Y", 0)])]
+    want = osv.pauli_expectation(psi, terms, n)
+    obs = {"terms": [{"coefficient": c, "operators": f} for c, f in terms]}
+    vals = {}
+    for route in ("network", "state", "auto"):
+        ev.EXPECTATION_ROUTE = route
+        try:
+            vals[route] = complex(ev.expectation_tn(circ, dtype, obs).get()[0])
+        finally:
+            ev.EXPECTATION_ROUTE = "auto"
+    for route, v in vals.items():
+        assert abs(v - want) < TOL[dtype] * 20, (route, v, want)
+    # inactive qubits stay |0>: Z acts as +1, X kills the term
+    from qibotn_b200.qibo_compat import Circuit, H, CNOT
+    c = Circuit(5)
+    c.add(H(1)); c.add(CNOT(1, 3))
+    obs = {"terms": [{"coefficient": 1.0, "operators": [("Z", 0), ("Z", 1), ("Z", 3)]},
+                     {"coefficient": 5.0, "operators": [("X", 2), ("Z", 1)]},
+                     {"coefficient": 0.5, "operators": [("X", 1), ("X", 3)]}]}
+    for route in ("network", "state"):
+        ev.EXPECTATION_ROUTE = route
+        try:
+            v = complex(ev.expectation_tn(c, dtype, obs).get()[0])
+        finally:
+            ev.EXPECTATION_ROUTE = "auto"
+        assert abs(v - 1.5) < TOL[dtype] * 10, (route, v)
