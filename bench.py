@@ -132,6 +132,16 @@ def cpu_plan(wl, net, name, seconds):
     return info
 
 
+def use_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=len(os.sched_getaffinity(0)))
+    except Exception:            # threadpoolctl missing: keep whatever the BLAS picked
+        pass
+    return len(os.sched_getaffinity(0))
+
+
 def cpu_sample(wl, net, info, seconds, max_slices=64):
     """Run slices of ``info`` with numpy.tensordot for about ``seconds``; returns
     (TFLOP/s, slices done, wall seconds, flops per slice)."""
@@ -164,7 +174,7 @@ def run_reference(a):
     wl = workloads.build(a.workload)
     net = wl.network()
     info = cpu_plan(wl, net, a.workload, a.plan_seconds)
-    cores = len(os.sched_getaffinity(0))
+    cores = use_all_cores()
     per_step = max(2.0, min(30.0, 150.0 / max(1, a.steps + a.warmup)))
     for _ in range(min(a.warmup, 1)):
         cpu_sample(wl, net, info, 1.0, max_slices=1)
@@ -379,6 +389,7 @@ def run_b200(a):
         line["mps"] = mps_metric()
     if size == 1 and not a.no_cpu_baseline:
         cinfo = cpu_plan(wl, net, a.workload, a.plan_seconds)
+        use_all_cores()
         r, done, wall, _ = cpu_sample(wl, net, cinfo, a.cpu_seconds)
         line["cpu_baseline"] = {
             "value": r, "unit": "TFLOP/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
@@ -388,9 +399,21 @@ def run_b200(a):
     print(json.dumps(line), flush=True)
 
 
+def _shutdown():
+    try:
+        import torch.distributed as td
+        if td.is_available() and td.is_initialized():
+            td.destroy_process_group()
+    except Exception:
+        pass
+
+
 if __name__ == "__main__":
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    finally:
+        _shutdown()

@@ -270,13 +270,13 @@ def mps_site_right_swap(mps_tensors, i, **kwargs):
 class QiboCircuitToMPS:
     """Circuit -> MPS (circuit_to_mps.py:9-47): |0..0>, then every gate in queue order."""
 
-    def __init__(self, circ_qibo, gate_algo, dtype="complex128", rand_seed=0):
+    def __init__(self, circ_qibo, gate_algo, dtype="complex128", rand_seed=0, tol=None):
         np.random.seed(rand_seed)
         self.num_qubits = circ_qibo.nqubits
         self.dtype = dtype
         self.handle = None                      # the reference keeps a cutensornet handle here
         conv = QiboCircuitToEinsum(circ_qibo, dtype=dtype)
-        self.engine = MPSEngine(self.num_qubits, dtype, gate_algo)
+        self.engine = MPSEngine(self.num_qubits, dtype, gate_algo, tol=tol)
         for gate, qubits in conv.gate_tensors:
             self.engine.apply_gate(gate, qubits)
         self.engine.flush()

@@ -471,7 +471,7 @@ def _slice(net: SymbolicNetwork, path, target_log2_width, min_slices, max_sliced
 # ------------------------------------------------------------------ front door
 def find_path(modes, out, samples=32, seed=0, target_log2_width=30, min_slices=1,
               methods=("greedy", "partition"), time_budget_s=None, refine=3, reconf_rounds=6,
-              subtree_size=8):
+              subtree_size=8, anneal_steps=None):
     """Search a contraction path and slicing for the network ``(modes, out)``.
 
     ``samples`` and ``seed`` play the role of cuTensorNet's ``samples`` hyper-
@@ -482,7 +482,9 @@ def find_path(modes, out, samples=32, seed=0, target_log2_width=30, min_slices=1
     Stages: rank-<=2 absorption; ``samples`` x ``methods`` candidate trees; the
     ``refine`` cheapest are polished by subtree reconfiguration, sliced down to
     ``2^target_log2_width`` elements (and >= ``min_slices`` slices) with the tree
-    re-polished as labels are removed; the cheapest sliced plan wins.
+    re-polished as labels are removed, then annealed over tree rotations (``anneal_steps``
+    moves; default scales with the network, 0 disables) with the sliced labels removed and
+    re-sliced; the cheapest sliced plan wins.
     """
     import time
 
@@ -542,6 +544,23 @@ def find_path(modes, out, samples=32, seed=0, target_log2_width=30, min_slices=1
                 more, sliced = tree.slice_greedy(target_log2_width, 1, removed=sliced,
                                                  reconf_every=0)
                 order += more
+            steps = anneal_steps
+            if steps is None:
+                steps = 0 if len(live) < 64 else 150 * len(live)
+            if steps > 0:
+                # annealing moves single subtrees across the tree, which reconfiguration (bounded
+                # subtrees) cannot; the result is kept only if the sliced total really went down
+                snap = (dict(tree.children), dict(tree.mask), dict(tree.parent), tree.next_id,
+                        list(order), sliced)
+                before = tree.total_cost(sliced) * (1 << len(order))
+                tree.anneal(steps, rng, removed=sliced, max_width=target_log2_width, deadline=deadline)
+                tree.reconfigure(rounds=2, k=min(8, subtree_size), removed=sliced, deadline=deadline)
+                if tree.width(sliced) > target_log2_width:
+                    more, sliced = tree.slice_greedy(target_log2_width, 1, removed=sliced, reconf_every=0)
+                    order = order + more
+                if tree.total_cost(sliced) * (1 << len(order)) >= before:
+                    tree.children, tree.mask, tree.parent, tree.next_id = snap[0], snap[1], snap[2], snap[3]
+                    order, sliced = snap[4], snap[5]
             path = pre + tree.ssa_pairs(nxt)
         cost, width, per_slice, hoisted = path_cost(net, path, sliced)
         if best is None or cost < best[0]:

@@ -255,3 +255,63 @@ class Tree:
             if reconf_every and len(order) % reconf_every == 0:
                 self.reconfigure(rounds=1, k=k, removed=removed, deadline=deadline)
         return order, removed
+
+    # ------------------------------------------------------------------ annealing
+    def anneal(self, steps, rng, removed=0, t_start=3e-3, t_end=3e-5, write_weight=128.0,
+               max_width=None, deadline=None):
+        """Simulated annealing over tree rotations.  A move takes an internal node p = (x, y) whose
+        child x = (a, b) is internal and regroups the three subtrees as (a, (b, y)) or ((a, y), b):
+        p keeps its legs, so only x changes and the cost difference is local.  Objective =
+        sum over nodes of MACs + write_weight * (elements of the intermediate), the same trade-off
+        between tensor-core time and HBM time the executor sees.  Moves that would create an
+        intermediate above 2^max_width are rejected.  Returns the number of accepted moves."""
+        import math
+        import time
+
+        keep = ~removed
+
+        def size(mask):
+            return 2.0 ** (mask & keep).bit_count()
+
+        def ncost(l, r):
+            return 2.0 ** ((self.mask[l] | self.mask[r]) & keep).bit_count()
+
+        total = sum(ncost(*self.children[n]) + write_weight * size(self.mask[n]) for n in self.children)
+        inner = [n for n in self.children]
+        accepted = 0
+        log_ratio = math.log(t_end / t_start)
+        for it in range(steps):
+            if deadline is not None and (it & 1023) == 0 and time.time() > deadline:
+                break
+            temp = t_start * math.exp(log_ratio * it / max(1, steps - 1))
+            p = inner[int(rng.random() * len(inner))]
+            l, r = self.children[p]
+            if rng.random() < 0.5:
+                l, r = r, l
+            x, y = l, r                                   # x must be internal
+            if x not in self.children:
+                x, y = y, x
+                if x not in self.children:
+                    continue
+            a, b = self.children[x]
+            if rng.random() < 0.5:
+                a, b = b, a
+            # new x = (b, y), new p = (a, x)
+            old = ncost(a, b) + ncost(x, y) + write_weight * size(self.mask[x])
+            new_mask = self._legs(self.mask[b], self.mask[y])
+            if max_width is not None and (new_mask & keep).bit_count() > max_width:
+                continue
+            new_x_cost = 2.0 ** ((self.mask[b] | self.mask[y]) & keep).bit_count()
+            new_p_cost = 2.0 ** ((self.mask[a] | new_mask) & keep).bit_count()
+            new = new_x_cost + new_p_cost + write_weight * size(new_mask)
+            delta = new - old
+            if delta > 0 and rng.random() >= math.exp(-(delta / total) / temp):
+                continue
+            self.children[x] = (b, y)
+            self.children[p] = (a, x)
+            self.parent[y] = x
+            self.parent[a] = p
+            self.mask[x] = new_mask
+            total += delta
+            accepted += 1
+        return accepted

@@ -24,6 +24,7 @@ ap.add_argument("--chi", type=int, default=256)
 ap.add_argument("--dtype", default="complex128")
 ap.add_argument("--cpu-seconds", type=float, default=0.0)
 ap.add_argument("--repeat", type=int, default=1)
+ap.add_argument("--tol", type=float, default=0.0, help="Jacobi convergence threshold (0 = library default)")
 a = ap.parse_args()
 
 circ = circuits.tfim_trotter(a.n, a.steps)
@@ -33,7 +34,7 @@ best = None
 for _ in range(a.repeat + 1):          # first pass warms up (module load, allocator)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    conv = gmps.QiboCircuitToMPS(circ, algo, dtype=a.dtype)
+    conv = gmps.QiboCircuitToMPS(circ, algo, dtype=a.dtype, tol=a.tol)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     best = dt if best is None else min(best, dt)
@@ -43,7 +44,7 @@ zz = complex(helper.pauli_expectation(conv.mps_tensors, {a.n // 2: "Z", a.n // 2
 bonds = [int(t.shape[2]) for t in conv.mps_tensors[:-1]]
 line = {"workload": f"{a.n}-site TFIM Trotter, {a.steps} steps, chi<={a.chi}, {a.dtype}", "gates": ngates,
         "seconds": best, "gates_per_s": ngates / best, "max_bond": max(bonds), "bonds": bonds, "norm": norm,
-        "zz_mid": [zz.real, zz.imag], "stats": conv.stats}
+        "zz_mid": [zz.real, zz.imag], "stats": conv.stats, "tol": a.tol}
 if a.cpu_seconds > 0:
     from oracle import mps as omps
     from oracle.network import gate_tensors

@@ -12,12 +12,29 @@ from qibotn_b200 import plans, workloads  # noqa: E402
 from qibotn_b200.planner import find_path  # noqa: E402
 
 
+def modeled_seconds(info, net, dtype, tc_tflops=200.0, ffma_tflops=25.0, hbm_tbs=3.0, launch_us=3.0):
+    """Time model of a plan on one B200: per tree node max(flops / kernel rate, bytes / HBM rate,
+    launch), summed over slices (hoisted nodes once).  Rates are the measured ones of
+    profiles/r01_tc_persistent_vs_nonpersistent_vs_ffma.jsonl, deliberately round."""
+    from qibotn_b200 import executor, lib
+
+    low = executor.lower(net.modes, net.out, info, dtype)
+    total = 0.0
+    for nd in low.nodes:
+        p = nd.plan
+        rate = tc_tflops if p.kernel == lib.KERNEL_TC else ffma_tflops
+        t = max(p.flops / (rate * 1e12), p.bytes / (hbm_tbs * 1e12), launch_us * 1e-6)
+        total += t * (info.num_slices if nd.depends else 1)
+    return total
+
+
 def _one(args):
     name, seed, width, min_slices, samples, k = args
     wl = workloads.build(name)
     net = wl.network()
     info = find_path(net.modes, net.out, samples=samples, seed=seed, target_log2_width=width,
                      min_slices=min_slices, refine=6, subtree_size=k)
+    info.extra = dict(info.extra, modeled_seconds=modeled_seconds(info, net, wl.dtype))
     return info
 
 
@@ -36,16 +53,21 @@ if __name__ == "__main__":
     net = wl.network()
     name = a.name or a.workload
     best = plans.load_plan(name, net.modes, net.out)
-    print("start:", None if best is None else "log10 flops %.2f" % math.log10(best.flops), flush=True)
+    if best is not None and "modeled_seconds" not in best.extra:
+        best.extra = dict(best.extra, modeled_seconds=modeled_seconds(best, net, wl.dtype))
+    print("start:", None if best is None else "log10 flops %.2f, modeled %.1f s" % (
+        math.log10(best.flops), best.extra["modeled_seconds"]), flush=True)
     t0 = time.time()
     with mp.Pool(a.procs) as pool:
         for r in range(a.rounds):
             jobs = [(a.workload, 1000 * r + p, a.width, a.min_slices, a.samples, a.k) for p in range(a.procs)]
             for info in pool.imap_unordered(_one, jobs):
-                if best is None or info.opt_cost < best.opt_cost:
+                print("%.0fs: seed %d %s log10 flops %.2f W %d slices %d modeled %.1f s" % (
+                    time.time() - t0, info.seed, info.method, math.log10(info.flops), info.log2_width,
+                    info.num_slices, info.extra["modeled_seconds"]), flush=True)
+                if best is None or info.extra["modeled_seconds"] < best.extra["modeled_seconds"]:
                     best = info
                     plans.save_plan(name, best, net.modes, net.out)
-                    print("%.0fs: new best seed %d %s log10 flops %.2f W %d slices %d" % (
-                        time.time() - t0, info.seed, info.method, math.log10(info.flops),
-                        info.log2_width, info.num_slices), flush=True)
-    print("done: log10 flops %.2f W %d slices %d" % (math.log10(best.flops), best.log2_width, best.num_slices))
+                    print("   -> new best (ranked by modeled wall time on one B200)", flush=True)
+    print("done: log10 flops %.2f W %d slices %d modeled %.1f s" % (
+        math.log10(best.flops), best.log2_width, best.num_slices, best.extra["modeled_seconds"]))
