@@ -81,6 +81,7 @@ typedef struct {
 #define QTN_KERNEL_TILE 0   /* shared-memory tiled FFMA/DFMA kernel */
 #define QTN_KERNEL_REDUCE 1 /* tiny output, long contracted extent: K-parallel reduction */
 #define QTN_KERNEL_TC 2     /* complex64, large tiles: tcgen05 TF32x3 MMAs, accumulators in TMEM */
+#define QTN_KERNEL_KRED 3   /* <= 16 x 16 outputs, long contracted extent: streaming K reduction */
 
 #define QTN_LO_MAX 16
 #define QTN_HI_MAX 40
@@ -133,6 +134,10 @@ typedef struct {
   int32_t tc_stages;
   int32_t tc_plane_a, tc_plane_b;
   int32_t tc_reserved;           /* > 0: persistent variant, number of CTAs to launch */
+  /* iteration part of the tile enumerations (bits 8.. of the element index): global offset and
+   * shared-memory offset of iteration i; kernel parameters, i.e. constant-bank operands */
+  int64_t tc_a_it_g[8], tc_b_it_g[16];
+  int32_t tc_a_it_s[8], tc_b_it_s[16];
 } qtn_pair_plan_t;
 
 /* Library-wide switches (thread-unsafe, meant for tests and A/B measurements):

@@ -362,6 +362,148 @@ reduce_final_kernel(const __grid_constant__ qtn_pair_plan_t P, cx<R> *__restrict
   }
 }
 
+// --------------------------------------------------------------------------
+// K-reduction kernel: at most 16 x 16 outputs, long contracted extent (inner-product-like
+// nodes: the closing contraction of two big halves, expectation sandwiches).
+// A CTA streams its share of K in chunks of 2^tkb (<= 64) values: each chunk of A (16 x chunk)
+// and B is gathered in ascending address order into shared memory (phantom rows = 0); thread
+// (kg, sb) accumulates the 4 x 4 output block sb over the k values kg, kg+16, ... of the chunk.
+// At the end the 16 k-groups are summed through shared memory and the CTA writes ONE partial
+// C (256 values) to the workspace; qtn_launch_splitk_sum adds the partials.
+// HBM-bound by design: 16 KiB of operands per 64K real FMAs.
+// --------------------------------------------------------------------------
+constexpr int KRED_ROW = 16;        // padded row count of the A / B chunk in shared memory
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restrict__ A,
+                 const cx<R> *__restrict__ B, cx<R> *__restrict__ ws,
+                 const int32_t *__restrict__ slice_id) {
+  using T = cx<R>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int KC = 1 << P.tkb;
+  T *sA = reinterpret_cast<T *>(smem_raw);                   // [2][KC][16]
+  T *sB = sA + 2 * KC * KRED_ROW;                            // [2][KC][16]
+  __shared__ long long a_it_g[4], b_it_g[4];
+  __shared__ int a_it_s[4], b_it_s[4];
+  const int t = threadIdx.x;
+  const long long a_base = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
+  const long long b_base = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
+  const int k_iters_bits = P.n_khi - P.split_bits;
+  const unsigned long long k_iters = 1ull << k_iters_bits;
+  const unsigned long long kh0 = (unsigned long long)blockIdx.x << k_iters_bits;
+  long long a_k = a_base | deposit(kh0, P.a_khi, P.n_khi);
+  long long b_k = b_base | deposit(kh0, P.b_khi, P.n_khi);
+  // enumeration: element index e = t + 256 * it; bits 0-7 from the thread, bits 8-9 from `it`
+  if (t < 4) {
+    long long g = 0; int s = 0;
+    for (int j = 8; j < P.na_lo; ++j)
+      if ((t >> (j - 8)) & 1) {
+        if (P.a_lo_pos[j] == 255) g = -1; else if (g >= 0) g |= 1ll << P.a_lo_pos[j];
+        s += P.a_lo_sstr[j];
+      }
+    a_it_g[t] = g; a_it_s[t] = s;
+    g = 0; s = 0;
+    for (int j = 8; j < P.nb_lo; ++j)
+      if ((t >> (j - 8)) & 1) {
+        if (P.b_lo_pos[j] == 255) g = -1; else if (g >= 0) g |= 1ll << P.b_lo_pos[j];
+        s += P.b_lo_sstr[j];
+      }
+    b_it_g[t] = g; b_it_s[t] = s;
+  }
+  long long a_t_g = 0, b_t_g = 0;
+  int a_t_s = 0, b_t_s = 0;
+  for (int j = 0; j < 8; ++j) {
+    if (!((t >> j) & 1)) continue;
+    if (j < P.na_lo) {
+      if (P.a_lo_pos[j] == 255) a_t_g = -1; else if (a_t_g >= 0) a_t_g |= 1ll << P.a_lo_pos[j];
+      a_t_s += P.a_lo_sstr[j];
+    }
+    if (j < P.nb_lo) {
+      if (P.b_lo_pos[j] == 255) b_t_g = -1; else if (b_t_g >= 0) b_t_g |= 1ll << P.b_lo_pos[j];
+      b_t_s += P.b_lo_sstr[j];
+    }
+  }
+  const bool a_act = P.na_lo >= 8 || t < (1 << P.na_lo);
+  const bool b_act = P.nb_lo >= 8 || t < (1 << P.nb_lo);
+  const int a_nit = P.na_lo > 8 ? 1 << (P.na_lo - 8) : 1;     // <= 4
+  const int b_nit = P.nb_lo > 8 ? 1 << (P.nb_lo - 8) : 1;
+  __syncthreads();
+
+  const int sb = t & 15, kg = t >> 4;
+  const int mi = (sb >> 2) * 4, ni = (sb & 3) * 4;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = cx_zero<R>();
+
+  T va[4], vb[4];
+  auto load = [&]() {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      va[u] = cx_zero<R>(); vb[u] = cx_zero<R>();
+      if (a_act && u < a_nit) { const long long g = a_it_g[u]; if (a_t_g >= 0 && g >= 0) va[u] = A[a_k | a_t_g | g]; }
+      if (b_act && u < b_nit) { const long long g = b_it_g[u]; if (b_t_g >= 0 && g >= 0) vb[u] = B[b_k | b_t_g | g]; }
+    }
+  };
+  auto stash = [&](int buf) {
+    T *da = sA + buf * KC * KRED_ROW, *db = sB + buf * KC * KRED_ROW;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (a_act && u < a_nit) { T v = va[u]; if (P.conj_a) v.y = -v.y; da[a_t_s + a_it_s[u]] = v; }
+      if (b_act && u < b_nit) { T v = vb[u]; if (P.conj_b) v.y = -v.y; db[b_t_s + b_it_s[u]] = v; }
+    }
+  };
+  load();
+  stash(0);
+  __syncthreads();
+  for (unsigned long long kk = 0; kk < k_iters; ++kk) {
+    const int buf = (int)(kk & 1);
+    const bool more = kk + 1 < k_iters;
+    if (more) {
+      const unsigned long long flip = kk ^ (kk + 1);
+      const int nflip = 64 - __clzll(flip);
+      for (int i = 0; i < nflip && i < k_iters_bits; ++i) {
+        a_k ^= 1ll << P.a_khi[i];
+        b_k ^= 1ll << P.b_khi[i];
+      }
+      load();                                   // next chunk in flight while this one is used
+    }
+    const T *pa = sA + buf * KC * KRED_ROW + mi, *pb = sB + buf * KC * KRED_ROW + ni;
+    for (int k = kg; k < KC; k += 16) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = pa[k * KRED_ROW + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = pb[k * KRED_ROW + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cfma<R>(acc[i][j], a[i], b[j]);
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+  }
+  // sum the 16 k-groups: red[kg][m * 16 + n] aliases the chunk buffers
+  T *red = reinterpret_cast<T *>(smem_raw);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[kg * 256 + (mi + i) * 16 + (ni + j)] = acc[i][j];
+  __syncthreads();
+  {
+    T s = cx_zero<R>();
+    for (int g = 0; g < 16; ++g) { const T v = red[g * 256 + t]; s.x += v.x; s.y += v.y; }
+    const int m = t >> 4, n = t & 15;
+    if (m < (1 << P.m_real) && n < (1 << P.n_real)) {
+      const long long off = deposit(m, P.c_mhi, P.m_real) | deposit(n, P.c_nhi, P.n_real);
+      ws[(long long)blockIdx.x * P.c_elems + off] = s;
+    }
+  }
+}
+
 template <typename R>
 int launch_tile(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
                 const int32_t *slice_id, cudaStream_t st) {
@@ -383,6 +525,22 @@ int launch_tile(const qtn_pair_plan_t &P, const void *a, const void *b, void *c,
     QTN_LAUNCH_CHECK();
   }
   return QTN_OK;
+}
+
+template <typename R>
+int launch_kred(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
+                const int32_t *slice_id, cudaStream_t st) {
+  using T = cx<R>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_kred_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        16 * 256 * (int)sizeof(T)));
+    attr_set = true;
+  }
+  gett_kred_kernel<R><<<(unsigned)P.grid, 256, P.smem_bytes, st>>>(P, (const T *)a, (const T *)b, (T *)ws,
+                                                                  slice_id);
+  QTN_LAUNCH_CHECK();
+  return qtn_launch_splitk_sum(P.dtype, c, ws, P.c_elems, (int)P.grid, P.accumulate, st);
 }
 
 template <typename R, int MB, int NB>
@@ -439,6 +597,9 @@ extern "C" int qtn_pair_run(const qtn_pair_plan_t *plan, const void *a, const vo
   if (plan->kernel == QTN_KERNEL_TILE)
     return f32 ? launch_tile<float>(*plan, a, b, c, workspace, slice_id, st)
                : launch_tile<double>(*plan, a, b, c, workspace, slice_id, st);
+  if (plan->kernel == QTN_KERNEL_KRED)
+    return f32 ? launch_kred<float>(*plan, a, b, c, workspace, slice_id, st)
+               : launch_kred<double>(*plan, a, b, c, workspace, slice_id, st);
   if (plan->kernel == QTN_KERNEL_REDUCE)
     return f32 ? launch_reduce<float>(*plan, a, b, c, workspace, slice_id, st)
                : launch_reduce<double>(*plan, a, b, c, workspace, slice_id, st);

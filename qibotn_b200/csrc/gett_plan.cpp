@@ -133,6 +133,53 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     p->grid = (int64_t)1 << (kbits - chunk);
     p->smem_bytes = 0;
     p->workspace_bytes = p->grid * 16 * esz;
+  } else if (bbits == 0 && mbits <= 4 && nbits <= 4 && kbits >= 10) {
+    // ---- streaming K reduction (<= 16 x 16 outputs) ----------------------------
+    p->kernel = QTN_KERNEL_KRED;
+    const int tkb = std::min(kbits, 6);
+    p->tmb = 4; p->tnb = 4; p->tkb = tkb;
+    p->m_real = mbits; p->n_real = nbits; p->k_real = tkb;
+    std::sort(M.begin(), M.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
+    std::sort(N.begin(), N.end(), [](const Lab &x, const Lab &y) { return x.pb < y.pb; });
+    // chunk labels = the K labels with the lowest addresses (in either operand): contiguous runs
+    std::sort(K.begin(), K.end(), [](const Lab &x, const Lab &y) {
+      return std::min(x.pa, x.pb) != std::min(y.pa, y.pb) ? std::min(x.pa, x.pb) < std::min(y.pa, y.pb)
+                                                          : x.label < y.label;
+    });
+    std::vector<Lab> klo(K.begin(), K.begin() + tkb), khi(K.begin() + tkb, K.end());
+    std::sort(khi.begin(), khi.end(), [](const Lab &x, const Lab &y) {
+      return std::max(x.pa, x.pb) < std::max(y.pa, y.pb);
+    });
+    if ((int)khi.size() > QTN_HI_MAX) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_plan: rank too large");
+    if (d->c_layout_free) {
+      int next_c = 0;
+      for (auto &l : N) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
+      for (auto &l : M) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
+    }
+    for (int i = 0; i < mbits; ++i) { p->a_mhi[i] = M[i].pa; p->c_mhi[i] = M[i].pc; }
+    for (int i = 0; i < nbits; ++i) { p->b_nhi[i] = N[i].pb; p->c_nhi[i] = N[i].pc; }
+    p->n_mhi = 0; p->n_nhi = 0; p->n_khi = (int)khi.size();
+    for (int i = 0; i < p->n_khi; ++i) { p->a_khi[i] = khi[i].pa; p->b_khi[i] = khi[i].pb; }
+    // shared-memory chunk: element (k, row) at k * 16 + row; enumerations in address order
+    struct E { int pos; int sstr; };
+    std::vector<E> ea, eb;
+    for (int i = 0; i < mbits; ++i) ea.push_back({M[i].pa, 1 << i});
+    for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, 16 << i});
+    for (int i = 0; i < nbits; ++i) eb.push_back({N[i].pb, 1 << i});
+    for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, 16 << i});
+    auto by_pos = [](const E &x, const E &y) { return x.pos < y.pos; };
+    std::sort(ea.begin(), ea.end(), by_pos);
+    std::sort(eb.begin(), eb.end(), by_pos);
+    p->na_lo = (int)ea.size(); p->nb_lo = (int)eb.size();
+    for (int i = 0; i < p->na_lo; ++i) { p->a_lo_pos[i] = (uint8_t)ea[i].pos; p->a_lo_sstr[i] = (uint16_t)ea[i].sstr; }
+    for (int i = 0; i < p->nb_lo; ++i) { p->b_lo_pos[i] = (uint8_t)eb[i].pos; p->b_lo_sstr[i] = (uint16_t)eb[i].sstr; }
+    // every CTA owns 2^(n_khi - split) chunks; about four CTAs per SM
+    int split = 0;
+    while (split < p->n_khi && (1 << split) < 4 * sm_count) ++split;
+    p->split_bits = split;
+    p->grid = (int64_t)1 << split;
+    p->workspace_bytes = ((int64_t)esz << d->rank_c) << split;
+    p->smem_bytes = 16 * 256 * esz;                 // max(2 x 2 chunk buffers, 16 x 256 partials)
   } else if (d->dtype == QTN_C64 && d->c_layout_free && bbits == 0 && mbits >= 7 && nbits >= 4 &&
              kbits >= 3 && mbits + nbits + kbits >= qtn_option_tc_min_log2() && qtn_option_tc_enable()) {
     // ---- tensor-core kernel (gett_tc.cu) ----------------------------------------
@@ -212,6 +259,18 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     p->na_lo = (int)ea.size(); p->nb_lo = (int)eb.size();
     for (int i = 0; i < p->na_lo; ++i) { p->a_lo_pos[i] = (uint8_t)ea[i].pos; p->a_lo_sstr[i] = (uint16_t)ea[i].sstr; }
     for (int i = 0; i < p->nb_lo; ++i) { p->b_lo_pos[i] = (uint8_t)eb[i].pos; p->b_lo_sstr[i] = (uint16_t)eb[i].sstr; }
+    for (int it = 0; it < 8; ++it) {
+      int64_t g = 0; int32_t so = 0;
+      for (int j = 8; j < p->na_lo; ++j)
+        if ((it >> (j - 8)) & 1) { g |= (int64_t)1 << p->a_lo_pos[j]; so += p->a_lo_sstr[j]; }
+      p->tc_a_it_g[it] = g; p->tc_a_it_s[it] = so;
+    }
+    for (int it = 0; it < 16; ++it) {
+      int64_t g = 0; int32_t so = 0;
+      for (int j = 8; j < p->nb_lo; ++j)
+        if ((it >> (j - 8)) & 1) { g |= (int64_t)1 << p->b_lo_pos[j]; so += p->b_lo_sstr[j]; }
+      p->tc_b_it_g[it] = g; p->tc_b_it_s[it] = so;
+    }
     p->nc_lo = tmb + tnb;
     for (int j = 0; j < tmb; ++j) p->c_lo_pos[j] = (uint8_t)mlo[j].pc;          // m bits, then n bits
     for (int j = 0; j < tnb; ++j) p->c_lo_pos[tmb + j] = (uint8_t)nlo[j].pc;

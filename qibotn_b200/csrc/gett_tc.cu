@@ -421,9 +421,6 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
   const int S = P.tc_stages;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * STAGE * sizeof(float));
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 2 * NBUF);
-  __shared__ long long a_it_g[8], b_it_g[16];
-  __shared__ int a_it_s[8], b_it_s[16];
-
   const int t = threadIdx.x;
   const int warp = t >> 5, lane = t & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -438,19 +435,6 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
   const long long a_slice = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
   const long long b_slice = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
 
-  if (t < 16) {
-    long long g = 0;
-    int s = 0;
-    if (t < 8) {
-      for (int j = 8; j < P.na_lo; ++j)
-        if ((t >> (j - 8)) & 1) { g |= 1ll << P.a_lo_pos[j]; s += P.a_lo_sstr[j]; }
-      a_it_g[t] = g; a_it_s[t] = s;
-    }
-    g = 0; s = 0;
-    for (int j = 8; j < P.nb_lo; ++j)
-      if ((t >> (j - 8)) & 1) { g |= 1ll << P.b_lo_pos[j]; s += P.b_lo_sstr[j]; }
-    b_it_g[t] = g; b_it_s[t] = s;
-  }
   if (t == 32) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), kProducerThreads); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < NBUF; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpilogueThreads); }
@@ -500,10 +484,10 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
     };
     auto load = [&](float2(&va)[NA], float2(&vb)[NB]) {
 #pragma unroll
-      for (int i = 0; i < NA; ++i) va[i] = __ldg(A + (a_k | a_t_g | a_it_g[i]));
+      for (int i = 0; i < NA; ++i) va[i] = __ldg(A + (a_k | a_t_g | P.tc_a_it_g[i]));
 #pragma unroll
       for (int i = 0; i < NB; ++i)
-        vb[i] = b_act ? __ldg(B + (b_k | b_t_g | b_it_g[i])) : make_float2(0.f, 0.f);
+        vb[i] = b_act ? __ldg(B + (b_k | b_t_g | P.tc_b_it_g[i])) : make_float2(0.f, 0.f);
     };
     int s = 0;
     uint32_t ph = 0;
@@ -513,7 +497,7 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
       float *sB = sA + 4 * PLANE_A;
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
-        const int o = a_t_s + a_it_s[i];
+        const int o = a_t_s + P.tc_a_it_s[i];
         float h, l;
         split_tf32(va[i].x, h, l);
         sA[o] = h; sA[PLANE_A + o] = l;
@@ -523,7 +507,7 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
       if (b_act) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-          const int o = b_t_s + b_it_s[i];
+          const int o = b_t_s + P.tc_b_it_s[i];
           float h, l;
           split_tf32(vb[i].x, h, l);
           sB[o] = h; sB[PLANE_B + o] = l;
@@ -535,17 +519,26 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
       mbar_arrive(full_bar(s));
       if (++s == S) { s = 0; ph ^= 1u; }
     };
-    float2 va0[NA], vb0[NB], va1[NA], vb1[NB];
-    bool have0 = tile < ntiles;
-    if (have0) { enter_tile(); load(va0, vb0); advance(); }
-    while (have0) {
-      const bool have1 = tile < ntiles;
-      if (have1) { load(va1, vb1); advance(); }
-      store(va0, vb0);
-      if (!have1) break;
-      have0 = tile < ntiles;
-      if (have0) { load(va0, vb0); advance(); }
-      store(va1, vb1);
+    // ring of D register buffers: D-1 chunks of global loads are in flight while one chunk is
+    // split and stored; deeper for the small tiles whose nodes are HBM-bound
+    constexpr int D = (NA + NB) <= 12 ? 4 : 2;
+    float2 va[D][NA], vb[D][NB];
+    bool have[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      have[d] = tile < ntiles;
+      if (have[d]) { if (d == 0) enter_tile(); load(va[d], vb[d]); advance(); }
+    }
+    bool done = false;
+    while (!done) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        if (done) continue;
+        if (!have[d]) { done = true; continue; }
+        store(va[d], vb[d]);
+        have[d] = tile < ntiles;
+        if (have[d]) { load(va[d], vb[d]); advance(); }
+      }
     }
   } else if (warp < 12) {
     // ================= epilogue: TMEM -> global, tile after tile =================

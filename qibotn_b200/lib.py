@@ -12,7 +12,7 @@ from functools import lru_cache
 
 QTN_C64, QTN_C128 = 0, 1
 QTN_MAX_RANK, QTN_MAX_SLICE, QTN_LO_MAX, QTN_HI_MAX = 48, 24, 16, 40
-KERNEL_TILE, KERNEL_REDUCE, KERNEL_TC = 0, 1, 2
+KERNEL_TILE, KERNEL_REDUCE, KERNEL_TC, KERNEL_KRED = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqibotn_b200.so")
@@ -63,6 +63,8 @@ class PairPlan(C.Structure):
         ("flops", C.c_double), ("bytes", C.c_double),
         ("tc_stages", C.c_int32), ("tc_plane_a", C.c_int32), ("tc_plane_b", C.c_int32),
         ("tc_reserved", C.c_int32),
+        ("tc_a_it_g", C.c_int64 * 8), ("tc_b_it_g", C.c_int64 * 16),
+        ("tc_a_it_s", C.c_int32 * 8), ("tc_b_it_s", C.c_int32 * 16),
     ]
 
 

@@ -63,6 +63,8 @@ def run_plan(P, a, b, c, slice_id=0):
         return _run_reduce(P, a, b, c, sa, sb)
     if P.kernel == 2:
         return _run_tc(P, a, b, c, sa, sb)
+    if P.kernel == 3:
+        return _run_kred(P, a, b, c, sa, sb)
     TM, TN, TK = 1 << P.tmb, 1 << P.tnb, 1 << P.tkb
     nsplit = 1 << P.split_bits
     ws = np.zeros((nsplit, P.c_elems), dtype=c.dtype)
@@ -203,4 +205,42 @@ def _run_tc(P, a, b, c, sa, sb):
                 out[c_base + (r & 31) + (n << 5) + ((r >> 5) << (5 + P.tnb))] = acc[r, n]
     if P.split_bits:
         c[: P.c_elems] = ws.sum(0)
+    return c
+
+
+def _run_kred(P, a, b, c, sa, sb):
+    """Emulate gett_kred_kernel: per CTA a range of k chunks, 16 x 16 (padded) outputs, one partial
+    per CTA summed at the end."""
+    KC = 1 << P.tkb
+    assert P.tmb == 4 and P.tnb == 4 and P.n_batch == 0 and P.n_mhi == 0 and P.n_nhi == 0
+    assert P.smem_bytes >= 2 * 2 * KC * 16 * c.itemsize and P.grid == 1 << P.split_bits
+    kbits = P.n_khi - P.split_bits
+    ws = np.zeros((P.grid, P.c_elems), dtype=np.complex128)
+    for cta in range(P.grid):
+        acc = np.zeros((16, 16), dtype=np.complex128)
+        for kk in range(1 << kbits):
+            kh = (cta << kbits) | kk
+            a_k = sa | dep(kh, P.a_khi, P.n_khi)
+            b_k = sb | dep(kh, P.b_khi, P.n_khi)
+            chunks = []
+            for (n_lo, lo_pos, lo_sstr, src, base) in ((P.na_lo, P.a_lo_pos, P.a_lo_sstr, a, a_k),
+                                                       (P.nb_lo, P.b_lo_pos, P.b_lo_sstr, b, b_k)):
+                buf = np.zeros(KC * 16, dtype=np.complex128)
+                for e in range(1 << n_lo):
+                    g = s = 0
+                    for j in range(n_lo):
+                        if (e >> j) & 1:
+                            g |= 1 << lo_pos[j]
+                            s += lo_sstr[j]
+                    buf[s] = src[base | g]
+                chunks.append(buf.reshape(KC, 16))
+            acc += chunks[0].T @ chunks[1]
+        for m in range(1 << P.m_real):
+            for n in range(1 << P.n_real):
+                ws[cta, dep(m, P.c_mhi, P.m_real) | dep(n, P.c_nhi, P.n_real)] = acc[m, n]
+    tot = ws.sum(0)
+    if P.accumulate:
+        c[: P.c_elems] += tot
+    else:
+        c[: P.c_elems] = tot
     return c

@@ -44,7 +44,7 @@ CASES = [
     (6, 6, 3, 0), (7, 7, 5, 0), (12, 2, 2, 0), (3, 13, 2, 0), (1, 1, 1, 0), (0, 0, 3, 0),
     (2, 0, 1, 0), (9, 8, 6, 0), (4, 4, 2, 2), (7, 3, 2, 1), (1, 1, 14, 0), (2, 2, 16, 0),
     (0, 0, 20, 0), (16, 0, 1, 0), (6, 7, 0, 0), (3, 3, 12, 0), (10, 10, 4, 0), (14, 3, 3, 0),
-    (5, 5, 10, 0), (8, 8, 8, 0),
+    (5, 5, 10, 0), (8, 8, 8, 0), (4, 4, 14, 0), (3, 4, 17, 0), (4, 2, 12, 0), (1, 4, 10, 0),
 ]
 
 

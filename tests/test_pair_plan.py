@@ -42,7 +42,8 @@ CASES = [
     (2, 0, 1, 0, 0, 0, False), (5, 4, 6, 0, 0, 0, True), (4, 4, 2, 2, 0, 0, False),
     (7, 3, 2, 1, 2, 1, True), (1, 1, 11, 0, 0, 0, True), (2, 2, 10, 0, 1, 1, False),
     (0, 0, 12, 0, 2, 0, True), (13, 0, 1, 0, 0, 0, True), (6, 7, 0, 0, 0, 0, True),
-    (3, 3, 8, 0, 0, 0, True),
+    (3, 3, 8, 0, 0, 0, True), (4, 4, 11, 0, 0, 0, True), (3, 4, 10, 0, 1, 2, False), (4, 1, 12, 0, 0, 0, True),
+    (0, 4, 10, 0, 0, 0, False),
 ]
 
 
