@@ -375,7 +375,7 @@ reduce_final_kernel(const __grid_constant__ qtn_pair_plan_t P, cx<R> *__restrict
 constexpr int KRED_ROW = 16;        // padded row count of the A / B chunk in shared memory
 
 template <typename R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restrict__ A,
                  const cx<R> *__restrict__ B, cx<R> *__restrict__ ws,
                  const int32_t *__restrict__ slice_id) {
@@ -389,11 +389,12 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   const int t = threadIdx.x;
   const long long a_base = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
   const long long b_base = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
-  const int k_iters_bits = P.n_khi - P.split_bits;
-  const unsigned long long k_iters = 1ull << k_iters_bits;
-  const unsigned long long kh0 = (unsigned long long)blockIdx.x << k_iters_bits;
-  long long a_k = a_base | deposit(kh0, P.a_khi, P.n_khi);
-  long long b_k = b_base | deposit(kh0, P.b_khi, P.n_khi);
+  // chunk c = blockIdx.x, blockIdx.x + gridDim.x, ...: at any moment the CTAs in flight work on
+  // NEIGHBOURING chunks, so the 32 operand streams stay inside a few DRAM pages / TLB entries
+  const unsigned long long nchunks = 1ull << P.n_khi;
+  unsigned long long chunk = blockIdx.x;
+  long long a_k = a_base | deposit(chunk, P.a_khi, P.n_khi);
+  long long b_k = b_base | deposit(chunk, P.b_khi, P.n_khi);
   // enumeration: element index e = t + 256 * it; bits 0-7 from the thread, bits 8-9 from `it`
   if (t < 4) {
     long long g = 0; int s = 0;
@@ -458,16 +459,11 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   load();
   stash(0);
   __syncthreads();
-  for (unsigned long long kk = 0; kk < k_iters; ++kk) {
-    const int buf = (int)(kk & 1);
-    const bool more = kk + 1 < k_iters;
+  for (int buf = 0; chunk < nchunks; chunk += gridDim.x, buf ^= 1) {
+    const bool more = chunk + gridDim.x < nchunks;
     if (more) {
-      const unsigned long long flip = kk ^ (kk + 1);
-      const int nflip = 64 - __clzll(flip);
-      for (int i = 0; i < nflip && i < k_iters_bits; ++i) {
-        a_k ^= 1ll << P.a_khi[i];
-        b_k ^= 1ll << P.b_khi[i];
-      }
+      a_k = a_base | deposit(chunk + gridDim.x, P.a_khi, P.n_khi);
+      b_k = b_base | deposit(chunk + gridDim.x, P.b_khi, P.n_khi);
       load();                                   // next chunk in flight while this one is used
     }
     const T *pa = sA + buf * KC * KRED_ROW + mi, *pb = sB + buf * KC * KRED_ROW + ni;

@@ -173,12 +173,12 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     p->na_lo = (int)ea.size(); p->nb_lo = (int)eb.size();
     for (int i = 0; i < p->na_lo; ++i) { p->a_lo_pos[i] = (uint8_t)ea[i].pos; p->a_lo_sstr[i] = (uint16_t)ea[i].sstr; }
     for (int i = 0; i < p->nb_lo; ++i) { p->b_lo_pos[i] = (uint8_t)eb[i].pos; p->b_lo_sstr[i] = (uint16_t)eb[i].sstr; }
-    // every CTA owns 2^(n_khi - split) chunks; about four CTAs per SM
-    int split = 0;
-    while (split < p->n_khi && (1 << split) < 4 * sm_count) ++split;
-    p->split_bits = split;
-    p->grid = (int64_t)1 << split;
-    p->workspace_bytes = ((int64_t)esz << d->rank_c) << split;
+    // three resident CTAs per SM stride over the chunks together (chunk = blockIdx.x + i * grid);
+    // every CTA leaves one partial C in the workspace
+    const int64_t nchunks = (int64_t)1 << p->n_khi;
+    p->split_bits = 0;
+    p->grid = std::min<int64_t>(nchunks, (int64_t)3 * sm_count);
+    p->workspace_bytes = ((int64_t)esz << d->rank_c) * p->grid;
     p->smem_bytes = 16 * 256 * esz;                 // max(2 x 2 chunk buffers, 16 x 256 partials)
   } else if (d->dtype == QTN_C64 && d->c_layout_free && bbits == 0 && mbits >= 7 && nbits >= 4 &&
              kbits >= 3 && mbits + nbits + kbits >= qtn_option_tc_min_log2() && qtn_option_tc_enable()) {
@@ -293,6 +293,7 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     const int budget = (tnb <= 6 && 2 * stage_bytes <= 110 * 1024) ? 110 * 1024 : 200 * 1024;
     int stages = std::max(1, std::min(4, budget / stage_bytes));
     if ((int64_t)stages > k_iters) stages = (int)k_iters;
+    p->tc_terms = qtn_option_tc_terms();
     p->tc_reserved = 0;
     if (qtn_option_tc_persistent()) {
       // persistent kernel: one CTA per SM streams over tiles, so the pipeline may be deeper than

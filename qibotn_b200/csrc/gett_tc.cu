@@ -143,12 +143,15 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// x = hi + lo, hi representable in tf32 (round to nearest, ties away), lo = x - hi exact
+// x ~ hi + lo, both representable in tf32: hi = rna(x), lo = rna(x - hi).  x - hi is exact in fp32
+// but can carry 13 significant bits; the tensor core would TRUNCATE it to 11, a biased 2^-23 |x|
+// error per cross term -- rounding it here first halves that and removes the bias.
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-  uint32_t u;
+  uint32_t u, v;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   hi = __uint_as_float(u);
-  lo = x - hi;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v) : "f"(x - hi));
+  lo = __uint_as_float(v);
 }
 
 __device__ __forceinline__ long long deposit(unsigned long long idx, const uint8_t *pos, int n) {
@@ -613,6 +616,12 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
           umma_tf32(ci, aih, brl, IDESC, 1u);
           umma_tf32(ci, arh, bih, IDESC, 1u);
           umma_tf32(ci, aih, brh, IDESC, 1u);
+          if (P.tc_terms >= 4) {                   // lo*lo as well
+            umma_tf32(cr, arl, brl, IDESC, 1u);
+            umma_tf32(cr, ail, bil, IDESC_NEG, 1u);
+            umma_tf32(ci, arl, bil, IDESC, 1u);
+            umma_tf32(ci, ail, brl, IDESC, 1u);
+          }
         }
         umma_commit(empty_bar(s));
         if (++s == S) { s = 0; ph ^= 1u; }

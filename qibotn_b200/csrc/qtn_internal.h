@@ -11,6 +11,7 @@ int qtn_fail(int code, const char *msg);
 int qtn_option_tc_enable(void);
 int qtn_option_tc_min_log2(void);
 int qtn_option_tc_persistent(void);
+int qtn_option_tc_terms(void);
 #ifdef __cplusplus
 }
 #endif

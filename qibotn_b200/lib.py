@@ -65,6 +65,7 @@ class PairPlan(C.Structure):
         ("tc_reserved", C.c_int32),
         ("tc_a_it_g", C.c_int64 * 8), ("tc_b_it_g", C.c_int64 * 16),
         ("tc_a_it_s", C.c_int32 * 8), ("tc_b_it_s", C.c_int32 * 16),
+        ("tc_terms", C.c_int32), ("tc_pad", C.c_int32),
     ]
 
 

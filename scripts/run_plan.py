@@ -20,13 +20,22 @@ ap = argparse.ArgumentParser()
 ap.add_argument("workload")
 ap.add_argument("--plan", action="append", required=True)
 ap.add_argument("--max-slices", type=int, default=0)
+ap.add_argument("--dtype", default=None, help="override the workload dtype (complex64 | complex128)")
+ap.add_argument("--no-tc", action="store_true", help="FFMA/DFMA kernels only")
+ap.add_argument("--tc-terms", type=int, default=3)
 a = ap.parse_args()
 wl = workloads.build(a.workload)
+if a.dtype:
+    wl.dtype = a.dtype
+from qibotn_b200 import lib  # noqa: E402
+if a.no_tc:
+    lib.set_option("tc_enable", 0)
+lib.set_option("tc_terms", a.tc_terms)
 net = wl.network()
 for name in a.plan:
     info = plans.load_plan(name, net.modes, net.out)
     if info is None:
-        print(json.dumps({"plan": name, "error": "missing or made for another network"}), flush=True)
+        print(json.dumps({"plan": name, "dtype": wl.dtype, "tensor_cores": not a.no_tc, "tc_terms": a.tc_terms, "error": "missing or made for another network"}), flush=True)
         continue
     low = executor.lower(net.modes, net.out, info, wl.dtype)
     runner = executor.ContractionRunner(low, use_graph=True)
@@ -40,7 +49,7 @@ for name in a.plan:
     dt = time.perf_counter() - t0
     amp = complex(out.reshape(-1)[0].item())
     flops = low.flops_hoisted + ns * low.flops_per_slice
-    print(json.dumps({"plan": name, "log10_flops": math.log10(info.flops), "num_slices": info.num_slices,
+    print(json.dumps({"plan": name, "dtype": wl.dtype, "tensor_cores": not a.no_tc, "tc_terms": a.tc_terms, "log10_flops": math.log10(info.flops), "num_slices": info.num_slices,
                       "slices_run": ns, "log2_width": info.log2_width, "seconds": dt, "tflops": flops / dt / 1e12,
                       "amplitude": [amp.real, amp.imag], "slice_arena_gb": low.slice_bytes / 2**30,
                       "launches_per_slice": low.launches_per_slice}), flush=True)

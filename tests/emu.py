@@ -213,13 +213,11 @@ def _run_kred(P, a, b, c, sa, sb):
     per CTA summed at the end."""
     KC = 1 << P.tkb
     assert P.tmb == 4 and P.tnb == 4 and P.n_batch == 0 and P.n_mhi == 0 and P.n_nhi == 0
-    assert P.smem_bytes >= 2 * 2 * KC * 16 * c.itemsize and P.grid == 1 << P.split_bits
-    kbits = P.n_khi - P.split_bits
+    assert P.smem_bytes >= 2 * 2 * KC * 16 * c.itemsize and 1 <= P.grid <= 1 << P.n_khi
     ws = np.zeros((P.grid, P.c_elems), dtype=np.complex128)
     for cta in range(P.grid):
         acc = np.zeros((16, 16), dtype=np.complex128)
-        for kk in range(1 << kbits):
-            kh = (cta << kbits) | kk
+        for kh in range(cta, 1 << P.n_khi, P.grid):      # neighbouring CTAs take neighbouring chunks
             a_k = sa | dep(kh, P.a_khi, P.n_khi)
             b_k = sb | dep(kh, P.b_khi, P.n_khi)
             chunks = []

@@ -212,3 +212,23 @@ def test_fused_pauli_kernel_route_equals_network_route(dtype):
         finally:
             ev.EXPECTATION_ROUTE = "auto"
         assert abs(v - 1.5) < TOL[dtype] * 10, (route, v)
+
+
+def test_c4_full_amplitude_within_tolerance_of_complex128():
+    """The benchmark contraction itself, all slices: the complex64 tensor-core result must agree
+    with the complex128 result of the same engine (FP64 FMA kernels, 70 s on a B200; value recorded
+    in tests/golden/c4_amplitude.json together with the complex64 FFMA and the other-plan values)
+    to the north-star tolerance of 1e-5 relative."""
+    import json
+    from qibotn_b200 import executor, plans, workloads
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c4_amplitude.json")))
+    want = complex(*ref["complex128"])
+    wl = workloads.build("c4")
+    net = wl.network()
+    info = plans.load_plan("c4", net.modes, net.out)
+    assert info is not None, "plans/c4.json does not match the workload"
+    low = executor.lower(net.modes, net.out, info, "complex64")
+    runner = executor.ContractionRunner(low, use_graph=True)
+    runner.upload(net.tensors)
+    got = complex(runner.run(range(info.num_slices)).reshape(-1)[0].item())
+    assert abs(got - want) <= 1e-5 * abs(want), (got, want, abs(got - want) / abs(want))
