@@ -139,13 +139,15 @@ typedef struct {
   int64_t tc_a_it_g[8], tc_b_it_g[16];
   int32_t tc_a_it_s[8], tc_b_it_s[16];
   int32_t tc_terms;              /* 3: hi*hi + hi*lo + lo*hi;  4: + lo*lo ("tc_terms" option) */
-  int32_t tc_pad;
+  int32_t tc_pad;                /* 1: cross terms accumulate in their own TMEM region ("tc_accum_split") */
 } qtn_pair_plan_t;
 
 /* Library-wide switches (thread-unsafe, meant for tests and A/B measurements):
  *   "tc_enable"    1 (default) lets qtn_pair_plan choose QTN_KERNEL_TC, 0 forbids it;
  *   "tc_min_log2"  smallest m+n+k (log2 of the MAC count) for which TC is chosen (default 18);
  *   "tc_terms"     3 (default) or 4: products kept by the TF32 split (4 adds lo*lo, +33% MMAs);
+ *   "tc_accum_split" 1 (default): hi*hi and the cross terms use separate TMEM accumulators, added in
+ *                  the epilogue (3x fewer truncating accumulations on the large sum; tile <= 128 columns);
  *   "tc_persistent" 1 (default): one CTA per SM streams over the tiles with loads, MMAs and
  *                  epilogue of neighbouring tiles overlapped; 0: one CTA per tile.
  * Returns QTN_ERR_ARG for an unknown name. */

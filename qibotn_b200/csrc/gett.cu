@@ -372,31 +372,27 @@ reduce_final_kernel(const __grid_constant__ qtn_pair_plan_t P, cx<R> *__restrict
 // C (256 values) to the workspace; qtn_launch_splitk_sum adds the partials.
 // HBM-bound by design: 16 KiB of operands per 64K real FMAs.
 // --------------------------------------------------------------------------
-constexpr int KRED_ROW = 16;        // padded row count of the A / B chunk in shared memory
+constexpr int KRED_ROW = 17;        // row stride (elements) of the A / B chunk in shared memory: 16 rows + 1
+                                    // pad, so that lanes walking k hit different banks when they store
 
 template <typename R>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restrict__ A,
                  const cx<R> *__restrict__ B, cx<R> *__restrict__ ws,
                  const int32_t *__restrict__ slice_id) {
   using T = cx<R>;
+  constexpr int NIT = sizeof(R) == 4 ? 8 : 4;                // loads per thread, operand and chunk
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int KC = 1 << P.tkb;
   T *sA = reinterpret_cast<T *>(smem_raw);                   // [2][KC][16]
   T *sB = sA + 2 * KC * KRED_ROW;                            // [2][KC][16]
-  __shared__ long long a_it_g[4], b_it_g[4];
-  __shared__ int a_it_s[4], b_it_s[4];
+  __shared__ long long a_it_g[NIT], b_it_g[NIT];
+  __shared__ int a_it_s[NIT], b_it_s[NIT];
   const int t = threadIdx.x;
   const long long a_base = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
   const long long b_base = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
-  // chunk c = blockIdx.x, blockIdx.x + gridDim.x, ...: at any moment the CTAs in flight work on
-  // NEIGHBOURING chunks, so the 32 operand streams stay inside a few DRAM pages / TLB entries
-  const unsigned long long nchunks = 1ull << P.n_khi;
-  unsigned long long chunk = blockIdx.x;
-  long long a_k = a_base | deposit(chunk, P.a_khi, P.n_khi);
-  long long b_k = b_base | deposit(chunk, P.b_khi, P.n_khi);
-  // enumeration: element index e = t + 256 * it; bits 0-7 from the thread, bits 8-9 from `it`
-  if (t < 4) {
+  // enumeration: element index e = t + 256 * it; bits 0-7 from the thread, bits 8.. from `it`
+  if (t < NIT) {
     long long g = 0; int s = 0;
     for (int j = 8; j < P.na_lo; ++j)
       if ((t >> (j - 8)) & 1) {
@@ -427,9 +423,30 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   }
   const bool a_act = P.na_lo >= 8 || t < (1 << P.na_lo);
   const bool b_act = P.nb_lo >= 8 || t < (1 << P.nb_lo);
-  const int a_nit = P.na_lo > 8 ? 1 << (P.na_lo - 8) : 1;     // <= 4
+  const int a_nit = P.na_lo > 8 ? 1 << (P.na_lo - 8) : 1;     // <= NIT
   const int b_nit = P.nb_lo > 8 ? 1 << (P.nb_lo - 8) : 1;
   __syncthreads();
+
+  // The CTA walks GROUPS of 2^IB consecutive chunks: group g = blockIdx.x, + gridDim.x, ... so that
+  // CTAs in flight stay on neighbouring addresses; inside a group the chunk offset advances by
+  // flipping address bits, the full bit-deposit is paid once per group.
+  const int IB = P.n_khi < 3 ? P.n_khi : 3;
+  const unsigned long long ngroups = 1ull << (P.n_khi - IB);
+  unsigned long long group = blockIdx.x;
+  unsigned inner = 0;
+  long long a_k = 0, b_k = 0;
+  auto enter_group = [&]() {
+    a_k = a_base | deposit(group, P.a_khi + IB, P.n_khi - IB);
+    b_k = b_base | deposit(group, P.b_khi + IB, P.n_khi - IB);
+    inner = 0;
+  };
+  auto advance = [&]() {                        // -> next chunk of the stream (or past the end)
+    if (inner + 1 == (1u << IB)) { group += gridDim.x; if (group < ngroups) enter_group(); return; }
+    const unsigned flip = inner ^ (inner + 1);
+    const int nflip = 32 - __clz(flip);
+    for (int i = 0; i < nflip; ++i) { a_k ^= 1ll << P.a_khi[i]; b_k ^= 1ll << P.b_khi[i]; }
+    ++inner;
+  };
 
   const int sb = t & 15, kg = t >> 4;
   const int mi = (sb >> 2) * 4, ni = (sb & 3) * 4;
@@ -439,10 +456,10 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = cx_zero<R>();
 
-  T va[4], vb[4];
+  T va[NIT], vb[NIT];
   auto load = [&]() {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NIT; ++u) {
       va[u] = cx_zero<R>(); vb[u] = cx_zero<R>();
       if (a_act && u < a_nit) { const long long g = a_it_g[u]; if (a_t_g >= 0 && g >= 0) va[u] = A[a_k | a_t_g | g]; }
       if (b_act && u < b_nit) { const long long g = b_it_g[u]; if (b_t_g >= 0 && g >= 0) vb[u] = B[b_k | b_t_g | g]; }
@@ -451,21 +468,17 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   auto stash = [&](int buf) {
     T *da = sA + buf * KC * KRED_ROW, *db = sB + buf * KC * KRED_ROW;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NIT; ++u) {
       if (a_act && u < a_nit) { T v = va[u]; if (P.conj_a) v.y = -v.y; da[a_t_s + a_it_s[u]] = v; }
       if (b_act && u < b_nit) { T v = vb[u]; if (P.conj_b) v.y = -v.y; db[b_t_s + b_it_s[u]] = v; }
     }
   };
-  load();
-  stash(0);
+  bool have = group < ngroups;
+  if (have) { enter_group(); load(); advance(); stash(0); }
   __syncthreads();
-  for (int buf = 0; chunk < nchunks; chunk += gridDim.x, buf ^= 1) {
-    const bool more = chunk + gridDim.x < nchunks;
-    if (more) {
-      a_k = a_base | deposit(chunk + gridDim.x, P.a_khi, P.n_khi);
-      b_k = b_base | deposit(chunk + gridDim.x, P.b_khi, P.n_khi);
-      load();                                   // next chunk in flight while this one is used
-    }
+  for (int buf = 0; have; buf ^= 1) {
+    const bool more = group < ngroups;            // the stream position after the current chunk
+    if (more) { load(); advance(); }              // next chunk in flight while this one is used
     const T *pa = sA + buf * KC * KRED_ROW + mi, *pb = sB + buf * KC * KRED_ROW + ni;
     for (int k = kg; k < KC; k += 16) {
       T a[4], b[4];
@@ -480,10 +493,10 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
     }
     if (more) stash(buf ^ 1);
     __syncthreads();
+    have = more;
   }
   // sum the 16 k-groups: red[kg][m * 16 + n] aliases the chunk buffers
   T *red = reinterpret_cast<T *>(smem_raw);
-  __syncthreads();
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -530,7 +543,7 @@ int launch_kred(const qtn_pair_plan_t &P, const void *a, const void *b, void *c,
   static bool attr_set = false;
   if (!attr_set) {
     QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_kred_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        16 * 256 * (int)sizeof(T)));
+                                        72 * 1024));
     attr_set = true;
   }
   gett_kred_kernel<R><<<(unsigned)P.grid, 256, P.smem_bytes, st>>>(P, (const T *)a, (const T *)b, (T *)ws,

@@ -136,7 +136,7 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
   } else if (bbits == 0 && mbits <= 4 && nbits <= 4 && kbits >= 10) {
     // ---- streaming K reduction (<= 16 x 16 outputs) ----------------------------
     p->kernel = QTN_KERNEL_KRED;
-    const int tkb = std::min(kbits, 6);
+    const int tkb = std::min(kbits, d->dtype == QTN_C64 ? 7 : 6);   // chunk: 128 / 64 contracted values
     p->tmb = 4; p->tnb = 4; p->tkb = tkb;
     p->m_real = mbits; p->n_real = nbits; p->k_real = tkb;
     std::sort(M.begin(), M.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
@@ -160,32 +160,36 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     for (int i = 0; i < nbits; ++i) { p->b_nhi[i] = N[i].pb; p->c_nhi[i] = N[i].pc; }
     p->n_mhi = 0; p->n_nhi = 0; p->n_khi = (int)khi.size();
     for (int i = 0; i < p->n_khi; ++i) { p->a_khi[i] = khi[i].pa; p->b_khi[i] = khi[i].pb; }
-    // shared-memory chunk: element (k, row) at k * 16 + row; enumerations in address order
+    // shared-memory chunk: element (k, row) at k * 17 + row (padded rows: conflict-free stores
+    // when a warp's lanes walk k); enumerations in address order
     struct E { int pos; int sstr; };
     std::vector<E> ea, eb;
     for (int i = 0; i < mbits; ++i) ea.push_back({M[i].pa, 1 << i});
-    for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, 16 << i});
+    for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, 17 << i});
     for (int i = 0; i < nbits; ++i) eb.push_back({N[i].pb, 1 << i});
-    for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, 16 << i});
+    for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, 17 << i});
     auto by_pos = [](const E &x, const E &y) { return x.pos < y.pos; };
     std::sort(ea.begin(), ea.end(), by_pos);
     std::sort(eb.begin(), eb.end(), by_pos);
     p->na_lo = (int)ea.size(); p->nb_lo = (int)eb.size();
     for (int i = 0; i < p->na_lo; ++i) { p->a_lo_pos[i] = (uint8_t)ea[i].pos; p->a_lo_sstr[i] = (uint16_t)ea[i].sstr; }
     for (int i = 0; i < p->nb_lo; ++i) { p->b_lo_pos[i] = (uint8_t)eb[i].pos; p->b_lo_sstr[i] = (uint16_t)eb[i].sstr; }
-    // three resident CTAs per SM stride over the chunks together (chunk = blockIdx.x + i * grid);
+    // two resident CTAs per SM stride over groups of chunks together (group = blockIdx.x + i * grid);
     // every CTA leaves one partial C in the workspace
-    const int64_t nchunks = (int64_t)1 << p->n_khi;
+    const int64_t ngroups = (int64_t)1 << std::max(0, p->n_khi - 3);   // groups of 8 chunks
     p->split_bits = 0;
-    p->grid = std::min<int64_t>(nchunks, (int64_t)3 * sm_count);
+    p->grid = std::min<int64_t>(ngroups, (int64_t)2 * sm_count);
     p->workspace_bytes = ((int64_t)esz << d->rank_c) * p->grid;
-    p->smem_bytes = 16 * 256 * esz;                 // max(2 x 2 chunk buffers, 16 x 256 partials)
+    // max(2 buffers x (A + B) chunk, 16 x 256 partials)
+    p->smem_bytes = std::max(2 * 2 * (1 << tkb) * 17 * esz, 16 * 256 * esz);
   } else if (d->dtype == QTN_C64 && d->c_layout_free && bbits == 0 && mbits >= 7 && nbits >= 4 &&
              kbits >= 3 && mbits + nbits + kbits >= qtn_option_tc_min_log2() && qtn_option_tc_enable()) {
     // ---- tensor-core kernel (gett_tc.cu) ----------------------------------------
     // Tile = 128 rows of A x 2^tnb rows of B, 2^tkb contracted values per pipeline stage.
     p->kernel = QTN_KERNEL_TC;
-    const int tmb = 7, tnb = std::min(nbits, 8), tkb = std::min(kbits, 4);
+    // separate accumulators for the cross terms need 4 TMEM regions per tile: 128 columns at most
+    const int sep = qtn_option_tc_accum_split() && qtn_option_tc_persistent();
+    const int tmb = 7, tnb = std::min(nbits, sep ? 7 : 8), tkb = std::min(kbits, 4);
     const int KT = 1 << tkb, TN = 1 << tnb;
     p->tmb = tmb; p->tnb = tnb; p->tkb = tkb;
     p->block = 288;
@@ -294,6 +298,7 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     int stages = std::max(1, std::min(4, budget / stage_bytes));
     if ((int64_t)stages > k_iters) stages = (int)k_iters;
     p->tc_terms = qtn_option_tc_terms();
+    p->tc_pad = sep;
     p->tc_reserved = 0;
     if (qtn_option_tc_persistent()) {
       // persistent kernel: one CTA per SM streams over tiles, so the pipeline may be deeper than

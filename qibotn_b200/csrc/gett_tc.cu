@@ -404,7 +404,7 @@ gett_tc_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restri
 constexpr int kThreadsP = 416;
 constexpr int kEpilogueThreads = 128;
 
-template <int TNB, int TKB>
+template <int TNB, int TKB, bool SEP>
 __global__ void __launch_bounds__(kThreadsP, 1)
 gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ A,
                           const float2 *__restrict__ B, float2 *__restrict__ C,
@@ -414,8 +414,14 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
   constexpr int STAGE = 4 * (PLANE_A + PLANE_B);
   constexpr int NA = PLANE_A / kProducerThreads;
   constexpr int NB = (PLANE_B + kProducerThreads - 1) / kProducerThreads;
-  constexpr int NBUF = 4 * TN <= 512 ? 2 : 1;
-  constexpr int TMEM_COLS = NBUF * 2 * TN < 32 ? 32 : NBUF * 2 * TN;
+  // SEP: the hi*hi products and the small cross terms accumulate in SEPARATE TMEM regions and are
+  // added in the epilogue.  The tensor core truncates (does not round) at every accumulation, a
+  // bias proportional to the number of MMAs that hit the accumulator holding the large sum: 2 per
+  // k step this way instead of 6 (measured on the full C4 amplitude: see DESIGN.md section 3.1).
+  constexpr int ACC = SEP ? 4 : 2;                   // TMEM regions of TN columns per buffer
+  static_assert(ACC * TN <= 512, "accumulators do not fit in TMEM");
+  constexpr int NBUF = 2 * ACC * TN <= 512 ? 2 : 1;
+  constexpr int TMEM_COLS = NBUF * ACC * TN < 32 ? 32 : NBUF * ACC * TN;
   constexpr uint32_t LBO = 128, SBO = KT * 32;
   constexpr uint32_t IDESC = umma_idesc_tf32(TN, 0), IDESC_NEG = umma_idesc_tf32(TN, 1);
 
@@ -562,16 +568,27 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
       float2 *out = (P.split_bits ? ws + (long long)split * P.c_elems : C) + c_base + row_off;
       mbar_wait(tfull_bar(buf), tph);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * TN);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC * TN);
 #pragma unroll 1
       for (int c0 = 0; c0 < TN; c0 += CH) {
         uint32_t re[CH], im[CH];
         tmem_ld<CH>::run(trow + (uint32_t)c0, re);
         tmem_ld<CH>::run(trow + (uint32_t)(TN + c0), im);
-        tmem_ld_wait();
+        if constexpr (SEP) {
+          uint32_t xr[CH], xi[CH];
+          tmem_ld<CH>::run(trow + (uint32_t)(2 * TN + c0), xr);
+          tmem_ld<CH>::run(trow + (uint32_t)(3 * TN + c0), xi);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < CH; ++j)
-          out[(long long)(c0 + j) << 5] = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+          for (int j = 0; j < CH; ++j)
+            out[(long long)(c0 + j) << 5] = make_float2(__uint_as_float(re[j]) + __uint_as_float(xr[j]),
+                                                        __uint_as_float(im[j]) + __uint_as_float(xi[j]));
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            out[(long long)(c0 + j) << 5] = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+        }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));                 // accumulator buffer may be overwritten
@@ -586,7 +603,8 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
       const uint32_t tph = (uint32_t)((it / NBUF) & 1);
       mbar_wait(tempty_bar(buf), tph ^ 1u);         // epilogue has drained this buffer
       tc_fence_after();
-      const uint32_t cr = tmem_base + (uint32_t)(buf * 2 * TN), ci = cr + TN;
+      const uint32_t cr = tmem_base + (uint32_t)(buf * ACC * TN), ci = cr + TN;
+      const uint32_t xr = SEP ? cr + 2 * TN : cr, xi = SEP ? cr + 3 * TN : ci;   // cross-term targets
       for (unsigned long long kk = 0; kk < k_iters; ++kk) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
@@ -604,23 +622,26 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
           const uint64_t bih = umma_desc(sb + 8u * PLANE_B + ko, LBO, SBO);
           const uint64_t bil = umma_desc(sb + 12u * PLANE_B + ko, LBO, SBO);
           const uint32_t acc = (kk | (unsigned)ks) ? 1u : 0u;
-          umma_tf32(cr, arl, brh, IDESC, acc);
-          umma_tf32(cr, arh, brl, IDESC, 1u);
-          umma_tf32(cr, ail, bih, IDESC_NEG, 1u);
-          umma_tf32(cr, aih, bil, IDESC_NEG, 1u);
-          umma_tf32(cr, arh, brh, IDESC, 1u);
+          const uint32_t accx = SEP ? acc : 1u;      // SEP: the cross region starts from zero too
+          if constexpr (!SEP) umma_tf32(cr, arh, brh, IDESC, acc);      // hi*hi first, then the rest
+          umma_tf32(xr, arl, brh, IDESC, accx);
+          umma_tf32(xr, arh, brl, IDESC, 1u);
+          umma_tf32(xr, ail, bih, IDESC_NEG, 1u);
+          umma_tf32(xr, aih, bil, IDESC_NEG, 1u);
+          if constexpr (SEP) umma_tf32(cr, arh, brh, IDESC, acc);
           umma_tf32(cr, aih, bih, IDESC_NEG, 1u);
-          umma_tf32(ci, arl, bih, IDESC, acc);
-          umma_tf32(ci, arh, bil, IDESC, 1u);
-          umma_tf32(ci, ail, brh, IDESC, 1u);
-          umma_tf32(ci, aih, brl, IDESC, 1u);
-          umma_tf32(ci, arh, bih, IDESC, 1u);
+          if constexpr (!SEP) umma_tf32(ci, arh, bih, IDESC, acc);
+          umma_tf32(xi, arl, bih, IDESC, accx);
+          umma_tf32(xi, arh, bil, IDESC, 1u);
+          umma_tf32(xi, ail, brh, IDESC, 1u);
+          umma_tf32(xi, aih, brl, IDESC, 1u);
+          if constexpr (SEP) umma_tf32(ci, arh, bih, IDESC, acc);
           umma_tf32(ci, aih, brh, IDESC, 1u);
           if (P.tc_terms >= 4) {                   // lo*lo as well
-            umma_tf32(cr, arl, brl, IDESC, 1u);
-            umma_tf32(cr, ail, bil, IDESC_NEG, 1u);
-            umma_tf32(ci, arl, bil, IDESC, 1u);
-            umma_tf32(ci, ail, brl, IDESC, 1u);
+            umma_tf32(xr, arl, brl, IDESC, 1u);
+            umma_tf32(xr, ail, bil, IDESC_NEG, 1u);
+            umma_tf32(xi, arl, bil, IDESC, 1u);
+            umma_tf32(xi, ail, brl, IDESC, 1u);
           }
         }
         umma_commit(empty_bar(s));
@@ -643,14 +664,30 @@ template <int TNB, int TKB>
 int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
                    const int32_t *slice_id, cudaStream_t st) {
   if (P.tc_reserved > 0) {                      // persistent variant: tc_reserved = CTAs to launch
+    const long long ctas = P.grid < P.tc_reserved ? P.grid : P.tc_reserved;
+    if (P.tc_pad) {                               // separate cross-term accumulators (TN <= 128)
+      if constexpr (TNB <= 7) {
+        static int smem_set_s = 0;
+        if (smem_set_s < P.smem_bytes) {
+          QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tc_persistent_kernel<TNB, TKB, true>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+          smem_set_s = P.smem_bytes;
+        }
+        gett_tc_persistent_kernel<TNB, TKB, true><<<(unsigned)ctas, kThreadsP, P.smem_bytes, st>>>(
+            P, (const float2 *)a, (const float2 *)b, (float2 *)c, (float2 *)ws, slice_id);
+        QTN_LAUNCH_CHECK();
+        return QTN_OK;
+      } else {
+        return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: split accumulators need a tile of at most 128 columns");
+      }
+    }
     static int smem_set_p = 0;
     if (smem_set_p < P.smem_bytes) {
-      QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tc_persistent_kernel<TNB, TKB>,
+      QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tc_persistent_kernel<TNB, TKB, false>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
       smem_set_p = P.smem_bytes;
     }
-    const long long ctas = P.grid < P.tc_reserved ? P.grid : P.tc_reserved;
-    gett_tc_persistent_kernel<TNB, TKB><<<(unsigned)ctas, kThreadsP, P.smem_bytes, st>>>(
+    gett_tc_persistent_kernel<TNB, TKB, false><<<(unsigned)ctas, kThreadsP, P.smem_bytes, st>>>(
         P, (const float2 *)a, (const float2 *)b, (float2 *)c, (float2 *)ws, slice_id);
     QTN_LAUNCH_CHECK();
     return QTN_OK;

@@ -23,6 +23,7 @@ ap.add_argument("--max-slices", type=int, default=0)
 ap.add_argument("--dtype", default=None, help="override the workload dtype (complex64 | complex128)")
 ap.add_argument("--no-tc", action="store_true", help="FFMA/DFMA kernels only")
 ap.add_argument("--tc-terms", type=int, default=3)
+ap.add_argument("--accum-split", type=int, default=1)
 a = ap.parse_args()
 wl = workloads.build(a.workload)
 if a.dtype:
@@ -31,11 +32,12 @@ from qibotn_b200 import lib  # noqa: E402
 if a.no_tc:
     lib.set_option("tc_enable", 0)
 lib.set_option("tc_terms", a.tc_terms)
+lib.set_option("tc_accum_split", a.accum_split)
 net = wl.network()
 for name in a.plan:
     info = plans.load_plan(name, net.modes, net.out)
     if info is None:
-        print(json.dumps({"plan": name, "dtype": wl.dtype, "tensor_cores": not a.no_tc, "tc_terms": a.tc_terms, "error": "missing or made for another network"}), flush=True)
+        print(json.dumps({"plan": name, "dtype": wl.dtype, "tensor_cores": not a.no_tc, "tc_terms": a.tc_terms, "accum_split": a.accum_split, "error": "missing or made for another network"}), flush=True)
         continue
     low = executor.lower(net.modes, net.out, info, wl.dtype)
     runner = executor.ContractionRunner(low, use_graph=True)
@@ -49,7 +51,7 @@ for name in a.plan:
     dt = time.perf_counter() - t0
     amp = complex(out.reshape(-1)[0].item())
     flops = low.flops_hoisted + ns * low.flops_per_slice
-    print(json.dumps({"plan": name, "dtype": wl.dtype, "tensor_cores": not a.no_tc, "tc_terms": a.tc_terms, "log10_flops": math.log10(info.flops), "num_slices": info.num_slices,
+    print(json.dumps({"plan": name, "dtype": wl.dtype, "tensor_cores": not a.no_tc, "tc_terms": a.tc_terms, "accum_split": a.accum_split, "log10_flops": math.log10(info.flops), "num_slices": info.num_slices,
                       "slices_run": ns, "log2_width": info.log2_width, "seconds": dt, "tflops": flops / dt / 1e12,
                       "amplitude": [amp.real, amp.imag], "slice_arena_gb": low.slice_bytes / 2**30,
                       "launches_per_slice": low.launches_per_slice}), flush=True)
