@@ -372,8 +372,9 @@ reduce_final_kernel(const __grid_constant__ qtn_pair_plan_t P, cx<R> *__restrict
 // C (256 values) to the workspace; qtn_launch_splitk_sum adds the partials.
 // HBM-bound by design: 16 KiB of operands per 64K real FMAs.
 // --------------------------------------------------------------------------
-constexpr int KRED_ROW = 17;        // row stride (elements) of the A / B chunk in shared memory: 16 rows + 1
-                                    // pad, so that lanes walking k hit different banks when they store
+constexpr int KRED_ROW = 18;        // row stride (elements) of the A / B chunk in shared memory: 16 rows + 2
+                                    // pad: lanes walking k spread over the banks when they store, and rows
+                                    // stay 16-byte aligned for 128-bit loads
 
 template <typename R>
 __global__ void __launch_bounds__(256, 2)
@@ -482,10 +483,21 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
     const T *pa = sA + buf * KC * KRED_ROW + mi, *pb = sB + buf * KC * KRED_ROW + ni;
     for (int k = kg; k < KC; k += 16) {
       T a[4], b[4];
+      if constexpr (sizeof(R) == 4) {           // two complex64 per 128-bit shared-memory load
+        const float4 *qa = reinterpret_cast<const float4 *>(pa + k * KRED_ROW);
+        const float4 *qb = reinterpret_cast<const float4 *>(pb + k * KRED_ROW);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = pa[k * KRED_ROW + i];
+        for (int i = 0; i < 2; ++i) {
+          const float4 u = qa[i], v = qb[i];
+          a[2 * i].x = u.x; a[2 * i].y = u.y; a[2 * i + 1].x = u.z; a[2 * i + 1].y = u.w;
+          b[2 * i].x = v.x; b[2 * i].y = v.y; b[2 * i + 1].x = v.z; b[2 * i + 1].y = v.w;
+        }
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = pb[k * KRED_ROW + j];
+        for (int i = 0; i < 4; ++i) a[i] = pa[k * KRED_ROW + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = pb[k * KRED_ROW + j];
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -543,7 +555,7 @@ int launch_kred(const qtn_pair_plan_t &P, const void *a, const void *b, void *c,
   static bool attr_set = false;
   if (!attr_set) {
     QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_kred_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        72 * 1024));
+                                        80 * 1024));
     attr_set = true;
   }
   gett_kred_kernel<R><<<(unsigned)P.grid, 256, P.smem_bytes, st>>>(P, (const T *)a, (const T *)b, (T *)ws,

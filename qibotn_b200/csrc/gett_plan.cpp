@@ -160,14 +160,14 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     for (int i = 0; i < nbits; ++i) { p->b_nhi[i] = N[i].pb; p->c_nhi[i] = N[i].pc; }
     p->n_mhi = 0; p->n_nhi = 0; p->n_khi = (int)khi.size();
     for (int i = 0; i < p->n_khi; ++i) { p->a_khi[i] = khi[i].pa; p->b_khi[i] = khi[i].pb; }
-    // shared-memory chunk: element (k, row) at k * 17 + row (padded rows: conflict-free stores
+    // shared-memory chunk: element (k, row) at k * 18 + row (padded rows: conflict-free stores
     // when a warp's lanes walk k); enumerations in address order
     struct E { int pos; int sstr; };
     std::vector<E> ea, eb;
     for (int i = 0; i < mbits; ++i) ea.push_back({M[i].pa, 1 << i});
-    for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, 17 << i});
+    for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, 18 << i});
     for (int i = 0; i < nbits; ++i) eb.push_back({N[i].pb, 1 << i});
-    for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, 17 << i});
+    for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, 18 << i});
     auto by_pos = [](const E &x, const E &y) { return x.pos < y.pos; };
     std::sort(ea.begin(), ea.end(), by_pos);
     std::sort(eb.begin(), eb.end(), by_pos);
@@ -181,7 +181,7 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     p->grid = std::min<int64_t>(ngroups, (int64_t)2 * sm_count);
     p->workspace_bytes = ((int64_t)esz << d->rank_c) * p->grid;
     // max(2 buffers x (A + B) chunk, 16 x 256 partials)
-    p->smem_bytes = std::max(2 * 2 * (1 << tkb) * 17 * esz, 16 * 256 * esz);
+    p->smem_bytes = std::max(2 * 2 * (1 << tkb) * 18 * esz, 16 * 256 * esz);
   } else if (d->dtype == QTN_C64 && d->c_layout_free && bbits == 0 && mbits >= 7 && nbits >= 4 &&
              kbits >= 3 && mbits + nbits + kbits >= qtn_option_tc_min_log2() && qtn_option_tc_enable()) {
     // ---- tensor-core kernel (gett_tc.cu) ----------------------------------------

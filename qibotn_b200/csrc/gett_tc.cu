@@ -530,7 +530,7 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
     };
     // ring of D register buffers: D-1 chunks of global loads are in flight while one chunk is
     // split and stored; deeper for the small tiles whose nodes are HBM-bound
-    constexpr int D = (NA + NB) <= 12 ? 4 : 2;
+    constexpr int D = (NA + NB) <= 12 ? 4 : ((NA + NB) <= 16 ? 3 : 2);
     float2 va[D][NA], vb[D][NB];
     bool have[D];
 #pragma unroll

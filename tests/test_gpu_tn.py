@@ -232,3 +232,35 @@ def test_c4_full_amplitude_within_tolerance_of_complex128():
     runner.upload(net.tensors)
     got = complex(runner.run(range(info.num_slices)).reshape(-1)[0].item())
     assert abs(got - want) <= 1e-5 * abs(want), (got, want, abs(got - want) / abs(want))
+
+
+def test_c2_full_size_expectation_properties():
+    """BASELINE config 2 at full size (30-qubit brickwork depth 12, <Z...Z>, one closed sandwich
+    network of 1158 tensors): no dense oracle reaches 30 qubits here, so the value is checked through
+    path independence (two planner seeds), precision independence (complex64 vs complex128) and
+    kernel independence (tensor-core vs FFMA).  Tolerance: 1e-5 of max(|value|, 1e-3) -- the
+    expectation of a 30-body Pauli string on a scrambled state is itself tiny."""
+    from qibotn_b200 import lib, workloads
+    wl = workloads.build("c2")
+    vals = {}
+    for dtype in ("complex128", "complex64"):
+        wl.dtype = dtype
+        net = wl.network()
+        for seed in (0, 1):
+            engine.clear_caches()
+            vals[(dtype, seed)] = complex(engine.contract(net, dtype, samples=4, seed=seed).cpu().numpy().reshape(-1)[0])
+    wl.dtype = "complex64"
+    net = wl.network()
+    lib.set_option("tc_enable", 0)
+    try:
+        engine.clear_caches()
+        vals[("complex64", "ffma")] = complex(engine.contract(net, "complex64", samples=4, seed=0).cpu().numpy().reshape(-1)[0])
+    finally:
+        lib.set_option("tc_enable", 1)
+    ref = vals[("complex128", 0)]
+    assert abs(ref.imag) < 1e-9                      # a Hermitian observable
+    scale = max(abs(ref), 1e-3)
+    assert abs(vals[("complex128", 1)] - ref) < 1e-10 * scale
+    for key, v in vals.items():
+        if key[0] == "complex64":
+            assert abs(v - ref) < 1e-5 * scale, (key, v, ref)
