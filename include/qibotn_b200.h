@@ -140,6 +140,11 @@ typedef struct {
   int32_t tc_a_it_s[8], tc_b_it_s[16];
   int32_t tc_terms;              /* 3: hi*hi + hi*lo + lo*hi;  4: + lo*lo ("tc_terms" option) */
   int32_t tc_pad;                /* 1: cross terms accumulate in their own TMEM region ("tc_accum_split") */
+  /* B pre-packing: when many m tiles share each B tile, a small pre-kernel writes B once, already
+   * split and laid out as shared-memory stage images, into the workspace at byte offset
+   * tc_prepack_off; the main kernel then fetches a whole B stage with one cp.async.bulk. */
+  int32_t tc_prepack, tc_pad2;
+  int64_t tc_prepack_off;
 } qtn_pair_plan_t;
 
 /* Library-wide switches (thread-unsafe, meant for tests and A/B measurements):
@@ -148,6 +153,7 @@ typedef struct {
  *   "tc_terms"     3 (default) or 4: products kept by the TF32 split (4 adds lo*lo, +33% MMAs);
  *   "tc_accum_split" 1 (default): hi*hi and the cross terms use separate TMEM accumulators, added in
  *                  the epilogue (3x fewer truncating accumulations on the large sum; tile <= 128 columns);
+ *   "tc_prepack"   1 (default): pre-pack the small operand once per launch (see tc_prepack above);
  *   "tc_persistent" 1 (default): one CTA per SM streams over the tiles with loads, MMAs and
  *                  epilogue of neighbouring tiles overlapped; 0: one CTA per tile.
  * Returns QTN_ERR_ARG for an unknown name. */

@@ -308,6 +308,18 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     }
     p->tc_stages = stages;
     p->smem_bytes = stages * stage_bytes + 256;
+    // pre-pack B when at least 8 m tiles reuse each B tile and the image (2 x |B| bytes) is small
+    p->tc_prepack = 0;
+    p->tc_prepack_off = 0;
+    {
+      const int64_t images = (int64_t)1 << (p->n_nhi + p->n_khi);
+      const int64_t image_bytes = 4 * (int64_t)p->tc_plane_b;
+      if (qtn_option_tc_prepack() && p->tc_reserved > 0 && p->n_mhi >= 3 && images * image_bytes <= ((int64_t)1 << 30)) {
+        p->tc_prepack = 1;
+        p->tc_prepack_off = (p->workspace_bytes + 255) & ~(int64_t)255;
+        p->workspace_bytes = p->tc_prepack_off + images * image_bytes;
+      }
+    }
     p->sa_stride = 0; p->sb_stride = 0;
   } else {
     // ---- shared-memory tiled kernel -----------------------------------------

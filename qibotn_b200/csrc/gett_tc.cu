@@ -60,6 +60,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// one arrival that also announces `bytes` of asynchronous (bulk-copy) traffic on the barrier
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (the TMA engine, no tensor map): completes `bytes` on the barrier
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -445,7 +456,9 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
   const long long b_slice = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
 
   if (t == 32) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), kProducerThreads); mbar_init(empty_bar(s), 1); }
+    // with a pre-packed B one producer thread arrives twice: early with the byte count of the bulk
+    // copy, and with everybody else once its A values are stored
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), kProducerThreads + (P.tc_prepack ? 1 : 0)); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < NBUF; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpilogueThreads); }
     fence_proxy_async_smem();
     fence_mbar_init();
@@ -470,6 +483,10 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
     const float sgn_a = P.conj_a ? -1.f : 1.f, sgn_b = P.conj_b ? -1.f : 1.f;
     unsigned long long tile = blockIdx.x, kk = 0;
     long long a_k = 0, b_k = 0;
+    const bool pre = P.tc_prepack != 0;            // B arrives as ready-made stage images
+    constexpr uint32_t kImageBytes = 16u * PLANE_B;
+    const unsigned char *images = reinterpret_cast<const unsigned char *>(ws) + P.tc_prepack_off;
+    unsigned long long image0 = 0;                 // image index of this tile's first k chunk
     auto enter_tile = [&]() {
       unsigned long long id = tile;
       const unsigned split = (unsigned)(id & ((1ull << P.split_bits) - 1));
@@ -479,6 +496,7 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
       const unsigned long long kh0 = (unsigned long long)split << k_iters_bits;
       a_k = a_slice | deposit(mh, P.a_mhi, P.n_mhi) | deposit(kh0, P.a_khi, P.n_khi);
       b_k = b_slice | deposit(nh, P.b_nhi, P.n_nhi) | deposit(kh0, P.b_khi, P.n_khi);
+      image0 = (nh << P.n_khi) | kh0;
       kk = 0;
     };
     auto advance = [&]() {                        // next k chunk, or the first one of the next tile
@@ -491,19 +509,26 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
       }
       ++kk;
     };
-    auto load = [&](float2(&va)[NA], float2(&vb)[NB]) {
+    auto load = [&](float2(&va)[NA], float2(&vb)[NB], unsigned long long &img) {
 #pragma unroll
       for (int i = 0; i < NA; ++i) va[i] = __ldg(A + (a_k | a_t_g | P.tc_a_it_g[i]));
+      img = image0 + kk;
+      if (!pre) {
 #pragma unroll
-      for (int i = 0; i < NB; ++i)
-        vb[i] = b_act ? __ldg(B + (b_k | b_t_g | P.tc_b_it_g[i])) : make_float2(0.f, 0.f);
+        for (int i = 0; i < NB; ++i)
+          vb[i] = b_act ? __ldg(B + (b_k | b_t_g | P.tc_b_it_g[i])) : make_float2(0.f, 0.f);
+      }
     };
     int s = 0;
     uint32_t ph = 0;
-    auto store = [&](const float2(&va)[NA], const float2(&vb)[NB]) {
+    auto store = [&](const float2(&va)[NA], const float2(&vb)[NB], unsigned long long img) {
       mbar_wait(empty_bar(s), ph ^ 1u);
       float *sA = stages + (size_t)s * STAGE;
       float *sB = sA + 4 * PLANE_A;
+      if (pre && t == 0) {                          // the whole B stage: one bulk copy
+        mbar_arrive_expect_tx(full_bar(s), kImageBytes);
+        bulk_copy_g2s(smem_u32(sB), images + img * kImageBytes, kImageBytes, full_bar(s));
+      }
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
         const int o = a_t_s + P.tc_a_it_s[i];
@@ -513,7 +538,7 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
         split_tf32(va[i].y * sgn_a, h, l);
         sA[2 * PLANE_A + o] = h; sA[3 * PLANE_A + o] = l;
       }
-      if (b_act) {
+      if (b_act && !pre) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
           const int o = b_t_s + P.tc_b_it_s[i];
@@ -530,13 +555,15 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
     };
     // ring of D register buffers: D-1 chunks of global loads are in flight while one chunk is
     // split and stored; deeper for the small tiles whose nodes are HBM-bound
-    constexpr int D = (NA + NB) <= 12 ? 4 : ((NA + NB) <= 16 ? 3 : 2);
+    constexpr int D = (NA + NB) <= 12 ? 4 : 2;
     float2 va[D][NA], vb[D][NB];
+    unsigned long long img[D];
     bool have[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       have[d] = tile < ntiles;
-      if (have[d]) { if (d == 0) enter_tile(); load(va[d], vb[d]); advance(); }
+      img[d] = 0;
+      if (have[d]) { if (d == 0) enter_tile(); load(va[d], vb[d], img[d]); advance(); }
     }
     bool done = false;
     while (!done) {
@@ -544,9 +571,9 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
       for (int d = 0; d < D; ++d) {
         if (done) continue;
         if (!have[d]) { done = true; continue; }
-        store(va[d], vb[d]);
+        store(va[d], vb[d], img[d]);
         have[d] = tile < ntiles;
-        if (have[d]) { load(va[d], vb[d]); advance(); }
+        if (have[d]) { load(va[d], vb[d], img[d]); advance(); }
       }
     }
   } else if (warp < 12) {
@@ -660,11 +687,53 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
   }
 }
 
+
+// B pre-pack: one CTA per (n tile, k chunk) writes that B stage -- split into hi/lo re/im planes
+// and laid out exactly as the main kernel's shared-memory stage -- to the workspace.
+template <int TNB, int TKB>
+__global__ void __launch_bounds__(kProducerThreads)
+tc_prepack_b_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ B,
+                    float *__restrict__ images, const int32_t *__restrict__ slice_id) {
+  constexpr int TN = 1 << TNB, KT = 1 << TKB;
+  constexpr int PLANE_B = TN * KT;
+  constexpr int NB = (PLANE_B + kProducerThreads - 1) / kProducerThreads;
+  const int t = threadIdx.x;
+  const unsigned long long nh = (unsigned long long)blockIdx.x >> P.n_khi;
+  const unsigned long long kh = (unsigned long long)blockIdx.x & ((1ull << P.n_khi) - 1);
+  const long long b_k = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b) |
+                        deposit(nh, P.b_nhi, P.n_nhi) | deposit(kh, P.b_khi, P.n_khi);
+  long long b_t_g = 0;
+  int b_t_s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (((t >> j) & 1) && j < P.nb_lo) { b_t_g |= 1ll << P.b_lo_pos[j]; b_t_s += P.b_lo_sstr[j]; }
+  if (!(P.nb_lo >= 8 || t < (1 << P.nb_lo))) return;
+  const float sgn_b = P.conj_b ? -1.f : 1.f;
+  float *dst = images + (size_t)blockIdx.x * 4 * PLANE_B;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const float2 v = __ldg(B + (b_k | b_t_g | P.tc_b_it_g[i]));
+    const int o = b_t_s + P.tc_b_it_s[i];
+    float h, l;
+    split_tf32(v.x, h, l);
+    dst[o] = h; dst[PLANE_B + o] = l;
+    split_tf32(v.y * sgn_b, h, l);
+    dst[2 * PLANE_B + o] = h; dst[3 * PLANE_B + o] = l;
+  }
+}
+
 template <int TNB, int TKB>
 int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
                    const int32_t *slice_id, cudaStream_t st) {
   if (P.tc_reserved > 0) {                      // persistent variant: tc_reserved = CTAs to launch
     const long long ctas = P.grid < P.tc_reserved ? P.grid : P.tc_reserved;
+    if (P.tc_prepack) {
+      const long long images = 1ll << (P.n_nhi + P.n_khi);
+      if (images > 0x7fffffffLL) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_run: too many B images");
+      tc_prepack_b_kernel<TNB, TKB><<<(unsigned)images, kProducerThreads, 0, st>>>(
+          P, (const float2 *)b, (float *)((unsigned char *)ws + P.tc_prepack_off), slice_id);
+      QTN_LAUNCH_CHECK();
+    }
     if (P.tc_pad) {                               // separate cross-term accumulators (TN <= 128)
       if constexpr (TNB <= 7) {
         static int smem_set_s = 0;

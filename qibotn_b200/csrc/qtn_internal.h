@@ -13,6 +13,7 @@ int qtn_option_tc_min_log2(void);
 int qtn_option_tc_persistent(void);
 int qtn_option_tc_terms(void);
 int qtn_option_tc_accum_split(void);
+int qtn_option_tc_prepack(void);
 #ifdef __cplusplus
 }
 #endif

@@ -78,7 +78,7 @@ def parse_algorithm(algorithm):
 class MPSEngine:
     """Owns the site tensors (torch, on the GPU) and applies gates to them."""
 
-    def __init__(self, num_qubits, dtype="complex128", algorithm=None, tol=None, max_sweeps=30):
+    def __init__(self, num_qubits, dtype="complex128", algorithm=None, tol=None, max_sweeps=60):
         torch = _torch()
         self.torch = torch
         self.lib = lib.load()
@@ -97,7 +97,7 @@ class MPSEngine:
         self._batch = []               # pending two-site updates on disjoint pairs: (i, gate 2x2x2x2)
         self._busy = set()
         self.stats = {"two_site": 0, "one_site": 0, "swaps": 0, "svd_batches": 0, "svd_sweeps": 0,
-                      "max_bond": 1, "launches": 0}
+                      "svd_max_sweeps": 0, "max_bond": 1, "launches": 0}
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -206,6 +206,7 @@ class MPSEngine:
                                         C.byref(sweeps), ws.data_ptr(), ws_bytes, self._stream()))
         self.stats["svd_batches"] += 1
         self.stats["svd_sweeps"] += int(sweeps.value)
+        self.stats["svd_max_sweeps"] = max(self.stats["svd_max_sweeps"], int(sweeps.value))
         esz = 8
         for k, (i, l, r, p, q, theta, w, transposed) in enumerate(work):
             kk = int(ranks[k])

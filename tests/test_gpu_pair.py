@@ -131,3 +131,37 @@ def test_general_permute():
                             torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert np.array_equal(dy.cpu().numpy(), x.transpose(perm))
+
+
+@pytest.mark.parametrize("shape", [(11, 7, 5), (10, 8, 4), (12, 5, 7), (10, 4, 3)])
+def test_tensor_core_variants_agree_with_einsum(shape):
+    """Every switch of the tcgen05 path (persistent or one CTA per tile, pre-packed B or gathered B,
+    split or single accumulators, 3 or 4 split terms) against a complex128 einsum, with a sliced
+    label on B so that the pre-pack kernel sees the slice offset."""
+    m, n, k = shape
+    rng = np.random.default_rng(7 * m + 3 * n + k)
+    labels = list(range(m + n + k))
+    M, N, K = labels[:m], labels[m:m + n], labels[m + n:]
+    la, lb, lc = M + K, K + N, M + N
+    rng.shuffle(la); rng.shuffle(lb)
+    pa = [int(x) for x in rng.permutation(len(la))]
+    pb_all = [int(x) for x in rng.permutation(len(lb) + 1)]
+    pb, sb = pb_all[:-1], [(0, pb_all[-1])]
+    a = (rng.normal(size=1 << len(la)) + 1j * rng.normal(size=1 << len(la))).astype(np.complex64)
+    b = (rng.normal(size=1 << (len(lb) + 1)) + 1j * rng.normal(size=1 << (len(lb) + 1))).astype(np.complex64)
+    A = _dense(a.astype(np.complex128), la, pa)
+    B = _dense(b.astype(np.complex128), lb, pb, off=1 << pb_all[-1])          # slice id 1
+    variants = [dict(), dict(tc_persistent=0), dict(tc_prepack=0), dict(tc_accum_split=0),
+                dict(tc_terms=4), dict(tc_prepack=0, tc_accum_split=0)]
+    defaults = dict(tc_persistent=1, tc_prepack=1, tc_accum_split=1, tc_terms=3, tc_min_log2=18)
+    for opts in variants:
+        try:
+            for key, val in dict(opts, tc_min_log2=0).items():
+                lib.set_option(key, val)
+            got, lc_used, plan = run_pair("complex64", la, pa, lb, pb, lc, None, a, b, slice_b=sb, slice_id=1)
+        finally:
+            for key, val in defaults.items():
+                lib.set_option(key, val)
+        assert plan.kernel == lib.KERNEL_TC
+        want = np.einsum(A, la, B, lb, lc_used)
+        assert np.abs(got - want).max() / np.abs(want).max() < 4e-6 * max(1, k), (shape, opts)
