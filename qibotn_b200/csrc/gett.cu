@@ -387,46 +387,31 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   const int KC = 1 << P.tkb;
   T *sA = reinterpret_cast<T *>(smem_raw);                   // [2][KC][16]
   T *sB = sA + 2 * KC * KRED_ROW;                            // [2][KC][16]
-  __shared__ long long a_it_g[NIT], b_it_g[NIT];
-  __shared__ int a_it_s[NIT], b_it_s[NIT];
   const int t = threadIdx.x;
   const long long a_base = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
   const long long b_base = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
-  // enumeration: element index e = t + 256 * it; bits 0-7 from the thread, bits 8.. from `it`
-  if (t < NIT) {
-    long long g = 0; int s = 0;
-    for (int j = 8; j < P.na_lo; ++j)
-      if ((t >> (j - 8)) & 1) {
-        if (P.a_lo_pos[j] == 255) g = -1; else if (g >= 0) g |= 1ll << P.a_lo_pos[j];
-        s += P.a_lo_sstr[j];
-      }
-    a_it_g[t] = g; a_it_s[t] = s;
-    g = 0; s = 0;
-    for (int j = 8; j < P.nb_lo; ++j)
-      if ((t >> (j - 8)) & 1) {
-        if (P.b_lo_pos[j] == 255) g = -1; else if (g >= 0) g |= 1ll << P.b_lo_pos[j];
-        s += P.b_lo_sstr[j];
-      }
-    b_it_g[t] = g; b_it_s[t] = s;
-  }
+  // enumeration: element index e = t + 256 * u.  Bits 0-7 come from the thread (a_t_*), bits 8-10
+  // from u: their global / shared strides are three per-operand constants, so the offset of
+  // iteration u is a sum of at most three registers (u is a compile-time constant below).
   long long a_t_g = 0, b_t_g = 0;
   int a_t_s = 0, b_t_s = 0;
   for (int j = 0; j < 8; ++j) {
     if (!((t >> j) & 1)) continue;
-    if (j < P.na_lo) {
-      if (P.a_lo_pos[j] == 255) a_t_g = -1; else if (a_t_g >= 0) a_t_g |= 1ll << P.a_lo_pos[j];
-      a_t_s += P.a_lo_sstr[j];
-    }
-    if (j < P.nb_lo) {
-      if (P.b_lo_pos[j] == 255) b_t_g = -1; else if (b_t_g >= 0) b_t_g |= 1ll << P.b_lo_pos[j];
-      b_t_s += P.b_lo_sstr[j];
-    }
+    if (j < P.na_lo) { a_t_g |= 1ll << P.a_lo_pos[j]; a_t_s += P.a_lo_sstr[j]; }
+    if (j < P.nb_lo) { b_t_g |= 1ll << P.b_lo_pos[j]; b_t_s += P.b_lo_sstr[j]; }
+  }
+  long long ag[3], bg[3];
+  int as_[3], bs_[3];
+  for (int j = 0; j < 3; ++j) {
+    ag[j] = 8 + j < P.na_lo ? 1ll << P.a_lo_pos[8 + j] : 0;
+    as_[j] = 8 + j < P.na_lo ? P.a_lo_sstr[8 + j] : 0;
+    bg[j] = 8 + j < P.nb_lo ? 1ll << P.b_lo_pos[8 + j] : 0;
+    bs_[j] = 8 + j < P.nb_lo ? P.b_lo_sstr[8 + j] : 0;
   }
   const bool a_act = P.na_lo >= 8 || t < (1 << P.na_lo);
   const bool b_act = P.nb_lo >= 8 || t < (1 << P.nb_lo);
   const int a_nit = P.na_lo > 8 ? 1 << (P.na_lo - 8) : 1;     // <= NIT
   const int b_nit = P.nb_lo > 8 ? 1 << (P.nb_lo - 8) : 1;
-  __syncthreads();
 
   // The CTA walks GROUPS of 2^IB consecutive chunks: group g = blockIdx.x, + gridDim.x, ... so that
   // CTAs in flight stay on neighbouring addresses; inside a group the chunk offset advances by
@@ -459,19 +444,26 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
 
   T va[NIT], vb[NIT];
   auto load = [&]() {
+    const T *pa_g = A + (a_k | a_t_g), *pb_g = B + (b_k | b_t_g);
 #pragma unroll
     for (int u = 0; u < NIT; ++u) {
       va[u] = cx_zero<R>(); vb[u] = cx_zero<R>();
-      if (a_act && u < a_nit) { const long long g = a_it_g[u]; if (a_t_g >= 0 && g >= 0) va[u] = A[a_k | a_t_g | g]; }
-      if (b_act && u < b_nit) { const long long g = b_it_g[u]; if (b_t_g >= 0 && g >= 0) vb[u] = B[b_k | b_t_g | g]; }
+      if (a_act && u < a_nit) va[u] = pa_g[((u & 1) ? ag[0] : 0) + ((u & 2) ? ag[1] : 0) + ((u & 4) ? ag[2] : 0)];
+      if (b_act && u < b_nit) vb[u] = pb_g[((u & 1) ? bg[0] : 0) + ((u & 2) ? bg[1] : 0) + ((u & 4) ? bg[2] : 0)];
     }
   };
   auto stash = [&](int buf) {
-    T *da = sA + buf * KC * KRED_ROW, *db = sB + buf * KC * KRED_ROW;
+    T *da = sA + buf * KC * KRED_ROW + a_t_s, *db = sB + buf * KC * KRED_ROW + b_t_s;
 #pragma unroll
     for (int u = 0; u < NIT; ++u) {
-      if (a_act && u < a_nit) { T v = va[u]; if (P.conj_a) v.y = -v.y; da[a_t_s + a_it_s[u]] = v; }
-      if (b_act && u < b_nit) { T v = vb[u]; if (P.conj_b) v.y = -v.y; db[b_t_s + b_it_s[u]] = v; }
+      if (a_act && u < a_nit) {
+        T v = va[u]; if (P.conj_a) v.y = -v.y;
+        da[((u & 1) ? as_[0] : 0) + ((u & 2) ? as_[1] : 0) + ((u & 4) ? as_[2] : 0)] = v;
+      }
+      if (b_act && u < b_nit) {
+        T v = vb[u]; if (P.conj_b) v.y = -v.y;
+        db[((u & 1) ? bs_[0] : 0) + ((u & 2) ? bs_[1] : 0) + ((u & 4) ? bs_[2] : 0)] = v;
+      }
     }
   };
   bool have = group < ngroups;

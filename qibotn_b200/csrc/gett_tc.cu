@@ -415,7 +415,7 @@ gett_tc_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restri
 constexpr int kThreadsP = 416;
 constexpr int kEpilogueThreads = 128;
 
-template <int TNB, int TKB, bool SEP>
+template <int TNB, int TKB, bool SEP, bool PRE>
 __global__ void __launch_bounds__(kThreadsP, 1)
 gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ A,
                           const float2 *__restrict__ B, float2 *__restrict__ C,
@@ -458,7 +458,7 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
   if (t == 32) {
     // with a pre-packed B one producer thread arrives twice: early with the byte count of the bulk
     // copy, and with everybody else once its A values are stored
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), kProducerThreads + (P.tc_prepack ? 1 : 0)); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), kProducerThreads + (PRE ? 1 : 0)); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < NBUF; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpilogueThreads); }
     fence_proxy_async_smem();
     fence_mbar_init();
@@ -483,7 +483,7 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
     const float sgn_a = P.conj_a ? -1.f : 1.f, sgn_b = P.conj_b ? -1.f : 1.f;
     unsigned long long tile = blockIdx.x, kk = 0;
     long long a_k = 0, b_k = 0;
-    const bool pre = P.tc_prepack != 0;            // B arrives as ready-made stage images
+    constexpr bool pre = PRE;                      // B arrives as ready-made stage images
     constexpr uint32_t kImageBytes = 16u * PLANE_B;
     const unsigned char *images = reinterpret_cast<const unsigned char *>(ws) + P.tc_prepack_off;
     unsigned long long image0 = 0;                 // image index of this tile's first k chunk
@@ -509,11 +509,12 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
       }
       ++kk;
     };
-    auto load = [&](float2(&va)[NA], float2(&vb)[NB], unsigned long long &img) {
+    constexpr int NBR = PRE ? 1 : NB;              // B registers (none needed when pre-packed)
+    auto load = [&](float2(&va)[NA], float2(&vb)[NBR], unsigned long long &img) {
 #pragma unroll
       for (int i = 0; i < NA; ++i) va[i] = __ldg(A + (a_k | a_t_g | P.tc_a_it_g[i]));
       img = image0 + kk;
-      if (!pre) {
+      if constexpr (!pre) {
 #pragma unroll
         for (int i = 0; i < NB; ++i)
           vb[i] = b_act ? __ldg(B + (b_k | b_t_g | P.tc_b_it_g[i])) : make_float2(0.f, 0.f);
@@ -521,7 +522,7 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
     };
     int s = 0;
     uint32_t ph = 0;
-    auto store = [&](const float2(&va)[NA], const float2(&vb)[NB], unsigned long long img) {
+    auto store = [&](const float2(&va)[NA], const float2(&vb)[NBR], unsigned long long img) {
       mbar_wait(empty_bar(s), ph ^ 1u);
       float *sA = stages + (size_t)s * STAGE;
       float *sB = sA + 4 * PLANE_A;
@@ -538,15 +539,17 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
         split_tf32(va[i].y * sgn_a, h, l);
         sA[2 * PLANE_A + o] = h; sA[3 * PLANE_A + o] = l;
       }
-      if (b_act && !pre) {
+      if constexpr (!pre) {
+        if (b_act) {
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-          const int o = b_t_s + P.tc_b_it_s[i];
-          float h, l;
-          split_tf32(vb[i].x, h, l);
-          sB[o] = h; sB[PLANE_B + o] = l;
-          split_tf32(vb[i].y * sgn_b, h, l);
-          sB[2 * PLANE_B + o] = h; sB[3 * PLANE_B + o] = l;
+          for (int i = 0; i < NB; ++i) {
+            const int o = b_t_s + P.tc_b_it_s[i];
+            float h, l;
+            split_tf32(vb[i].x, h, l);
+            sB[o] = h; sB[PLANE_B + o] = l;
+            split_tf32(vb[i].y * sgn_b, h, l);
+            sB[2 * PLANE_B + o] = h; sB[3 * PLANE_B + o] = l;
+          }
         }
       }
       fence_proxy_async_smem();
@@ -555,8 +558,8 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
     };
     // ring of D register buffers: D-1 chunks of global loads are in flight while one chunk is
     // split and stored; deeper for the small tiles whose nodes are HBM-bound
-    constexpr int D = (NA + NB) <= 12 ? 4 : 2;
-    float2 va[D][NA], vb[D][NB];
+    constexpr int D = (NA + (PRE ? 0 : NB)) <= 12 ? 4 : 2;
+    float2 va[D][NA], vb[D][NBR];
     unsigned long long img[D];
     bool have[D];
 #pragma unroll
@@ -734,32 +737,27 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
           P, (const float2 *)b, (float *)((unsigned char *)ws + P.tc_prepack_off), slice_id);
       QTN_LAUNCH_CHECK();
     }
+    auto go = [&](auto kernel, int &smem_set) -> int {
+      if (smem_set < P.smem_bytes) {
+        QTN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+        smem_set = P.smem_bytes;
+      }
+      kernel<<<(unsigned)ctas, kThreadsP, P.smem_bytes, st>>>(P, (const float2 *)a, (const float2 *)b, (float2 *)c,
+                                                             (float2 *)ws, slice_id);
+      QTN_LAUNCH_CHECK();
+      return QTN_OK;
+    };
+    static int set_sp = 0, set_s = 0, set_p = 0, set_0 = 0;
     if (P.tc_pad) {                               // separate cross-term accumulators (TN <= 128)
       if constexpr (TNB <= 7) {
-        static int smem_set_s = 0;
-        if (smem_set_s < P.smem_bytes) {
-          QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tc_persistent_kernel<TNB, TKB, true>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-          smem_set_s = P.smem_bytes;
-        }
-        gett_tc_persistent_kernel<TNB, TKB, true><<<(unsigned)ctas, kThreadsP, P.smem_bytes, st>>>(
-            P, (const float2 *)a, (const float2 *)b, (float2 *)c, (float2 *)ws, slice_id);
-        QTN_LAUNCH_CHECK();
-        return QTN_OK;
+        return P.tc_prepack ? go(gett_tc_persistent_kernel<TNB, TKB, true, true>, set_sp)
+                            : go(gett_tc_persistent_kernel<TNB, TKB, true, false>, set_s);
       } else {
         return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: split accumulators need a tile of at most 128 columns");
       }
     }
-    static int smem_set_p = 0;
-    if (smem_set_p < P.smem_bytes) {
-      QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tc_persistent_kernel<TNB, TKB, false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-      smem_set_p = P.smem_bytes;
-    }
-    gett_tc_persistent_kernel<TNB, TKB, false><<<(unsigned)ctas, kThreadsP, P.smem_bytes, st>>>(
-        P, (const float2 *)a, (const float2 *)b, (float2 *)c, (float2 *)ws, slice_id);
-    QTN_LAUNCH_CHECK();
-    return QTN_OK;
+    return P.tc_prepack ? go(gett_tc_persistent_kernel<TNB, TKB, false, true>, set_p)
+                        : go(gett_tc_persistent_kernel<TNB, TKB, false, false>, set_0);
   }
   static int smem_set = 0;
   if (smem_set < P.smem_bytes) {
