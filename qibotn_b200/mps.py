@@ -201,9 +201,13 @@ class MPSEngine:
         ranks = (C.c_int32 * nb)()
         scales = (C.c_double * nb)()
         sweeps = C.c_int32(0)
+        import time as _time
+        torch.cuda.synchronize()
+        t_svd = _time.perf_counter()
         lib.check(self.lib.qtn_svd_rows(self.code, nb, items, self.tol, self.max_sweeps, C.byref(self.trunc),
                                         sigma.data_ptr(), perm.data_ptr(), ld, ranks, scales,
                                         C.byref(sweeps), ws.data_ptr(), ws_bytes, self._stream()))
+        self.stats["svd_seconds"] = self.stats.get("svd_seconds", 0.0) + _time.perf_counter() - t_svd
         self.stats["svd_batches"] += 1
         self.stats["svd_sweeps"] += int(sweeps.value)
         self.stats["svd_max_sweeps"] = max(self.stats["svd_max_sweeps"], int(sweeps.value))
