@@ -1,0 +1,62 @@
+"""OpenQASM 2 ingest (the wire format of the reference's CPU paths, eval_qu.py:39-41) against the
+independent dense simulator and hand-built circuits."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import statevector as osv
+from qibotn_b200 import circuits
+from qibotn_b200.qasm import from_openqasm2_str
+
+QFT3 = """OPENQASM 2.0;
+include "qelib1.inc";
+qreg q[3];
+creg c[3];
+h q[0];
+cu1(pi/2) q[1],q[0];   // controlled phase
+cu1(pi/4) q[2],q[0];
+h q[1];
+cu1(pi/2) q[2],q[1];
+h q[2];
+swap q[0],q[2];
+barrier q;
+measure q -> c;
+"""
+
+
+def test_qft_text_matches_the_builtin_qft():
+    got = osv.simulate(from_openqasm2_str(QFT3))
+    want = osv.simulate(circuits.qft(3, True))
+    assert np.abs(got - want).max() < 1e-14
+
+
+def test_gate_set_parameters_and_broadcast():
+    text = """OPENQASM 2.0; include "qelib1.inc"; qreg a[2]; qreg b[1];
+    h a; rx(0.3) a[0]; ry(-pi/3) a[1]; rz(2*pi/5) b[0]; u3(0.1,0.2,0.3) a[0]; u2(0.4,-0.5) b[0];
+    cx a[0],b[0]; cz a[1],a[0]; cy a[0],a[1]; crz(0.7) b[0],a[1]; rzz(0.9) a[0],a[1]; sdg b[0]; t a[1]; sx a[0];"""
+    circ = from_openqasm2_str(text)
+    assert circ.nqubits == 3
+    psi = osv.simulate(circ)
+    assert abs(np.vdot(psi, psi) - 1) < 1e-13
+    # the same circuit by hand on a dense vector
+    g = circuits.gates
+    ref = circuits.Circuit(3)
+    for q in (0, 1):
+        ref.add(g.H(q))
+    ref.add(g.RX(0, theta=0.3)); ref.add(g.RY(1, theta=-math.pi / 3)); ref.add(g.RZ(2, theta=2 * math.pi / 5))
+    from qibotn_b200.qasm import _u3        # qelib1's u3 (no global phase), not qibo's U3
+    ref.add(g.Unitary(_u3(0.1, 0.2, 0.3), 0)); ref.add(g.Unitary(_u3(math.pi / 2, 0.4, -0.5), 2))
+    ref.add(g.CNOT(0, 2)); ref.add(g.CZ(1, 0))
+    ref.add(g.Unitary(np.array([[0, -1j], [1j, 0]]), 1, controls=(0,), name="cy"))
+    ref.add(g.CRZ(2, 1, theta=0.7)); ref.add(g.RZZ(0, 1, theta=0.9)); ref.add(g.SDG(2)); ref.add(g.T(1)); ref.add(g.SX(0))
+    assert np.abs(psi - osv.simulate(ref)).max() < 1e-13
+
+
+def test_unsupported_statements_raise():
+    with pytest.raises(NotImplementedError):
+        from_openqasm2_str("OPENQASM 2.0; qreg q[1]; gate foo a { h a; } foo q[0];")
+    with pytest.raises(NotImplementedError):
+        from_openqasm2_str("OPENQASM 2.0; qreg q[3]; ccx q[0],q[1],q[2];")
+    with pytest.raises(ValueError):
+        from_openqasm2_str("OPENQASM 2.0; h q[0];")
