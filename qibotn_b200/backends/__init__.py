@@ -4,9 +4,9 @@ from .abstract import QibotnBackend
 from .cutensornet import CuTensorNet, raise_error
 
 # "qutensornet" is what the reference's README still calls the platform
-# (README.md:85); it is accepted as an alias.  The quimb and qmatchatea
-# platforms are separate simulators outside this engine's scope.
-PLATFORMS = ("cutensornet", "qutensornet")
+# (README.md:85); it is accepted as an alias.  "quimb" keeps the quimb platform's API
+# (backends/quimb.py) on this engine; qmatchatea is a separate simulator, out of scope.
+PLATFORMS = ("cutensornet", "qutensornet", "quimb")
 
 
 class MetaBackend:
@@ -14,6 +14,12 @@ class MetaBackend:
 
     @staticmethod
     def load(platform: str, runcard: dict = None, **kwargs) -> QibotnBackend:
+        if platform == "quimb":
+            from .quimb import QuimbBackend
+
+            quimb_backend = kwargs.get("quimb_backend", "numpy")
+            contraction_optimizer = kwargs.get("contraction_optimizer", "auto-hq")
+            return QuimbBackend(quimb_backend=quimb_backend, contraction_optimizer=contraction_optimizer)
         if platform in PLATFORMS:
             return CuTensorNet(runcard)
         raise_error(NotImplementedError,

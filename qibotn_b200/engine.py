@@ -83,6 +83,18 @@ def contract(net: TensorNetwork, dtype="complex64", samples=32, seed=0, min_slic
              slice_ids=None, info: PathInfo = None, target_log2_width=None, use_graph=True):
     """Contract ``net`` on the current CUDA device; returns a complex torch tensor
     (the sum over ``slice_ids``, all slices by default)."""
+    if len(net.tensors) == 0:
+        # a circuit without gates has no active qubit: the empty product (the reference would hand
+        # cuTensorNet an empty operand list)
+        import torch
+
+        if not torch.cuda.is_available():
+            from .lib import QtnError
+            raise QtnError("qibotn_b200 needs a CUDA device; there is no CPU fallback")
+        LAST.h2d_bytes = LAST.launches = 0
+        LAST.flops = LAST.bytes = 0.0
+        return torch.ones((), dtype=torch.complex64 if str(dtype) == "complex64" else torch.complex128,
+                          device="cuda")
     info, lowered = plan(net, dtype, samples, seed, min_slices, target_log2_width, info)
     run = runner_for(lowered, use_graph)
     LAST.h2d_bytes = run.upload(net.tensors)

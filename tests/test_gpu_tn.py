@@ -264,3 +264,61 @@ def test_c2_full_size_expectation_properties():
     for key, v in vals.items():
         if key[0] == "complex64":
             assert abs(v - ref) < 1e-5 * scale, (key, v, ref)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_edge_cases(dtype):
+    """Empty and degenerate inputs: no gates, measurement markers only, one gate, repeated gates
+    on one qubit, a qubit untouched in the middle, expectation on an empty circuit."""
+    from qibotn_b200.qibo_compat import Circuit, H, X, Z, CNOT, M, RX
+    b = _backend(dtype)
+    c = Circuit(3)
+    assert b.execute_circuit(c).statevector.flatten().get().tolist() == [1]         # no active qubit
+    c.add(M(0, 1, 2))
+    assert b.execute_circuit(c).statevector.flatten().get().tolist() == [1]
+    c = Circuit(1); c.add(X(0))
+    assert np.allclose(b.execute_circuit(c).statevector.flatten().get(), [0, 1])
+    c = Circuit(4)
+    for _ in range(5):
+        c.add(RX(2, theta=0.3))
+    c.add(H(0)); c.add(CNOT(0, 3))
+    got = b.execute_circuit(c).statevector.flatten().get()                          # qubits 0, 2, 3 active
+    want = osv.simulate(c).reshape(2, 2, 2, 2)[:, 0, :, :].reshape(-1)
+    assert np.abs(got - want).max() < TOL[dtype] * 4
+    # expectation of Z0 on an empty circuit is <0|Z|0> = 1, X0 gives 0
+    for letter, want in (("Z", 1.0), ("X", 0.0)):
+        b.configure_tn_simulation({"MPI_enabled": False, "MPS_enabled": False, "NCCL_enabled": False,
+                                   "expectation_enabled": {"terms": [{"coefficient": 1.0, "operators": [(letter, 0)]}]}})
+        assert abs(float(b.execute_circuit(Circuit(2))[0]) - want) < 1e-6
+    # MPS on the same degenerate circuits
+    b.configure_tn_simulation({"MPI_enabled": False, "MPS_enabled": True, "NCCL_enabled": False,
+                               "expectation_enabled": False})
+    got = b.execute_circuit(Circuit(3)).statevector.flatten().get()
+    assert np.allclose(got, np.eye(8)[0])
+    got = b.execute_circuit(c).statevector.flatten().get()
+    assert np.abs(got - osv.simulate(c)).max() < TOL[dtype] * 10
+
+
+@pytest.mark.parametrize("ansatz", ["mps", None])
+def test_quimb_platform_api(ansatz):
+    """The quimb platform's calls (reference backends/quimb.py:123-261) on this engine: dense state,
+    symbolic expectation, sampling."""
+    n = 7
+    circ = circuits.ry_rz_cnot_ring(n, 2, seed=3)
+    psi = osv.simulate(circ)
+    b = MetaBackend.load("quimb")
+    b.configure_tn_simulation(ansatz=ansatz, max_bond_dimension=None, svd_cutoff=1e-12)
+    res = b.execute_circuit(circ, return_array=True)
+    assert np.abs(res.statevector.get() - psi).max() < 1e-9
+    ops, sites, coeffs = ["xz", "yy", "z", "zxz"], [(0, 1), (2, 5), (6,), (1, 3, 4)], [0.5, -1.25, 2.0, 0.75]
+    want = osv.pauli_expectation(psi, [(c, [(l.upper(), s) for l, s in zip(o, st)])
+                                       for o, st, c in zip(ops, sites, coeffs)], n).real
+    got = b.exp_value_observable_symbolic(circ, ops, sites, coeffs, n)
+    assert abs(got - want) < 1e-8
+    res = b.execute_circuit(circ, nshots=4000)
+    assert sum(res.frequencies().values()) == 4000 and res.statevector is None
+    probs = np.abs(psi) ** 2
+    for state, p in res.probabilities().items():
+        assert abs(p - probs[int(state, 2)]) < 1e-9
+    top = max(res.frequencies(), key=res.frequencies().get)
+    assert abs(res.frequencies()[top] / 4000 - probs[int(top, 2)]) < 5 * np.sqrt(probs[int(top, 2)] / 4000)

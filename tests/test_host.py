@@ -25,7 +25,23 @@ def test_plugin_alias_and_platforms():
     assert MetaBackend.load("qutensornet").platform == "cutensornet"        # README's spelling
     with pytest.raises(NotImplementedError):
         MetaBackend.load("qmatchatea")
-    assert MetaBackend().list_available() == {"cutensornet": True, "qutensornet": True}
+    assert MetaBackend().list_available() == {"cutensornet": True, "qutensornet": True, "quimb": True}
+
+
+def test_quimb_platform_surface():
+    """reference backends/quimb.py:40-83,123-135,205-236: constructor, configuration, validation."""
+    b = MetaBackend.load("quimb", quimb_backend="numpy", contraction_optimizer="greedy")
+    assert (b.name, b.platform, b.backend, b.contractions_optimizer) == ("qibotn", "quimb", "numpy", "greedy")
+    assert (b.ansatz, b.max_bond_dimension, b.svd_cutoff, b.n_most_frequent_states) == ("mps", None, 1e-10, 100)
+    b.configure_tn_simulation(ansatz=None, max_bond_dimension=16, svd_cutoff=1e-6, n_most_frequent_states=5)
+    assert (b.ansatz, b.max_bond_dimension) == (None, 16)
+    assert b._gate_algo()["svd_method"] == {"partition": "UV", "abs_cutoff": 1e-6, "max_extent": 16}
+    with pytest.raises(ValueError):
+        MetaBackend.load("quimb", quimb_backend="tensorflow")
+    with pytest.raises(ValueError):
+        b.execute_circuit(circuits.qft(2, True), initial_state=np.ones(4))
+    with pytest.raises(ValueError):
+        b.exp_value_observable_symbolic(circuits.qft(3, True), ["zz"], [(1, 1)], [1.0], 3)
 
 
 def test_runcard_type_rules():
