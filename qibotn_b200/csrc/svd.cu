@@ -67,7 +67,8 @@ template <typename R>
 __global__ void __launch_bounds__(256)
 jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, int max_inner, R tol,
                    double tiny_rel, const double *__restrict__ fro2, const int *__restrict__ rot_prev,
-                   int *__restrict__ rot_cur) {
+                   int *__restrict__ rot_cur, int *__restrict__ changed, long long ld, int gstep,
+                   int steps_per_sweep) {
   using T = cx<R>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *rows = reinterpret_cast<T *>(smem_raw);
@@ -91,6 +92,14 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
     if ((int)blockIdx.x >= nbe / 2) return;
     circle(step, blockIdx.x, nbe, I, J);
     if (I >= nb || J >= nb) return;                           // paired with the dummy block: idle
+  }
+  // Skip the visit when neither block has been rotated since this very pair was last checked (one
+  // sweep ago, same step): its rows are unchanged, hence still mutually orthogonal.  In the late
+  // sweeps of a graded matrix only the small rows still move, and most visits end here.
+  int *chg = changed + (long long)item_id * ld;
+  if (nb > 1 && sweep > 0) {
+    const int t_prev = gstep - steps_per_sweep;
+    if (chg[I] < t_prev && (J < 0 || chg[J] < t_prev)) return;
   }
   const int nr = J < 0 ? b : 2 * b;                            // rows held by this CTA (even)
   T *W = (T *)it.w;
@@ -161,7 +170,11 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
     T *dst = W + (size_t)g * m;
     for (int c = lane; c < m; c += 32) dst[c] = src[c];
   }
-  if (t == 0 && rotated_any) atomicAdd(&rot_cur[item_id], 1);
+  if (t == 0 && rotated_any) {
+    atomicAdd(&rot_cur[item_id], 1);
+    chg[I] = gstep;
+    if (J >= 0) chg[J] = gstep;
+  }
 }
 
 // Row norms -> singular values sorted descending (+ permutation), truncation rank, S normalisation.
@@ -290,7 +303,9 @@ int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, co
   int *d_rot = (int *)(ws + off); off += ((size_t)batch * 8 + 255) & ~(size_t)255;
   int32_t *d_rank = (int32_t *)(ws + off); off += ((size_t)batch * 4 + 255) & ~(size_t)255;
   double *d_scale = (double *)(ws + off); off += ((size_t)batch * 8 + 255) & ~(size_t)255;
-  double *d_scratch = (double *)(ws + off);
+  double *d_scratch = (double *)(ws + off); off += ((size_t)batch * ld * 8 + 255) & ~(size_t)255;
+  int *d_changed = (int *)(ws + off);                         // [batch][ld]: step of the last rotation per block
+  QTN_CUDA_CHECK(cudaMemsetAsync(d_changed, 0x7f, (size_t)batch * ld * sizeof(int), st));
   QTN_CUDA_CHECK(cudaMemcpyAsync(d_items, items, (size_t)batch * sizeof(qtn_svd_item), cudaMemcpyHostToDevice, st));
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -309,7 +324,8 @@ int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, co
     dim3 grid((unsigned)max_pairs, (unsigned)batch);
     for (int step = 0; step < max_steps; ++step) {
       jacobi_step_kernel<R><<<grid, 256, smem, st>>>(d_items, step, sweep, max_sweeps, (R)tol, tiny_rel, d_fro2,
-                                                    rot_prev, rot_cur);
+                                                    rot_prev, rot_cur, d_changed, (long long)ld,
+                                                    sweep * max_steps + step + 1, max_steps);
       QTN_LAUNCH_CHECK();
     }
     QTN_CUDA_CHECK(cudaMemcpyAsync(rot.data(), rot_cur, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -333,7 +349,7 @@ extern "C" int64_t qtn_svd_workspace_bytes(int batch, int64_t ld) {
   if (batch < 1 || ld < 1) return 0;
   int64_t off = ((int64_t)batch * (int64_t)sizeof(qtn_svd_item) + 255) & ~(int64_t)255;
   off += 4 * (((int64_t)batch * 8 + 255) & ~(int64_t)255);
-  off += (int64_t)batch * ld * 8 + 256;
+  off += (((int64_t)batch * ld * 8 + 255) & ~(int64_t)255) + (int64_t)batch * ld * 4 + 512;
   return off;
 }
 
