@@ -333,7 +333,8 @@ def run_b200(a):
     k_ms = float(np.mean(ts[1:]))
     k_tfs = node.plan.flops / (k_ms * 1e-3) / 1e12
     intensity = node.plan.flops / node.plan.bytes
-    names = {0: "gett_tile_kernel<float>", 1: "gett_reduce_kernel<float>", 2: "gett_tc_kernel"}
+    names = {0: "gett_tile_kernel<float>", 1: "gett_reduce_kernel<float>", 2: "gett_tc_persistent_kernel",
+             3: "gett_kred_kernel<float>"}
     if node.plan.kernel == lib.KERNEL_TC:
         # tcgen05 kind::tf32, 3 MMAs per product (hi*hi + hi*lo + lo*hi): the tensor pipe does 3x
         # the algorithmic flops at the tf32 rate (half the bf16 rate measured in MEASURED_PEAKS.json)
@@ -343,6 +344,8 @@ def run_b200(a):
                  "tf32_peak_assumed_tflops": peaks["bf16_tflops"] / 2,
                  "tensor_pipe_frac_tf32": 3.0 * k_tfs / (peaks["bf16_tflops"] / 2),
                  "hbm_gbs_at_this_speed": node.plan.bytes / (k_ms * 1e-3) / 1e9,
+                 "traffic_note": "ncu --set full of this kernel on the same shape class: dram bytes = algorithmic "
+                                 "bytes within 1% (profiles/r01_ncu_full_prof_tc_m22n7k7_prepack.txt)",
                  "note": "frac is algorithmic complex64 flops over the measured bf16 cuBLAS burst; "
                          "tensor_pipe_frac_tf32 is the share of the tf32 pipe the 3x split keeps busy"}
     else:

@@ -49,26 +49,9 @@ __device__ __forceinline__ R warp_sum(R v) {
 
 template <typename R>
 __global__ void __launch_bounds__(256)
-fro2_kernel(const qtn_svd_item *__restrict__ items, double *__restrict__ fro2) {
-  using T = cx<R>;
-  __shared__ double red[kWarps];
-  const qtn_svd_item it = items[blockIdx.x];
-  const T *w = (const T *)it.w;
-  const long long total = (long long)it.n * it.m;
-  double s = 0;
-  for (long long e = threadIdx.x; e < total; e += 256) { const T v = w[e]; s += (double)v.x * v.x + (double)v.y * v.y; }
-  s = warp_sum<double>(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) { double tsum = 0; for (int i = 0; i < kWarps; ++i) tsum += red[i]; fro2[blockIdx.x] = tsum; }
-}
-
-template <typename R>
-__global__ void __launch_bounds__(256)
 jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, int max_inner, R tol,
-                   double tiny_rel, const double *__restrict__ fro2, const int *__restrict__ rot_prev,
-                   int *__restrict__ rot_cur, int *__restrict__ changed, long long ld, int gstep,
-                   int steps_per_sweep) {
+                   const int *__restrict__ rot_prev, int *__restrict__ rot_cur, int *__restrict__ changed,
+                   long long ld, int gstep, int steps_per_sweep) {
   using T = cx<R>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *rows = reinterpret_cast<T *>(smem_raw);
@@ -112,7 +95,6 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
     else { T z; z.x = 0; z.y = 0; for (int c = lane; c < m; c += 32) dst[c] = z; }
   }
   __syncthreads();
-  (void)tiny_rel; (void)fro2;
   const int inner_max = nb == 1 ? max_inner : 1;
   int rotated_any = 0;
   for (int inner = 0; inner < inner_max; ++inner) {
@@ -296,10 +278,10 @@ int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, co
     const int nr = it.nblocks == 1 ? it.block : 2 * it.block;
     smem = std::max(smem, (size_t)nr * it.m * esz);
   }
-  // workspace: items | fro2 | rot[2] | rank | scale | scratch sigma
+  // workspace: items | (unused) | rot[2] | rank | scale | scratch sigma | last-rotation step per block
   qtn_svd_item *d_items = (qtn_svd_item *)ws;
   size_t off = ((size_t)batch * sizeof(qtn_svd_item) + 255) & ~(size_t)255;
-  double *d_fro2 = (double *)(ws + off); off += ((size_t)batch * 8 + 255) & ~(size_t)255;
+  off += ((size_t)batch * 8 + 255) & ~(size_t)255;
   int *d_rot = (int *)(ws + off); off += ((size_t)batch * 8 + 255) & ~(size_t)255;
   int32_t *d_rank = (int32_t *)(ws + off); off += ((size_t)batch * 4 + 255) & ~(size_t)255;
   double *d_scale = (double *)(ws + off); off += ((size_t)batch * 8 + 255) & ~(size_t)255;
@@ -313,9 +295,6 @@ int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, co
                                         (int)std::max(smem, (size_t)kSmemBudget)));
     smem_set = std::max(smem, (size_t)kSmemBudget);
   }
-  fro2_kernel<R><<<batch, 256, 0, st>>>(d_items, d_fro2);
-  QTN_LAUNCH_CHECK();
-  const double tiny_rel = sizeof(R) == 8 ? 1e-30 : 1e-14;
   std::vector<int> rot(batch);
   int sweep = 0;
   for (; sweep < max_sweeps; ++sweep) {
@@ -323,9 +302,9 @@ int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, co
     QTN_CUDA_CHECK(cudaMemsetAsync(rot_cur, 0, (size_t)batch * sizeof(int), st));
     dim3 grid((unsigned)max_pairs, (unsigned)batch);
     for (int step = 0; step < max_steps; ++step) {
-      jacobi_step_kernel<R><<<grid, 256, smem, st>>>(d_items, step, sweep, max_sweeps, (R)tol, tiny_rel, d_fro2,
-                                                    rot_prev, rot_cur, d_changed, (long long)ld,
-                                                    sweep * max_steps + step + 1, max_steps);
+      jacobi_step_kernel<R><<<grid, 256, smem, st>>>(d_items, step, sweep, max_sweeps, (R)tol, rot_prev, rot_cur,
+                                                    d_changed, (long long)ld, sweep * max_steps + step + 1,
+                                                    max_steps);
       QTN_LAUNCH_CHECK();
     }
     QTN_CUDA_CHECK(cudaMemcpyAsync(rot.data(), rot_cur, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -39,7 +39,11 @@ def worker(args):
     tn = wl.network()
     net = SymbolicNetwork(tn.modes, tn.out)
     pre, live, nxt = _absorb_small(net)
-    info0 = plans.load_plan(start, tn.modes, tn.out)
+    if start == "fresh":                    # own starting tree: a different basin per worker
+        from qibotn_b200.planner import find_path
+        info0 = find_path(tn.modes, tn.out, samples=8, seed=seed, target_log2_width=width, anneal_steps=0)
+    else:
+        info0 = plans.load_plan(start, tn.modes, tn.out)
     rng = random.Random(seed)
     deadline = time.time() + 60 * minutes
     best = None
@@ -82,9 +86,10 @@ if __name__ == "__main__":
     out = a.out or (a.workload + "_anneal")
     wl = workloads.build(a.workload)
     tn = wl.network()
-    base = plans.load_plan(start, tn.modes, tn.out)
-    print("start: log10 flops %.2f modeled %.1f s" % (
-        math.log10(base.flops), search_plan.modeled_seconds(base, tn, wl.dtype)), flush=True)
+    if start != "fresh":
+        base = plans.load_plan(start, tn.modes, tn.out)
+        print("start: log10 flops %.2f modeled %.1f s" % (
+            math.log10(base.flops), search_plan.modeled_seconds(base, tn, wl.dtype)), flush=True)
     with mp.Pool(a.procs) as pool:
         results = pool.map(worker, [(a.workload, start, 100 + p, a.minutes, a.width) for p in range(a.procs)])
     best = min(results, key=lambda r: r.extra["modeled_seconds"])
