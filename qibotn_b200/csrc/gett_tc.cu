@@ -154,21 +154,43 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// x ~ hi + lo, both representable in tf32: hi = rna(x), lo = rna(x - hi).  x - hi is exact in fp32
-// but can carry 13 significant bits; the tensor core would TRUNCATE it to 11, a biased 2^-23 |x|
-// error per cross term -- rounding it here first halves that and removes the bias.
+// x ~ hi + lo, both representable in tf32 (10 explicit mantissa bits): hi = round-to-nearest(x),
+// lo = round-to-nearest(x - hi).  x - hi is exact in fp32 but can carry 13 significant bits, which
+// the tensor core would TRUNCATE; rounding it here keeps every operand exactly representable.
+// The rounding is done on the bit pattern (add half an ulp of the 13 dropped bits, clear them:
+// ties away from zero, like cvt.rna) -- two integer instructions, where ptxas expands
+// cvt.rna.tf32.f32 into a ~15-instruction sequence on sm_100a.
+__device__ __forceinline__ float round_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-  uint32_t u, v;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  hi = __uint_as_float(u);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v) : "f"(x - hi));
-  lo = __uint_as_float(v);
+  hi = round_tf32(x);
+  lo = round_tf32(x - hi);
 }
 
 __device__ __forceinline__ long long deposit(unsigned long long idx, const uint8_t *pos, int n) {
   long long off = 0;
   for (int i = 0; i < n; ++i) off |= (long long)((idx >> i) & 1ull) << pos[i];
   return off;
+}
+
+// The same bit deposit computed by a whole (converged) warp: lane l places bit l, one OR-reduction
+// combines them.  Used once per tile, where a per-thread loop over ~20 labels with 64-bit variable
+// shifts was a third of the producers' instructions.
+__device__ __forceinline__ long long deposit_warp(unsigned long long idx, const uint8_t *pos, int n) {
+  const int lane = threadIdx.x & 31;
+  unsigned lo = 0, hi = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    if (i < n && ((idx >> i) & 1ull)) {
+      const unsigned long long b = 1ull << pos[i];
+      lo |= (unsigned)b;
+      hi |= (unsigned)(b >> 32);
+    }
+  }
+  lo = __reduce_or_sync(0xffffffffu, lo);
+  hi = __reduce_or_sync(0xffffffffu, hi);
+  return (long long)(((unsigned long long)hi << 32) | lo);
 }
 
 __device__ __forceinline__ long long slice_offset(const int32_t *slice_id, int n, const uint8_t *bit,
@@ -494,8 +516,8 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
       const unsigned long long nh = id & ((1ull << P.n_nhi) - 1);
       const unsigned long long mh = id >> P.n_nhi;
       const unsigned long long kh0 = (unsigned long long)split << k_iters_bits;
-      a_k = a_slice | deposit(mh, P.a_mhi, P.n_mhi) | deposit(kh0, P.a_khi, P.n_khi);
-      b_k = b_slice | deposit(nh, P.b_nhi, P.n_nhi) | deposit(kh0, P.b_khi, P.n_khi);
+      a_k = a_slice | deposit_warp(mh, P.a_mhi, P.n_mhi) | deposit_warp(kh0, P.a_khi, P.n_khi);
+      if constexpr (!PRE) b_k = b_slice | deposit_warp(nh, P.b_nhi, P.n_nhi) | deposit_warp(kh0, P.b_khi, P.n_khi);
       image0 = (nh << P.n_khi) | kh0;
       kk = 0;
     };
@@ -594,7 +616,7 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
       id >>= P.split_bits;
       const unsigned long long nh = id & ((1ull << P.n_nhi) - 1);
       const unsigned long long mh = id >> P.n_nhi;
-      const long long c_base = deposit(mh, P.c_mhi, P.n_mhi) | deposit(nh, P.c_nhi, P.n_nhi);
+      const long long c_base = deposit_warp(mh, P.c_mhi, P.n_mhi) | deposit_warp(nh, P.c_nhi, P.n_nhi);
       float2 *out = (P.split_bits ? ws + (long long)split * P.c_elems : C) + c_base + row_off;
       mbar_wait(tfull_bar(buf), tph);
       tc_fence_after();
