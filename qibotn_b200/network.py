@@ -137,22 +137,49 @@ class QiboCircuitToEinsum:
         """<bitstring| U |0...0> as a closed network (scalar output)."""
         return self.amplitude_network(bitstring).interleaved()
 
-    def expectation_network(self, ham_gates) -> TensorNetwork:
+    def _light_cone(self, ham):
+        """Indices of the circuit gates inside the reverse light cone of the observable: walking the
+        circuit backwards, a gate is kept iff it touches a qubit on which the operator accumulated so
+        far acts non-trivially.  Every other gate G meets its own inverse in <0|U^dag P U|0> with
+        nothing in between, and G^dag G = 1 exactly -- dropping the pair changes no value."""
+        live = set()
+        for t, qubits in ham:
+            if len(qubits) != 1 or not np.allclose(t, t[0, 0] * np.eye(2)):
+                live.update(qubits)            # anything but a multiple of the identity
+        keep = []
+        for idx in range(len(self.gate_tensors) - 1, -1, -1):
+            qubits = self.gate_tensors[idx][1]
+            if live.intersection(qubits):
+                live.update(qubits)
+                keep.append(idx)
+        return sorted(keep)
+
+    def expectation_network(self, ham_gates, light_cone=True) -> TensorNetwork:
         n = self.circuit.nqubits
         frontier = {q: q for q in range(n)}
         kets = [self.basis_map["0"]] * n
         tensors, modes = list(kets), [[q] for q in range(n)]
-        g_t, g_m, nxt = self._thread(self.gate_tensors, frontier, n)
         ham = [(np.asarray(t, dtype=self.dtype), tuple(q)) for t, q in ham_gates]
-        b_t, b_m, _ = self._thread(ham + self.gate_tensors_inverse, frontier, nxt)
+        forward, inverse = self.gate_tensors, self.gate_tensors_inverse
+        if light_cone and len(inverse) == len(forward):
+            keep = self._light_cone(ham)
+            if len(keep) < len(forward):
+                total = len(forward)
+                forward = [forward[i] for i in keep]
+                # circuit.invert() lists the daggered gates in reverse order
+                inverse = [inverse[total - 1 - i] for i in reversed(keep)]
+        g_t, g_m, nxt = self._thread(forward, frontier, n)
+        b_t, b_m, _ = self._thread(ham + inverse, frontier, nxt)
         tensors += g_t + b_t + kets
         modes += g_m + b_m + [[frontier[q]] for q in range(n)]
         return TensorNetwork(tensors, modes, [])
 
     def expectation_operands(self, ham_gates):
         """<0| U^dagger (prod of ham_gates) U |0> over all ``nqubits`` (:198-246).
-        Returned without a trailing output list, as the reference does."""
-        return self.expectation_network(ham_gates).interleaved()[:-1]
+        Returned without a trailing output list, as the reference does, and with every gate of
+        the circuit and of its inverse present, as the reference does (the engine's own drivers use
+        ``expectation_network``, which drops the pairs outside the observable's light cone)."""
+        return self.expectation_network(ham_gates, light_cone=False).interleaved()[:-1]
 
     def get_pauli_gates(self, pauli_map, dtype=None):
         """{qubit: letter} -> [(sigma, (qubit,))]; kept for the older

@@ -322,3 +322,25 @@ def test_quimb_platform_api(ansatz):
         assert abs(p - probs[int(state, 2)]) < 1e-9
     top = max(res.frequencies(), key=res.frequencies().get)
     assert abs(res.frequencies()[top] / 4000 - probs[int(top, 2)]) < 5 * np.sqrt(probs[int(top, 2)] / 4000)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_light_cone_cancellation_changes_no_value(dtype):
+    """Dropping the gate / inverse-gate pairs outside the observable's reverse light cone is exact:
+    same expectation with and without it, and equal to the dense simulator's."""
+    from qibotn_b200.observables import get_ham_gates
+    n = 12
+    circ = circuits.brickwork(n, 4, seed=9)
+    psi = osv.simulate(circ)
+    conv = QiboCircuitToEinsum(circ, dtype)
+    for term in ([(5, "Z", 0.7)], [(0, "X", 1.0), (11, "Y", -2.0)], [(6, "Z", 1.0), (7, "Z", 1.0)]):
+        hg = get_ham_gates(term, dtype)
+        full = conv.expectation_network(hg, light_cone=False)
+        cone = conv.expectation_network(hg)
+        assert len(cone.tensors) < len(full.tensors)
+        engine.clear_caches()
+        a = complex(engine.contract(full, dtype).cpu().numpy().reshape(-1)[0])
+        b = complex(engine.contract(cone, dtype).cpu().numpy().reshape(-1)[0])
+        coeff = np.prod([c for _, _, c in term])
+        want = coeff * osv.pauli_expectation(psi, [(1.0, [(l, q) for q, l, _ in term])], n)
+        assert abs(a - want) < TOL[dtype] * 10 and abs(b - want) < TOL[dtype] * 10

@@ -142,6 +142,9 @@ def test_converter_operand_conventions():
     assert conv.gate_tensors[1][0].shape == (2, 2, 2, 2) and conv.gate_tensors[1][1] == (1, 3)
     exp = conv.expectation_operands(obs.get_ham_gates([(0, "Z", 1.0)], "complex64"))
     assert len(exp) == 2 * (4 + 2 + 1 + 2 + 4)
+    # the engine's own network drops gate / inverse pairs outside the observable's light cone
+    assert len(conv.expectation_network(obs.get_ham_gates([(0, "Z", 1.0)], "complex64")).tensors) == 4 + 1 + 4
+    assert len(conv.expectation_network(obs.get_ham_gates([(3, "Z", 1.0)], "complex64")).tensors) == 4 + 2 + 1 + 2 + 4
     with pytest.raises(ValueError):
         conv.amplitude_operands("012")
 
