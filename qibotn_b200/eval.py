@@ -78,7 +78,7 @@ def _distributed_contract(net, dtype, n_samples, method):
 def dense_vector_tn(qibo_circ, datatype):
     """Dense state vector over the active qubits on one GPU (eval.py:301-313)."""
     conv = QiboCircuitToEinsum(qibo_circ, dtype=datatype)
-    return DeviceArray(engine.contract(conv.state_vector_network(), datatype))
+    return DeviceArray(engine.contract(conv.state_vector_network(), datatype, samples=PLAN_SAMPLES))
 
 
 def dense_vector_tn_MPI(qibo_circ, datatype, n_samples=8):
@@ -114,6 +114,10 @@ def _term_networks(qibo_circ, datatype, observable):
         yield conv.expectation_network(get_ham_gates(term, dtype=datatype))
 
 
+# Planner effort of the single-GPU drivers (seeds tried per network structure; the distributed
+# drivers receive n_samples from the backend, 32, like the reference's cutensornet.py:110-147).
+PLAN_SAMPLES = 32
+
 # How expectation_tn evaluates a Hamiltonian: "network" = one closed <0|U^dag P U|0> contraction
 # per term, as the reference does; "state" = contract U|0> once to a dense vector and run the fused
 # Pauli kernel (one streaming pass per term); "auto" = "state" when the active qubits fit easily
@@ -139,7 +143,7 @@ def expectation_from_state(qibo_circ, datatype, terms):
     if n == 0 or n > _STATE_ROUTE_MAX_QUBITS:
         raise ValueError("state route needs between 1 and %d active qubits" % _STATE_ROUTE_MAX_QUBITS)
     bit = {q: n - 1 - k for k, q in enumerate(active)}          # qubit -> address bit of the dense state
-    state = engine.contract(conv.state_vector_network(), datatype).reshape(-1)
+    state = engine.contract(conv.state_vector_network(), datatype, samples=PLAN_SAMPLES).reshape(-1)
     xm, zm, ny, coeffs = [], [], [], []
     for term in terms:
         coeff, fx, fz, cy, dead = 1.0, 0, 0, 0, False
@@ -190,7 +194,7 @@ def expectation_tn(qibo_circ, datatype, observable):
 
     total = None
     for net in _term_networks(qibo_circ, datatype, observable):
-        val = engine.contract(net, datatype).reshape(1)
+        val = engine.contract(net, datatype, samples=PLAN_SAMPLES).reshape(1)
         total = val.clone() if total is None else total + val
     if total is None:
         raise ValueError("No valid Hamiltonian terms were added.")

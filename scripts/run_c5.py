@@ -1,0 +1,41 @@
+"""BASELINE config 5 at the depths this round can plan: 40-qubit QAOA MaxCut on a 3-regular graph,
+sum of the 60 ZZ expectations, one light-cone-reduced contraction per term (complex64).
+    python scripts/run_c5.py [--p 3]
+p = 4 needs diagonal gates as hyper-indices to be tractable and is not run."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from qibotn_b200 import circuits, engine  # noqa: E402
+from qibotn_b200 import eval as ev  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--p", type=int, default=3)
+ap.add_argument("--n", type=int, default=40)
+ap.add_argument("--samples", type=int, default=4)
+a = ap.parse_args()
+circ, edges = circuits.qaoa_maxcut(a.n, a.p, seed=0)
+obs = circuits.zz_terms(edges)
+out = {}
+ev.PLAN_SAMPLES = a.samples
+for dtype in ("complex64", "complex128"):
+    ev.EXPECTATION_ROUTE = "network"
+    engine.clear_caches()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    val = float(ev.expectation_tn(circ, dtype, obs).real.get().reshape(-1)[0])
+    torch.cuda.synchronize()
+    first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    val2 = float(ev.expectation_tn(circ, dtype, obs).real.get().reshape(-1)[0])       # plans cached
+    torch.cuda.synchronize()
+    out[dtype] = {"value": val, "seconds_first_call": first, "seconds_cached_plans": time.perf_counter() - t0,
+                  "repeat_equal": val == val2}
+out["workload"] = f"{a.n}-qubit QAOA MaxCut p={a.p}, {len(edges)} ZZ terms"
+out["rel_diff_c64_c128"] = abs(out["complex64"]["value"] - out["complex128"]["value"]) / max(1e-3, abs(out["complex128"]["value"]))
+print(json.dumps(out), flush=True)

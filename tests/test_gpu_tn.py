@@ -344,3 +344,21 @@ def test_light_cone_cancellation_changes_no_value(dtype):
         coeff = np.prod([c for _, _, c in term])
         want = coeff * osv.pauli_expectation(psi, [(1.0, [(l, q) for q, l, _ in term])], n)
         assert abs(a - want) < TOL[dtype] * 10 and abs(b - want) < TOL[dtype] * 10
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_qaoa_maxcut_expectation(dtype):
+    """BASELINE config 5's kind of workload at sizes a dense oracle reaches: QAOA MaxCut on a
+    3-regular graph, sum of Z_a Z_b over the edges (one light-cone-reduced contraction per term,
+    plans shared between terms of equal structure)."""
+    n, p = 14, 3
+    circ, edges = circuits.qaoa_maxcut(n, p, seed=1)
+    psi = osv.simulate(circ)
+    want = osv.pauli_expectation(psi, [(1.0, [("Z", a), ("Z", b)]) for a, b in edges], n).real
+    for route in ("network", "state"):
+        ev.EXPECTATION_ROUTE = route
+        try:
+            got = float(ev.expectation_tn(circ, dtype, circuits.zz_terms(edges)).real.get().reshape(-1)[0])
+        finally:
+            ev.EXPECTATION_ROUTE = "auto"
+        assert abs(got - want) < TOL[dtype] * 50, (route, got, want)
