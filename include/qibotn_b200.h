@@ -143,7 +143,8 @@ typedef struct {
   /* B pre-packing: when many m tiles share each B tile, a small pre-kernel writes B once, already
    * split and laid out as shared-memory stage images, into the workspace at byte offset
    * tc_prepack_off; the main kernel then fetches a whole B stage with one cp.async.bulk. */
-  int32_t tc_prepack, tc_pad2;
+  int32_t tc_prepack;
+  int32_t tc_pair;               /* 1: CTA-pair kernel (tcgen05 cta_group::2), tc_reserved even ("tc_pair") */
   int64_t tc_prepack_off;
 } qtn_pair_plan_t;
 
@@ -154,6 +155,8 @@ typedef struct {
  *   "tc_accum_split" 1 (default): hi*hi and the cross terms use separate TMEM accumulators, added in
  *                  the epilogue (3x fewer truncating accumulations on the large sum; tile <= 128 columns);
  *   "tc_prepack"   1 (default): pre-pack the small operand once per launch (see tc_prepack above);
+ *   "tc_pair"      0: off; n >= 5: tiles of 2^n .. 128 columns run on CTA pairs (tcgen05 cta_group::2,
+ *                  two m tiles share one B tile, each SM stages half of it);
  *   "tc_persistent" 1 (default): one CTA per SM streams over the tiles with loads, MMAs and
  *                  epilogue of neighbouring tiles overlapped; 0: one CTA per tile.
  * Returns QTN_ERR_ARG for an unknown name. */

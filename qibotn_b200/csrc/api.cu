@@ -22,6 +22,7 @@ int g_tc_persistent = 1;
 int g_tc_terms = 3;
 int g_tc_accum_split = 1;
 int g_tc_prepack = 1;
+int g_tc_pair = 0;
 }  // namespace
 
 extern "C" int qtn_option_tc_enable(void) { return g_tc_enable; }
@@ -30,6 +31,7 @@ extern "C" int qtn_option_tc_persistent(void) { return g_tc_persistent; }
 extern "C" int qtn_option_tc_terms(void) { return g_tc_terms; }
 extern "C" int qtn_option_tc_accum_split(void) { return g_tc_accum_split; }
 extern "C" int qtn_option_tc_prepack(void) { return g_tc_prepack; }
+extern "C" int qtn_option_tc_pair(void) { return g_tc_pair; }
 
 extern "C" int qtn_set_option(const char *name, int value) {
   if (!name) return qtn_fail(QTN_ERR_ARG, "qtn_set_option: null name");
@@ -39,6 +41,7 @@ extern "C" int qtn_set_option(const char *name, int value) {
   if (!std::strcmp(name, "tc_terms")) { g_tc_terms = value >= 4 ? 4 : 3; return QTN_OK; }
   if (!std::strcmp(name, "tc_accum_split")) { g_tc_accum_split = value != 0; return QTN_OK; }
   if (!std::strcmp(name, "tc_prepack")) { g_tc_prepack = value != 0; return QTN_OK; }
+  if (!std::strcmp(name, "tc_pair")) { g_tc_pair = value < 0 ? 0 : value; return QTN_OK; }
   return qtn_fail(QTN_ERR_ARG, "qtn_set_option: unknown option");
 }
 
@@ -50,6 +53,7 @@ extern "C" int qtn_get_option(const char *name, int *value) {
   if (!std::strcmp(name, "tc_terms")) { *value = g_tc_terms; return QTN_OK; }
   if (!std::strcmp(name, "tc_accum_split")) { *value = g_tc_accum_split; return QTN_OK; }
   if (!std::strcmp(name, "tc_prepack")) { *value = g_tc_prepack; return QTN_OK; }
+  if (!std::strcmp(name, "tc_pair")) { *value = g_tc_pair; return QTN_OK; }
   return qtn_fail(QTN_ERR_ARG, "qtn_get_option: unknown option");
 }
 

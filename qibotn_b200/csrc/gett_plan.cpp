@@ -320,6 +320,16 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
         p->workspace_bytes = p->tc_prepack_off + images * image_bytes;
       }
     }
+    // CTA pairs (cta_group::2): two m tiles that share a B tile run on the two SMs of a TPC, each
+    // staging half of B -- for the tiles whose MMAs saturate shared-memory bandwidth on one SM
+    p->tc_pair = 0;
+    if (qtn_option_tc_pair() && p->tc_prepack && sep && tnb >= qtn_option_tc_pair() && tnb <= 7 && p->n_mhi >= 1) {
+      p->tc_pair = 1;
+      const int pair_stage = 4 * (p->tc_plane_a + p->tc_plane_b / 2);
+      p->tc_stages = std::max(2, std::min(6, (200 * 1024) / pair_stage));
+      p->smem_bytes = p->tc_stages * pair_stage + 256;
+      p->tc_reserved = sm_count & ~1;
+    }
     p->sa_stride = 0; p->sb_stride = 0;
   } else {
     // ---- shared-memory tiled kernel -----------------------------------------

@@ -713,6 +713,342 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
 }
 
 
+// --------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of one cluster, resident on the two SMs of a
+// TPC, work on two tiles that share the same B tile (m tile indices 2j and 2j+1).  Each CTA stages
+// its own 128 rows of A and only HALF of the B rows; the leader's MMA thread issues one
+// 256 x TN x 8 instruction that reads both shared memories and writes each CTA's 128 accumulator
+// lanes into that CTA's TMEM.  Per SM and per MMA this is 4 KB (A) + 2 KB (B) of operand reads
+// instead of 4 + 4 -- the single-CTA M = 128, N = 128 tf32 MMA needs the whole 128 B/clk of
+// shared-memory bandwidth by itself, leaving nothing for the producers' stores -- and half the
+// bulk-copy traffic for B.  Always split accumulators (SEP) and pre-packed B (PRE).
+//
+// Protocol (per CTA unless noted):
+//   full[s]    256 producer arrivals + 1 expect_tx (the four half-plane bulk copies)
+//   pfull[s]   (leader's) 1 arrival: the peer's forwarder thread waits the peer's full[s] and
+//              arrives remotely -- the leader issues once both are complete
+//   empty[s]   1 arrival in BOTH CTAs: tcgen05.commit ... multicast::cluster
+//   tfull[b]   1 arrival in BOTH CTAs by the same multicast commit
+//   tempty[b]  (leader's) 256 arrivals: the 128 epilogue threads of each CTA
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  unsigned spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t slot_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in both CTAs once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_m256(int n, int neg_a) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)neg_a << 13) | ((uint32_t)(n >> 3) << 17) |
+         ((256u >> 4) << 24);
+}
+
+template <int TNB, int TKB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP, 1)
+gett_tc_pair_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ A,
+                    float2 *__restrict__ C, float2 *__restrict__ ws, const int32_t *__restrict__ slice_id) {
+  constexpr int TN = 1 << TNB, KT = 1 << TKB;
+  constexpr int PLANE_A = 128 * KT, PLANE_B = TN * KT, PLANE_BH = PLANE_B / 2;
+  constexpr int STAGE = 4 * (PLANE_A + PLANE_BH);
+  constexpr int NA = PLANE_A / kProducerThreads;
+  constexpr int ACC = 4;
+  static_assert(TN >= 32 && ACC * TN <= 512, "tile does not fit the pair kernel");
+  constexpr int NBUF = 2 * ACC * TN <= 512 ? 2 : 1;
+  constexpr int TMEM_COLS = NBUF * ACC * TN;
+  constexpr uint32_t LBO = 128, SBO = KT * 32;
+  constexpr uint32_t IDESC = umma_idesc_tf32_m256(TN, 0), IDESC_NEG = umma_idesc_tf32_m256(TN, 1);
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float *stages = reinterpret_cast<float *>(smem_raw);
+  const int S = P.tc_stages;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * STAGE * sizeof(float));
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + 2 * NBUF);
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto pfull_bar = [&](int s) { return bar0 + 8u * (2 * S + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (3 * S + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (3 * S + NBUF + b); };
+
+  // a "super tile" = the two tiles (mh = 2j, 2j+1) of one (split, nh, j); CTA pairs stride over them
+  const unsigned long long nsuper = (unsigned long long)P.grid >> 1;
+  const unsigned long long pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int k_iters_bits = P.n_khi - P.split_bits;
+  const unsigned long long k_iters = 1ull << k_iters_bits;
+  const long long a_slice = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
+  auto decode = [&](unsigned long long u, unsigned &split, unsigned long long &nh, unsigned long long &mh) {
+    split = (unsigned)(u & ((1ull << P.split_bits) - 1));
+    u >>= P.split_bits;
+    nh = u & ((1ull << P.n_nhi) - 1);
+    mh = ((u >> P.n_nhi) << 1) | rank;
+  };
+
+  if (t == 32) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), kProducerThreads + 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(pfull_bar(s), 1);
+    }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 2 * kEpilogueThreads); }
+    fence_proxy_async_smem();
+    fence_mbar_init();
+  }
+  if (warp == 12) tmem_alloc_pair<TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  cluster_sync_all();                              // barriers of both CTAs are initialised
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ================= producers: this CTA's A rows, its half of the B rows =================
+    long long a_t_g = 0;
+    int a_t_s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!((t >> j) & 1)) continue;
+      if (j < P.na_lo) { a_t_g |= 1ll << P.a_lo_pos[j]; a_t_s += P.a_lo_sstr[j]; }
+    }
+    const float sgn_a = P.conj_a ? -1.f : 1.f;
+    unsigned long long u = pair0, kk = 0;
+    long long a_k = 0;
+    constexpr uint32_t kImageBytes = 16u * PLANE_B, kHalfBytes = 4u * PLANE_BH;
+    const unsigned char *images = reinterpret_cast<const unsigned char *>(ws) + P.tc_prepack_off;
+    unsigned long long image0 = 0;
+    auto enter_tile = [&]() {
+      unsigned split;
+      unsigned long long nh, mh;
+      decode(u, split, nh, mh);
+      const unsigned long long kh0 = (unsigned long long)split << k_iters_bits;
+      a_k = a_slice | deposit_warp(mh, P.a_mhi, P.n_mhi) | deposit_warp(kh0, P.a_khi, P.n_khi);
+      image0 = (nh << P.n_khi) | kh0;
+      kk = 0;
+    };
+    auto advance = [&]() {
+      if (kk + 1 == k_iters) { u += npairs; if (u < nsuper) enter_tile(); return; }
+      const unsigned long long flip = kk ^ (kk + 1);
+      const int nflip = 64 - __clzll(flip);
+      for (int i = 0; i < nflip && i < k_iters_bits; ++i) a_k ^= 1ll << P.a_khi[i];
+      ++kk;
+    };
+    auto load = [&](float2(&va)[NA], unsigned long long &img) {
+#pragma unroll
+      for (int i = 0; i < NA; ++i) va[i] = __ldg(A + (a_k | a_t_g | P.tc_a_it_g[i]));
+      img = image0 + kk;
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    auto store = [&](const float2(&va)[NA], unsigned long long img) {
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      float *sA = stages + (size_t)s * STAGE;
+      float *sB = sA + 4 * PLANE_A;
+      if (t == 0) {                                 // rows [rank*TN/2, (rank+1)*TN/2) of the four B planes
+        mbar_arrive_expect_tx(full_bar(s), 4u * kHalfBytes);
+        const unsigned char *src = images + img * kImageBytes + (size_t)rank * kHalfBytes;
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl)
+          bulk_copy_g2s(smem_u32(sB + pl * PLANE_BH), src + (size_t)pl * 4u * PLANE_B, kHalfBytes, full_bar(s));
+      }
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        const int o = a_t_s + P.tc_a_it_s[i];
+        float h, l;
+        split_tf32(va[i].x, h, l);
+        sA[o] = h; sA[PLANE_A + o] = l;
+        split_tf32(va[i].y * sgn_a, h, l);
+        sA[2 * PLANE_A + o] = h; sA[3 * PLANE_A + o] = l;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(full_bar(s));
+      if (++s == S) { s = 0; ph ^= 1u; }
+    };
+    constexpr int D = 4;
+    float2 va[D][NA];
+    unsigned long long img[D];
+    bool have[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      have[d] = u < nsuper;
+      img[d] = 0;
+      if (have[d]) { if (d == 0) enter_tile(); load(va[d], img[d]); advance(); }
+    }
+    bool done = false;
+    while (!done) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        if (done) continue;
+        if (!have[d]) { done = true; continue; }
+        store(va[d], img[d]);
+        have[d] = u < nsuper;
+        if (have[d]) { load(va[d], img[d]); advance(); }
+      }
+    }
+  } else if (warp < 12) {
+    // ================= epilogue: this CTA's 128 accumulator lanes -> its tile of C =================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const long long row_off = (r & 31) + ((long long)(r >> 5) << (5 + TNB));
+    constexpr int CH = 16;
+    unsigned long long it = 0;
+    for (unsigned long long u = pair0; u < nsuper; u += npairs, ++it) {
+      const int buf = (int)(it % NBUF);
+      const uint32_t tph = (uint32_t)((it / NBUF) & 1);
+      unsigned split;
+      unsigned long long nh, mh;
+      decode(u, split, nh, mh);
+      const long long c_base = deposit_warp(mh, P.c_mhi, P.n_mhi) | deposit_warp(nh, P.c_nhi, P.n_nhi);
+      float2 *out = (P.split_bits ? ws + (long long)split * P.c_elems : C) + c_base + row_off;
+      mbar_wait(tfull_bar(buf), tph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC * TN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += CH) {
+        uint32_t re[CH], im[CH], xr[CH], xi[CH];
+        tmem_ld<CH>::run(trow + (uint32_t)c0, re);
+        tmem_ld<CH>::run(trow + (uint32_t)(TN + c0), im);
+        tmem_ld<CH>::run(trow + (uint32_t)(2 * TN + c0), xr);
+        tmem_ld<CH>::run(trow + (uint32_t)(3 * TN + c0), xi);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          out[(long long)(c0 + j) << 5] = make_float2(__uint_as_float(re[j]) + __uint_as_float(xr[j]),
+                                                      __uint_as_float(im[j]) + __uint_as_float(xi[j]));
+      }
+      tc_fence_before();
+      if (rank == 0) mbar_arrive(tempty_bar(buf));
+      else mbar_arrive_remote(tempty_bar(buf), 0);
+    }
+  } else if (lane == 0 && rank == 0) {
+    // ================= MMA issuer (leader CTA) =================
+    int s = 0;
+    uint32_t ph = 0;
+    unsigned long long it = 0;
+    for (unsigned long long u = pair0; u < nsuper; u += npairs, ++it) {
+      const int buf = (int)(it % NBUF);
+      const uint32_t tph = (uint32_t)((it / NBUF) & 1);
+      mbar_wait_cluster(tempty_bar(buf), tph ^ 1u);
+      tc_fence_after();
+      const uint32_t cr = tmem_base + (uint32_t)(buf * ACC * TN), ci = cr + TN;
+      const uint32_t xr = cr + 2 * TN, xi = cr + 3 * TN;
+      for (unsigned long long kk = 0; kk < k_iters; ++kk) {
+        mbar_wait(full_bar(s), ph);
+        mbar_wait_cluster(pfull_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(stages + (size_t)s * STAGE);
+        const uint32_t sb = sa + 16u * PLANE_A;
+#pragma unroll
+        for (int ks = 0; ks < KT / 8; ++ks) {
+          const uint32_t ko = (uint32_t)ks * 2u * LBO;
+          const uint64_t arh = umma_desc(sa + ko, LBO, SBO);
+          const uint64_t arl = umma_desc(sa + 4u * PLANE_A + ko, LBO, SBO);
+          const uint64_t aih = umma_desc(sa + 8u * PLANE_A + ko, LBO, SBO);
+          const uint64_t ail = umma_desc(sa + 12u * PLANE_A + ko, LBO, SBO);
+          const uint64_t brh = umma_desc(sb + ko, LBO, SBO);
+          const uint64_t brl = umma_desc(sb + 4u * PLANE_BH + ko, LBO, SBO);
+          const uint64_t bih = umma_desc(sb + 8u * PLANE_BH + ko, LBO, SBO);
+          const uint64_t bil = umma_desc(sb + 12u * PLANE_BH + ko, LBO, SBO);
+          const uint32_t acc = (kk | (unsigned)ks) ? 1u : 0u;
+          umma_tf32_pair(xr, arl, brh, IDESC, acc);
+          umma_tf32_pair(xr, arh, brl, IDESC, 1u);
+          umma_tf32_pair(xr, ail, bih, IDESC_NEG, 1u);
+          umma_tf32_pair(xr, aih, bil, IDESC_NEG, 1u);
+          umma_tf32_pair(cr, arh, brh, IDESC, acc);
+          umma_tf32_pair(cr, aih, bih, IDESC_NEG, 1u);
+          umma_tf32_pair(xi, arl, bih, IDESC, acc);
+          umma_tf32_pair(xi, arh, bil, IDESC, 1u);
+          umma_tf32_pair(xi, ail, brh, IDESC, 1u);
+          umma_tf32_pair(xi, aih, brl, IDESC, 1u);
+          umma_tf32_pair(ci, arh, bih, IDESC, acc);
+          umma_tf32_pair(ci, aih, brh, IDESC, 1u);
+          if (P.tc_terms >= 4) {
+            umma_tf32_pair(xr, arl, brl, IDESC, 1u);
+            umma_tf32_pair(xr, ail, bil, IDESC_NEG, 1u);
+            umma_tf32_pair(xi, arl, bil, IDESC, 1u);
+            umma_tf32_pair(xi, ail, brl, IDESC, 1u);
+          }
+        }
+        umma_commit_pair(empty_bar(s));
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+      umma_commit_pair(tfull_bar(buf));
+    }
+  } else if (lane == 0) {
+    // ================= forwarder (peer CTA): "my stage is full" -> the leader =================
+    int s = 0;
+    uint32_t ph = 0;
+    for (unsigned long long u = pair0; u < nsuper; u += npairs) {
+      for (unsigned long long kk = 0; kk < k_iters; ++kk) {
+        mbar_wait(full_bar(s), ph);
+        mbar_arrive_remote(pfull_bar(s), 0);
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();                              // nobody leaves while the other still signals / reads it
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+  }
+}
+
+
 // B pre-pack: one CTA per (n tile, k chunk) writes that B stage -- split into hi/lo re/im planes
 // and laid out exactly as the main kernel's shared-memory stage -- to the workspace.
 template <int TNB, int TKB>
@@ -770,6 +1106,24 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
       return QTN_OK;
     };
     static int set_sp = 0, set_s = 0, set_p = 0, set_0 = 0;
+    if (P.tc_pair) {                              // CTA pairs (cta_group::2): tc_reserved is even
+      if constexpr (TNB >= 5 && TNB <= 7) {
+        if (!P.tc_pad || !P.tc_prepack || (P.grid & 1) || (ctas & 1))
+          return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: malformed CTA-pair plan");
+        static int set_pair = 0;
+        if (set_pair < P.smem_bytes) {
+          QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tc_pair_kernel<TNB, TKB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              P.smem_bytes));
+          set_pair = P.smem_bytes;
+        }
+        gett_tc_pair_kernel<TNB, TKB><<<(unsigned)ctas, kThreadsP, P.smem_bytes, st>>>(P, (const float2 *)a, (float2 *)c,
+                                                                                    (float2 *)ws, slice_id);
+        QTN_LAUNCH_CHECK();
+        return QTN_OK;
+      } else {
+        return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: CTA pairs need a tile of 32 to 128 columns");
+      }
+    }
     if (P.tc_pad) {                               // separate cross-term accumulators (TN <= 128)
       if constexpr (TNB <= 7) {
         return P.tc_prepack ? go(gett_tc_persistent_kernel<TNB, TKB, true, true>, set_sp)

@@ -14,6 +14,7 @@ int qtn_option_tc_persistent(void);
 int qtn_option_tc_terms(void);
 int qtn_option_tc_accum_split(void);
 int qtn_option_tc_prepack(void);
+int qtn_option_tc_pair(void);
 #ifdef __cplusplus
 }
 #endif

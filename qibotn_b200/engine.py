@@ -67,16 +67,36 @@ def plan(net: TensorNetwork, dtype="complex64", samples=32, seed=0, min_slices=1
     return info, lowered
 
 
+def _runner_bytes(lowered):
+    return int(lowered.leaf_bytes + lowered.hoist_bytes + lowered.slice_bytes + lowered.workspace_bytes)
+
+
 def runner_for(lowered, use_graph=True):
+    """Runner (device arenas + captured graphs) of a lowered contraction, cached by identity.
+
+    The cache is bounded by count AND by device bytes (half of the GPU's memory): an expectation
+    value with many differently shaped terms (light cones) would otherwise pin one multi-GB arena
+    per term."""
+    import torch
+
     key = id(lowered)
     r = _RUNNER_CACHE.get(key)
-    if r is None:
-        if len(_RUNNER_CACHE) >= _CACHE_LIMIT:
-            _RUNNER_CACHE.pop(next(iter(_RUNNER_CACHE)))
-        r = executor.ContractionRunner(lowered, use_graph=use_graph)
-        _RUNNER_CACHE[key] = (lowered, r)          # keep `lowered` alive so the id stays unique
-        return r
-    return r[1]
+    if r is not None:
+        return r[1]
+    need = _runner_bytes(lowered)
+    budget = 0
+    if torch.cuda.is_available():
+        budget = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory // 2
+    evicted = False
+    while _RUNNER_CACHE and (len(_RUNNER_CACHE) >= _CACHE_LIMIT or
+                             need + sum(_runner_bytes(v[0]) for v in _RUNNER_CACHE.values()) > budget):
+        _RUNNER_CACHE.pop(next(iter(_RUNNER_CACHE)))
+        evicted = True
+    if evicted and need > (64 << 20):
+        torch.cuda.empty_cache()               # hand the evicted arenas back before asking for a large one
+    r = executor.ContractionRunner(lowered, use_graph=use_graph)
+    _RUNNER_CACHE[key] = (lowered, r)          # keep `lowered` alive so the id stays unique
+    return r
 
 
 def contract(net: TensorNetwork, dtype="complex64", samples=32, seed=0, min_slices=1,

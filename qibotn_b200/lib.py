@@ -66,7 +66,7 @@ class PairPlan(C.Structure):
         ("tc_a_it_g", C.c_int64 * 8), ("tc_b_it_g", C.c_int64 * 16),
         ("tc_a_it_s", C.c_int32 * 8), ("tc_b_it_s", C.c_int32 * 16),
         ("tc_terms", C.c_int32), ("tc_pad", C.c_int32),
-        ("tc_prepack", C.c_int32), ("tc_pad2", C.c_int32), ("tc_prepack_off", C.c_int64),
+        ("tc_prepack", C.c_int32), ("tc_pair", C.c_int32), ("tc_prepack_off", C.c_int64),
     ]
 
 
