@@ -97,6 +97,22 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel, plan):
+    """DRAM bytes per launch of this node, if an ncu capture of it is on file (profiles/ncu_traffic.json:
+    entries keyed by kernel name and the node's algorithmic flops and bytes)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            table = json.load(f)
+    except (OSError, ValueError):
+        return None
+    for e in table.get("entries", []):
+        if (e["kernel"] == kernel and abs(e["algorithmic_flops"] - plan.flops) < 1 and
+                abs(e["algorithmic_bytes"] - plan.bytes) < 1):
+            return e["dram_bytes"]
+    return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -335,6 +351,8 @@ def run_b200(a):
     intensity = node.plan.flops / node.plan.bytes
     names = {0: "gett_tile_kernel<float>", 1: "gett_reduce_kernel<float>", 2: "gett_tc_persistent_kernel",
              3: "gett_kred_kernel<float>"}
+    if node.plan.kernel == lib.KERNEL_TC and node.plan.tc_pair:
+        names[2] = "gett_tc_pair_kernel"
     if node.plan.kernel == lib.KERNEL_TC:
         # tcgen05 kind::tf32, 3 MMAs per product (hi*hi + hi*lo + lo*hi): the tensor pipe does 3x
         # the algorithmic flops at the tf32 rate (half the bf16 rate measured in MEASURED_PEAKS.json)
@@ -344,8 +362,9 @@ def run_b200(a):
                  "tf32_peak_assumed_tflops": peaks["bf16_tflops"] / 2,
                  "tensor_pipe_frac_tf32": 3.0 * k_tfs / (peaks["bf16_tflops"] / 2),
                  "hbm_gbs_at_this_speed": node.plan.bytes / (k_ms * 1e-3) / 1e9,
-                 "traffic_note": "ncu --set full of this kernel on the same shape class: dram bytes = algorithmic "
-                                 "bytes within 1% (profiles/r01_ncu_full_prof_tc_m22n7k7_prepack.txt)",
+                 "traffic_note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum of this very node from an "
+                                 "ncu --set full capture of one slice (profiles/ncu_traffic.json); null when the "
+                                 "node was not captured",
                  "note": "frac is algorithmic complex64 flops over the measured bf16 cuBLAS burst; "
                          "tensor_pipe_frac_tf32 is the share of the tf32 pipe the 3x split keeps busy"}
     else:
@@ -359,7 +378,7 @@ def run_b200(a):
         extra = {"fp32_pipe_tflops_measured": fp32_peak, "fp32_pipe_frac": k_tfs / fp32_peak,
                  "note": "complex64 FFMA kernel on the FP32 pipe; tensor peak is the bf16 cuBLAS burst"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof.update({"traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json, burst)",
+    roof.update({"traffic": ncu_traffic(names.get(node.plan.kernel, "?"), node.plan), "peak_source": peak_src + " (MEASURED_PEAKS.json, burst)",
                  "kernel": names.get(node.plan.kernel, "?"),
                  "kernel_ms": k_ms, "kernel_flops": node.plan.flops, "kernel_bytes": node.plan.bytes,
                  "tile_log2": [node.plan.tmb, node.plan.tnb, node.plan.tkb],

@@ -155,8 +155,9 @@ typedef struct {
  *   "tc_accum_split" 1 (default): hi*hi and the cross terms use separate TMEM accumulators, added in
  *                  the epilogue (3x fewer truncating accumulations on the large sum; tile <= 128 columns);
  *   "tc_prepack"   1 (default): pre-pack the small operand once per launch (see tc_prepack above);
- *   "tc_pair"      0: off; n >= 5: tiles of 2^n .. 128 columns run on CTA pairs (tcgen05 cta_group::2,
- *                  two m tiles share one B tile, each SM stages half of it);
+ *   "tc_pair"      5 (default): tiles of 2^5 .. 128 columns with a pre-packed B run on CTA pairs
+ *                  (tcgen05 cta_group::2: two m tiles share one B tile, each SM stages half of it);
+ *                  n = 6, 7 raises the smallest paired tile to 2^n columns, 0 turns pairs off;
  *   "tc_persistent" 1 (default): one CTA per SM streams over the tiles with loads, MMAs and
  *                  epilogue of neighbouring tiles overlapped; 0: one CTA per tile.
  * Returns QTN_ERR_ARG for an unknown name. */

@@ -22,7 +22,7 @@ int g_tc_persistent = 1;
 int g_tc_terms = 3;
 int g_tc_accum_split = 1;
 int g_tc_prepack = 1;
-int g_tc_pair = 0;
+int g_tc_pair = 5;
 }  // namespace
 
 extern "C" int qtn_option_tc_enable(void) { return g_tc_enable; }

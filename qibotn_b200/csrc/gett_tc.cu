@@ -97,6 +97,20 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
                : "memory");
 }
 
+// One lane of a fully converged warp.  Code under `if (elect_one())` inside warp-uniform control
+// flow lets ptxas keep descriptors in uniform registers and issue the MMAs back to back; under a
+// `lane == 0` branch it wraps EVERY tcgen05.mma in an ELECT / BRA.U.ANY loop (~6 extra
+// instructions and a branch per MMA), which made the issuing thread the bottleneck of the kernel.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc]^T, tf32 inputs, fp32 accumulate
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                           uint32_t idesc, uint32_t accumulate) {
@@ -464,7 +478,7 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * STAGE * sizeof(float));
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 2 * NBUF);
   const int t = threadIdx.x;
-  const int warp = t >> 5, lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0), lane = t & 31;   // provably warp-uniform
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
@@ -645,61 +659,66 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));                 // accumulator buffer may be overwritten
     }
-  } else if (lane == 0) {
-    // ================= MMA issuer =================
+  } else {
+    // ================= MMA issuer: the whole warp walks the loops, one elected lane issues =================
     int s = 0;
     uint32_t ph = 0;
     unsigned long long it = 0;
+    const uint32_t tmem_b = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t stage0 = smem_u32(stages);
     for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int buf = (int)(it % NBUF);
       const uint32_t tph = (uint32_t)((it / NBUF) & 1);
       mbar_wait(tempty_bar(buf), tph ^ 1u);         // epilogue has drained this buffer
       tc_fence_after();
-      const uint32_t cr = tmem_base + (uint32_t)(buf * ACC * TN), ci = cr + TN;
+      const uint32_t cr = tmem_b + (uint32_t)(buf * ACC * TN), ci = cr + TN;
       const uint32_t xr = SEP ? cr + 2 * TN : cr, xi = SEP ? cr + 3 * TN : ci;   // cross-term targets
       for (unsigned long long kk = 0; kk < k_iters; ++kk) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(stages + (size_t)s * STAGE);
-        const uint32_t sb = sa + 16u * PLANE_A;
+        if (elect_one()) {
+          const uint32_t sa = stage0 + (uint32_t)s * (uint32_t)(STAGE * sizeof(float));
+          const uint32_t sb = sa + 16u * PLANE_A;
 #pragma unroll
-        for (int ks = 0; ks < KT / 8; ++ks) {
-          const uint32_t ko = (uint32_t)ks * 2u * LBO;
-          const uint64_t arh = umma_desc(sa + ko, LBO, SBO);
-          const uint64_t arl = umma_desc(sa + 4u * PLANE_A + ko, LBO, SBO);
-          const uint64_t aih = umma_desc(sa + 8u * PLANE_A + ko, LBO, SBO);
-          const uint64_t ail = umma_desc(sa + 12u * PLANE_A + ko, LBO, SBO);
-          const uint64_t brh = umma_desc(sb + ko, LBO, SBO);
-          const uint64_t brl = umma_desc(sb + 4u * PLANE_B + ko, LBO, SBO);
-          const uint64_t bih = umma_desc(sb + 8u * PLANE_B + ko, LBO, SBO);
-          const uint64_t bil = umma_desc(sb + 12u * PLANE_B + ko, LBO, SBO);
-          const uint32_t acc = (kk | (unsigned)ks) ? 1u : 0u;
-          const uint32_t accx = SEP ? acc : 1u;      // SEP: the cross region starts from zero too
-          if constexpr (!SEP) umma_tf32(cr, arh, brh, IDESC, acc);      // hi*hi first, then the rest
-          umma_tf32(xr, arl, brh, IDESC, accx);
-          umma_tf32(xr, arh, brl, IDESC, 1u);
-          umma_tf32(xr, ail, bih, IDESC_NEG, 1u);
-          umma_tf32(xr, aih, bil, IDESC_NEG, 1u);
-          if constexpr (SEP) umma_tf32(cr, arh, brh, IDESC, acc);
-          umma_tf32(cr, aih, bih, IDESC_NEG, 1u);
-          if constexpr (!SEP) umma_tf32(ci, arh, bih, IDESC, acc);
-          umma_tf32(xi, arl, bih, IDESC, accx);
-          umma_tf32(xi, arh, bil, IDESC, 1u);
-          umma_tf32(xi, ail, brh, IDESC, 1u);
-          umma_tf32(xi, aih, brl, IDESC, 1u);
-          if constexpr (SEP) umma_tf32(ci, arh, bih, IDESC, acc);
-          umma_tf32(ci, aih, brh, IDESC, 1u);
-          if (P.tc_terms >= 4) {                   // lo*lo as well
-            umma_tf32(xr, arl, brl, IDESC, 1u);
-            umma_tf32(xr, ail, bil, IDESC_NEG, 1u);
-            umma_tf32(xi, arl, bil, IDESC, 1u);
-            umma_tf32(xi, ail, brl, IDESC, 1u);
+          for (int ks = 0; ks < KT / 8; ++ks) {
+            const uint32_t ko = (uint32_t)ks * 2u * LBO;
+            const uint64_t arh = umma_desc(sa + ko, LBO, SBO);
+            const uint64_t arl = umma_desc(sa + 4u * PLANE_A + ko, LBO, SBO);
+            const uint64_t aih = umma_desc(sa + 8u * PLANE_A + ko, LBO, SBO);
+            const uint64_t ail = umma_desc(sa + 12u * PLANE_A + ko, LBO, SBO);
+            const uint64_t brh = umma_desc(sb + ko, LBO, SBO);
+            const uint64_t brl = umma_desc(sb + 4u * PLANE_B + ko, LBO, SBO);
+            const uint64_t bih = umma_desc(sb + 8u * PLANE_B + ko, LBO, SBO);
+            const uint64_t bil = umma_desc(sb + 12u * PLANE_B + ko, LBO, SBO);
+            const uint32_t acc = (kk | (unsigned)ks) ? 1u : 0u;
+            const uint32_t accx = SEP ? acc : 1u;      // SEP: the cross region starts from zero too
+            if constexpr (!SEP) umma_tf32(cr, arh, brh, IDESC, acc);      // hi*hi first, then the rest
+            umma_tf32(xr, arl, brh, IDESC, accx);
+            umma_tf32(xr, arh, brl, IDESC, 1u);
+            umma_tf32(xr, ail, bih, IDESC_NEG, 1u);
+            umma_tf32(xr, aih, bil, IDESC_NEG, 1u);
+            if constexpr (SEP) umma_tf32(cr, arh, brh, IDESC, acc);
+            umma_tf32(cr, aih, bih, IDESC_NEG, 1u);
+            if constexpr (!SEP) umma_tf32(ci, arh, bih, IDESC, acc);
+            umma_tf32(xi, arl, bih, IDESC, accx);
+            umma_tf32(xi, arh, bil, IDESC, 1u);
+            umma_tf32(xi, ail, brh, IDESC, 1u);
+            umma_tf32(xi, aih, brl, IDESC, 1u);
+            if constexpr (SEP) umma_tf32(ci, arh, bih, IDESC, acc);
+            umma_tf32(ci, aih, brh, IDESC, 1u);
+            if (P.tc_terms >= 4) {                   // lo*lo as well
+              umma_tf32(xr, arl, brl, IDESC, 1u);
+              umma_tf32(xr, ail, bil, IDESC_NEG, 1u);
+              umma_tf32(xi, arl, bil, IDESC, 1u);
+              umma_tf32(xi, ail, brl, IDESC, 1u);
+            }
           }
+          umma_commit(empty_bar(s));
+          if (kk + 1 == k_iters) umma_commit(tfull_bar(buf));
         }
-        umma_commit(empty_bar(s));
+        __syncwarp();
         if (++s == S) { s = 0; ph ^= 1u; }
       }
-      umma_commit(tfull_bar(buf));
     }
   }
 
@@ -816,8 +835,8 @@ gett_tc_pair_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__r
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * STAGE * sizeof(float));
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + 2 * NBUF);
   const int t = threadIdx.x;
-  const int warp = t >> 5, lane = t & 31;
-  const uint32_t rank = cluster_ctarank();
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0), lane = t & 31;   // provably warp-uniform
+  const uint32_t rank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
@@ -972,68 +991,73 @@ gett_tc_pair_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__r
       if (rank == 0) mbar_arrive(tempty_bar(buf));
       else mbar_arrive_remote(tempty_bar(buf), 0);
     }
-  } else if (lane == 0 && rank == 0) {
-    // ================= MMA issuer (leader CTA) =================
+  } else if (rank == 0) {
+    // ================= MMA issuer (leader CTA): whole warp walks the loops, one elected lane issues =================
     int s = 0;
     uint32_t ph = 0;
     unsigned long long it = 0;
+    const uint32_t tmem_b = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t stage0 = smem_u32(stages);
     for (unsigned long long u = pair0; u < nsuper; u += npairs, ++it) {
       const int buf = (int)(it % NBUF);
       const uint32_t tph = (uint32_t)((it / NBUF) & 1);
       mbar_wait_cluster(tempty_bar(buf), tph ^ 1u);
       tc_fence_after();
-      const uint32_t cr = tmem_base + (uint32_t)(buf * ACC * TN), ci = cr + TN;
+      const uint32_t cr = tmem_b + (uint32_t)(buf * ACC * TN), ci = cr + TN;
       const uint32_t xr = cr + 2 * TN, xi = cr + 3 * TN;
       for (unsigned long long kk = 0; kk < k_iters; ++kk) {
         mbar_wait(full_bar(s), ph);
         mbar_wait_cluster(pfull_bar(s), ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(stages + (size_t)s * STAGE);
-        const uint32_t sb = sa + 16u * PLANE_A;
+        if (elect_one()) {
+          const uint32_t sa = stage0 + (uint32_t)s * (uint32_t)(STAGE * sizeof(float));
+          const uint32_t sb = sa + 16u * PLANE_A;
 #pragma unroll
-        for (int ks = 0; ks < KT / 8; ++ks) {
-          const uint32_t ko = (uint32_t)ks * 2u * LBO;
-          const uint64_t arh = umma_desc(sa + ko, LBO, SBO);
-          const uint64_t arl = umma_desc(sa + 4u * PLANE_A + ko, LBO, SBO);
-          const uint64_t aih = umma_desc(sa + 8u * PLANE_A + ko, LBO, SBO);
-          const uint64_t ail = umma_desc(sa + 12u * PLANE_A + ko, LBO, SBO);
-          const uint64_t brh = umma_desc(sb + ko, LBO, SBO);
-          const uint64_t brl = umma_desc(sb + 4u * PLANE_BH + ko, LBO, SBO);
-          const uint64_t bih = umma_desc(sb + 8u * PLANE_BH + ko, LBO, SBO);
-          const uint64_t bil = umma_desc(sb + 12u * PLANE_BH + ko, LBO, SBO);
-          const uint32_t acc = (kk | (unsigned)ks) ? 1u : 0u;
-          umma_tf32_pair(xr, arl, brh, IDESC, acc);
-          umma_tf32_pair(xr, arh, brl, IDESC, 1u);
-          umma_tf32_pair(xr, ail, bih, IDESC_NEG, 1u);
-          umma_tf32_pair(xr, aih, bil, IDESC_NEG, 1u);
-          umma_tf32_pair(cr, arh, brh, IDESC, acc);
-          umma_tf32_pair(cr, aih, bih, IDESC_NEG, 1u);
-          umma_tf32_pair(xi, arl, bih, IDESC, acc);
-          umma_tf32_pair(xi, arh, bil, IDESC, 1u);
-          umma_tf32_pair(xi, ail, brh, IDESC, 1u);
-          umma_tf32_pair(xi, aih, brl, IDESC, 1u);
-          umma_tf32_pair(ci, arh, bih, IDESC, acc);
-          umma_tf32_pair(ci, aih, brh, IDESC, 1u);
-          if (P.tc_terms >= 4) {
-            umma_tf32_pair(xr, arl, brl, IDESC, 1u);
-            umma_tf32_pair(xr, ail, bil, IDESC_NEG, 1u);
-            umma_tf32_pair(xi, arl, bil, IDESC, 1u);
-            umma_tf32_pair(xi, ail, brl, IDESC, 1u);
+          for (int ks = 0; ks < KT / 8; ++ks) {
+            const uint32_t ko = (uint32_t)ks * 2u * LBO;
+            const uint64_t arh = umma_desc(sa + ko, LBO, SBO);
+            const uint64_t arl = umma_desc(sa + 4u * PLANE_A + ko, LBO, SBO);
+            const uint64_t aih = umma_desc(sa + 8u * PLANE_A + ko, LBO, SBO);
+            const uint64_t ail = umma_desc(sa + 12u * PLANE_A + ko, LBO, SBO);
+            const uint64_t brh = umma_desc(sb + ko, LBO, SBO);
+            const uint64_t brl = umma_desc(sb + 4u * PLANE_BH + ko, LBO, SBO);
+            const uint64_t bih = umma_desc(sb + 8u * PLANE_BH + ko, LBO, SBO);
+            const uint64_t bil = umma_desc(sb + 12u * PLANE_BH + ko, LBO, SBO);
+            const uint32_t acc = (kk | (unsigned)ks) ? 1u : 0u;
+            umma_tf32_pair(xr, arl, brh, IDESC, acc);
+            umma_tf32_pair(xr, arh, brl, IDESC, 1u);
+            umma_tf32_pair(xr, ail, bih, IDESC_NEG, 1u);
+            umma_tf32_pair(xr, aih, bil, IDESC_NEG, 1u);
+            umma_tf32_pair(cr, arh, brh, IDESC, acc);
+            umma_tf32_pair(cr, aih, bih, IDESC_NEG, 1u);
+            umma_tf32_pair(xi, arl, bih, IDESC, acc);
+            umma_tf32_pair(xi, arh, bil, IDESC, 1u);
+            umma_tf32_pair(xi, ail, brh, IDESC, 1u);
+            umma_tf32_pair(xi, aih, brl, IDESC, 1u);
+            umma_tf32_pair(ci, arh, bih, IDESC, acc);
+            umma_tf32_pair(ci, aih, brh, IDESC, 1u);
+            if (P.tc_terms >= 4) {
+              umma_tf32_pair(xr, arl, brl, IDESC, 1u);
+              umma_tf32_pair(xr, ail, bil, IDESC_NEG, 1u);
+              umma_tf32_pair(xi, arl, bil, IDESC, 1u);
+              umma_tf32_pair(xi, ail, brl, IDESC, 1u);
+            }
           }
+          umma_commit_pair(empty_bar(s));
+          if (kk + 1 == k_iters) umma_commit_pair(tfull_bar(buf));
         }
-        umma_commit_pair(empty_bar(s));
+        __syncwarp();
         if (++s == S) { s = 0; ph ^= 1u; }
       }
-      umma_commit_pair(tfull_bar(buf));
     }
-  } else if (lane == 0) {
+  } else {
     // ================= forwarder (peer CTA): "my stage is full" -> the leader =================
     int s = 0;
     uint32_t ph = 0;
     for (unsigned long long u = pair0; u < nsuper; u += npairs) {
       for (unsigned long long kk = 0; kk < k_iters; ++kk) {
         mbar_wait(full_bar(s), ph);
-        mbar_arrive_remote(pfull_bar(s), 0);
+        if (lane == 0) mbar_arrive_remote(pfull_bar(s), 0);
         if (++s == S) { s = 0; ph ^= 1u; }
       }
     }

@@ -24,11 +24,17 @@ ap.add_argument("--dtype", default=None, help="override the workload dtype (comp
 ap.add_argument("--no-tc", action="store_true", help="FFMA/DFMA kernels only")
 ap.add_argument("--tc-terms", type=int, default=3)
 ap.add_argument("--accum-split", type=int, default=1)
+ap.add_argument("--tc-pair", type=int, default=None, help="CTA-pair kernel for tiles of >= 2^N columns (0 = off)")
+ap.add_argument("--lib", default=None, help="another build of libqibotn_b200.so (A/B runs)")
 a = ap.parse_args()
 wl = workloads.build(a.workload)
 if a.dtype:
     wl.dtype = a.dtype
 from qibotn_b200 import lib  # noqa: E402
+if a.lib:
+    lib.LIB_PATH = os.path.abspath(a.lib)
+if a.tc_pair is not None:
+    lib.set_option("tc_pair", a.tc_pair)
 if a.no_tc:
     lib.set_option("tc_enable", 0)
 lib.set_option("tc_terms", a.tc_terms)
@@ -51,7 +57,7 @@ for name in a.plan:
     dt = time.perf_counter() - t0
     amp = complex(out.reshape(-1)[0].item())
     flops = low.flops_hoisted + ns * low.flops_per_slice
-    print(json.dumps({"plan": name, "dtype": wl.dtype, "tensor_cores": not a.no_tc, "tc_terms": a.tc_terms, "accum_split": a.accum_split, "log10_flops": math.log10(info.flops), "num_slices": info.num_slices,
+    print(json.dumps({"plan": name, "dtype": wl.dtype, "tensor_cores": not a.no_tc, "tc_terms": a.tc_terms, "accum_split": a.accum_split, "tc_pair": lib.get_option("tc_pair") if a.lib is None or "old" not in a.lib else 0, "lib": a.lib, "log10_flops": math.log10(info.flops), "num_slices": info.num_slices,
                       "slices_run": ns, "log2_width": info.log2_width, "seconds": dt, "tflops": flops / dt / 1e12,
                       "amplitude": [amp.real, amp.imag], "slice_arena_gb": low.slice_bytes / 2**30,
                       "launches_per_slice": low.launches_per_slice}), flush=True)

@@ -12,6 +12,9 @@ import torch
 sys.path.insert(0, ".")
 from qibotn_b200 import lib  # noqa: E402
 
+import os  # noqa: E402
+if os.environ.get("QTN_LIB"):                     # A/B runs against another build of the library
+    lib.LIB_PATH = os.environ["QTN_LIB"]
 h = lib.load()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -94,7 +97,15 @@ def time_case(m, n, k):
     print(json.dumps(res), flush=True)
 
 
-if sys.argv[1] == "check":
+if sys.argv[1] == "one":                          # one launch pair (warm-up + 1) for ncu: one m n k [pair]
+    m, n, k = (int(x) for x in sys.argv[2:5])
+    la, pa, lb, pb, lc = layouts(m, n, k, 0)
+    a = torch.randn(1 << len(la), dtype=torch.complex64, device="cuda")
+    b = torch.randn(1 << len(lb), dtype=torch.complex64, device="cuda")
+    _, plan = plan_for(la, pa, lb, pb, lc, int(sys.argv[5]) if len(sys.argv) > 5 else 0)
+    _, ms = launch(plan, a, b, len(lc), reps=1)
+    print(json.dumps({"mode": "one", "m": m, "n": n, "k": k, "pair": plan.tc_pair, "ms": ms}), flush=True)
+elif sys.argv[1] == "check":
     for (m, n, k), seed in (((10, 7, 7), 1), ((12, 6, 5), 2), ((11, 5, 8), 3), ((13, 7, 4), 4), ((10, 9, 6), 5), ((14, 7, 9), 6)):
         check(m, n, k, seed)
 else:

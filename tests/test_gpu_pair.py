@@ -152,9 +152,8 @@ def test_tensor_core_variants_agree_with_einsum(shape):
     A = _dense(a.astype(np.complex128), la, pa)
     B = _dense(b.astype(np.complex128), lb, pb, off=1 << pb_all[-1])          # slice id 1
     variants = [dict(), dict(tc_persistent=0), dict(tc_prepack=0), dict(tc_accum_split=0),
-                dict(tc_terms=4), dict(tc_prepack=0, tc_accum_split=0), dict(tc_pair=5), dict(tc_pair=5, tc_terms=4)]
-    defaults = dict(tc_persistent=1, tc_prepack=1, tc_accum_split=1, tc_terms=3, tc_min_log2=18,
-                    tc_pair=lib.get_option("tc_pair"))
+                dict(tc_terms=4), dict(tc_prepack=0, tc_accum_split=0), dict(tc_pair=0), dict(tc_pair=0, tc_terms=4), dict(tc_pair=7)]
+    defaults = dict(tc_persistent=1, tc_prepack=1, tc_accum_split=1, tc_terms=3, tc_min_log2=18, tc_pair=5)
     for opts in variants:
         try:
             for key, val in dict(opts, tc_min_log2=0).items():
@@ -164,7 +163,9 @@ def test_tensor_core_variants_agree_with_einsum(shape):
             for key, val in defaults.items():
                 lib.set_option(key, val)
         assert plan.kernel == lib.KERNEL_TC
-        if opts.get("tc_pair"):
-            assert plan.tc_pair == (1 if n >= 5 else 0)
+        want_pair = opts.get("tc_pair", 5)
+        paired = (want_pair and n >= want_pair and opts.get("tc_persistent", 1) and opts.get("tc_prepack", 1)
+                  and opts.get("tc_accum_split", 1))
+        assert plan.tc_pair == (1 if paired else 0), (shape, opts)
         want = np.einsum(A, la, B, lb, lc_used)
         assert np.abs(got - want).max() / np.abs(want).max() < 4e-6 * max(1, k), (shape, opts)
