@@ -362,9 +362,9 @@ def run_b200(a):
                  "tf32_peak_assumed_tflops": peaks["bf16_tflops"] / 2,
                  "tensor_pipe_frac_tf32": 3.0 * k_tfs / (peaks["bf16_tflops"] / 2),
                  "hbm_gbs_at_this_speed": node.plan.bytes / (k_ms * 1e-3) / 1e9,
-                 "traffic_note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum of this very node from an "
-                                 "ncu --set full capture of one slice (profiles/ncu_traffic.json); null when the "
-                                 "node was not captured",
+                 "traffic_note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch from an ncu "
+                                 "--set full capture of this kernel on this node's (m, n, k) shape, launched "
+                                 "stand-alone (profiles/ncu_traffic.json); null when that shape was not captured",
                  "note": "frac is algorithmic complex64 flops over the measured bf16 cuBLAS burst; "
                          "tensor_pipe_frac_tf32 is the share of the tf32 pipe the 3x split keeps busy"}
     else:
