@@ -12,18 +12,25 @@ from qibotn_b200 import plans, workloads  # noqa: E402
 from qibotn_b200.planner import find_path  # noqa: E402
 
 
-def modeled_seconds(info, net, dtype, tc_tflops=200.0, ffma_tflops=25.0, hbm_tbs=3.0, launch_us=3.0):
-    """Time model of a plan on one B200: per tree node max(flops / kernel rate, bytes / HBM rate,
-    launch), summed over slices (hoisted nodes once).  Rates are the measured ones of
-    profiles/r01_tc_persistent_vs_nonpersistent_vs_ffma.jsonl, deliberately round."""
+def modeled_seconds(info, net, dtype, tc_tflops=280.0, ffma_tflops=25.0, hbm_tbs=3.5, launch_us=3.0,
+                    tile_us=3.2, sms=148):
+    """Time model of a plan on one B200: per tree node max(compute, bytes / HBM rate, launch), summed over
+    slices (hoisted nodes once).  For the tcgen05 kernel compute = flops / 280 TFLOP/s + 3.2 us per
+    128 x 2^tnb tile per SM (accumulator hand-off; with split accumulators a 128-column tile has no second
+    TMEM buffer): fitted to profiles/r01_tc_issue_and_pair_ab.jsonl (m24n7k7 10.7 ms, m20n7k10 4.1 ms,
+    m19n8k8 1.2 ms); HBM-bound nodes stream at ~3.5 TB/s (m24n5k5, m24n6k6)."""
     from qibotn_b200 import executor, lib
 
     low = executor.lower(net.modes, net.out, info, dtype)
     total = 0.0
     for nd in low.nodes:
         p = nd.plan
-        rate = tc_tflops if p.kernel == lib.KERNEL_TC else ffma_tflops
-        t = max(p.flops / (rate * 1e12), p.bytes / (hbm_tbs * 1e12), launch_us * 1e-6)
+        if p.kernel == lib.KERNEL_TC:
+            tiles = float(p.grid)
+            comp = p.flops / (tc_tflops * 1e12) + tile_us * 1e-6 * max(1.0, tiles / sms)
+        else:
+            comp = p.flops / (ffma_tflops * 1e12)
+        t = max(comp, p.bytes / (hbm_tbs * 1e12), launch_us * 1e-6)
         total += t * (info.num_slices if nd.depends else 1)
     return total
 

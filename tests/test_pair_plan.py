@@ -145,3 +145,32 @@ def test_tensor_core_kernel_is_optional():
     finally:
         lib.set_option("tc_enable", 1)
         lib.set_option("tc_min_log2", 18)
+
+
+@pytest.mark.parametrize("shape", [(10, 5, 4), (11, 6, 5), (12, 7, 7), (10, 9, 4), (10, 4, 5), (8, 7, 4)])
+def test_cta_pair_plans_are_well_formed(shape):
+    """The CTA-pair variant (tcgen05 cta_group::2) is chosen for pre-packed tiles of 32..128 columns;
+    its launch geometry must pair up: even tile count, even CTA count, half of B per stage."""
+    m, n, k = shape
+    la = [(i, i) for i in range(m + k)]                   # m labels then k labels
+    lb = [(m + i, i) for i in range(k)] + [(m + k + j, k + j) for j in range(n)]
+    lib.set_option("tc_min_log2", 0)
+    try:
+        plan = lib.pair_plan(lib.make_pair_desc("complex64", la, lb))
+        lib.set_option("tc_pair", 0)
+        single = lib.pair_plan(lib.make_pair_desc("complex64", la, lb))
+    finally:
+        lib.set_option("tc_min_log2", 18)
+        lib.set_option("tc_pair", 5)
+    assert plan.kernel == lib.KERNEL_TC and single.kernel == lib.KERNEL_TC and single.tc_pair == 0
+    eligible = plan.tc_prepack == 1 and plan.tc_pad == 1 and 5 <= plan.tnb <= 7
+    assert plan.tc_pair == (1 if eligible else 0)
+    assert (m >= 10 and n >= 5) == bool(plan.tc_pair)
+    if plan.tc_pair:
+        assert plan.grid % 2 == 0 and plan.tc_reserved % 2 == 0 and plan.tc_reserved > 0
+        stage = 4 * (plan.tc_plane_a + plan.tc_plane_b // 2)
+        assert plan.smem_bytes == plan.tc_stages * stage + 256 <= 227 * 1024
+        assert 2 <= plan.tc_stages <= 6 and plan.tc_stages >= single.tc_stages
+        # same tiling and C layout as the single-CTA plan: the two kernels are interchangeable
+        assert (plan.tmb, plan.tnb, plan.tkb, plan.split_bits) == (single.tmb, single.tnb, single.tkb, single.split_bits)
+        assert plan.c_elems == single.c_elems and plan.workspace_bytes == single.workspace_bytes
