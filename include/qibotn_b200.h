@@ -243,6 +243,15 @@ typedef struct {
 } qtn_svd_trunc;
 
 int64_t qtn_svd_workspace_bytes(int batch, int64_t ld);
+/* LQ preconditioner for qtn_svd_rows (the QR preconditioning of Drmac-Veselic's Jacobi SVD, which
+ * cuSOLVER's gesvdj-class routines behind contract_decompose use as well): right-looking modified
+ * Gram-Schmidt over the ROWS of each items[i].w (n x m, n <= m, overwritten), keeping only
+ * X = L^H (n x n) in xitems[i].w (xitems[i].n = xitems[i].m = items[i].n).  theta = L Q and L share
+ * singular values and left vectors, so qtn_svd_rows is then run on `xitems`: its rows converge to
+ * sigma_i z_i^H with Z the LEFT singular vectors of the input -- see qtn_svd_emit. */
+int64_t qtn_svd_lq_workspace_bytes(int batch);
+int qtn_svd_lq(int dtype, int batch, const qtn_svd_item *items, const qtn_svd_item *xitems,
+               void *workspace, int64_t workspace_bytes, void *stream);
 /* On return every W holds J*W_in with mutually orthogonal rows; sigma[i*ld + c] is the c-th
  * largest row norm (= singular value) of matrix i and perm[i*ld + c] the row that carries it;
  * rank_host[i] = number of singular values kept, scale_host[i] = factor the kept values are
@@ -259,6 +268,8 @@ int qtn_svd_rows(int dtype, int batch, qtn_svd_item *items, double tol, int max_
  *                                      out2 = fa/s^2 * row (left factor = theta * out2^H)
  *   transposed == 1 (W_in = theta^T):  out1 = fa/s * row   (left factor transposed, k x m)
  *                                      out2 = fb/s^2 * row (right factor = conj(out2) * theta)
+ * `transposed` + 2 additionally conjugates out1 (used with qtn_svd_lq, where the rows are
+ * sigma * z^H of the LEFT vectors).
  * sigma/perm point at this matrix's row of the arrays qtn_svd_rows filled. */
 int qtn_svd_emit(int dtype, const void *w, int32_t m, const int32_t *perm, const double *sigma,
                  double scale, int32_t k, int32_t partition, int32_t transposed, void *out1, void *out2,

@@ -220,8 +220,10 @@ finalize_kernel(const qtn_svd_item *__restrict__ items, qtn_svd_trunc tr, double
 template <typename R>
 __global__ void __launch_bounds__(256)
 emit_kernel(const cx<R> *__restrict__ W, int m, const int32_t *__restrict__ perm,
-            const double *__restrict__ sigma, double scale, int partition, int transposed,
+            const double *__restrict__ sigma, double scale, int partition, int flags,
             cx<R> *__restrict__ out1, cx<R> *__restrict__ out2) {
+  const int transposed = flags & 1;
+  const double cj = (flags & 2) ? -1.0 : 1.0;       // bit 1: out1 is conjugated
   using T = cx<R>;
   const int c = blockIdx.x;
   const double s = sigma[c], sn = s * scale;
@@ -238,11 +240,171 @@ emit_kernel(const cx<R> *__restrict__ W, int m, const int32_t *__restrict__ perm
   for (int col = threadIdx.x; col < m; col += 256) {
     const T v = src[col];
     T o1, o2;
-    o1.x = (R)(f1 * v.x); o1.y = (R)(f1 * v.y);
+    o1.x = (R)(f1 * v.x); o1.y = (R)(cj * f1 * v.y);
     o2.x = (R)(f2 * v.x); o2.y = (R)(f2 * v.y);
     out1[(size_t)c * m + col] = o1;
     out2[(size_t)c * m + col] = o2;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LQ preconditioner (Drmac-Veselic style, without pivoting): W = L Q by right-looking modified
+// Gram-Schmidt on the rows, panel by panel; only L is kept, as X = L^H (n x n, upper triangular).
+// Row-Jacobi on X converges in ~3x fewer sweeps than on a strongly graded W (the rows of X are
+// graded and nearly orthogonal), and theta = L Q = Z Sigma (J Q) has the same singular values and
+// LEFT vectors Z: the caller takes the left factor from the rows of the converged X and the right
+// factor from one GEMM with theta (the mirror image of the un-preconditioned path).
+// MGS computes L as accurately as Householder QR would (Bjorck): what is lost is the orthogonality of
+// Q, which is discarded.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLqPanel = 16;
+constexpr int kLqRowsPerCta = 32;
+
+template <typename R>
+__device__ __forceinline__ void lq_project(cx<R> *w, const cx<R> *q, int m, int lane, R &cr, R &ci) {
+  // c = sum w * conj(q);  w -= c q
+  R ar = 0, ai = 0;
+  for (int c = lane; c < m; c += 32) {
+    const cx<R> u = w[c], v = q[c];
+    ar = fma(u.x, v.x, fma(u.y, v.y, ar));
+    ai = fma(u.y, v.x, fma(-u.x, v.y, ai));
+  }
+  ar = warp_sum<R>(ar); ai = warp_sum<R>(ai);
+  for (int c = lane; c < m; c += 32) {
+    const cx<R> v = q[c];
+    cx<R> u = w[c];
+    u.x -= ar * v.x - ai * v.y;
+    u.y -= ar * v.y + ai * v.x;
+    w[c] = u;
+  }
+  cr = ar; ci = ai;
+}
+
+// One CTA per matrix: orthonormalise the rows of panel p among themselves (they were already
+// projected against every earlier panel), record the diagonal block of L.
+template <typename R>
+__global__ void __launch_bounds__(256)
+lq_panel_kernel(const qtn_svd_item *__restrict__ items, const qtn_svd_item *__restrict__ xitems, int p, int pb) {
+  using T = cx<R>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *rows = reinterpret_cast<T *>(smem_raw);
+  __shared__ R s_norm;
+  const qtn_svd_item it = items[blockIdx.x];
+  const int n = it.n, m = it.m;
+  const int r0 = p * pb;
+  if (r0 >= n) return;
+  const int nr = min(pb, n - r0);
+  T *W = (T *)it.w;
+  T *X = (T *)xitems[blockIdx.x].w;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int lr = warp; lr < nr; lr += kWarps)
+    for (int c = lane; c < m; c += 32) rows[(size_t)lr * m + c] = W[(size_t)(r0 + lr) * m + c];
+  __syncthreads();
+  for (int i = 0; i < nr; ++i) {
+    T *qi = rows + (size_t)i * m;
+    if (warp == 0) {
+      R a = 0;
+      for (int c = lane; c < m; c += 32) { const T v = qi[c]; a = fma(v.x, v.x, fma(v.y, v.y, a)); }
+      a = warp_sum<R>(a);
+      if (lane == 0) s_norm = sqrt(a);
+    }
+    __syncthreads();
+    const R nrm = s_norm;
+    const R inv = nrm > (R)0 ? (R)1 / nrm : (R)0;
+    for (int c = t; c < m; c += 256) { T v = qi[c]; v.x *= inv; v.y *= inv; qi[c] = v; }
+    if (t == 0) { T d; d.x = nrm; d.y = 0; X[(size_t)(r0 + i) * n + (r0 + i)] = d; }
+    __syncthreads();
+    for (int j = i + 1 + warp; j < nr; j += kWarps) {
+      R cr, ci;
+      lq_project<R>(rows + (size_t)j * m, qi, m, lane, cr, ci);
+      if (lane == 0) { T d; d.x = cr; d.y = -ci; X[(size_t)(r0 + i) * n + (r0 + j)] = d; }   // X = L^H
+    }
+    __syncthreads();
+  }
+  for (int lr = warp; lr < nr; lr += kWarps)
+    for (int c = lane; c < m; c += 32) W[(size_t)(r0 + lr) * m + c] = rows[(size_t)lr * m + c];
+}
+
+// Project the rows behind panel p against its (now orthonormal) rows, one after the other (true MGS
+// order); a warp owns a trailing row, kept in shared memory while the 16 projections run.
+template <typename R>
+__global__ void __launch_bounds__(256)
+lq_update_kernel(const qtn_svd_item *__restrict__ items, const qtn_svd_item *__restrict__ xitems, int p, int pb) {
+  using T = cx<R>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const qtn_svd_item it = items[blockIdx.y];
+  const int n = it.n, m = it.m;
+  const int r0 = p * pb;
+  const int t0 = r0 + pb;                                   // first trailing row
+  const int first = t0 + (int)blockIdx.x * kLqRowsPerCta;
+  if (r0 >= n || first >= n) return;
+  T *q = reinterpret_cast<T *>(smem_raw);                   // pb x m
+  T *mine = q + (size_t)pb * m;                             // kWarps x m
+  T *W = (T *)it.w;
+  T *X = (T *)xitems[blockIdx.y].w;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int lr = warp; lr < pb; lr += kWarps)
+    for (int c = lane; c < m; c += 32) q[(size_t)lr * m + c] = W[(size_t)(r0 + lr) * m + c];
+  __syncthreads();
+  T *w = mine + (size_t)warp * m;
+  const int last = min(n, first + kLqRowsPerCta);
+  for (int j = first + warp; j < last; j += kWarps) {
+    for (int c = lane; c < m; c += 32) w[c] = W[(size_t)j * m + c];
+    __syncwarp();
+    for (int i = 0; i < pb; ++i) {
+      R cr, ci;
+      lq_project<R>(w, q + (size_t)i * m, m, lane, cr, ci);
+      if (lane == 0) { T d; d.x = cr; d.y = -ci; X[(size_t)(r0 + i) * n + j] = d; }
+      __syncwarp();
+    }
+    for (int c = lane; c < m; c += 32) W[(size_t)j * m + c] = w[c];
+    __syncwarp();
+  }
+}
+
+template <typename R>
+int svd_lq_impl(int batch, const qtn_svd_item *items, const qtn_svd_item *xitems, unsigned char *ws, cudaStream_t st) {
+  const int esz = (int)sizeof(cx<R>);
+  int max_n = 1, max_m = 1;
+  for (int i = 0; i < batch; ++i) {
+    if (items[i].n < 1 || items[i].m < 1 || !items[i].w || !xitems[i].w || xitems[i].n != items[i].n ||
+        xitems[i].m != items[i].n)
+      return qtn_fail(QTN_ERR_ARG, "qtn_svd_lq: bad item");
+    max_n = std::max(max_n, (int)items[i].n);
+    max_m = std::max(max_m, (int)items[i].m);
+  }
+  int pb = kLqPanel;
+  while (pb > 1 && (size_t)(pb + kWarps) * max_m * esz > (size_t)200 * 1024) pb >>= 1;
+  if ((size_t)(pb + kWarps) * max_m * esz > (size_t)200 * 1024)
+    return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_svd_lq: rows too long for shared memory");
+  qtn_svd_item *d_items = (qtn_svd_item *)ws;
+  qtn_svd_item *d_x = d_items + batch;
+  QTN_CUDA_CHECK(cudaMemcpyAsync(d_items, items, (size_t)batch * sizeof(qtn_svd_item), cudaMemcpyHostToDevice, st));
+  QTN_CUDA_CHECK(cudaMemcpyAsync(d_x, xitems, (size_t)batch * sizeof(qtn_svd_item), cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < batch; ++i)
+    QTN_CUDA_CHECK(cudaMemsetAsync(xitems[i].w, 0, (size_t)items[i].n * items[i].n * esz, st));
+  const size_t smem_panel = (size_t)pb * max_m * esz, smem_upd = (size_t)(pb + kWarps) * max_m * esz;
+  static size_t set_panel = 0, set_upd = 0;
+  if (smem_panel > set_panel) {
+    QTN_CUDA_CHECK(cudaFuncSetAttribute(lq_panel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel));
+    set_panel = smem_panel;
+  }
+  if (smem_upd > set_upd) {
+    QTN_CUDA_CHECK(cudaFuncSetAttribute(lq_update_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
+    set_upd = smem_upd;
+  }
+  const int panels = (max_n + pb - 1) / pb;
+  for (int p = 0; p < panels; ++p) {
+    lq_panel_kernel<R><<<batch, 256, smem_panel, st>>>(d_items, d_x, p, pb);
+    QTN_LAUNCH_CHECK();
+    const int trailing = max_n - (p + 1) * pb;
+    if (trailing > 0) {
+      dim3 grid((unsigned)((trailing + kLqRowsPerCta - 1) / kLqRowsPerCta), (unsigned)batch);
+      lq_update_kernel<R><<<grid, 256, smem_upd, st>>>(d_items, d_x, p, pb);
+      QTN_LAUNCH_CHECK();
+    }
+  }
+  return QTN_OK;
 }
 
 int choose_block(int n, int m, int esz, int *block, int *nblocks) {
@@ -355,11 +517,26 @@ extern "C" int qtn_svd_rows(int dtype, int batch, qtn_svd_item *items, double to
                                      sweeps_host, (unsigned char *)workspace, st);
 }
 
+extern "C" int64_t qtn_svd_lq_workspace_bytes(int batch) {
+  return batch < 1 ? 0 : 2 * (int64_t)batch * (int64_t)sizeof(qtn_svd_item) + 256;
+}
+
+extern "C" int qtn_svd_lq(int dtype, int batch, const qtn_svd_item *items, const qtn_svd_item *xitems,
+                          void *workspace, int64_t workspace_bytes, void *stream) {
+  if (dtype != QTN_C64 && dtype != QTN_C128) return qtn_fail(QTN_ERR_ARG, "qtn_svd_lq: bad dtype");
+  if (batch < 1 || !items || !xitems || !workspace) return qtn_fail(QTN_ERR_ARG, "qtn_svd_lq: null argument");
+  if (workspace_bytes < qtn_svd_lq_workspace_bytes(batch))
+    return qtn_fail(QTN_ERR_WORKSPACE, "qtn_svd_lq: workspace too small (qtn_svd_lq_workspace_bytes)");
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == QTN_C64 ? svd_lq_impl<float>(batch, items, xitems, (unsigned char *)workspace, st)
+                          : svd_lq_impl<double>(batch, items, xitems, (unsigned char *)workspace, st);
+}
+
 extern "C" int qtn_svd_emit(int dtype, const void *w, int32_t m, const int32_t *perm, const double *sigma,
                             double scale, int32_t k, int32_t partition, int32_t transposed, void *out1,
                             void *out2, void *stream) {
   if (dtype != QTN_C64 && dtype != QTN_C128) return qtn_fail(QTN_ERR_ARG, "qtn_svd_emit: bad dtype");
-  if (!w || !perm || !sigma || !out1 || !out2 || m < 1 || k < 1 || partition < 0 || partition > 3)
+  if (!w || !perm || !sigma || !out1 || !out2 || m < 1 || k < 1 || partition < 0 || partition > 3 || transposed < 0 || transposed > 3)
     return qtn_fail(QTN_ERR_ARG, "qtn_svd_emit: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == QTN_C64)

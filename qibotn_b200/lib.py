@@ -106,6 +106,9 @@ _SIGNATURES = {
     "qtn_mps_apply_1q": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qtn_mps_apply_2q": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qtn_svd_workspace_bytes": (C.c_int64, [C.c_int, C.c_int64]),
+    "qtn_svd_lq_workspace_bytes": (C.c_int64, [C.c_int]),
+    "qtn_svd_lq": (C.c_int, [C.c_int, C.c_int, C.POINTER(SvdItem), C.POINTER(SvdItem), C.c_void_p, C.c_int64,
+                             C.c_void_p]),
     "qtn_svd_rows": (C.c_int, [C.c_int, C.c_int, C.POINTER(SvdItem), C.c_double, C.c_int,
                                C.POINTER(SvdTrunc), C.c_void_p, C.c_void_p, C.c_int64,
                                C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32),

@@ -75,6 +75,11 @@ def parse_algorithm(algorithm):
     return tr, part, False
 
 
+# Two-site blocks with at least this many rows are LQ-preconditioned before the Jacobi sweeps
+# (qtn_svd_lq): ~3x fewer sweeps on the strongly graded blocks of a truncated MPS.  0 disables.
+LQ_MIN_ROWS = 96
+
+
 class MPSEngine:
     """Owns the site tensors (torch, on the GPU) and applies gates to them."""
 
@@ -204,6 +209,22 @@ class MPSEngine:
         import time as _time
         torch.cuda.synchronize()
         t_svd = _time.perf_counter()
+        precond = LQ_MIN_ROWS > 0 and ld >= LQ_MIN_ROWS
+        xs = []
+        if precond:
+            # W = L Q (rows, modified Gram-Schmidt), Jacobi on X = L^H: rows converge to sigma_i z_i^H,
+            # Z = LEFT singular vectors of W
+            xitems = (lib.SvdItem * nb)()
+            for k in range(nb):
+                n_k = items[k].n
+                x = torch.empty(n_k * n_k, dtype=self.cdtype, device=self.device)
+                xs.append(x)
+                xitems[k].w, xitems[k].n, xitems[k].m = x.data_ptr(), n_k, n_k
+            lq_bytes = int(self.lib.qtn_svd_lq_workspace_bytes(nb))
+            lq_ws = torch.empty(lq_bytes, dtype=torch.uint8, device=self.device)
+            lib.check(self.lib.qtn_svd_lq(self.code, nb, items, xitems, lq_ws.data_ptr(), lq_bytes, self._stream()))
+            self.stats["launches"] += 1
+            items = xitems
         lib.check(self.lib.qtn_svd_rows(self.code, nb, items, self.tol, self.max_sweeps, C.byref(self.trunc),
                                         sigma.data_ptr(), perm.data_ptr(), ld, ranks, scales,
                                         C.byref(sweeps), ws.data_ptr(), ws_bytes, self._stream()))
@@ -214,22 +235,43 @@ class MPSEngine:
         esz = 8
         for k, (i, l, r, p, q, theta, w, transposed) in enumerate(work):
             kk = int(ranks[k])
-            mcols = p if transposed else q
-            out1 = torch.empty(kk * mcols, dtype=self.cdtype, device=self.device)
-            out2 = torch.empty(kk * mcols, dtype=self.cdtype, device=self.device)
-            lib.check(self.lib.qtn_svd_emit(self.code, w.data_ptr(), mcols, perm.data_ptr() + 4 * k * ld,
-                                            sigma.data_ptr() + esz * k * ld, float(scales[k]), kk,
-                                            self.partition, int(transposed), out1.data_ptr(),
-                                            out2.data_ptr(), self._stream()))
-            self.stats["launches"] += 1
-            if not transposed:
-                right = out1                                             # (kk x q)
-                left = torch.empty(p * kk, dtype=self.cdtype, device=self.device)
-                self._gemm(lib.OP_N, lib.OP_H, p, kk, q, theta, q, out2, q, left, kk)   # theta * out2^H
+            if precond:
+                # rows of the converged X (n x n, n = min(p, q)) are sigma_c z_c^H
+                n_k = q if transposed else p
+                out1 = torch.empty(kk * n_k, dtype=self.cdtype, device=self.device)
+                out2 = torch.empty(kk * n_k, dtype=self.cdtype, device=self.device)
+                lib.check(self.lib.qtn_svd_emit(self.code, xs[k].data_ptr(), n_k, perm.data_ptr() + 4 * k * ld,
+                                                sigma.data_ptr() + esz * k * ld, float(scales[k]), kk,
+                                                self.partition, 2 + int(not transposed), out1.data_ptr(),
+                                                out2.data_ptr(), self._stream()))
+                self.stats["launches"] += 1
+                if not transposed:
+                    # theta = Z S (JQ):  left = Z fa = (conj(fa/s row))^T,  right = (fb/s^2 row) theta
+                    left = self._transpose(out1, kk, p)                  # (p x kk)
+                    right = torch.empty(kk * q, dtype=self.cdtype, device=self.device)
+                    self._gemm(lib.OP_N, lib.OP_N, kk, q, p, out2, p, theta, q, right, q)
+                else:
+                    # theta^T = Z S V'^H:  right = fb Z^T = conj(fb/s row),  left = theta (fa/s^2 row)^T
+                    right = out1                                         # (kk x q)
+                    left = torch.empty(p * kk, dtype=self.cdtype, device=self.device)
+                    self._gemm(lib.OP_N, lib.OP_T, p, kk, q, theta, q, out2, q, left, kk)
             else:
-                left = self._transpose(out1, kk, p)                      # (p x kk)
-                right = torch.empty(kk * q, dtype=self.cdtype, device=self.device)
-                self._gemm(lib.OP_C, lib.OP_N, kk, q, p, out2, p, theta, q, right, q)   # conj(out2) * theta
+                mcols = p if transposed else q
+                out1 = torch.empty(kk * mcols, dtype=self.cdtype, device=self.device)
+                out2 = torch.empty(kk * mcols, dtype=self.cdtype, device=self.device)
+                lib.check(self.lib.qtn_svd_emit(self.code, w.data_ptr(), mcols, perm.data_ptr() + 4 * k * ld,
+                                                sigma.data_ptr() + esz * k * ld, float(scales[k]), kk,
+                                                self.partition, int(transposed), out1.data_ptr(),
+                                                out2.data_ptr(), self._stream()))
+                self.stats["launches"] += 1
+                if not transposed:
+                    right = out1                                             # (kk x q)
+                    left = torch.empty(p * kk, dtype=self.cdtype, device=self.device)
+                    self._gemm(lib.OP_N, lib.OP_H, p, kk, q, theta, q, out2, q, left, kk)   # theta * out2^H
+                else:
+                    left = self._transpose(out1, kk, p)                      # (p x kk)
+                    right = torch.empty(kk * q, dtype=self.cdtype, device=self.device)
+                    self._gemm(lib.OP_C, lib.OP_N, kk, q, p, out2, p, theta, q, right, q)   # conj(out2) * theta
             self.sites[i] = left.view(l, 2, kk)
             self.sites[i + 1] = right.view(kk, 2, r)
             self.stats["max_bond"] = max(self.stats["max_bond"], kk)

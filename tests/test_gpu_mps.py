@@ -138,6 +138,50 @@ def test_truncation_rules(dtype):
         assert np.allclose(sig, f(s[:4]), rtol=1e-4 if dtype == "complex64" else 1e-10)
 
 
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("lmr", [(64, 128, 64), (48, 100, 80), (80, 100, 48), (128, 40, 128)])
+@pytest.mark.parametrize("graded", [False, True])
+def test_lq_preconditioned_split(lmr, graded, dtype, monkeypatch):
+    """Two-site blocks of >= LQ_MIN_ROWS rows go through qtn_svd_lq (LQ preconditioner) before the
+    Jacobi sweeps; the split must agree with LAPACK and with the un-preconditioned path."""
+    l, m, r = lmr
+    rng = np.random.default_rng(l * 7 + m * 3 + r + graded)
+    # theta = U diag(s) V^H with a known spectrum: condition number 10, or 10 decades (5 for complex64);
+    # rank min(2l, m, 2r) (the last shape is rank-deficient)
+    m = min(2 * l, m, 2 * r)
+    u, _ = np.linalg.qr(_rand(rng, 2 * l, m))
+    v, _ = np.linalg.qr(_rand(rng, 2 * r, m))
+    span = (10 if dtype == "complex128" else 5) if graded else 1
+    a, b = u * 10.0 ** (-span * np.arange(m) / m), v.conj().T
+    theta = (a.astype(dtype) @ b.astype(dtype)).astype(np.complex128)
+    s_ref = np.linalg.svd(theta, compute_uv=False)
+    tol = 3e-5 if dtype == "complex64" else 1e-11
+    results = {}
+    for lq_rows in (0, 96):
+        monkeypatch.setattr(gmps, "LQ_MIN_ROWS", lq_rows)
+        for part in ("UV", "U", "V"):
+            eng = gmps.MPSEngine(2, dtype, {"qr_method": False, "svd_method": {"partition": part}})
+            eng.sites = [torch.from_numpy(a.astype(dtype)).cuda().reshape(l, 2, m).contiguous(),
+                         torch.from_numpy(b.astype(dtype)).cuda().reshape(m, 2, r).contiguous()]
+            eng.apply_gate(np.eye(4).reshape(2, 2, 2, 2), (0, 1))
+            eng.flush()
+            left = eng.sites[0].reshape(2 * l, -1).cpu().numpy().astype(np.complex128)
+            right = eng.sites[1].reshape(-1, 2 * r).cpu().numpy().astype(np.complex128)
+            k = left.shape[1]
+            floor = 16 * (1.1e-16 if dtype == "complex128" else 6e-8) * s_ref[0]
+            assert int((s_ref > 8 * floor).sum()) <= k <= m
+            assert np.abs(left @ right - theta).max() <= tol * 20 * s_ref[0]
+            if not graded:
+                if part == "V":
+                    assert np.abs(left.conj().T @ left - np.eye(k)).max() < tol * 100
+                    assert np.abs(np.linalg.norm(right, axis=1) - s_ref[:k]).max() <= tol * s_ref[0]
+                if part == "U":
+                    assert np.abs(right @ right.conj().T - np.eye(k)).max() < tol * 100
+                    assert np.abs(np.linalg.norm(left, axis=0) - s_ref[:k]).max() <= tol * s_ref[0]
+            results[(lq_rows, part)] = eng.stats["svd_sweeps"]
+    assert results[(96, "UV")] <= results[(0, "UV")] + 2       # the preconditioner never costs sweeps
+
+
 def _mps_state(circ, dtype, algorithm):
     conv = gmps.QiboCircuitToMPS(circ, algorithm, dtype=dtype)
     dense = gmps.MPSContractionHelper(circ.nqubits).contract_state_vector(conv.mps_tensors)
