@@ -160,6 +160,13 @@ typedef struct {
  *                  n = 6, 7 raises the smallest paired tile to 2^n columns, 0 turns pairs off;
  *   "tc_persistent" 1 (default): one CTA per SM streams over the tiles with loads, MMAs and
  *                  epilogue of neighbouring tiles overlapped; 0: one CTA per tile.
+ *   "svd_wide"     1 (default): qtn_svd_rows runs 512-thread CTAs holding twice the block rows (200 KB of
+ *                  shared memory, row pairs split across warps); 0: 256-thread CTAs, 160 KB.
+ *   "svd_reg"      1 (default): block pairs of qtn_svd_rows matrices with rows of <= 512 (complex128) /
+ *                  1024 (complex64) columns are rotated by the register-resident kernel (8 + 8 rows per CTA,
+ *                  2 warps per row pair); 2: 4 warps per row pair; 0: shared-memory kernel only.
+ *   "svd_group_mb" qtn_svd_rows sweeps the batch in groups of at most this many MiB of rows, so that a
+ *                  group stays L2-resident over the launches of a sweep; 0 = the whole batch at once.
  * Returns QTN_ERR_ARG for an unknown name. */
 int qtn_set_option(const char *name, int value);
 int qtn_get_option(const char *name, int *value);

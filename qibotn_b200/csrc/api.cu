@@ -23,6 +23,9 @@ int g_tc_terms = 3;
 int g_tc_accum_split = 1;
 int g_tc_prepack = 1;
 int g_tc_pair = 5;
+int g_svd_wide = 1;
+int g_svd_group_mb = 0;
+int g_svd_reg = 3;
 }  // namespace
 
 extern "C" int qtn_option_tc_enable(void) { return g_tc_enable; }
@@ -32,6 +35,9 @@ extern "C" int qtn_option_tc_terms(void) { return g_tc_terms; }
 extern "C" int qtn_option_tc_accum_split(void) { return g_tc_accum_split; }
 extern "C" int qtn_option_tc_prepack(void) { return g_tc_prepack; }
 extern "C" int qtn_option_tc_pair(void) { return g_tc_pair; }
+extern "C" int qtn_option_svd_wide(void) { return g_svd_wide; }
+extern "C" int qtn_option_svd_group_mb(void) { return g_svd_group_mb; }
+extern "C" int qtn_option_svd_reg(void) { return g_svd_reg; }
 
 extern "C" int qtn_set_option(const char *name, int value) {
   if (!name) return qtn_fail(QTN_ERR_ARG, "qtn_set_option: null name");
@@ -42,6 +48,9 @@ extern "C" int qtn_set_option(const char *name, int value) {
   if (!std::strcmp(name, "tc_accum_split")) { g_tc_accum_split = value != 0; return QTN_OK; }
   if (!std::strcmp(name, "tc_prepack")) { g_tc_prepack = value != 0; return QTN_OK; }
   if (!std::strcmp(name, "tc_pair")) { g_tc_pair = value < 0 ? 0 : value; return QTN_OK; }
+  if (!std::strcmp(name, "svd_wide")) { g_svd_wide = value != 0; return QTN_OK; }
+  if (!std::strcmp(name, "svd_group_mb")) { g_svd_group_mb = value < 0 ? 0 : value; return QTN_OK; }
+  if (!std::strcmp(name, "svd_reg")) { g_svd_reg = value < 0 ? 0 : (value > 3 ? 3 : value); return QTN_OK; }
   return qtn_fail(QTN_ERR_ARG, "qtn_set_option: unknown option");
 }
 
@@ -54,6 +63,9 @@ extern "C" int qtn_get_option(const char *name, int *value) {
   if (!std::strcmp(name, "tc_accum_split")) { *value = g_tc_accum_split; return QTN_OK; }
   if (!std::strcmp(name, "tc_prepack")) { *value = g_tc_prepack; return QTN_OK; }
   if (!std::strcmp(name, "tc_pair")) { *value = g_tc_pair; return QTN_OK; }
+  if (!std::strcmp(name, "svd_wide")) { *value = g_svd_wide; return QTN_OK; }
+  if (!std::strcmp(name, "svd_group_mb")) { *value = g_svd_group_mb; return QTN_OK; }
+  if (!std::strcmp(name, "svd_reg")) { *value = g_svd_reg; return QTN_OK; }
   return qtn_fail(QTN_ERR_ARG, "qtn_get_option: unknown option");
 }
 

@@ -15,6 +15,9 @@ int qtn_option_tc_terms(void);
 int qtn_option_tc_accum_split(void);
 int qtn_option_tc_prepack(void);
 int qtn_option_tc_pair(void);
+int qtn_option_svd_wide(void);
+int qtn_option_svd_group_mb(void);
+int qtn_option_svd_reg(void);
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,8 @@ template <typename R> using cx = typename cx_of<R>::type;
 
 constexpr int kWarps = 8;
 constexpr int kSmemBudget = 160 * 1024;
+constexpr int kWarpsWide = 16;                 // "svd_wide": 512-thread CTAs, one per SM, twice the block rows
+constexpr int kSmemBudgetWide = 200 * 1024;
 
 // Round-robin tournament ("circle method") on n players, n even: step in [0, n-1), p in [0, n/2).
 __host__ __device__ inline void circle(int step, int p, int n, int &a, int &b) {
@@ -47,11 +49,66 @@ __device__ __forceinline__ R warp_sum(R v) {
   return v;
 }
 
+// Sums of four values over the warp with 6 shuffles instead of 20: the halves of the warp trade two of
+// the four values, then quarters trade one.  On return lane 0 holds sum(a), lane 8 sum(b), lane 16 sum(c),
+// lane 24 sum(d) (in `a`); the other lanes hold copies of one of them.
 template <typename R>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ R warp_sum4(R a, R b, R c, R d, int lane) {
+  const bool h16 = lane & 16;
+  R k0 = h16 ? c : a, k1 = h16 ? d : b;
+  const R s0 = h16 ? a : c, s1 = h16 ? b : d;
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  const bool h8 = lane & 8;
+  R k = h8 ? k1 : k0;
+  const R sx = h8 ? k0 : k1;
+  k += __shfl_xor_sync(0xffffffffu, sx, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
+}
+
+// Rotation that orthogonalises rows x, y with |x|^2 = a, |y|^2 = b, x.y^H = g:  x' = c x - sp y,
+// y' = conj(sp) x + c y, the smaller of the two angles.  cos 2t = |d| / r with d = b - a, r = sqrt(d^2 + 4|g|^2);
+// c = sqrt((1 + cos 2t) / 2), sp = sign(d) g / (r c): two rsqrt and no division (a double-precision sqrt or
+// division costs ~20 FP64 instructions, which every lane of the warp issues).
+// `shift` = |g|^2 / (r c^2) = 2|g|^2 / (r + |d|), signed like d: the rotated rows have |x'|^2 = a - shift and
+// |y'|^2 = b + shift (the larger row grows).
+__device__ __forceinline__ void jacobi_rotation(double a, double b, double gr, double gi, double &c, double &spr,
+                                                double &spi, double &shift) {
+  const double d = b - a;
+  const double g2 = fma(gr, gr, gi * gi);
+  const double r2 = fma(d, d, 4.0 * g2);
+  const double inv_r = rsqrt(r2);
+  const double c2 = fma(0.5 * fabs(d), inv_r, 0.5);
+  const double inv_c = rsqrt(c2);
+  c = c2 * inv_c;
+  const double k = copysign(inv_r * inv_c, d);
+  spr = gr * k;
+  spi = gi * k;
+  shift = g2 * k * inv_c;
+}
+__device__ __forceinline__ void jacobi_rotation(double a, double b, double gr, double gi, double &c, double &spr,
+                                                double &spi) {
+  double shift;
+  jacobi_rotation(a, b, gr, gi, c, spr, spi, shift);
+}
+
+// Items whose cross steps run in jacobi_cross_reg_kernel (chosen by the host in choose_block).
+constexpr int kRegBlockRows = 8;
+__host__ __device__ inline bool reg_mode(const qtn_svd_item &it, int reg_cap) {
+  return reg_cap > 0 && it.nblocks > 1 && it.block == kRegBlockRows && it.m <= reg_cap;
+}
+
+// NW warps per CTA.  When a round has fewer row pairs than warps, each pair is shared by wpp = NW / pairs
+// warps: every warp takes a contiguous 1/wpp of the columns, the partial dot products meet in shared
+// memory behind a named barrier of the pair's warps, and all of them derive the same rotation.
+template <typename R, int NW>
+__global__ void __launch_bounds__(32 * NW)
 jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, int max_inner, R tol,
                    const int *__restrict__ rot_prev, int *__restrict__ rot_cur, int *__restrict__ changed,
-                   long long ld, int gstep, int steps_per_sweep) {
+                   long long ld, int gstep, int steps_per_sweep, int reg_cap) {
   using T = cx<R>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *rows = reinterpret_cast<T *>(smem_raw);
@@ -61,6 +118,7 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
   const int n = it.n, m = it.m, b = it.block, nb = it.nblocks;
   if (n < 2) return;
   const int nbe = nb + (nb & 1);
+  if (reg_mode(it, reg_cap) && step != nbe - 1) return;     // its cross steps run in jacobi_cross_reg_kernel
   // steps 0 .. nbe-2: block PAIRS (I, J), only the b*b cross pairs are rotated;
   // step nbe-1: every block alone, its b(b-1)/2 internal pairs.  One sweep = all of them.
   const int nsteps = nb == 1 ? 1 : nbe;
@@ -88,7 +146,8 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
   T *W = (T *)it.w;
   auto grow = [&](int lr) { return lr < b ? I * b + lr : J * b + (lr - b); };
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  for (int lr = warp; lr < nr; lr += kWarps) {
+  __shared__ R s_part[NW][4];
+  for (int lr = warp; lr < nr; lr += NW) {
     const int g = grow(lr);
     T *dst = rows + (size_t)lr * m;
     if (g < n) { const T *src = W + (size_t)g * m; for (int c = lane; c < m; c += 32) dst[c] = src[c]; }
@@ -101,15 +160,21 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
     int rotated = 0;
     const int nrounds = J < 0 ? nr - 1 : b;
     const int npairs = J < 0 ? nr / 2 : b;
+    // warps per pair (power of two; block sizes are powers of two), columns per warp
+    int wpp = 1;
+    while (wpp * 2 * npairs <= NW && (m / (wpp * 2)) >= 64) wpp <<= 1;
+    const int sub = warp & (wpp - 1), group = warp / wpp, ngroups = NW / wpp;
+    const int cchunk = (m + wpp - 1) / wpp;
+    const int c0 = sub * cchunk, c1 = min(m, c0 + cchunk);
     for (int round = 0; round < nrounds; ++round) {
-      for (int q = warp; q < npairs; q += kWarps) {
+      for (int q = group; q < npairs; q += ngroups) {
         int x, y;
         if (J < 0) circle(round, q, nr, x, y);                  // all pairs inside one block
         else { x = q; y = b + ((q + round) & (b - 1)); }        // row q of I with row (q+round)%b of J
         if (grow(x) >= n || grow(y) >= n) continue;
         T *X = rows + (size_t)x * m, *Y = rows + (size_t)y * m;
         R a = 0, bb = 0, gr = 0, gi = 0;
-        for (int c = lane; c < m; c += 32) {
+        for (int c = c0 + lane; c < c1; c += 32) {
           const T u = X[c], v = Y[c];
           a = fma(u.x, u.x, fma(u.y, u.y, a));
           bb = fma(v.x, v.x, fma(v.y, v.y, bb));
@@ -117,18 +182,24 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
           gi = fma(u.y, v.x, fma(-u.x, v.y, gi));
         }
         a = warp_sum<R>(a); bb = warp_sum<R>(bb); gr = warp_sum<R>(gr); gi = warp_sum<R>(gi);
+        if (wpp > 1) {
+          if (lane == 0) { s_part[warp][0] = a; s_part[warp][1] = bb; s_part[warp][2] = gr; s_part[warp][3] = gi; }
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * wpp) : "memory");
+          a = 0; bb = 0; gr = 0; gi = 0;
+          for (int w = group * wpp; w < (group + 1) * wpp; ++w) {   // same order in every warp
+            a += s_part[w][0]; bb += s_part[w][1]; gr += s_part[w][2]; gi += s_part[w][3];
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * wpp) : "memory");   // s_part is reused
+        }
         const R g2 = gr * gr + gi * gi;
         // relative criterion at every scale (rows far below sigma_max are orthogonalised as
         // accurately as the leading ones); a row whose squared norm underflowed is left alone
         if (!(g2 > tol * tol * a * bb) || !(fmin(a, bb) > (R)0)) continue;
         rotated = 1;
-        const double gabs = sqrt((double)g2);
-        const double zeta = ((double)bb - (double)a) / (2.0 * gabs);
-        const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double cd = 1.0 / sqrt(1.0 + tt * tt), sd = cd * tt;
-        const R c = (R)cd;
-        const R spr = (R)(sd * gr / gabs), spi = (R)(sd * gi / gabs);   // s * e^{i phi}
-        for (int col = lane; col < m; col += 32) {
+        double cd, sprd, spid;
+        jacobi_rotation((double)a, (double)bb, (double)gr, (double)gi, cd, sprd, spid);
+        const R c = (R)cd, spr = (R)sprd, spi = (R)spid;                // s * e^{i phi}
+        for (int col = c0 + lane; col < c1; col += 32) {
           const T u = X[col], v = Y[col];
           T xn, yn;
           // x' = c x - s e^{i phi} y ;  y' = s e^{-i phi} x + c y
@@ -145,7 +216,7 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
     rotated_any = rotated;
     if (!rotated) break;
   }
-  for (int lr = warp; lr < nr; lr += kWarps) {
+  for (int lr = warp; lr < nr; lr += NW) {
     const int g = grow(lr);
     if (g >= n) continue;
     const T *src = rows + (size_t)lr * m;
@@ -156,6 +227,309 @@ jacobi_step_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, 
     atomicAdd(&rot_cur[item_id], 1);
     chg[I] = gstep;
     if (J >= 0) chg[J] = gstep;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Register-resident cross step.  The shared-memory kernel above moves 48 KB through shared memory per
+// 512-column complex128 row pair (two reads + one write of both rows) against ~10 k DFMAs: it is bound
+// by shared-memory bandwidth, not by the FP64 pipe.  Here a block pair is 8 + 8 rows; row q of block I
+// lives in the REGISTERS of warp group q (WPP warps, CPL columns per lane each) for the whole visit and
+// goes global -> registers -> global without touching shared memory; only block J is staged in shared
+// memory, read and written once per pair (16 KB).  The pairs of a block (step nbe-1) and matrices that
+// fit one block pair stay with jacobi_step_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRegBlock = kRegBlockRows;
+
+template <typename R, int CPL, int WPP>
+__global__ void __launch_bounds__(32 * kRegBlock * WPP)
+jacobi_cross_reg_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, R tol,
+                        const int *__restrict__ rot_prev, int *__restrict__ rot_cur, int *__restrict__ changed,
+                        long long ld, int gstep, int steps_per_sweep, int reg_cap) {
+  using T = cx<R>;
+  constexpr int b = kRegBlock;
+  constexpr int NW = b * WPP;
+  constexpr int MP = 32 * WPP * CPL;                         // padded row length held by a warp group
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *ys = reinterpret_cast<T *>(smem_raw);                  // b x MP
+  __shared__ R s_part[NW][4];
+  const int item_id = blockIdx.y;
+  if (sweep > 0 && rot_prev[item_id] == 0) return;
+  const qtn_svd_item it = items[item_id];
+  if (!reg_mode(it, reg_cap)) return;
+  const int n = it.n, m = it.m, nb = it.nblocks;
+  const int nbe = nb + (nb & 1);
+  if (step >= nbe - 1 || (int)blockIdx.x >= nbe / 2) return;
+  int I, J;
+  circle(step, blockIdx.x, nbe, I, J);
+  if (I >= nb || J >= nb) return;
+  int *chg = changed + (long long)item_id * ld;
+  if (sweep > 0) {
+    const int t_prev = gstep - steps_per_sweep;
+    if (chg[I] < t_prev && chg[J] < t_prev) return;
+  }
+  T *W = (T *)it.w;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int group = warp / WPP, sub = warp % WPP;
+  const int cbase = sub * 32 * CPL + lane;                   // my columns: cbase + 32 k
+  T xr[CPL];
+  {
+    const int gx = I * b + group, gy = J * b + group;
+    const T *sx = W + (size_t)gx * m, *sy = W + (size_t)gy * m;
+    T *dy = ys + (size_t)group * MP;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int c = cbase + 32 * k;
+      T z; z.x = 0; z.y = 0;
+      xr[k] = (gx < n && c < m) ? sx[c] : z;
+      dy[c] = (gy < n && c < m) ? sy[c] : z;
+    }
+  }
+  __syncthreads();
+  int rotated = 0;
+  for (int round = 0; round < b; ++round) {
+    T *Y = ys + (size_t)((group + round) & (b - 1)) * MP;
+    T yr[CPL];
+    R a = 0, bb = 0, gr = 0, gi = 0;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      yr[k] = Y[cbase + 32 * k];
+      const T u = xr[k], v = yr[k];
+      a = fma(u.x, u.x, fma(u.y, u.y, a));
+      bb = fma(v.x, v.x, fma(v.y, v.y, bb));
+      gr = fma(u.x, v.x, fma(u.y, v.y, gr));                   // g = sum u * conj(v)
+      gi = fma(u.y, v.x, fma(-u.x, v.y, gi));
+    }
+    if (WPP > 1) {
+      const R part = warp_sum4<R>(a, bb, gr, gi, lane);
+      if ((lane & 7) == 0) s_part[warp][lane >> 3] = part;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * WPP) : "memory");
+      a = 0; bb = 0; gr = 0; gi = 0;
+#pragma unroll
+      for (int w = 0; w < WPP; ++w) {                          // same order in every warp of the group
+        a += s_part[group * WPP + w][0]; bb += s_part[group * WPP + w][1];
+        gr += s_part[group * WPP + w][2]; gi += s_part[group * WPP + w][3];
+      }
+    } else {
+      a = warp_sum<R>(a); bb = warp_sum<R>(bb); gr = warp_sum<R>(gr); gi = warp_sum<R>(gi);
+    }
+    const R g2 = gr * gr + gi * gi;
+    if ((g2 > tol * tol * a * bb) && (fmin(a, bb) > (R)0)) {
+      rotated = 1;
+      double cd, sprd, spid;
+      jacobi_rotation((double)a, (double)bb, (double)gr, (double)gi, cd, sprd, spid);
+      const R c = (R)cd, spr = (R)sprd, spi = (R)spid;             // s * e^{i phi}
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const T u = xr[k], v = yr[k];
+        T xn, yn;
+        xn.x = c * u.x - (spr * v.x - spi * v.y);
+        xn.y = c * u.y - (spr * v.y + spi * v.x);
+        yn.x = c * v.x + (spr * u.x + spi * u.y);
+        yn.y = c * v.y + (spr * u.y - spi * u.x);
+        xr[k] = xn;
+        Y[cbase + 32 * k] = yn;
+      }
+    }
+    __syncthreads();                                           // the Y rows change hands; s_part is reused
+  }
+  {
+    const int gx = I * b + group, gy = J * b + group;
+    T *dx = W + (size_t)gx * m, *dyg = W + (size_t)gy * m;
+    const T *sy = ys + (size_t)group * MP;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int c = cbase + 32 * k;
+      if (gx < n && c < m) dx[c] = xr[k];
+      if (gy < n && c < m) dyg[c] = sy[c];
+    }
+  }
+  rotated = __syncthreads_or(rotated);
+  if (t == 0 && rotated) {
+    atomicAdd(&rot_cur[item_id], 1);
+    chg[I] = gstep;
+    chg[J] = gstep;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming variant of the register-resident cross step: a persistent CTA walks the (matrix, block pair)
+// visits of one step; while a visit is being rotated the rows of the next one arrive in shared memory by
+// cp.async (X rows into a staging buffer, Y rows into the second of two Y buffers), so the DRAM/L2 latency
+// of a visit start is hidden and the tail of one visit overlaps the head of the next.  Row norms are
+// computed once per visit (when the rows arrive) and carried through the 8 rounds with the exact update
+// |x'|^2 = a - shift, |y'|^2 = b + shift, which halves the dot-product work per pair; a sweep without
+// rotations -- the only kind that ends the iteration -- uses freshly computed norms only.
+// ---------------------------------------------------------------------------------------------
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void *smem_dst, const void *gsrc, bool valid) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int src_bytes = valid ? BYTES : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst), "l"(gsrc), "n"(BYTES), "r"(src_bytes)
+               : "memory");
+}
+
+template <typename R, int CPL, int WPP>
+__global__ void __launch_bounds__(32 * kRegBlock * WPP, 1)
+jacobi_cross_stream_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, R tol,
+                           const int *__restrict__ rot_prev, int *__restrict__ rot_cur, int *__restrict__ changed,
+                           long long ld, int gstep, int steps_per_sweep, int reg_cap, int pairs_max, int batch) {
+  using T = cx<R>;
+  constexpr int b = kRegBlock;
+  constexpr int NW = b * WPP;
+  constexpr int MP = 32 * WPP * CPL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *xbuf = reinterpret_cast<T *>(smem_raw);                 // b x MP: X rows of the coming visit
+  T *ybufs = xbuf + (size_t)b * MP;                          // 2 x (b x MP): Y rows, current / coming
+  __shared__ R s_part[NW][2];
+  __shared__ R s_yn[b][WPP];                                 // |y row|^2 as WPP partial sums
+  __shared__ R s_xn[NW];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int group = warp / WPP, sub = warp % WPP;
+  const int cbase = sub * 32 * CPL + lane;
+  const int total = pairs_max * batch;
+
+  // next visit at or after virtual index w that has work (same answer in every thread)
+  auto next_work = [&](int w, int &item_id, int &I, int &J) {
+    for (; w < total; w += (int)gridDim.x) {
+      item_id = w / pairs_max;
+      const int p = w - item_id * pairs_max;
+      if (sweep > 0 && rot_prev[item_id] == 0) continue;
+      const qtn_svd_item it = items[item_id];
+      if (!reg_mode(it, reg_cap)) continue;
+      const int nb = it.nblocks, nbe = nb + (nb & 1);
+      if (step >= nbe - 1 || p >= nbe / 2) continue;
+      circle(step, p, nbe, I, J);
+      if (I >= nb || J >= nb) continue;
+      if (sweep > 0) {
+        const int *chg = changed + (long long)item_id * ld;
+        const int t_prev = gstep - steps_per_sweep;
+        if (chg[I] < t_prev && chg[J] < t_prev) continue;
+      }
+      return w;
+    }
+    return total;
+  };
+  auto prefetch = [&](int item_id, int I, int J, T *ydst) {
+    const qtn_svd_item it = items[item_id];
+    const T *W = (const T *)it.w;
+    const int n = it.n, m = it.m;
+    const int gx = I * b + group, gy = J * b + group;
+    const T *sx = W + (size_t)gx * m, *sy = W + (size_t)gy * m;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int c = cbase + 32 * k;
+      const bool vx = gx < n && c < m, vy = gy < n && c < m;
+      cp_async_zfill<(int)sizeof(T)>(xbuf + (size_t)group * MP + c, vx ? (const void *)(sx + c) : (const void *)W, vx);
+      cp_async_zfill<(int)sizeof(T)>(ydst + (size_t)group * MP + c, vy ? (const void *)(sy + c) : (const void *)W, vy);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int item_id = 0, I = 0, J = 0, ycur = 0;
+  int w = next_work((int)blockIdx.x, item_id, I, J);
+  if (w < total) prefetch(item_id, I, J, ybufs);
+  while (w < total) {
+    T *Yb = ybufs + (size_t)ycur * b * MP;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    T xr[CPL];
+    {
+      R pa = 0, pb = 0;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const int c = cbase + 32 * k;
+        xr[k] = xbuf[(size_t)group * MP + c];
+        const T v = Yb[(size_t)group * MP + c];
+        pa = fma(xr[k].x, xr[k].x, fma(xr[k].y, xr[k].y, pa));
+        pb = fma(v.x, v.x, fma(v.y, v.y, pb));
+      }
+      pa = warp_sum<R>(pa); pb = warp_sum<R>(pb);
+      if (lane == 0) { s_xn[warp] = pa; s_yn[group][sub] = pb; }
+    }
+    __syncthreads();                                           // xbuf is free, the norms are visible
+    int n_item, nI, nJ;
+    const int wn = next_work(w + (int)gridDim.x, n_item, nI, nJ);
+    if (wn < total) prefetch(n_item, nI, nJ, ybufs + (size_t)(ycur ^ 1) * b * MP);
+    R ax = 0;
+#pragma unroll
+    for (int q = 0; q < WPP; ++q) ax += s_xn[group * WPP + q];
+    int rotated = 0;
+    for (int round = 0; round < b; ++round) {
+      const int yrow = (group + round) & (b - 1);
+      T *Y = Yb + (size_t)yrow * MP;
+      T yr[CPL];
+      R gr = 0, gi = 0;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        yr[k] = Y[cbase + 32 * k];
+        const T u = xr[k], v = yr[k];
+        gr = fma(u.x, v.x, fma(u.y, v.y, gr));                 // g = sum u * conj(v)
+        gi = fma(u.y, v.x, fma(-u.x, v.y, gi));
+      }
+      {
+        const bool h16 = lane & 16;
+        R k = h16 ? gi : gr;
+        const R sx = h16 ? gr : gi;
+        k += __shfl_xor_sync(0xffffffffu, sx, 16);
+        k += __shfl_xor_sync(0xffffffffu, k, 8);
+        k += __shfl_xor_sync(0xffffffffu, k, 4);
+        k += __shfl_xor_sync(0xffffffffu, k, 2);
+        k += __shfl_xor_sync(0xffffffffu, k, 1);
+        if ((lane & 15) == 0) s_part[warp][lane >> 4] = k;
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * WPP) : "memory");
+      gr = 0; gi = 0;
+      R bb = 0;
+#pragma unroll
+      for (int q = 0; q < WPP; ++q) {                          // same order in every warp of the group
+        gr += s_part[group * WPP + q][0]; gi += s_part[group * WPP + q][1];
+        bb += s_yn[yrow][q];
+      }
+      const R g2 = gr * gr + gi * gi;
+      if ((g2 > tol * tol * ax * bb) && (fmin(ax, bb) > (R)0)) {
+        rotated = 1;
+        double cd, sprd, spid, shift;
+        jacobi_rotation((double)ax, (double)bb, (double)gr, (double)gi, cd, sprd, spid, shift);
+        const R c = (R)cd, spr = (R)sprd, spi = (R)spid;           // s * e^{i phi}
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          const T u = xr[k], v = yr[k];
+          T xn, yn;
+          xn.x = c * u.x - (spr * v.x - spi * v.y);
+          xn.y = c * u.y - (spr * v.y + spi * v.x);
+          yn.x = c * v.x + (spr * u.x + spi * u.y);
+          yn.y = c * v.y + (spr * u.y - spi * u.x);
+          xr[k] = xn;
+          Y[cbase + 32 * k] = yn;
+        }
+        ax = (R)fmax((double)ax - shift, 0.0);
+        if (lane == 0) s_yn[yrow][sub] = sub == 0 ? (R)fmax((double)bb + shift, 0.0) : (R)0;
+      }
+      __syncthreads();                                         // the Y rows change hands; s_part, s_yn reused
+    }
+    {
+      const qtn_svd_item it = items[item_id];
+      T *W = (T *)it.w;
+      const int n = it.n, m = it.m;
+      const int gx = I * b + group, gy = J * b + group;
+      T *dx = W + (size_t)gx * m, *dyg = W + (size_t)gy * m;
+      const T *sy = Yb + (size_t)group * MP;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const int c = cbase + 32 * k;
+        if (gx < n && c < m) dx[c] = xr[k];
+        if (gy < n && c < m) dyg[c] = sy[c];
+      }
+    }
+    rotated = __syncthreads_or(rotated);                       // also: Yb may be overwritten from here on
+    if (t == 0 && rotated) {
+      atomicAdd(&rot_cur[item_id], 1);
+      int *chg = changed + (long long)item_id * ld;
+      chg[I] = gstep;
+      chg[J] = gstep;
+    }
+    w = wn; item_id = n_item; I = nI; J = nJ; ycur ^= 1;
   }
 }
 
@@ -407,9 +781,9 @@ int svd_lq_impl(int batch, const qtn_svd_item *items, const qtn_svd_item *xitems
   return QTN_OK;
 }
 
-int choose_block(int n, int m, int esz, int *block, int *nblocks) {
+int choose_block(int n, int m, int esz, int budget, int *block, int *nblocks) {
   int b = 32;
-  while (b >= 1 && (long long)2 * b * m * esz > kSmemBudget) b >>= 1;
+  while (b >= 1 && (long long)2 * b * m * esz > budget) b >>= 1;
   if (b < 1) return -1;
   if (n <= 2 * b) {                       // the whole matrix is one resident block
     int p = 2;
@@ -421,24 +795,84 @@ int choose_block(int n, int m, int esz, int *block, int *nblocks) {
   return 0;
 }
 
-template <typename R>
+template <typename R, int CPL, int WPP>
+cudaError_t launch_cross_reg(dim3 grid, cudaStream_t st, const qtn_svd_item *d_items, int step, int sweep, R tol,
+                             const int *rot_prev, int *rot_cur, int *changed, long long ld, int gstep,
+                             int steps_per_sweep, int reg_cap) {
+  constexpr size_t smem = (size_t)kRegBlock * 32 * WPP * CPL * sizeof(cx<R>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(jacobi_cross_reg_kernel<R, CPL, WPP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  jacobi_cross_reg_kernel<R, CPL, WPP><<<grid, 32 * kRegBlock * WPP, smem, st>>>(
+      d_items, step, sweep, tol, rot_prev, rot_cur, changed, ld, gstep, steps_per_sweep, reg_cap);
+  return cudaGetLastError();
+}
+
+template <typename R, int CPL, int WPP>
+cudaError_t launch_cross_stream(int pairs_max, int batch, cudaStream_t st, const qtn_svd_item *d_items, int step,
+                                int sweep, R tol, const int *rot_prev, int *rot_cur, int *changed, long long ld,
+                                int gstep, int steps_per_sweep, int reg_cap) {
+  constexpr size_t smem = (size_t)3 * kRegBlock * 32 * WPP * CPL * sizeof(cx<R>);
+  static int sms = 0;
+  if (!sms) {
+    cudaError_t e = cudaFuncSetAttribute(jacobi_cross_stream_kernel<R, CPL, WPP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  }
+  const int grid = std::max(1, std::min(sms, pairs_max * batch));
+  jacobi_cross_stream_kernel<R, CPL, WPP><<<grid, 32 * kRegBlock * WPP, smem, st>>>(
+      d_items, step, sweep, tol, rot_prev, rot_cur, changed, ld, gstep, steps_per_sweep, reg_cap, pairs_max, batch);
+  return cudaGetLastError();
+}
+
+// register-kernel capacity (columns) for a dtype: 64 registers of row data per thread at most
+template <typename R> constexpr int reg_cap_of() { return sizeof(R) == 8 ? 512 : 1024; }
+
+template <typename R, int NW>
 int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, const qtn_svd_trunc *trunc,
                   double *sigma, int32_t *perm, int64_t ld, int32_t *rank_host, double *scale_host,
-                  int32_t *sweeps_host, unsigned char *ws, cudaStream_t st) {
+                  int32_t *sweeps_host, unsigned char *ws, cudaStream_t st, int reg_variant) {
   const int esz = (int)sizeof(cx<R>);
-  int max_steps = 1, max_pairs = 1;
+  constexpr int kBudget = NW > kWarps ? kSmemBudgetWide : kSmemBudget;
+  const int reg_cap = reg_variant > 0 ? reg_cap_of<R>() : 0;
+  int max_steps = 1, max_pairs = 1, reg_max_m = 0, reg_cross_steps = 0, reg_pairs = 1;
   size_t smem = 0;
+  std::vector<char> need_smem_kernel;                     // per step: does jacobi_step_kernel have work?
   for (int i = 0; i < batch; ++i) {
     qtn_svd_item &it = items[i];
     if (it.n < 1 || it.m < 1 || !it.w) return qtn_fail(QTN_ERR_ARG, "qtn_svd_rows: bad item");
     if (it.n > ld) return qtn_fail(QTN_ERR_ARG, "qtn_svd_rows: ld smaller than a row count");
-    if (choose_block(it.n, it.m, esz, &it.block, &it.nblocks))
+    if (choose_block(it.n, it.m, esz, kBudget, &it.block, &it.nblocks))
       return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_svd_rows: rows too long for shared memory");
+    if (reg_cap > 0 && it.nblocks > 1 && it.m <= reg_cap) {
+      it.block = kRegBlock;
+      it.nblocks = (it.n + kRegBlock - 1) / kRegBlock;
+    }
     const int nbe = it.nblocks + (it.nblocks & 1);
-    max_steps = std::max(max_steps, it.nblocks == 1 ? 1 : nbe);
-    max_pairs = std::max(max_pairs, it.nblocks == 1 ? 1 : std::max(nbe / 2, it.nblocks));
-    const int nr = it.nblocks == 1 ? it.block : 2 * it.block;
-    smem = std::max(smem, (size_t)nr * it.m * esz);
+    const int nsteps = it.nblocks == 1 ? 1 : nbe;
+    max_steps = std::max(max_steps, nsteps);
+    if ((int)need_smem_kernel.size() < nsteps) need_smem_kernel.resize(nsteps, 0);
+    const bool reg = reg_mode(it, reg_cap);
+    if (reg) {
+      reg_max_m = std::max(reg_max_m, (int)it.m);
+      reg_cross_steps = std::max(reg_cross_steps, nbe - 1);
+      reg_pairs = std::max(reg_pairs, nbe / 2);
+      need_smem_kernel[nbe - 1] = 1;
+      max_pairs = std::max(max_pairs, (int)it.nblocks);
+      smem = std::max(smem, (size_t)it.block * it.m * esz);
+    } else {
+      for (int sidx = 0; sidx < nsteps; ++sidx) need_smem_kernel[sidx] = 1;
+      max_pairs = std::max(max_pairs, it.nblocks == 1 ? 1 : std::max(nbe / 2, it.nblocks));
+      const int nr = it.nblocks == 1 ? it.block : 2 * it.block;
+      smem = std::max(smem, (size_t)nr * it.m * esz);
+    }
   }
   // workspace: items | (unused) | rot[2] | rank | scale | scratch sigma | last-rotation step per block
   qtn_svd_item *d_items = (qtn_svd_item *)ws;
@@ -453,9 +887,9 @@ int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, co
   QTN_CUDA_CHECK(cudaMemcpyAsync(d_items, items, (size_t)batch * sizeof(qtn_svd_item), cudaMemcpyHostToDevice, st));
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    QTN_CUDA_CHECK(cudaFuncSetAttribute(jacobi_step_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)std::max(smem, (size_t)kSmemBudget)));
-    smem_set = std::max(smem, (size_t)kSmemBudget);
+    QTN_CUDA_CHECK(cudaFuncSetAttribute(jacobi_step_kernel<R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)std::max(smem, (size_t)kBudget)));
+    smem_set = std::max(smem, (size_t)kBudget);
   }
   std::vector<int> rot(batch);
   int sweep = 0;
@@ -463,11 +897,36 @@ int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, co
     int *rot_cur = d_rot + (sweep & 1) * batch, *rot_prev = d_rot + ((sweep & 1) ^ 1) * batch;
     QTN_CUDA_CHECK(cudaMemsetAsync(rot_cur, 0, (size_t)batch * sizeof(int), st));
     dim3 grid((unsigned)max_pairs, (unsigned)batch);
+    dim3 rgrid((unsigned)reg_pairs, (unsigned)batch);
     for (int step = 0; step < max_steps; ++step) {
-      jacobi_step_kernel<R><<<grid, 256, smem, st>>>(d_items, step, sweep, max_sweeps, (R)tol, rot_prev, rot_cur,
-                                                    d_changed, (long long)ld, sweep * max_steps + step + 1,
-                                                    max_steps);
-      QTN_LAUNCH_CHECK();
+      const int gstep = sweep * max_steps + step + 1;
+      if (step < reg_cross_steps) {
+        cudaError_t e;
+#define QTN_REG(CPL, WPP)                                                                                    \
+  launch_cross_reg<R, CPL, WPP>(rgrid, st, d_items, step, sweep, (R)tol, rot_prev, rot_cur, d_changed,        \
+                                (long long)ld, gstep, max_steps, reg_cap)
+#define QTN_STREAM(CPL, WPP)                                                                                 \
+  launch_cross_stream<R, CPL, WPP>(reg_pairs, batch, st, d_items, step, sweep, (R)tol, rot_prev, rot_cur,     \
+                                   d_changed, (long long)ld, gstep, max_steps, reg_cap)
+        if constexpr (sizeof(R) == 8) {
+          if (reg_variant == 3) e = reg_max_m <= 256 ? QTN_STREAM(4, 2) : QTN_STREAM(8, 2);
+          else if (reg_variant == 2) e = reg_max_m <= 256 ? QTN_REG(2, 4) : QTN_REG(4, 4);
+          else e = reg_max_m <= 256 ? QTN_REG(4, 2) : QTN_REG(8, 2);
+        } else {
+          if (reg_variant == 3) e = reg_max_m <= 512 ? QTN_STREAM(8, 2) : QTN_STREAM(16, 2);
+          else if (reg_variant == 2) e = reg_max_m <= 512 ? QTN_REG(4, 4) : QTN_REG(8, 4);
+          else e = reg_max_m <= 512 ? QTN_REG(8, 2) : QTN_REG(16, 2);
+        }
+#undef QTN_REG
+#undef QTN_STREAM
+        if (e != cudaSuccess) return qtn_fail(QTN_ERR_CUDA, cudaGetErrorString(e));
+      }
+      if (need_smem_kernel[step]) {
+        jacobi_step_kernel<R, NW><<<grid, 32 * NW, smem, st>>>(d_items, step, sweep, max_sweeps, (R)tol, rot_prev,
+                                                               rot_cur, d_changed, (long long)ld, gstep, max_steps,
+                                                               reg_cap);
+        QTN_LAUNCH_CHECK();
+      }
     }
     QTN_CUDA_CHECK(cudaMemcpyAsync(rot.data(), rot_cur, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, st));
     QTN_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -510,11 +969,36 @@ extern "C" int qtn_svd_rows(int dtype, int batch, qtn_svd_item *items, double to
     tol = 8.0 * std::sqrt((double)max_m) * (dtype == QTN_C64 ? 6.0e-8 : 1.1e-16);
   }
   cudaStream_t st = (cudaStream_t)stream;
-  return dtype == QTN_C64
-             ? svd_rows_impl<float>(batch, items, tol, max_sweeps, trunc, sigma, perm, ld, rank_host, scale_host,
-                                    sweeps_host, (unsigned char *)workspace, st)
-             : svd_rows_impl<double>(batch, items, tol, max_sweeps, trunc, sigma, perm, ld, rank_host, scale_host,
-                                     sweeps_host, (unsigned char *)workspace, st);
+  // "svd_group_mb": matrices are swept in groups whose rows fit that many MiB, so that a group stays in L2 over
+  // the ~n/b launches of a sweep (0 = the whole batch at once)
+  const int64_t esz = dtype == QTN_C64 ? 8 : 16;
+  const int64_t group_bytes = (int64_t)qtn_option_svd_group_mb() << 20;
+  const bool wide = qtn_option_svd_wide() != 0;
+  const int reg_variant = qtn_option_svd_reg();
+  int sweeps_max = 0;
+  for (int g0 = 0; g0 < batch;) {
+    int g1 = g0;
+    int64_t bytes = 0;
+    while (g1 < batch) {
+      const int64_t add = (int64_t)items[g1].n * items[g1].m * esz;
+      if (g1 > g0 && group_bytes > 0 && bytes + add > group_bytes) break;
+      bytes += add; ++g1;
+    }
+    int32_t sw = 0;
+    const int nb = g1 - g0;
+    int rc;
+#define QTN_SVD_CALL(R, NW)                                                                                      \
+  svd_rows_impl<R, NW>(nb, items + g0, tol, max_sweeps, trunc, sigma + (int64_t)g0 * ld, perm + (int64_t)g0 * ld, \
+                       ld, rank_host + g0, scale_host + g0, &sw, (unsigned char *)workspace, st, reg_variant)
+    if (dtype == QTN_C64) rc = wide ? QTN_SVD_CALL(float, kWarpsWide) : QTN_SVD_CALL(float, kWarps);
+    else rc = wide ? QTN_SVD_CALL(double, kWarpsWide) : QTN_SVD_CALL(double, kWarps);
+#undef QTN_SVD_CALL
+    if (rc != QTN_OK) return rc;
+    sweeps_max = std::max(sweeps_max, (int)sw);
+    g0 = g1;
+  }
+  if (sweeps_host) *sweeps_host = sweeps_max;
+  return QTN_OK;
 }
 
 extern "C" int64_t qtn_svd_lq_workspace_bytes(int batch) {

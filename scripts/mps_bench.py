@@ -26,7 +26,12 @@ ap.add_argument("--cpu-seconds", type=float, default=0.0)
 ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--tol", type=float, default=0.0, help="Jacobi convergence threshold (0 = library default)")
 ap.add_argument("--lq-min-rows", type=int, default=-1, help="override mps.LQ_MIN_ROWS (0 = no LQ preconditioner)")
+ap.add_argument("--opt", action="append", default=[], help="library option name=value (qtn_set_option)")
 a = ap.parse_args()
+from qibotn_b200 import lib as _lib  # noqa: E402
+for kv in a.opt:
+    _k, _v = kv.split("=")
+    _lib.set_option(_k, int(_v))
 if a.lq_min_rows >= 0:
     gmps.LQ_MIN_ROWS = a.lq_min_rows
 
@@ -47,7 +52,7 @@ zz = complex(helper.pauli_expectation(conv.mps_tensors, {a.n // 2: "Z", a.n // 2
 bonds = [int(t.shape[2]) for t in conv.mps_tensors[:-1]]
 line = {"workload": f"{a.n}-site TFIM Trotter, {a.steps} steps, chi<={a.chi}, {a.dtype}", "gates": ngates,
         "seconds": best, "gates_per_s": ngates / best, "max_bond": max(bonds), "bonds": bonds, "norm": norm,
-        "zz_mid": [zz.real, zz.imag], "stats": conv.stats, "tol": a.tol, "lq_min_rows": gmps.LQ_MIN_ROWS}
+        "zz_mid": [zz.real, zz.imag], "stats": conv.stats, "tol": a.tol, "lq_min_rows": gmps.LQ_MIN_ROWS, "options": a.opt}
 if a.cpu_seconds > 0:
     from oracle import mps as omps
     from oracle.network import gate_tensors
