@@ -459,14 +459,19 @@ jacobi_cross_stream_kernel(const qtn_svd_item *__restrict__ items, int step, int
       const int yrow = (group + round) & (b - 1);
       T *Y = Yb + (size_t)yrow * MP;
       T yr[CPL];
-      R gr = 0, gi = 0;
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) {
-        yr[k] = Y[cbase + 32 * k];
-        const T u = xr[k], v = yr[k];
-        gr = fma(u.x, v.x, fma(u.y, v.y, gr));                 // g = sum u * conj(v)
-        gi = fma(u.y, v.x, fma(-u.x, v.y, gi));
+      for (int k = 0; k < CPL; ++k) yr[k] = Y[cbase + 32 * k];
+      R gr = 0, gi = 0, gr1 = 0, gi1 = 0, gr2 = 0, gi2 = 0, gr3 = 0, gi3 = 0;   // four chains each: DFMA latency
+#pragma unroll
+      for (int k = 0; k < CPL; k += 2) {
+        const T u = xr[k], v = yr[k], u1 = xr[k + 1], v1 = yr[k + 1];
+        gr = fma(u.x, v.x, gr); gr1 = fma(u.y, v.y, gr1);       // g = sum u * conj(v)
+        gi = fma(u.y, v.x, gi); gi1 = fma(-u.x, v.y, gi1);
+        gr2 = fma(u1.x, v1.x, gr2); gr3 = fma(u1.y, v1.y, gr3);
+        gi2 = fma(u1.y, v1.x, gi2); gi3 = fma(-u1.x, v1.y, gi3);
       }
+      gr = (gr + gr1) + (gr2 + gr3);
+      gi = (gi + gi1) + (gi2 + gi3);
       {
         const bool h16 = lane & 16;
         R k = h16 ? gi : gr;
@@ -478,13 +483,14 @@ jacobi_cross_stream_kernel(const qtn_svd_item *__restrict__ items, int step, int
         k += __shfl_xor_sync(0xffffffffu, k, 1);
         if ((lane & 15) == 0) s_part[warp][lane >> 4] = k;
       }
+      R bb = 0;                                                // read before the barrier: a partner warp that
+#pragma unroll                                                 // is ahead rewrites s_yn[yrow] after its rotation
+      for (int q = 0; q < WPP; ++q) bb += s_yn[yrow][q];
       asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * WPP) : "memory");
       gr = 0; gi = 0;
-      R bb = 0;
 #pragma unroll
       for (int q = 0; q < WPP; ++q) {                          // same order in every warp of the group
         gr += s_part[group * WPP + q][0]; gi += s_part[group * WPP + q][1];
-        bb += s_yn[yrow][q];
       }
       const R g2 = gr * gr + gi * gi;
       if ((g2 > tol * tol * ax * bb) && (fmin(ax, bb) > (R)0)) {
@@ -530,6 +536,142 @@ jacobi_cross_stream_kernel(const qtn_svd_item *__restrict__ items, int step, int
       chg[J] = gstep;
     }
     w = wn; item_id = n_item; I = nI; J = nJ; ycur ^= 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-pass variant for TWO resident CTAs per SM.  With every warp of a CTA walking the same phases
+// (shared-memory read, dot, shuffle reduction, scalar rotation set-up, rotation, shared-memory write) the
+// FP64 pipe and the shared-memory pipe take turns idling (ncu: both ~35-40 % busy).  Here the Y row is not
+// held in registers between the dot product and the rotation but read from shared memory twice, which keeps
+// the kernel within 64 registers so that two CTAs (two independent block pairs) share an SM and fill each
+// other's gaps; the price is 24 KB instead of 16 KB of shared-memory traffic per row pair.  One visit per CTA
+// (the second CTA hides the load/store latency), norms carried as in the streaming kernel.
+// ---------------------------------------------------------------------------------------------
+template <typename R, int CPL, int WPP>
+__global__ void __launch_bounds__(32 * kRegBlock * WPP, 2)
+jacobi_cross_dual_kernel(const qtn_svd_item *__restrict__ items, int step, int sweep, R tol,
+                         const int *__restrict__ rot_prev, int *__restrict__ rot_cur, int *__restrict__ changed,
+                         long long ld, int gstep, int steps_per_sweep, int reg_cap) {
+  using T = cx<R>;
+  constexpr int b = kRegBlock;
+  constexpr int NW = b * WPP;
+  constexpr int MP = 32 * WPP * CPL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *ys = reinterpret_cast<T *>(smem_raw);                  // b x MP
+  __shared__ R s_part[NW][2];
+  __shared__ R s_yn[b][WPP];
+  __shared__ R s_xn[NW];
+  const int item_id = blockIdx.y;
+  if (sweep > 0 && rot_prev[item_id] == 0) return;
+  const qtn_svd_item it = items[item_id];
+  if (!reg_mode(it, reg_cap)) return;
+  const int n = it.n, m = it.m, nb = it.nblocks;
+  const int nbe = nb + (nb & 1);
+  if (step >= nbe - 1 || (int)blockIdx.x >= nbe / 2) return;
+  int I, J;
+  circle(step, blockIdx.x, nbe, I, J);
+  if (I >= nb || J >= nb) return;
+  int *chg = changed + (long long)item_id * ld;
+  if (sweep > 0) {
+    const int t_prev = gstep - steps_per_sweep;
+    if (chg[I] < t_prev && chg[J] < t_prev) return;
+  }
+  T *W = (T *)it.w;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int group = warp / WPP, sub = warp % WPP;
+  const int cbase = sub * 32 * CPL + lane;                   // my columns: cbase + 32 k
+  T xr[CPL];
+  {
+    const int gx = I * b + group, gy = J * b + group;
+    const T *sx = W + (size_t)gx * m, *sy = W + (size_t)gy * m;
+    T *dy = ys + (size_t)group * MP;
+    R pa = 0, pb = 0;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int c = cbase + 32 * k;
+      T z; z.x = 0; z.y = 0;
+      xr[k] = (gx < n && c < m) ? sx[c] : z;
+      const T v = (gy < n && c < m) ? sy[c] : z;
+      dy[c] = v;
+      pa = fma(xr[k].x, xr[k].x, fma(xr[k].y, xr[k].y, pa));
+      pb = fma(v.x, v.x, fma(v.y, v.y, pb));
+    }
+    pa = warp_sum<R>(pa); pb = warp_sum<R>(pb);
+    if (lane == 0) { s_xn[warp] = pa; s_yn[group][sub] = pb; }
+  }
+  __syncthreads();
+  R ax = 0;
+#pragma unroll
+  for (int q = 0; q < WPP; ++q) ax += s_xn[group * WPP + q];
+  int rotated = 0;
+  for (int round = 0; round < b; ++round) {
+    const int yrow = (group + round) & (b - 1);
+    T *Y = ys + (size_t)yrow * MP + cbase;
+    R gr = 0, gi = 0, gr1 = 0, gi1 = 0;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const T u = xr[k], v = Y[32 * k];
+      gr = fma(u.x, v.x, gr); gr1 = fma(u.y, v.y, gr1);         // g = sum u * conj(v)
+      gi = fma(u.y, v.x, gi); gi1 = fma(-u.x, v.y, gi1);
+    }
+    gr += gr1; gi += gi1;
+    {
+      const bool h16 = lane & 16;
+      R k = h16 ? gi : gr;
+      const R sx = h16 ? gr : gi;
+      k += __shfl_xor_sync(0xffffffffu, sx, 16);
+      k += __shfl_xor_sync(0xffffffffu, k, 8);
+      k += __shfl_xor_sync(0xffffffffu, k, 4);
+      k += __shfl_xor_sync(0xffffffffu, k, 2);
+      k += __shfl_xor_sync(0xffffffffu, k, 1);
+      if ((lane & 15) == 0) s_part[warp][lane >> 4] = k;
+    }
+    R bb = 0;                                                  // before the barrier (see the streaming kernel)
+#pragma unroll
+    for (int q = 0; q < WPP; ++q) bb += s_yn[yrow][q];
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * WPP) : "memory");
+    gr = 0; gi = 0;
+#pragma unroll
+    for (int q = 0; q < WPP; ++q) { gr += s_part[group * WPP + q][0]; gi += s_part[group * WPP + q][1]; }
+    const R g2 = gr * gr + gi * gi;
+    if ((g2 > tol * tol * ax * bb) && (fmin(ax, bb) > (R)0)) {
+      rotated = 1;
+      double cd, sprd, spid, shift;
+      jacobi_rotation((double)ax, (double)bb, (double)gr, (double)gi, cd, sprd, spid, shift);
+      const R c = (R)cd, spr = (R)sprd, spi = (R)spid;             // s * e^{i phi}
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const T u = xr[k], v = Y[32 * k];
+        T xn, yn;
+        xn.x = c * u.x - (spr * v.x - spi * v.y);
+        xn.y = c * u.y - (spr * v.y + spi * v.x);
+        yn.x = c * v.x + (spr * u.x + spi * u.y);
+        yn.y = c * v.y + (spr * u.y - spi * u.x);
+        xr[k] = xn;
+        Y[32 * k] = yn;
+      }
+      ax = (R)fmax((double)ax - shift, 0.0);
+      if (lane == 0) s_yn[yrow][sub] = sub == 0 ? (R)fmax((double)bb + shift, 0.0) : (R)0;
+    }
+    __syncthreads();                                           // the Y rows change hands; s_part, s_yn reused
+  }
+  {
+    const int gx = I * b + group, gy = J * b + group;
+    T *dx = W + (size_t)gx * m, *dyg = W + (size_t)gy * m;
+    const T *sy = ys + (size_t)group * MP;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int c = cbase + 32 * k;
+      if (gx < n && c < m) dx[c] = xr[k];
+      if (gy < n && c < m) dyg[c] = sy[c];
+    }
+  }
+  rotated = __syncthreads_or(rotated);
+  if (t == 0 && rotated) {
+    atomicAdd(&rot_cur[item_id], 1);
+    chg[I] = gstep;
+    chg[J] = gstep;
   }
 }
 
@@ -813,6 +955,23 @@ cudaError_t launch_cross_reg(dim3 grid, cudaStream_t st, const qtn_svd_item *d_i
 }
 
 template <typename R, int CPL, int WPP>
+cudaError_t launch_cross_dual(dim3 grid, cudaStream_t st, const qtn_svd_item *d_items, int step, int sweep, R tol,
+                              const int *rot_prev, int *rot_cur, int *changed, long long ld, int gstep,
+                              int steps_per_sweep, int reg_cap) {
+  constexpr size_t smem = (size_t)kRegBlock * 32 * WPP * CPL * sizeof(cx<R>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(jacobi_cross_dual_kernel<R, CPL, WPP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  jacobi_cross_dual_kernel<R, CPL, WPP><<<grid, 32 * kRegBlock * WPP, smem, st>>>(
+      d_items, step, sweep, tol, rot_prev, rot_cur, changed, ld, gstep, steps_per_sweep, reg_cap);
+  return cudaGetLastError();
+}
+
+template <typename R, int CPL, int WPP>
 cudaError_t launch_cross_stream(int pairs_max, int batch, cudaStream_t st, const qtn_svd_item *d_items, int step,
                                 int sweep, R tol, const int *rot_prev, int *rot_cur, int *changed, long long ld,
                                 int gstep, int steps_per_sweep, int reg_cap) {
@@ -908,17 +1067,23 @@ int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, co
 #define QTN_STREAM(CPL, WPP)                                                                                 \
   launch_cross_stream<R, CPL, WPP>(reg_pairs, batch, st, d_items, step, sweep, (R)tol, rot_prev, rot_cur,     \
                                    d_changed, (long long)ld, gstep, max_steps, reg_cap)
+#define QTN_DUAL(CPL, WPP)                                                                                   \
+  launch_cross_dual<R, CPL, WPP>(rgrid, st, d_items, step, sweep, (R)tol, rot_prev, rot_cur, d_changed,       \
+                                 (long long)ld, gstep, max_steps, reg_cap)
         if constexpr (sizeof(R) == 8) {
-          if (reg_variant == 3) e = reg_max_m <= 256 ? QTN_STREAM(4, 2) : QTN_STREAM(8, 2);
+          if (reg_variant == 4) e = reg_max_m <= 256 ? QTN_DUAL(4, 2) : QTN_DUAL(8, 2);
+          else if (reg_variant == 3) e = reg_max_m <= 256 ? QTN_STREAM(4, 2) : QTN_STREAM(8, 2);
           else if (reg_variant == 2) e = reg_max_m <= 256 ? QTN_REG(2, 4) : QTN_REG(4, 4);
           else e = reg_max_m <= 256 ? QTN_REG(4, 2) : QTN_REG(8, 2);
         } else {
-          if (reg_variant == 3) e = reg_max_m <= 512 ? QTN_STREAM(8, 2) : QTN_STREAM(16, 2);
+          if (reg_variant == 4) e = reg_max_m <= 512 ? QTN_DUAL(8, 2) : QTN_DUAL(16, 2);
+          else if (reg_variant == 3) e = reg_max_m <= 512 ? QTN_STREAM(8, 2) : QTN_STREAM(16, 2);
           else if (reg_variant == 2) e = reg_max_m <= 512 ? QTN_REG(4, 4) : QTN_REG(8, 4);
           else e = reg_max_m <= 512 ? QTN_REG(8, 2) : QTN_REG(16, 2);
         }
 #undef QTN_REG
 #undef QTN_STREAM
+#undef QTN_DUAL
         if (e != cudaSuccess) return qtn_fail(QTN_ERR_CUDA, cudaGetErrorString(e));
       }
       if (need_smem_kernel[step]) {

@@ -78,6 +78,8 @@ def parse_algorithm(algorithm):
 # Two-site blocks with at least this many rows are LQ-preconditioned before the Jacobi sweeps
 # (qtn_svd_lq): ~3x fewer sweeps on the strongly graded blocks of a truncated MPS.  0 disables.
 LQ_MIN_ROWS = 96
+# scripts/mps_bench.py --phases: extra device synchronisations that split the SVD time into LQ and Jacobi
+PROFILE_PHASES = False
 
 
 class MPSEngine:
@@ -225,6 +227,9 @@ class MPSEngine:
             lib.check(self.lib.qtn_svd_lq(self.code, nb, items, xitems, lq_ws.data_ptr(), lq_bytes, self._stream()))
             self.stats["launches"] += 1
             items = xitems
+            if PROFILE_PHASES:
+                torch.cuda.synchronize()
+                self.stats["lq_seconds"] = self.stats.get("lq_seconds", 0.0) + _time.perf_counter() - t_svd
         lib.check(self.lib.qtn_svd_rows(self.code, nb, items, self.tol, self.max_sweeps, C.byref(self.trunc),
                                         sigma.data_ptr(), perm.data_ptr(), ld, ranks, scales,
                                         C.byref(sweeps), ws.data_ptr(), ws_bytes, self._stream()))

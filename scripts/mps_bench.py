@@ -26,12 +26,14 @@ ap.add_argument("--cpu-seconds", type=float, default=0.0)
 ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--tol", type=float, default=0.0, help="Jacobi convergence threshold (0 = library default)")
 ap.add_argument("--lq-min-rows", type=int, default=-1, help="override mps.LQ_MIN_ROWS (0 = no LQ preconditioner)")
+ap.add_argument("--phases", action="store_true", help="time the LQ preconditioner separately (extra syncs)")
 ap.add_argument("--opt", action="append", default=[], help="library option name=value (qtn_set_option)")
 a = ap.parse_args()
 from qibotn_b200 import lib as _lib  # noqa: E402
 for kv in a.opt:
     _k, _v = kv.split("=")
     _lib.set_option(_k, int(_v))
+gmps.PROFILE_PHASES = a.phases
 if a.lq_min_rows >= 0:
     gmps.LQ_MIN_ROWS = a.lq_min_rows
 

@@ -141,9 +141,20 @@ def test_truncation_rules(dtype):
 @pytest.mark.parametrize("dtype", ["complex64", "complex128"])
 @pytest.mark.parametrize("lmr", [(64, 128, 64), (48, 100, 80), (80, 100, 48), (128, 40, 128)])
 @pytest.mark.parametrize("graded", [False, True])
-def test_lq_preconditioned_split(lmr, graded, dtype, monkeypatch):
+@pytest.mark.parametrize("svd_reg", [0, 1, 3, 4])
+def test_lq_preconditioned_split(lmr, graded, dtype, svd_reg, monkeypatch):
     """Two-site blocks of >= LQ_MIN_ROWS rows go through qtn_svd_lq (LQ preconditioner) before the
-    Jacobi sweeps; the split must agree with LAPACK and with the un-preconditioned path."""
+    Jacobi sweeps; the split must agree with LAPACK and with the un-preconditioned path, for every
+    cross-step kernel (``svd_reg``: 0 shared-memory, 1 register-resident, 3 streaming, 4 two-pass)."""
+    default = lib.get_option("svd_reg")
+    lib.set_option("svd_reg", svd_reg)
+    try:
+        _lq_split_case(lmr, graded, dtype, monkeypatch)
+    finally:
+        lib.set_option("svd_reg", default)
+
+
+def _lq_split_case(lmr, graded, dtype, monkeypatch):
     l, m, r = lmr
     rng = np.random.default_rng(l * 7 + m * 3 + r + graded)
     # theta = U diag(s) V^H with a known spectrum: condition number 10, or 10 decades (5 for complex64);
