@@ -255,7 +255,10 @@ def mps_metric(n=64, steps=20, chi=256):
     return {"workload": f"{n}-site TFIM Trotter, {steps} steps, bond<={chi}, complex128", "gates": gates,
             "seconds": dt, "gates_per_s": gates / dt, "max_bond": conv.stats["max_bond"],
             "two_site_updates": conv.stats["two_site"], "svd_batches": conv.stats["svd_batches"],
-            "svd_sweeps": conv.stats["svd_sweeps"]}
+            "svd_sweeps": conv.stats["svd_sweeps"], "svd_seconds": conv.stats.get("svd_seconds"),
+            "svd_credited_tflops": conv.stats.get("svd_credited_flops", 0.0) / max(conv.stats.get("svd_seconds", 0.0), 1e-9) / 1e12,
+            "svd_note": "credited flops = 4(14 p q^2 + 8 q^3) per p x q block (SURVEY 8d); LQ-preconditioned one-sided "
+                        "Jacobi, FP64 FMA pipe (rotation-bound, not GEMM-shaped)"}
 
 
 def run_b200(a):

@@ -235,6 +235,9 @@ class MPSEngine:
                                         C.byref(sweeps), ws.data_ptr(), ws_bytes, self._stream()))
         self.stats["svd_seconds"] = self.stats.get("svd_seconds", 0.0) + _time.perf_counter() - t_svd
         self.stats["svd_batches"] += 1
+        # credited work, SURVEY 8(d): thin complex SVD with vectors of a p x q block (p >= q) = 4 (14 p q^2 + 8 q^3)
+        self.stats["svd_credited_flops"] = self.stats.get("svd_credited_flops", 0.0) + sum(
+            4.0 * (14.0 * max(p, q) * min(p, q) ** 2 + 8.0 * min(p, q) ** 3) for _, _, _, p, q, _, _, _ in work)
         self.stats["svd_sweeps"] += int(sweeps.value)
         self.stats["svd_max_sweeps"] = max(self.stats["svd_max_sweeps"], int(sweeps.value))
         esz = 8
