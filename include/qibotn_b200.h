@@ -234,6 +234,19 @@ int qtn_mps_apply_1q(int dtype, int64_t chi_l, int64_t chi_r, void *site, const 
  * elements.  With the SWAP matrix this is the leg exchange "ipj,jqk->iqj,jpk" (mps_utils.py:32-37). */
 int qtn_mps_apply_2q(int dtype, int64_t chi_l, int64_t chi_r, void *theta, const void *gate, void *stream);
 
+/* One site of perfect sampling from an MPS, all shots at once -- what `nshots` of the quimb platform's
+ * execute_circuit asks of the state (backends/quimb.py:172-186: Counter(circ.sample(nshots)), then
+ * |amplitude|^2 of the most frequent strings) and what result.py:50-57 `frequencies()` hands out, without
+ * the dense vector.  For the site with tensor A (chi_l, 2, r) the caller has computed, with qtn_gemm,
+ * w_p = v A^p (nshots x r; v = the shots' left boundary vectors, normalised so that v R_prev v^H = 1) and
+ * z_p = w_p R (R = right environment of the bond to the right, r x r).  The kernel forms the outcome weights
+ * q_p[s] = Re <z_p[s,:], w_p[s,:]>, draws bit[s] = (u[s] (q_0 + q_1) >= q_0), writes it to bits[s * bit_stride],
+ * multiplies ptotal[s] by the conditional probability q_bit / (q_0 + q_1) and emits the next boundary
+ * vectors vnext[s,:] = w_bit[s,:] / sqrt(q_bit).  u: nshots uniforms in [0, 1) (device, double). */
+int qtn_mps_sample_step(int dtype, int64_t nshots, int64_t r, const void *w0, const void *w1, const void *z0,
+                        const void *z1, const double *u, uint8_t *bits, int64_t bit_stride, double *ptotal,
+                        void *vnext, void *stream);
+
 /* Batched one-sided Jacobi SVD with truncation: the decompose half of contract_decompose
  * (mps_utils.py:32,78; cuTensorNet SVDMethod semantics: abs_cutoff, rel_cutoff,
  * discarded_weight_cutoff, max_extent, normalization, partition). */

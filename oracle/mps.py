@@ -158,3 +158,41 @@ def expectation(mps, operator, qubits, normalize=False):
         # for Hermitian operators both orders agree.
         val = np.vdot(psi, phi)
     return val / (norm(mps) if normalize else 1)
+
+
+def right_environments(mps):
+    """R[i] = sum_p A_i^p R[i+1] (A_i^p)^H, R[n] = [[1]] (test infrastructure, numpy)."""
+    n = len(mps)
+    envs = [None] * (n + 1)
+    envs[n] = np.ones((1, 1), dtype=np.complex128)
+    for i in range(n - 1, -1, -1):
+        a = mps[i].astype(np.complex128)
+        envs[i] = np.einsum("ipj,jk,lpk->il", a, envs[i + 1], a.conj())
+    return envs
+
+
+def sample(mps, uniforms):
+    """Perfect sampling of an (unnormalised) MPS, the CPU restatement of what quimb's
+    ``Circuit.sample`` delivers for the reference's ``execute_circuit(nshots=...)``
+    (backends/quimb.py:172-186): qubit by qubit from the left, bit = 1 iff u >= P(0 | earlier bits).
+    ``uniforms``: (n, nshots) in [0, 1).  Returns (bits nshots x n uint8, |amplitude|^2 per shot)."""
+    n = len(mps)
+    uniforms = np.asarray(uniforms, dtype=np.float64)
+    nshots = uniforms.shape[1]
+    envs = right_environments(mps)
+    norm2 = envs[0][0, 0].real
+    bits = np.zeros((nshots, n), dtype=np.uint8)
+    probs = np.ones(nshots)
+    for s in range(nshots):
+        v = np.ones((1,), dtype=np.complex128) / np.sqrt(norm2)
+        for i in range(n):
+            a = mps[i].astype(np.complex128)
+            w = [v @ a[:, p, :] for p in range(2)]
+            q = [max(float(np.real(np.vdot(wp, wp @ envs[i + 1]).conjugate())), 0.0) for wp in w]
+            tot = q[0] + q[1]
+            bit = int(uniforms[i, s] * tot >= q[0]) if tot > 0 else 0
+            bits[s, i] = bit
+            probs[s] *= q[bit] / tot if tot > 0 else 0.0
+            v = w[bit] / np.sqrt(q[bit]) if q[bit] > 0 else w[bit] * 0
+    return bits, probs * norm2
+

@@ -11,7 +11,9 @@ that ``qibo.set_backend(backend="qibotn", platform="quimb")`` and
   relatively; at the default near-lossless cutoff both give the same state);
 * any other ansatz -> the tensor-network contraction engine.
 
-Sampling (``nshots``) draws from the dense distribution and is limited to 26 qubits.
+Sampling (``nshots``): with the MPS ansatz, perfect sampling site by site on the GPU
+(``MPSContractionHelper.sample``, any number of qubits); with a contraction ansatz the dense
+distribution is drawn from, which is limited to 26 qubits.
 """
 
 from __future__ import annotations
@@ -95,9 +97,21 @@ class QuimbBackend(QibotnBackend, NumpyBackend):
         n = circuit.nqubits
         frequencies = measured_probabilities = None
         psi = None
-        if nshots:
+        if nshots and self.ansatz == "mps":
+            from ..mps import MPSContractionHelper
+            bits, probs = MPSContractionHelper(n).sample(self._mps(circuit), int(nshots),
+                                                         seed=getattr(self, "sampling_seed", None))
+            strings = ["".join("1" if b else "0" for b in row) for row in bits]
+            frequencies = Counter(strings)
+            main = dict(frequencies.most_common(self.n_most_frequent_states))
+            first = {}
+            for st_, pr in zip(strings, probs):
+                first.setdefault(st_, float(pr))
+            measured_probabilities = {state: first[state] for state in main}
+        elif nshots:
             if n > _MAX_SAMPLING_QUBITS:
-                raise_error(NotImplementedError, f"sampling is limited to {_MAX_SAMPLING_QUBITS} qubits")
+                raise_error(NotImplementedError, f"sampling is limited to {_MAX_SAMPLING_QUBITS} qubits "
+                                                 "for contraction ansaetze; use ansatz='mps'")
             import torch
 
             psi = self._dense(circuit)

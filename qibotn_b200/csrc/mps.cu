@@ -144,6 +144,47 @@ apply_2q_kernel(long long chi_l, long long chi_r, cx<R> *__restrict__ theta, con
     }
 }
 
+// One site of perfect sampling from an MPS (see qtn_mps_sample_step): a warp per shot.
+// w_p[s,:] = v[s,:] A^p, z_p[s,:] = w_p[s,:] R with R the right environment of the next bond, so that
+// q_p = Re <z_p[s,:], w_p[s,:]> is the weight of outcome p given the bits already drawn.
+template <typename R>
+__global__ void __launch_bounds__(256)
+sample_step_kernel(long long nshots, long long r, const cx<R> *__restrict__ w0, const cx<R> *__restrict__ w1,
+                   const cx<R> *__restrict__ z0, const cx<R> *__restrict__ z1, const double *__restrict__ u,
+                   uint8_t *__restrict__ bits, long long bit_stride, double *__restrict__ ptotal,
+                   cx<R> *__restrict__ vnext) {
+  const long long s = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (s >= nshots) return;
+  const cx<R> *a0 = w0 + s * r, *a1 = w1 + s * r, *b0 = z0 + s * r, *b1 = z1 + s * r;
+  double q0 = 0, q1 = 0;
+  for (long long c = lane; c < r; c += 32) {
+    q0 += (double)b0[c].x * a0[c].x + (double)b0[c].y * a0[c].y;
+    q1 += (double)b1[c].x * a1[c].x + (double)b1[c].y * a1[c].y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+  }
+  q0 = fmax(q0, 0.0); q1 = fmax(q1, 0.0);
+  const double tot = q0 + q1;
+  // outcome 1 iff u >= P(0); a shot whose weight vanished (numerically impossible prefix) reads 0
+  const int bit = tot > 0 ? (u[s] * tot >= q0 ? 1 : 0) : 0;
+  const double qb = bit ? q1 : q0;
+  const cx<R> *src = bit ? a1 : a0;
+  const double scale = qb > 0 ? rsqrt(qb) : 0.0;             // keeps v R v^H = 1 along the chain
+  for (long long c = lane; c < r; c += 32) {
+    cx<R> v;
+    v.x = (R)(src[c].x * scale); v.y = (R)(src[c].y * scale);
+    vnext[s * r + c] = v;
+  }
+  if (lane == 0) {
+    bits[s * bit_stride] = (uint8_t)bit;
+    ptotal[s] *= tot > 0 ? qb / tot : 0.0;
+  }
+}
+
 template <typename R>
 int gemm_launch(int opa, int opb, long long m, long long n, long long k, const void *a, long long lda,
                 const void *b, long long ldb, void *c, long long ldc, int accumulate, cudaStream_t st) {
@@ -193,6 +234,26 @@ extern "C" int qtn_mps_apply_2q(int dtype, int64_t chi_l, int64_t chi_r, void *t
     apply_2q_kernel<float><<<grid, 256, 0, st>>>(chi_l, chi_r, (float2 *)theta, (const float2 *)gate);
   else
     apply_2q_kernel<double><<<grid, 256, 0, st>>>(chi_l, chi_r, (double2 *)theta, (const double2 *)gate);
+  QTN_LAUNCH_CHECK();
+  return QTN_OK;
+}
+
+extern "C" int qtn_mps_sample_step(int dtype, int64_t nshots, int64_t r, const void *w0, const void *w1,
+                                   const void *z0, const void *z1, const double *u, uint8_t *bits,
+                                   int64_t bit_stride, double *ptotal, void *vnext, void *stream) {
+  if (dtype != QTN_C64 && dtype != QTN_C128) return qtn_fail(QTN_ERR_ARG, "qtn_mps_sample_step: bad dtype");
+  if (nshots <= 0 || r <= 0 || bit_stride <= 0 || !w0 || !w1 || !z0 || !z1 || !u || !bits || !ptotal || !vnext)
+    return qtn_fail(QTN_ERR_ARG, "qtn_mps_sample_step: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((nshots + 7) / 8);
+  if (dtype == QTN_C64)
+    sample_step_kernel<float><<<grid, 256, 0, st>>>(nshots, r, (const float2 *)w0, (const float2 *)w1,
+                                                    (const float2 *)z0, (const float2 *)z1, u, bits, bit_stride,
+                                                    ptotal, (float2 *)vnext);
+  else
+    sample_step_kernel<double><<<grid, 256, 0, st>>>(nshots, r, (const double2 *)w0, (const double2 *)w1,
+                                                     (const double2 *)z0, (const double2 *)z1, u, bits, bit_stride,
+                                                     ptotal, (double2 *)vnext);
   QTN_LAUNCH_CHECK();
   return QTN_OK;
 }

@@ -105,6 +105,8 @@ _SIGNATURES = {
                            C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "qtn_mps_apply_1q": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qtn_mps_apply_2q": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qtn_mps_sample_step": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qtn_svd_workspace_bytes": (C.c_int64, [C.c_int, C.c_int64]),
     "qtn_svd_lq_workspace_bytes": (C.c_int64, [C.c_int]),
     "qtn_svd_lq": (C.c_int, [C.c_int, C.c_int, C.POINTER(SvdItem), C.POINTER(SvdItem), C.c_void_p, C.c_int64,

@@ -440,3 +440,76 @@ class MPSContractionHelper:
                                                     torch.cuda.current_stream().cuda_stream))
             env = self._transfer(env, ket, t, torch, code)
         return env.reshape(())
+
+    def right_environments(self, mps_tensors):
+        """R[i] (chi_{i-1} x chi_{i-1}) = sum over the physical legs of sites i..n-1 of ket x conj(bra):
+        R[n] = [[1]], R[i] = sum_p A_i^p R[i+1] (A_i^p)^H; R[0] is <psi|psi>."""
+        torch, dt, code, cdtype, dev = self._setup(mps_tensors)
+        n = len(mps_tensors)
+        envs = [None] * (n + 1)
+        envs[n] = torch.ones(1, 1, dtype=cdtype, device=dev)
+        for i in range(n - 1, -1, -1):
+            a = mps_tensors[i].contiguous()
+            l, _, r = a.shape
+            t = torch.empty(2 * l * r, dtype=cdtype, device=dev)                    # (l,p) x r
+            self._gemm(code, lib.OP_N, lib.OP_N, 2 * l, r, r, a, r, envs[i + 1], r, t, r, torch)
+            out = torch.empty(l * l, dtype=cdtype, device=dev)                      # t (l x 2r) . a (l x 2r)^H
+            self._gemm(code, lib.OP_N, lib.OP_H, l, l, 2 * r, t, 2 * r, a, 2 * r, out, l, torch)
+            envs[i] = out.view(l, l)
+        return envs
+
+    def sample(self, mps_tensors, nshots, seed=None, uniforms=None):
+        """``nshots`` computational-basis samples of the (unnormalised) MPS without densification -- the
+        ``circ.sample(nshots)`` of the quimb platform (backends/quimb.py:172-186) for any number of qubits.
+        Site by site from the left, all shots at once: two GEMMs give the candidate boundary vectors
+        w_p = v A^p, one more each their images under the right environment, and
+        ``qtn_mps_sample_step`` draws the bit from the outcome weights.
+
+        Returns ``(bits, probs)``: ``bits`` (nshots x n, uint8, numpy, qubit 0 first) and
+        ``probs[s] = |<bits_s|psi>|^2`` (numpy float64, the unnormalised amplitude squared, as the
+        reference reports it).  ``uniforms`` (n x nshots in [0,1)) overrides the seeded generator
+        (``numpy.random.default_rng(seed)``), which is how the parity test drives the CPU oracle
+        (oracle/mps.py ``sample``) with the same draws."""
+        torch, dt, code, cdtype, dev = self._setup(mps_tensors)
+        n = len(mps_tensors)
+        nshots = int(nshots)
+        if nshots < 1:
+            raise ValueError("nshots must be positive")
+        if uniforms is None:
+            uniforms = np.random.default_rng(seed).random((n, nshots))
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+        if uniforms.shape != (n, nshots):
+            raise ValueError(f"uniforms must have shape {(n, nshots)}")
+        u_dev = torch.from_numpy(uniforms).to(dev)
+        envs = self.right_environments(mps_tensors)
+        norm2 = float(envs[0].reshape(()).real.cpu())
+        if not norm2 > 0:
+            raise ValueError("cannot sample from a state of zero norm")
+        stream = torch.cuda.current_stream().cuda_stream
+        bits = torch.zeros(nshots, n, dtype=torch.uint8, device=dev)
+        ptotal = torch.ones(nshots, dtype=torch.float64, device=dev)
+        # boundary vectors, normalised so that v R v^H = 1 (R[0] = norm2 is 1 x 1)
+        v = torch.full((nshots, 1), 1.0 / np.sqrt(norm2), dtype=cdtype, device=dev)
+        for i, a in enumerate(mps_tensors):
+            a = a.contiguous()
+            l, _, r = a.shape
+            env = envs[i + 1]
+            w, z = [], []
+            for p in range(2):
+                wp = torch.empty(nshots * r, dtype=cdtype, device=dev)
+                # A^p = a[:, p, :]: l x r with row stride 2r, starting p*r elements in
+                lib.check(self.lib.qtn_gemm(code, lib.OP_N, lib.OP_N, nshots, r, l, v.data_ptr(), l,
+                                            a.data_ptr() + p * r * a.element_size(), 2 * r, wp.data_ptr(), r, 0,
+                                            stream))
+                zp = torch.empty(nshots * r, dtype=cdtype, device=dev)
+                self._gemm(code, lib.OP_N, lib.OP_N, nshots, r, r, wp, r, env, r, zp, r, torch)
+                w.append(wp)
+                z.append(zp)
+            vnext = torch.empty(nshots, r, dtype=cdtype, device=dev)
+            lib.check(self.lib.qtn_mps_sample_step(code, nshots, r, w[0].data_ptr(), w[1].data_ptr(),
+                                                   z[0].data_ptr(), z[1].data_ptr(), u_dev[i].data_ptr(),
+                                                   bits.data_ptr() + i, n, ptotal.data_ptr(), vnext.data_ptr(),
+                                                   stream))
+            v = vnext
+        return bits.cpu().numpy(), ptotal.cpu().numpy() * norm2
+

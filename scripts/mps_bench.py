@@ -26,6 +26,7 @@ ap.add_argument("--cpu-seconds", type=float, default=0.0)
 ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--tol", type=float, default=0.0, help="Jacobi convergence threshold (0 = library default)")
 ap.add_argument("--lq-min-rows", type=int, default=-1, help="override mps.LQ_MIN_ROWS (0 = no LQ preconditioner)")
+ap.add_argument("--shots", type=int, default=0, help="also draw this many samples from the final MPS (timed)")
 ap.add_argument("--phases", action="store_true", help="time the LQ preconditioner separately (extra syncs)")
 ap.add_argument("--opt", action="append", default=[], help="library option name=value (qtn_set_option)")
 a = ap.parse_args()
@@ -55,6 +56,15 @@ bonds = [int(t.shape[2]) for t in conv.mps_tensors[:-1]]
 line = {"workload": f"{a.n}-site TFIM Trotter, {a.steps} steps, chi<={a.chi}, {a.dtype}", "gates": ngates,
         "seconds": best, "gates_per_s": ngates / best, "max_bond": max(bonds), "bonds": bonds, "norm": norm,
         "zz_mid": [zz.real, zz.imag], "stats": conv.stats, "tol": a.tol, "lq_min_rows": gmps.LQ_MIN_ROWS, "options": a.opt}
+if a.shots > 0:
+    helper.sample(conv.mps_tensors, 16, seed=0)                       # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    bits, probs = helper.sample(conv.mps_tensors, a.shots, seed=1)
+    dt = time.perf_counter() - t0
+    line["sampling"] = {"shots": a.shots, "seconds": dt, "shots_per_s": a.shots / dt,
+                        "mean_log2_prob_over_norm": float(np.mean(np.log2(np.maximum(probs / norm, 1e-300)))),
+                        "first": "".join(map(str, bits[0]))}
 if a.cpu_seconds > 0:
     from oracle import mps as omps
     from oracle.network import gate_tensors

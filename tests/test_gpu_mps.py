@@ -283,3 +283,45 @@ def test_mps_rejects_three_qubit_gates_and_pure_qr_keeps_the_state():
         eng.apply_gate(np.eye(8).reshape((2,) * 6), (0, 1, 2))
     gts, _ = gate_tensors(circ, np.complex128)
     assert len(gts) > 0
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_mps_sampling_matches_oracle_draw_for_draw(dtype):
+    """Perfect sampling on the GPU (qtn_mps_sample_step) against the numpy restatement with the SAME
+    uniforms: identical bit strings, |amplitude|^2 per shot equal to the dense simulator's."""
+    n, nshots = 8, 1500
+    circ = circuits.ry_rz_cnot_ring(n, 3, seed=5)
+    psi = osv.simulate(circ)
+    conv = gmps.QiboCircuitToMPS(circ, DEFAULT_ALGO, dtype=dtype)
+    u = np.random.default_rng(11).random((n, nshots))
+    bits, probs = gmps.MPSContractionHelper(n).sample(conv.mps_tensors, nshots, uniforms=u)
+    ref_bits, ref_probs = omps.sample(omps.evolve(circ, DEFAULT_ALGO), u)
+    differing = int((bits != ref_bits).any(axis=1).sum())
+    # a uniform within rounding of a threshold may fall on the other side in single precision
+    assert differing <= (0 if dtype == "complex128" else 3)
+    idx = (bits.astype(np.int64) << np.arange(n - 1, -1, -1)).sum(axis=1)
+    assert np.abs(probs - np.abs(psi[idx]) ** 2).max() < TOL[dtype] * 10
+    same = ~(bits != ref_bits).any(axis=1)
+    assert np.abs(probs[same] - ref_probs[same]).max() < TOL[dtype] * 10
+    emp = np.bincount(idx, minlength=1 << n) / nshots
+    assert np.abs(emp - np.abs(psi) ** 2).max() < 0.03
+
+
+def test_mps_sampling_at_48_qubits_through_the_quimb_platform():
+    """GHZ state on 48 qubits: no dense vector can exist, every shot is all zeros or all ones, and the
+    reported probabilities are |amplitude|^2 = 1/2 (reference backends/quimb.py:172-186)."""
+    n = 48
+    circ = circuits.Circuit(n)
+    circ.add(circuits.gates.H(0))
+    for q in range(n - 1):
+        circ.add(circuits.gates.CNOT(q, q + 1))
+    b = MetaBackend.load("quimb")
+    b.configure_tn_simulation(ansatz="mps", max_bond_dimension=8, svd_cutoff=1e-12)
+    b.sampling_seed = 7
+    res = b.execute_circuit(circ, nshots=400)
+    freq = res.frequencies()
+    assert set(freq) == {"0" * n, "1" * n} and sum(freq.values()) == 400
+    assert abs(freq["0" * n] - 200) < 60
+    for state, p in res.probabilities().items():
+        assert abs(p - 0.5) < 1e-10
+

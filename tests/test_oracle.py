@@ -132,3 +132,18 @@ def test_truncation_rank_rules():
     assert omps.truncation_rank(s, {"discarded_weight_cutoff": 0.01}) == 4
     assert omps.truncation_rank(s, {"abs_cutoff": 10.0}) == 1
     assert omps.truncation_rank(s, {}) == 8
+
+
+def test_oracle_mps_sampler_against_the_dense_state():
+    """oracle.mps.sample (the checker of the GPU sampler): per-shot |amplitude|^2 and the empirical
+    distribution agree with the dense simulator."""
+    n, nshots = 6, 3000
+    circ = circuits.ry_rz_cnot_ring(n, 2, seed=3)
+    algo = {"qr_method": False, "svd_method": {"partition": "UV", "abs_cutoff": 1e-12}}
+    psi = osv.simulate(circ)
+    bits, probs = omps.sample(omps.evolve(circ, algo), np.random.default_rng(0).random((n, nshots)))
+    idx = (bits.astype(np.int64) << np.arange(n - 1, -1, -1)).sum(axis=1)
+    assert np.abs(probs - np.abs(psi[idx]) ** 2).max() < 1e-12
+    emp = np.bincount(idx, minlength=1 << n) / nshots
+    assert np.abs(emp - np.abs(psi) ** 2).max() < 0.03
+
