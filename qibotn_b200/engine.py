@@ -18,6 +18,10 @@ from .network import TensorNetwork
 from .planner import PathInfo, find_path
 
 _PLAN_CACHE: dict = {}
+# Optional on-disk plan store (a directory): plans found for a network structure are written there and
+# read back by later processes, so that Hamiltonians with many differently shaped terms (light cones)
+# can be planned offline on CPU cores (scripts/plan_c5.py) and only executed on the GPU.
+PLAN_STORE = None
 _RUNNER_CACHE: dict = {}
 _CACHE_LIMIT = 8
 
@@ -54,8 +58,11 @@ def plan(net: TensorNetwork, dtype="complex64", samples=32, seed=0, min_slices=1
         return _PLAN_CACHE[key]
     t0 = time.perf_counter()
     if info is None:
+        info = _stored_plan(net, width, min_slices)
+    if info is None:
         info = find_path(net.modes, net.out, samples=samples, seed=seed,
                          target_log2_width=width, min_slices=min_slices)
+        _store_plan(net, width, min_slices, info)
     t1 = time.perf_counter()
     lowered = executor.lower(net.modes, net.out, info, str(dtype))
     t2 = time.perf_counter()
@@ -65,6 +72,35 @@ def plan(net: TensorNetwork, dtype="complex64", samples=32, seed=0, min_slices=1
             _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
         _PLAN_CACHE[key] = (info, lowered)
     return info, lowered
+
+
+def _store_file(net, width, min_slices):
+    import os
+
+    from .plans import structure_hash
+    return os.path.join(PLAN_STORE, f"{structure_hash(net.modes, net.out)}_w{int(width)}_s{int(min_slices)}.json")
+
+
+def _stored_plan(net, width, min_slices):
+    import os
+
+    if not PLAN_STORE:
+        return None
+    path = _store_file(net, width, min_slices)
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return PathInfo.from_json(f.read())
+
+
+def _store_plan(net, width, min_slices, info):
+    import os
+
+    if not PLAN_STORE:
+        return
+    os.makedirs(PLAN_STORE, exist_ok=True)
+    with open(_store_file(net, width, min_slices), "w") as f:
+        f.write(info.to_json())
 
 
 def _runner_bytes(lowered):

@@ -107,11 +107,17 @@ def amplitude_tn(qibo_circ, datatype, bitstring, n_samples=32, distributed=False
 
 
 # -------------------------------------------------------------------- expectation
+# Diagonal gates (RZ, CZ, CU1, RZZ, ...) and diagonal Pauli factors enter the expectation networks as
+# hyper-indexed diagonals instead of full rank-2k tensors (network.QiboCircuitToEinsum._thread): same
+# value, much smaller treewidth when the entangling gates are diagonal (QAOA: BASELINE config 5).
+HYPER_DIAGONAL = True
+
+
 def _term_networks(qibo_circ, datatype, observable):
     conv = QiboCircuitToEinsum(qibo_circ, dtype=datatype)
     ham = check_observable(observable, qibo_circ.nqubits)
     for term in extract_gates_and_qubits(ham):
-        yield conv.expectation_network(get_ham_gates(term, dtype=datatype))
+        yield conv.expectation_network(get_ham_gates(term, dtype=datatype), hyper=HYPER_DIAGONAL)
 
 
 # Planner effort of the single-GPU drivers (seeds tried per network structure; the distributed

@@ -226,6 +226,93 @@ def _absorb_small(net: SymbolicNetwork):
     return path, live, nxt
 
 
+# ------------------------------------------------------- variable elimination
+def _elimination_path(live, out, hyper, nxt, rng, temperature=0.0):
+    """Bucket (variable) elimination for networks with hyper labels: repeatedly pick the label whose
+    elimination -- contracting every tensor that owns it -- yields the smallest tensor (ties and, with
+    ``temperature`` > 0, near-ties broken at random), and contract its owners pairwise, smallest first.
+    For circuits whose entangling gates are diagonal (QAOA) the labels are the vertices of a sparse
+    "line graph" and this is the classic min-width heuristic on it; pairwise greedy on the tensors,
+    which scores one merge at a time, does far worse there.  Returns ssa pairs."""
+    live = dict(live)
+    owners = {}
+    for i, m in live.items():
+        mm = m
+        while mm:
+            low = mm & -mm
+            owners.setdefault(low, set()).add(i)
+            mm ^= low
+    path = []
+
+    def merged_size(low):
+        u = 0
+        for t in owners[low]:
+            u |= live[t]
+        return (u & ~low).bit_count() if not (low & out) else u.bit_count()
+
+    size = {low: merged_size(low) for low in owners if not (low & out)}
+    while size:
+        if temperature > 0:
+            best = min(size, key=lambda low: (size[low] - temperature * math.log(rng.random() + 1e-300) * -1.0, low))
+        else:
+            best = min(size, key=lambda low: (size[low], low))
+        low = best
+        del size[low]
+        ids = sorted(owners[low], key=lambda t: (live[t].bit_count(), t))
+        touched = 0
+        while len(ids) > 1:
+            i, j = ids[0], ids[1]
+            a, b = live.pop(i), live.pop(j)
+            shared = a & b
+            keep = shared & out
+            hs = shared & hyper
+            while hs:
+                l2 = hs & -hs
+                hs ^= l2
+                if len(owners[l2] - {i, j}) > 0:
+                    keep |= l2
+            c = (a ^ b) | keep
+            for t, m in ((i, a), (j, b)):
+                mm = m
+                while mm:
+                    l2 = mm & -mm
+                    owners[l2].discard(t)
+                    mm ^= l2
+            live[nxt] = c
+            mm = c
+            while mm:
+                l2 = mm & -mm
+                owners.setdefault(l2, set()).add(nxt)
+                mm ^= l2
+            touched |= a | b
+            path.append((i, j))
+            ids = sorted(ids[2:] + [nxt], key=lambda t: (live[t].bit_count(), t))
+            nxt += 1
+        if len(ids) == 1 and not (low & out):
+            # a label owned by a single tensor (trace-free dangling index cannot occur in circuit
+            # networks; a label summed inside one tensor would need a reduction we do not have)
+            touched |= live[ids[0]]
+        mm = touched
+        while mm:
+            l2 = mm & -mm
+            mm ^= l2
+            if l2 in size:
+                if owners.get(l2):
+                    size[l2] = merged_size(l2)
+                else:
+                    del size[l2]
+    # whatever is left shares no summed label: outer products, smallest first
+    ids = sorted(live, key=lambda t: (live[t].bit_count(), t))
+    while len(ids) > 1:
+        i, j = ids[0], ids[1]
+        a, b = live.pop(i), live.pop(j)
+        live[nxt] = a | b
+        path.append((i, j))
+        ids = sorted(ids[2:] + [nxt], key=lambda t: (live[t].bit_count(), t))
+        nxt += 1
+    return path
+
+
 # ----------------------------------------------------------------------- greedy
 def _greedy(live, out, hyper, nxt, rng, alpha=1.0, temperature=0.0):
     """Boltzmann greedy on {id: mask}; returns ssa pairs finishing the contraction."""
@@ -450,7 +537,7 @@ def _slice(net: SymbolicNetwork, path, target_log2_width, min_slices, max_sliced
             for m in (a, b, c):
                 if m.bit_count() >= width - (0 if width > target_log2_width else 2):
                     cand |= m
-        cand &= ~net.out_mask & ~net.hyper_mask
+        cand &= ~net.out_mask                # hyper labels included: every owner leaf is indexed at the slice bit
         if not cand:
             break
         best = None
@@ -500,8 +587,11 @@ def find_path(modes, out, samples=32, seed=0, target_log2_width=30, min_slices=1
         cands.append((0.0, "trivial", []))
     else:
         for s in range(max(1, samples)):
-            for meth in methods:
-                if meth == "greedy":
+            for meth in (tuple(methods) + ("eliminate",) if net.hyper_mask else methods):
+                if meth == "eliminate":
+                    temp = 0.0 if s == 0 else rng.choice([0.3, 0.6, 1.0, 1.5])
+                    tail = _elimination_path(live, net.out_mask, net.hyper_mask, nxt, rng, temp)
+                elif meth == "greedy":
                     temp = 0.0 if s == 0 else rng.choice([0.01, 0.03, 0.1, 0.3])
                     alpha = 1.0 if s == 0 else rng.choice([0.0, 0.5, 1.0, 1.0, 2.0])
                     tail = _greedy(live, net.out_mask, net.hyper_mask, nxt, rng, alpha, temp)

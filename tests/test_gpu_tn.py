@@ -355,11 +355,15 @@ def test_qaoa_maxcut_expectation(dtype):
     circ, edges = circuits.qaoa_maxcut(n, p, seed=1)
     psi = osv.simulate(circ)
     want = osv.pauli_expectation(psi, [(1.0, [("Z", a), ("Z", b)]) for a, b in edges], n).real
-    for route in ("network", "state"):
-        ev.EXPECTATION_ROUTE, samples = route, ev.PLAN_SAMPLES
+    # "network" twice: diagonal gates as hyper-indexed diagonals (the default) and as the reference's
+    # full rank-4 tensors -- same value
+    for route, hyper in (("network", True), ("network", False), ("state", True)):
+        ev.EXPECTATION_ROUTE, samples, hyper_default = route, ev.PLAN_SAMPLES, ev.HYPER_DIAGONAL
         ev.PLAN_SAMPLES = 4                      # 21 differently shaped terms: keep the planner's share of the test small
+        ev.HYPER_DIAGONAL = hyper
+        engine.clear_caches()
         try:
             got = float(ev.expectation_tn(circ, dtype, circuits.zz_terms(edges)).real.get().reshape(-1)[0])
         finally:
-            ev.EXPECTATION_ROUTE, ev.PLAN_SAMPLES = "auto", samples
-        assert abs(got - want) < TOL[dtype] * 50, (route, got, want)
+            ev.EXPECTATION_ROUTE, ev.PLAN_SAMPLES, ev.HYPER_DIAGONAL = "auto", samples, hyper_default
+        assert abs(got - want) < TOL[dtype] * 50, (route, hyper, got, want)

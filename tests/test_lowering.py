@@ -81,3 +81,32 @@ def test_amplitude_and_expectation_lowering(min_slices):
     got = emulate(low, enet.tensors, range(info.num_slices))
     want = osv.pauli_expectation(psi, [(0.5, [("X", 0), ("Z", 1), ("Y", 4)])], 6)
     assert np.allclose(got, want, atol=1e-12)
+
+
+@pytest.mark.parametrize("min_slices", [1, 4, 16])
+def test_hyper_indexed_diagonal_gates_lower_to_the_same_value(min_slices):
+    """QAOA expectation networks with the diagonal gates (RZZ) and the ZZ observable emitted as
+    hyper-indexed diagonals: planned (variable elimination is among the candidates), sliced -- hyper
+    labels included -- lowered and emulated; equal to the dense simulator and to the reference-style
+    network with full rank-4 gate tensors."""
+    from qibotn_b200.observables import check_observable, extract_gates_and_qubits, get_ham_gates
+    n = 10
+    circ, edges = circuits.qaoa_maxcut(n, 2, seed=1)
+    psi = osv.simulate(circ)
+    conv = QiboCircuitToEinsum(circ, "complex128")
+    ham = check_observable(circuits.zz_terms(edges), n)
+    for term in list(extract_gates_and_qubits(ham))[:3]:
+        hg = get_ham_gates(term, dtype="complex128")
+        want = osv.pauli_expectation(psi, [(1.0, [(l, q) for q, l, _ in term])], n) * np.prod([c for _, _, c in term])
+        plain = conv.expectation_network(hg)
+        net = conv.expectation_network(hg, hyper=True)
+        assert len(net.tensors) == len(plain.tensors)
+        assert sum(len(m) for m in net.modes) < sum(len(m) for m in plain.modes)
+        info = find_path(net.modes, net.out, samples=2, seed=0, min_slices=min_slices)
+        assert info.num_slices >= min_slices
+        low = executor.lower(net.modes, net.out, info, "complex128")
+        got = emulate(low, net.tensors, range(info.num_slices)).reshape(-1)[0]
+        assert abs(got - want) < 1e-12
+        ref = ocontract.contract(plain.interleaved())
+        assert abs(np.asarray(ref).reshape(-1)[0] - want) < 1e-12
+
