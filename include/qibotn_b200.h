@@ -114,7 +114,7 @@ typedef struct {
   uint8_t a_mhi[QTN_HI_MAX], c_mhi[QTN_HI_MAX];
   uint8_t b_nhi[QTN_HI_MAX], c_nhi[QTN_HI_MAX];
   uint8_t a_khi[QTN_HI_MAX], b_khi[QTN_HI_MAX];
-  uint8_t a_bat[QTN_LO_MAX], b_bat[QTN_LO_MAX], c_bat[QTN_LO_MAX];
+  uint8_t a_bat[QTN_HI_MAX], b_bat[QTN_HI_MAX], c_bat[QTN_HI_MAX];   /* batch (hyper) labels */
   int32_t n_slice_a, n_slice_b;
   uint8_t slice_bit_a[QTN_MAX_SLICE], slice_pos_a[QTN_MAX_SLICE];
   uint8_t slice_bit_b[QTN_MAX_SLICE], slice_pos_b[QTN_MAX_SLICE];

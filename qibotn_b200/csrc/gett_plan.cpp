@@ -379,7 +379,7 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     p->m_real = (int)mlo.size(); p->n_real = (int)nlo.size(); p->k_real = (int)klo.size();
     p->n_mhi = (int)mhi.size(); p->n_nhi = (int)nhi.size(); p->n_khi = (int)khi.size();
     p->n_batch = bbits;
-    if (bbits > QTN_LO_MAX) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_plan: too many batch labels");
+    if (bbits > QTN_HI_MAX) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_plan: too many batch labels");
 
     // C layout when free: tile bits lowest (n then m), then n-hi, m-hi, batch
     if (d->c_layout_free) {

@@ -52,8 +52,8 @@ class PairPlan(C.Structure):
         ("a_mhi", C.c_uint8 * QTN_HI_MAX), ("c_mhi", C.c_uint8 * QTN_HI_MAX),
         ("b_nhi", C.c_uint8 * QTN_HI_MAX), ("c_nhi", C.c_uint8 * QTN_HI_MAX),
         ("a_khi", C.c_uint8 * QTN_HI_MAX), ("b_khi", C.c_uint8 * QTN_HI_MAX),
-        ("a_bat", C.c_uint8 * QTN_LO_MAX), ("b_bat", C.c_uint8 * QTN_LO_MAX),
-        ("c_bat", C.c_uint8 * QTN_LO_MAX),
+        ("a_bat", C.c_uint8 * QTN_HI_MAX), ("b_bat", C.c_uint8 * QTN_HI_MAX),
+        ("c_bat", C.c_uint8 * QTN_HI_MAX),
         ("n_slice_a", C.c_int32), ("n_slice_b", C.c_int32),
         ("slice_bit_a", C.c_uint8 * QTN_MAX_SLICE), ("slice_pos_a", C.c_uint8 * QTN_MAX_SLICE),
         ("slice_bit_b", C.c_uint8 * QTN_MAX_SLICE), ("slice_pos_b", C.c_uint8 * QTN_MAX_SLICE),
