@@ -226,6 +226,18 @@ int qtn_add_i32(int32_t *dst, int32_t delta, void *stream);
 int qtn_gemm(int dtype, int opa, int opb, int64_t m, int64_t n, int64_t k, const void *a, int64_t lda,
              const void *b, int64_t ldb, void *c, int64_t ldc, int accumulate, void *stream);
 
+/* `count` independent products C_i = opA_i(A_i) * opB_i(B_i) (+ C_i) in ceil(count / 32) launches: the A.B
+ * products and the factor recoveries of one brickwork layer of two-site gates (mps_utils.py:78-84 is called once
+ * per gate by the reference; disjoint bonds of a layer are independent).  `items` is a HOST array. */
+typedef struct {
+  const void *a, *b;
+  void *c;
+  int32_t m, n, k;
+  int32_t lda, ldb, ldc;
+  int32_t opa, opb;
+} qtn_gemm_item;
+int qtn_gemm_batched(int dtype, int count, const qtn_gemm_item *items, int accumulate, void *stream);
+
 /* site[i][q][j] = sum_p gate[q][p] site[i][p][j] in place; gate = 4 device elements.
  * Takes over contract("ipj,qp->iqj") (mps_utils.py:64-69). */
 int qtn_mps_apply_1q(int dtype, int64_t chi_l, int64_t chi_r, void *site, const void *gate, void *stream);

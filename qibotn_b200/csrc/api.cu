@@ -75,6 +75,7 @@ extern "C" int64_t qtn_sizeof(const char *name) {
   if (!std::strcmp(name, "qtn_pair_plan_t")) return (int64_t)sizeof(qtn_pair_plan_t);
   if (!std::strcmp(name, "qtn_svd_item")) return (int64_t)sizeof(qtn_svd_item);
   if (!std::strcmp(name, "qtn_svd_trunc")) return (int64_t)sizeof(qtn_svd_trunc);
+  if (!std::strcmp(name, "qtn_gemm_item")) return (int64_t)sizeof(qtn_gemm_item);
   return -1;
 }
 

@@ -7,6 +7,7 @@
 //                                                    SWAP gate it is the exchange of mps_utils.py:32-37)
 // The GEMM is a shared-memory tiled FFMA/DFMA kernel (64x64x16 tile, 4x4 outputs per thread);
 // MPS bonds are not powers of two, so the bit-tensor kernels of gett*.cu do not apply here.
+#include <algorithm>
 #include <cstdint>
 
 #include "qtn_internal.h"
@@ -31,15 +32,14 @@ constexpr int GK = 16;   // k step
 
 // op: bit 0 = conjugate, bit 1 = transpose (stored matrix is the transpose of the operand)
 template <typename R>
-__global__ void __launch_bounds__(256)
-gemm_kernel(int opa, int opb, long long M, long long N, long long K, const cx<R> *__restrict__ A,
-            long long lda, const cx<R> *__restrict__ B, long long ldb, cx<R> *__restrict__ C,
-            long long ldc, int accumulate) {
+__device__ __forceinline__ void gemm_tile(int opa, int opb, long long M, long long N, long long K,
+                                          const cx<R> *__restrict__ A, long long lda, const cx<R> *__restrict__ B,
+                                          long long ldb, cx<R> *__restrict__ C, long long ldc, int accumulate,
+                                          long long m0, long long n0) {
   using T = cx<R>;
   __shared__ T sA[GK][GT + 1];
   __shared__ T sB[GK][GT + 1];
   const int t = threadIdx.x;
-  const long long m0 = (long long)blockIdx.y * GT, n0 = (long long)blockIdx.x * GT;
   const int tm = (t >> 4) * 4, tn = (t & 15) * 4;
   T acc[4][4];
 #pragma unroll
@@ -95,6 +95,33 @@ gemm_kernel(int opa, int opb, long long M, long long N, long long K, const cx<R>
       C[gm * ldc + gn] = v;
     }
   }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+gemm_kernel(int opa, int opb, long long M, long long N, long long K, const cx<R> *__restrict__ A,
+            long long lda, const cx<R> *__restrict__ B, long long ldb, cx<R> *__restrict__ C,
+            long long ldc, int accumulate) {
+  gemm_tile<R>(opa, opb, M, N, K, A, lda, B, ldb, C, ldc, accumulate, (long long)blockIdx.y * GT,
+               (long long)blockIdx.x * GT);
+}
+
+// Up to kGemmBatch independent products in one launch (blockIdx.z = product): the 62 small GEMMs of an MPS
+// layer fill 64 of 148 SMs each when launched one by one.
+constexpr int kGemmBatch = 32;
+struct GemmBatch {
+  int count;
+  qtn_gemm_item it[kGemmBatch];
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+gemm_batched_kernel(const __grid_constant__ GemmBatch batch, int accumulate) {
+  const qtn_gemm_item &g = batch.it[blockIdx.z];
+  const long long m0 = (long long)blockIdx.y * GT, n0 = (long long)blockIdx.x * GT;
+  if (m0 >= g.m || n0 >= g.n) return;
+  gemm_tile<R>(g.opa, g.opb, g.m, g.n, g.k, (const cx<R> *)g.a, g.lda, (const cx<R> *)g.b, g.ldb, (cx<R> *)g.c,
+               g.ldc, accumulate, m0, n0);
 }
 
 // site[i][q][j] = sum_p G[q][p] site[i][p][j]
@@ -255,5 +282,35 @@ extern "C" int qtn_mps_sample_step(int dtype, int64_t nshots, int64_t r, const v
                                                      (const double2 *)z0, (const double2 *)z1, u, bits, bit_stride,
                                                      ptotal, (double2 *)vnext);
   QTN_LAUNCH_CHECK();
+  return QTN_OK;
+}
+
+extern "C" int qtn_gemm_batched(int dtype, int count, const qtn_gemm_item *items, int accumulate, void *stream) {
+  if (dtype != QTN_C64 && dtype != QTN_C128) return qtn_fail(QTN_ERR_ARG, "qtn_gemm_batched: bad dtype");
+  if (count < 0 || (count > 0 && !items)) return qtn_fail(QTN_ERR_ARG, "qtn_gemm_batched: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int base = 0; base < count; base += kGemmBatch) {
+    GemmBatch batch;
+    batch.count = std::min(kGemmBatch, count - base);
+    long long tm = 0, tn = 0;
+    int live = 0;
+    for (int i = 0; i < batch.count; ++i) {
+      const qtn_gemm_item &g = items[base + i];
+      if (g.m < 0 || g.n < 0 || g.k < 0 || (g.opa & ~3) || (g.opb & ~3))
+        return qtn_fail(QTN_ERR_ARG, "qtn_gemm_batched: bad item");
+      if (g.m == 0 || g.n == 0) continue;
+      if (!g.a || !g.b || !g.c) return qtn_fail(QTN_ERR_ARG, "qtn_gemm_batched: null pointer");
+      batch.it[live++] = g;
+      tm = std::max(tm, ((long long)g.m + GT - 1) / GT);
+      tn = std::max(tn, ((long long)g.n + GT - 1) / GT);
+    }
+    if (!live) continue;
+    if (tm > 65535) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_gemm_batched: m too large");
+    batch.count = live;
+    dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)live);
+    if (dtype == QTN_C64) gemm_batched_kernel<float><<<grid, 256, 0, st>>>(batch, accumulate);
+    else gemm_batched_kernel<double><<<grid, 256, 0, st>>>(batch, accumulate);
+    QTN_LAUNCH_CHECK();
+  }
   return QTN_OK;
 }

@@ -878,6 +878,97 @@ lq_update_kernel(const qtn_svd_item *__restrict__ items, const qtn_svd_item *__r
   }
 }
 
+// Register variant of lq_update_kernel for rows of at most 32 * CPL columns: the trailing row lives in the
+// registers of its warp for the 16 projections, each panel row is read from shared memory once per projection
+// (kept in registers between the dot product and the update): a third of the shared-memory traffic, and 16
+// warps per CTA since the rows no longer need a shared-memory slot each.
+// (8 warps when the two register rows need more than 64 registers, i.e. rows of 257..512 complex128 columns)
+template <typename R, int CPL> constexpr int lq_warps_reg() { return CPL * (int)sizeof(cx<R>) / 4 * 2 > 64 ? 8 : 16; }
+template <typename R, int CPL>
+__global__ void __launch_bounds__(32 * lq_warps_reg<R, CPL>())
+lq_update_reg_kernel(const qtn_svd_item *__restrict__ items, const qtn_svd_item *__restrict__ xitems, int p, int pb) {
+  using T = cx<R>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const qtn_svd_item it = items[blockIdx.y];
+  const int n = it.n, m = it.m;
+  const int r0 = p * pb;
+  const int t0 = r0 + pb;                                   // first trailing row
+  const int first = t0 + (int)blockIdx.x * kLqRowsPerCta;
+  if (r0 >= n || first >= n) return;
+  constexpr int MP = 32 * CPL;
+  constexpr int kLqWarpsReg = lq_warps_reg<R, CPL>();
+  T *q = reinterpret_cast<T *>(smem_raw);                   // pb x MP, zero-padded
+  T *W = (T *)it.w;
+  T *X = (T *)xitems[blockIdx.y].w;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int lr = warp; lr < pb; lr += kLqWarpsReg)
+    for (int c = lane; c < MP; c += 32) {
+      T z; z.x = 0; z.y = 0;
+      q[(size_t)lr * MP + c] = (r0 + lr < n && c < m) ? W[(size_t)(r0 + lr) * m + c] : z;
+    }
+  __syncthreads();
+  const int last = min(n, first + kLqRowsPerCta);
+  for (int j = first + warp; j < last; j += kLqWarpsReg) {
+    T w[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int c = lane + 32 * k;
+      T z; z.x = 0; z.y = 0;
+      w[k] = c < m ? W[(size_t)j * m + c] : z;
+    }
+    for (int i = 0; i < pb; ++i) {
+      const T *qi = q + (size_t)i * MP + lane;
+      T v[CPL];
+      R ar = 0, ai = 0, ar1 = 0, ai1 = 0;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {                        // c = sum w * conj(q)
+        v[k] = qi[32 * k];
+        ar = fma(w[k].x, v[k].x, ar); ar1 = fma(w[k].y, v[k].y, ar1);
+        ai = fma(w[k].y, v[k].x, ai); ai1 = fma(-w[k].x, v[k].y, ai1);
+      }
+      ar += ar1; ai += ai1;
+      {
+        const bool h16 = lane & 16;
+        R kk = h16 ? ai : ar;
+        const R sx = h16 ? ar : ai;
+        kk += __shfl_xor_sync(0xffffffffu, sx, 16);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 8);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+        ar = __shfl_sync(0xffffffffu, kk, 0);
+        ai = __shfl_sync(0xffffffffu, kk, 16);
+      }
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {                        // w -= c q
+        w[k].x -= ar * v[k].x - ai * v[k].y;
+        w[k].y -= ar * v[k].y + ai * v[k].x;
+      }
+      if (lane == 0) { T d; d.x = ar; d.y = -ai; X[(size_t)(r0 + i) * n + j] = d; }
+    }
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int c = lane + 32 * k;
+      if (c < m) W[(size_t)j * m + c] = w[k];
+    }
+  }
+}
+
+template <typename R, int CPL>
+cudaError_t launch_lq_update_reg(dim3 grid, cudaStream_t st, const qtn_svd_item *d_items, const qtn_svd_item *d_x,
+                                 int p, int pb) {
+  const size_t smem = (size_t)pb * 32 * CPL * sizeof(cx<R>);
+  static size_t set = 0;
+  if (smem > set) {
+    cudaError_t e = cudaFuncSetAttribute(lq_update_reg_kernel<R, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    set = smem;
+  }
+  lq_update_reg_kernel<R, CPL><<<grid, 32 * lq_warps_reg<R, CPL>(), smem, st>>>(d_items, d_x, p, pb);
+  return cudaGetLastError();
+}
+
 template <typename R>
 int svd_lq_impl(int batch, const qtn_svd_item *items, const qtn_svd_item *xitems, unsigned char *ws, cudaStream_t st) {
   const int esz = (int)sizeof(cx<R>);
@@ -916,8 +1007,16 @@ int svd_lq_impl(int batch, const qtn_svd_item *items, const qtn_svd_item *xitems
     const int trailing = max_n - (p + 1) * pb;
     if (trailing > 0) {
       dim3 grid((unsigned)((trailing + kLqRowsPerCta - 1) / kLqRowsPerCta), (unsigned)batch);
-      lq_update_kernel<R><<<grid, 256, smem_upd, st>>>(d_items, d_x, p, pb);
-      QTN_LAUNCH_CHECK();
+      // rows of <= 512 (complex128) / 1024 (complex64) columns: register variant (64 registers of row data)
+      constexpr int kCplMax = sizeof(R) == 8 ? 16 : 32;
+      if (max_m <= 32 * kCplMax) {
+        cudaError_t e = max_m <= 16 * kCplMax ? launch_lq_update_reg<R, kCplMax / 2>(grid, st, d_items, d_x, p, pb)
+                                              : launch_lq_update_reg<R, kCplMax>(grid, st, d_items, d_x, p, pb);
+        if (e != cudaSuccess) return qtn_fail(QTN_ERR_CUDA, cudaGetErrorString(e));
+      } else {
+        lq_update_kernel<R><<<grid, 256, smem_upd, st>>>(d_items, d_x, p, pb);
+        QTN_LAUNCH_CHECK();
+      }
     }
   }
   return QTN_OK;

@@ -70,6 +70,12 @@ class PairPlan(C.Structure):
     ]
 
 
+class GemmItem(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p), ("m", C.c_int32), ("n", C.c_int32),
+                ("k", C.c_int32), ("lda", C.c_int32), ("ldb", C.c_int32), ("ldc", C.c_int32),
+                ("opa", C.c_int32), ("opb", C.c_int32)]
+
+
 class SvdItem(C.Structure):
     _fields_ = [("w", C.c_void_p), ("n", C.c_int32), ("m", C.c_int32),
                 ("block", C.c_int32), ("nblocks", C.c_int32)]
@@ -105,6 +111,7 @@ _SIGNATURES = {
                            C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "qtn_mps_apply_1q": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qtn_mps_apply_2q": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qtn_gemm_batched": (C.c_int, [C.c_int, C.c_int, C.POINTER(GemmItem), C.c_int, C.c_void_p]),
     "qtn_mps_sample_step": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qtn_svd_workspace_bytes": (C.c_int64, [C.c_int, C.c_int64]),

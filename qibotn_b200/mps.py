@@ -101,6 +101,7 @@ class MPSEngine:
         zero = torch.zeros(1, 2, 1, dtype=self.cdtype, device=self.device)
         zero[0, 0, 0] = 1
         self.sites = [zero.clone() for _ in range(self.n)]
+        self._gate_cache = {}
         self._batch = []               # pending two-site updates on disjoint pairs: (i, gate 2x2x2x2)
         self._busy = set()
         self.stats = {"two_site": 0, "one_site": 0, "swaps": 0, "svd_batches": 0, "svd_sweeps": 0,
@@ -113,6 +114,29 @@ class MPSEngine:
     def _dev(self, host_array):
         t = self.torch.from_numpy(np.ascontiguousarray(host_array, dtype=self.np_dtype))
         return t.to(self.device, non_blocking=False)
+
+    def _dev_gate(self, gate):
+        """Device copy of a small gate matrix, cached by value (a Trotter circuit repeats the same
+        one-qubit rotation on every site of every layer: one upload instead of one per gate)."""
+        host = np.ascontiguousarray(gate, dtype=self.np_dtype)
+        key = host.tobytes()
+        g = self._gate_cache.get(key)
+        if g is None:
+            if len(self._gate_cache) >= 256:
+                self._gate_cache.clear()
+            g = self._gate_cache[key] = self._dev(host)
+        return g
+
+    def _gemm_batched(self, jobs):
+        """jobs: [(opa, opb, m, n, k, a, lda, b, ldb, c, ldc)] -> qtn_gemm_batched (one launch per 32)."""
+        if not jobs:
+            return
+        items = (lib.GemmItem * len(jobs))()
+        for it, (opa, opb, m, n, k, a, lda, b, ldb, c, ldc) in zip(items, jobs):
+            it.a, it.b, it.c = a.data_ptr(), b.data_ptr(), c.data_ptr()
+            it.m, it.n, it.k, it.lda, it.ldb, it.ldc, it.opa, it.opb = m, n, k, lda, ldb, ldc, opa, opb
+        lib.check(self.lib.qtn_gemm_batched(self.code, len(jobs), items, 0, self._stream()))
+        self.stats["launches"] += (len(jobs) + 31) // 32
 
     def _gemm(self, opa, opb, m, n, k, a, lda, b, ldb, c, ldc, accumulate=0):
         lib.check(self.lib.qtn_gemm(self.code, opa, opb, m, n, k, a.data_ptr(), lda, b.data_ptr(), ldb,
@@ -161,7 +185,7 @@ class MPSEngine:
         if i in self._busy:
             self.flush()
         site = self.sites[i]
-        g = self._dev(gate)
+        g = self._dev_gate(gate)
         lib.check(self.lib.qtn_mps_apply_1q(self.code, site.shape[0], site.shape[2], site.data_ptr(),
                                             g.data_ptr(), self._stream()))
         self.stats["one_site"] += 1
@@ -181,13 +205,16 @@ class MPSEngine:
         torch = self.torch
         batch, self._batch, self._busy = self._batch, [], set()
         gates = self._dev(np.stack([g.reshape(16) for _, g in batch]))
-        work = []
+        work, thetas, jobs = [], [], []
         for k, (i, _) in enumerate(batch):
             a, b = self.sites[i], self.sites[i + 1]
             l, m, r = a.shape[0], a.shape[2], b.shape[2]
             p, q = 2 * l, 2 * r
             theta = torch.empty(p * q, dtype=self.cdtype, device=self.device)
-            self._gemm(lib.OP_N, lib.OP_N, p, q, m, a, m, b, q, theta, q)
+            jobs.append((lib.OP_N, lib.OP_N, p, q, m, a, m, b, q, theta, q))
+            thetas.append((i, l, r, p, q, theta))
+        self._gemm_batched(jobs)                               # theta = A.B for the whole layer
+        for k, (i, l, r, p, q, theta) in enumerate(thetas):
             lib.check(self.lib.qtn_mps_apply_2q(self.code, l, r, theta.data_ptr(), gates[k].data_ptr(),
                                                 self._stream()))
             self.stats["launches"] += 1
@@ -241,6 +268,7 @@ class MPSEngine:
         self.stats["svd_sweeps"] += int(sweeps.value)
         self.stats["svd_max_sweeps"] = max(self.stats["svd_max_sweeps"], int(sweeps.value))
         esz = 8
+        post = []                                              # factor recoveries, one batched launch
         for k, (i, l, r, p, q, theta, w, transposed) in enumerate(work):
             kk = int(ranks[k])
             if precond:
@@ -257,12 +285,12 @@ class MPSEngine:
                     # theta = Z S (JQ):  left = Z fa = (conj(fa/s row))^T,  right = (fb/s^2 row) theta
                     left = self._transpose(out1, kk, p)                  # (p x kk)
                     right = torch.empty(kk * q, dtype=self.cdtype, device=self.device)
-                    self._gemm(lib.OP_N, lib.OP_N, kk, q, p, out2, p, theta, q, right, q)
+                    post.append((lib.OP_N, lib.OP_N, kk, q, p, out2, p, theta, q, right, q))
                 else:
                     # theta^T = Z S V'^H:  right = fb Z^T = conj(fb/s row),  left = theta (fa/s^2 row)^T
                     right = out1                                         # (kk x q)
                     left = torch.empty(p * kk, dtype=self.cdtype, device=self.device)
-                    self._gemm(lib.OP_N, lib.OP_T, p, kk, q, theta, q, out2, q, left, kk)
+                    post.append((lib.OP_N, lib.OP_T, p, kk, q, theta, q, out2, q, left, kk))
             else:
                 mcols = p if transposed else q
                 out1 = torch.empty(kk * mcols, dtype=self.cdtype, device=self.device)
@@ -275,14 +303,15 @@ class MPSEngine:
                 if not transposed:
                     right = out1                                             # (kk x q)
                     left = torch.empty(p * kk, dtype=self.cdtype, device=self.device)
-                    self._gemm(lib.OP_N, lib.OP_H, p, kk, q, theta, q, out2, q, left, kk)   # theta * out2^H
+                    post.append((lib.OP_N, lib.OP_H, p, kk, q, theta, q, out2, q, left, kk))   # theta * out2^H
                 else:
                     left = self._transpose(out1, kk, p)                      # (p x kk)
                     right = torch.empty(kk * q, dtype=self.cdtype, device=self.device)
-                    self._gemm(lib.OP_C, lib.OP_N, kk, q, p, out2, p, theta, q, right, q)   # conj(out2) * theta
+                    post.append((lib.OP_C, lib.OP_N, kk, q, p, out2, p, theta, q, right, q))   # conj(out2) * theta
             self.sites[i] = left.view(l, 2, kk)
             self.sites[i + 1] = right.view(kk, 2, r)
             self.stats["max_bond"] = max(self.stats["max_bond"], kk)
+        self._gemm_batched(post)
 
     def bond_dimensions(self):
         self.flush()

@@ -50,6 +50,41 @@ def test_gemm_all_ops(shape, ops, dtype):
     assert np.abs(dc.cpu().numpy() - 2 * want).max() <= 2 * tol * (np.abs(want).max() + 1)
 
 
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_gemm_batched_mixed_shapes_and_ops(dtype):
+    """qtn_gemm_batched: 40 products of different shapes and operand forms (two launches of <= 32)."""
+    rng = np.random.default_rng(3)
+    h = lib.load()
+    shapes = [(1, 1, 1), (5, 7, 3), (64, 64, 16), (130, 70, 33), (2, 300, 129), (96, 200, 64), (0, 4, 4), (65, 1, 257)]
+    ops = [(0, 0), (2, 0), (0, 3), (3, 1), (1, 2)]
+    items = (lib.GemmItem * 40)()
+    keep, wants = [], []
+    for i in range(40):
+        m, n, k = shapes[i % len(shapes)]
+        opa, opb = ops[i % len(ops)]
+        a = _rand(rng, *((k, m) if opa & 2 else (m, k)), dtype=dtype)
+        b = _rand(rng, *((n, k) if opb & 2 else (k, n)), dtype=dtype)
+        A = a.T if opa & 2 else a
+        A = A.conj() if opa & 1 else A
+        B = b.T if opb & 2 else b
+        B = B.conj() if opb & 1 else B
+        wants.append(A.astype(np.complex128) @ B.astype(np.complex128))
+        da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        dc = torch.full((m, n), float("nan"), dtype=da.dtype, device="cuda")
+        keep.append((da, db, dc))
+        it = items[i]
+        it.a, it.b, it.c = da.data_ptr() or 1, db.data_ptr() or 1, dc.data_ptr() or 1
+        it.m, it.n, it.k, it.lda, it.ldb, it.ldc = m, n, k, max(a.shape[1], 1), max(b.shape[1], 1), max(n, 1)
+        it.opa, it.opb = opa, opb
+    lib.check(h.qtn_gemm_batched(lib.dtype_code(dtype), 40, items, 0, torch.cuda.current_stream().cuda_stream))
+    tol = 1e-5 if dtype == "complex64" else 1e-12
+    for (_, _, dc), want in zip(keep, wants):
+        got = dc.cpu().numpy()
+        assert got.shape == want.shape
+        if want.size:
+            assert np.abs(got - want).max() <= tol * (np.abs(want).max() + 1)
+
+
 def _svd_split(theta, dtype, algorithm):
     """theta (p x q numpy) -> (left p x k, right k x q, sigma) through the C ABI, the way
     MPSEngine.flush drives it."""
