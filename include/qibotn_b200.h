@@ -162,9 +162,13 @@ typedef struct {
  *                  epilogue of neighbouring tiles overlapped; 0: one CTA per tile.
  *   "svd_wide"     1 (default): qtn_svd_rows runs 512-thread CTAs holding twice the block rows (200 KB of
  *                  shared memory, row pairs split across warps); 0: 256-thread CTAs, 160 KB.
- *   "svd_reg"      1 (default): block pairs of qtn_svd_rows matrices with rows of <= 512 (complex128) /
- *                  1024 (complex64) columns are rotated by the register-resident kernel (8 + 8 rows per CTA,
- *                  2 warps per row pair); 2: 4 warps per row pair; 0: shared-memory kernel only.
+ *   "svd_reg"      which kernel rotates the block pairs (8 + 8 rows) of qtn_svd_rows matrices whose rows have
+ *                  <= 512 (complex128) / 1024 (complex64) columns:
+ *                  4 (default) two-pass kernel within 64 registers, two CTAs per SM, 2 warps per row pair;
+ *                  5 the same with one warp per row pair; 3 persistent streaming kernel (cp.async prefetch of the
+ *                  next block pair); 1 / 2 first register-resident kernel with 2 / 4 warps per row pair;
+ *                  0 shared-memory kernel only (also used for longer rows, the pairs inside a block and
+ *                  matrices that fit one block pair).  All give the same singular values (tests/test_gpu_mps.py).
  *   "svd_group_mb" qtn_svd_rows sweeps the batch in groups of at most this many MiB of rows, so that a
  *                  group stays L2-resident over the launches of a sweep; 0 = the whole batch at once.
  * Returns QTN_ERR_ARG for an unknown name. */

@@ -50,7 +50,7 @@ extern "C" int qtn_set_option(const char *name, int value) {
   if (!std::strcmp(name, "tc_pair")) { g_tc_pair = value < 0 ? 0 : value; return QTN_OK; }
   if (!std::strcmp(name, "svd_wide")) { g_svd_wide = value != 0; return QTN_OK; }
   if (!std::strcmp(name, "svd_group_mb")) { g_svd_group_mb = value < 0 ? 0 : value; return QTN_OK; }
-  if (!std::strcmp(name, "svd_reg")) { g_svd_reg = value < 0 ? 0 : (value > 4 ? 4 : value); return QTN_OK; }
+  if (!std::strcmp(name, "svd_reg")) { g_svd_reg = value < 0 ? 0 : (value > 5 ? 5 : value); return QTN_OK; }
   return qtn_fail(QTN_ERR_ARG, "qtn_set_option: unknown option");
 }
 

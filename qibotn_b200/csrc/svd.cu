@@ -616,6 +616,9 @@ jacobi_cross_dual_kernel(const qtn_svd_item *__restrict__ items, int step, int s
       gi = fma(u.y, v.x, gi); gi1 = fma(-u.x, v.y, gi1);
     }
     gr += gr1; gi += gi1;
+    R bb = 0;                                                  // before the barrier (see the streaming kernel)
+#pragma unroll
+    for (int q = 0; q < WPP; ++q) bb += s_yn[yrow][q];
     {
       const bool h16 = lane & 16;
       R k = h16 ? gi : gr;
@@ -625,15 +628,19 @@ jacobi_cross_dual_kernel(const qtn_svd_item *__restrict__ items, int step, int s
       k += __shfl_xor_sync(0xffffffffu, k, 4);
       k += __shfl_xor_sync(0xffffffffu, k, 2);
       k += __shfl_xor_sync(0xffffffffu, k, 1);
-      if ((lane & 15) == 0) s_part[warp][lane >> 4] = k;
+      if (WPP > 1) {
+        if ((lane & 15) == 0) s_part[warp][lane >> 4] = k;
+      } else {                                                 // one warp per pair: no exchange
+        gr = __shfl_sync(0xffffffffu, k, 0);
+        gi = __shfl_sync(0xffffffffu, k, 16);
+      }
     }
-    R bb = 0;                                                  // before the barrier (see the streaming kernel)
+    if (WPP > 1) {
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * WPP) : "memory");
+      gr = 0; gi = 0;
 #pragma unroll
-    for (int q = 0; q < WPP; ++q) bb += s_yn[yrow][q];
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(32 * WPP) : "memory");
-    gr = 0; gi = 0;
-#pragma unroll
-    for (int q = 0; q < WPP; ++q) { gr += s_part[group * WPP + q][0]; gi += s_part[group * WPP + q][1]; }
+      for (int q = 0; q < WPP; ++q) { gr += s_part[group * WPP + q][0]; gi += s_part[group * WPP + q][1]; }
+    }
     const R g2 = gr * gr + gi * gi;
     if ((g2 > tol * tol * ax * bb) && (fmin(ax, bb) > (R)0)) {
       rotated = 1;
@@ -1170,12 +1177,14 @@ int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, co
   launch_cross_dual<R, CPL, WPP>(rgrid, st, d_items, step, sweep, (R)tol, rot_prev, rot_cur, d_changed,       \
                                  (long long)ld, gstep, max_steps, reg_cap)
         if constexpr (sizeof(R) == 8) {
-          if (reg_variant == 4) e = reg_max_m <= 256 ? QTN_DUAL(4, 2) : QTN_DUAL(8, 2);
+          if (reg_variant == 5) e = reg_max_m <= 256 ? QTN_DUAL(8, 1) : QTN_DUAL(16, 1);
+          else if (reg_variant == 4) e = reg_max_m <= 256 ? QTN_DUAL(4, 2) : QTN_DUAL(8, 2);
           else if (reg_variant == 3) e = reg_max_m <= 256 ? QTN_STREAM(4, 2) : QTN_STREAM(8, 2);
           else if (reg_variant == 2) e = reg_max_m <= 256 ? QTN_REG(2, 4) : QTN_REG(4, 4);
           else e = reg_max_m <= 256 ? QTN_REG(4, 2) : QTN_REG(8, 2);
         } else {
-          if (reg_variant == 4) e = reg_max_m <= 512 ? QTN_DUAL(8, 2) : QTN_DUAL(16, 2);
+          if (reg_variant == 5) e = reg_max_m <= 512 ? QTN_DUAL(16, 1) : QTN_DUAL(32, 1);
+          else if (reg_variant == 4) e = reg_max_m <= 512 ? QTN_DUAL(8, 2) : QTN_DUAL(16, 2);
           else if (reg_variant == 3) e = reg_max_m <= 512 ? QTN_STREAM(8, 2) : QTN_STREAM(16, 2);
           else if (reg_variant == 2) e = reg_max_m <= 512 ? QTN_REG(4, 4) : QTN_REG(8, 4);
           else e = reg_max_m <= 512 ? QTN_REG(8, 2) : QTN_REG(16, 2);

@@ -176,7 +176,7 @@ def test_truncation_rules(dtype):
 @pytest.mark.parametrize("dtype", ["complex64", "complex128"])
 @pytest.mark.parametrize("lmr", [(64, 128, 64), (48, 100, 80), (80, 100, 48), (128, 40, 128)])
 @pytest.mark.parametrize("graded", [False, True])
-@pytest.mark.parametrize("svd_reg", [0, 1, 3, 4])
+@pytest.mark.parametrize("svd_reg", [0, 1, 3, 4, 5])
 def test_lq_preconditioned_split(lmr, graded, dtype, svd_reg, monkeypatch):
     """Two-site blocks of >= LQ_MIN_ROWS rows go through qtn_svd_lq (LQ preconditioner) before the
     Jacobi sweeps; the split must agree with LAPACK and with the un-preconditioned path, for every
