@@ -28,6 +28,23 @@ __all__ = ["initialize", "rank_size", "vote_best", "reduce_result", "compute_sli
 _STATE = {"initialized": False, "rank": 0, "size": 1, "device_id": 0, "backend": None}
 
 
+def partition_units(counts, rank, size):
+    """Work of a many-term observable is the flat list of (term, slice) units, term-major; rank ``rank``
+    takes the contiguous range ``compute_slices(sum(counts), rank, size)`` of it (the reference's
+    partition rule, eval.py:197-205, applied to the flattened list instead of once per term as
+    eval.py:352-380 does).  ``counts[t]`` = number of slices of term t.  Returns ``{term: range}`` with the
+    slice ids of each term this rank owns (terms it does not touch are absent)."""
+    total = int(sum(counts))
+    mine = compute_slices(total, rank, size) if total else range(0)
+    out, begin = {}, 0
+    for t, c in enumerate(counts):
+        lo, hi = max(mine.start, begin), min(mine.stop, begin + int(c))
+        if lo < hi:
+            out[t] = range(lo - begin, hi - begin)
+        begin += int(c)
+    return out
+
+
 def is_initialized():
     return _STATE["initialized"]
 

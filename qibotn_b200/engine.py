@@ -18,12 +18,13 @@ from .network import TensorNetwork
 from .planner import PathInfo, find_path
 
 _PLAN_CACHE: dict = {}
+_INFO_CACHE: dict = {}
 # Optional on-disk plan store (a directory): plans found for a network structure are written there and
 # read back by later processes, so that Hamiltonians with many differently shaped terms (light cones)
 # can be planned offline on CPU cores (scripts/plan_c5.py) and only executed on the GPU.
 PLAN_STORE = None
 _RUNNER_CACHE: dict = {}
-_CACHE_LIMIT = 8
+_CACHE_LIMIT = 128          # runners kept (the device-byte budget in runner_for is the binding limit)
 
 
 @dataclass
@@ -49,12 +50,36 @@ def default_width(dtype):
     return 31 if str(dtype) == "complex64" else 30
 
 
+def find_info(net: TensorNetwork, dtype="complex64", samples=32, seed=0, min_slices=1, target_log2_width=None):
+    """Path + slicing only (no lowering): what a rank needs of a term it votes on but may not own."""
+    width = default_width(dtype) if target_log2_width is None else target_log2_width
+    key = _key(net, dtype, min_slices, width, seed, samples)
+    if key in _PLAN_CACHE:
+        return _PLAN_CACHE[key][0]
+    info = _INFO_CACHE.get(key)
+    if info is None:
+        info = _stored_plan(net, width, min_slices)
+        if info is None:
+            info = find_path(net.modes, net.out, samples=samples, seed=seed, target_log2_width=width,
+                             min_slices=min_slices)
+            _store_plan(net, width, min_slices, info)
+        if len(_INFO_CACHE) >= 256:
+            _INFO_CACHE.pop(next(iter(_INFO_CACHE)))
+        _INFO_CACHE[key] = info
+    return info
+
+
 def plan(net: TensorNetwork, dtype="complex64", samples=32, seed=0, min_slices=1,
          target_log2_width=None, info: PathInfo = None):
     """Find (or take) a path and lower it.  Returns ``(info, lowered)``."""
     width = default_width(dtype) if target_log2_width is None else target_log2_width
-    key = _key(net, dtype, min_slices, width, seed, samples) if info is None else None
-    if key is not None and key in _PLAN_CACHE:
+    if info is None:
+        key = _key(net, dtype, min_slices, width, seed, samples)
+    else:
+        # a plan handed in (the distributed drivers' voted plan): lowered once per (structure, plan)
+        key = (tuple(tuple(m) for m in net.modes), tuple(net.out), str(dtype), "given", tuple(info.path),
+               tuple(info.sliced_labels))
+    if key in _PLAN_CACHE:
         return _PLAN_CACHE[key]
     t0 = time.perf_counter()
     if info is None:
@@ -67,10 +92,9 @@ def plan(net: TensorNetwork, dtype="complex64", samples=32, seed=0, min_slices=1
     lowered = executor.lower(net.modes, net.out, info, str(dtype))
     t2 = time.perf_counter()
     LAST.plan_s, LAST.lower_s = t1 - t0, t2 - t1
-    if key is not None:
-        if len(_PLAN_CACHE) >= 64:
-            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
-        _PLAN_CACHE[key] = (info, lowered)
+    if len(_PLAN_CACHE) >= 64:
+        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    _PLAN_CACHE[key] = (info, lowered)
     return info, lowered
 
 
@@ -164,4 +188,5 @@ def contract(net: TensorNetwork, dtype="complex64", samples=32, seed=0, min_slic
 
 def clear_caches():
     _PLAN_CACHE.clear()
+    _INFO_CACHE.clear()
     _RUNNER_CACHE.clear()

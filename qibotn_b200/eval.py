@@ -208,22 +208,34 @@ def expectation_tn(qibo_circ, datatype, observable):
 
 
 def _expectation_distributed(qibo_circ, datatype, observable, n_samples, method):
+    """Terms AND slices are sharded: the unit of work is (term, slice), the flat list is cut into ``size``
+    contiguous ranges (``dist.partition_units``), each rank contracts its units and ONE all-reduce of the
+    per-term partials ends the job (the reference repeats plan-vote + reduce per term, eval.py:352-380).
+    With fewer terms than ranks every term is sliced into >= max(32, size) slices as the reference does
+    (eval.py:186); with many terms the slicing is left to the width limit alone, so that small light-cone
+    networks are not cut into 32 pieces just to be spread."""
     import torch
 
     _, rank, size, _ = initialize_mpi()
-    partials, plans = [], {}
-    for net in _term_networks(qibo_circ, datatype, observable):
+    nets = list(_term_networks(qibo_circ, datatype, observable))
+    if not nets:
+        raise ValueError("No valid Hamiltonian terms were added.")
+    forced = max(32, size) if len(nets) < size else 1
+    plans, infos = {}, []
+    for net in nets:
         key = (tuple(tuple(m) for m in net.modes),)
         if key not in plans:                       # one vote per network structure
-            plans[key] = compute_optimal_path(net, n_samples, size, datatype)
-        info = plans[key]
-        slices = compute_slices(info.num_slices, rank, size)
-        partials.append(engine.contract(net, datatype, info=info, slice_ids=slices).reshape(1).clone())
-    if not partials:
-        raise ValueError("No valid Hamiltonian terms were added.")
-    stacked = torch.cat(partials)                  # one collective for all terms
-    stacked = dist.reduce_result(stacked, method=method)
-    return DeviceArray(stacked.sum().reshape(1)), rank
+            rk, _ = dist.rank_size()
+            info = engine.find_info(net, datatype, samples=n_samples, seed=rk, min_slices=forced)
+            plans[key], _winner = dist.vote_best(info.opt_cost, info)   # lowered by its owners only
+        infos.append(plans[key])
+    mine = dist.partition_units([info.num_slices for info in infos], rank, size)
+    cdtype = torch.complex64 if str(datatype) == "complex64" else torch.complex128
+    partials = torch.zeros(len(nets), dtype=cdtype, device="cuda")
+    for t, slices in mine.items():
+        partials[t] = engine.contract(nets[t], datatype, info=infos[t], slice_ids=slices).reshape(())
+    partials = dist.reduce_result(partials, method=method)        # one collective for all terms
+    return DeviceArray(partials.sum().reshape(1)), rank
 
 
 def expectation_tn_nccl(qibo_circ, datatype, observable, n_samples=8):

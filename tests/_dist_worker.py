@@ -37,9 +37,31 @@ try:
 except TypeError as exc:
     bad = str(exc)
 want = complex(osv.simulate(circ)[0])
+# many-term observable: (term, slice) units sharded over the ranks, one reduction of the per-term partials
+from qibotn_b200.network import QiboCircuitToEinsum  # noqa: E402
+from qibotn_b200.observables import check_observable, extract_gates_and_qubits, get_ham_gates  # noqa: E402
+
+qcirc, edges = circuits.qaoa_maxcut(8, 2, seed=3)
+conv = QiboCircuitToEinsum(qcirc, "complex128")
+terms = list(extract_gates_and_qubits(check_observable(circuits.zz_terms(edges), 8)))
+nets = [conv.expectation_network(get_ham_gates(t, dtype="complex128"), hyper=True) for t in terms]
+infos = []
+for k, net in enumerate(nets):
+    info_k = find_path(net.modes, net.out, samples=1, seed=rank, min_slices=1 if k % 3 else 4)
+    infos.append(dist.vote_best(info_k.opt_cost, info_k)[0])
+units = dist.partition_units([i.num_slices for i in infos], rank, size)
+part = torch.zeros(len(nets), dtype=torch.complex128)
+for tk, sl in units.items():
+    part[tk] = complex(np.asarray(oc.contract_sliced(nets[tk].interleaved(), infos[tk].path,
+                                                     infos[tk].sliced_labels, sl)).reshape(-1)[0])
+ham_sum = dist.reduce_result(part, method="NCCL").sum()
+psi = osv.simulate(qcirc)
+ham_want = osv.pauli_expectation(psi, [(1.0, [("Z", a), ("Z", b)]) for a, b in edges], 8)
 print("RESULT " + json.dumps({
     "rank": rank, "size": size, "winner": winner, "costs": costs, "best_cost": float(best.opt_cost),
     "slices": [mine.start, mine.stop], "num_slices": best.num_slices, "sum": res,
-    "want": [want.real, want.imag], "f32": [float(f32[0].real), float(f32[1].imag)], "bad": bad}), flush=True)
+    "want": [want.real, want.imag], "ham": [float(ham_sum.real), float(ham_want.real)],
+    "units": {str(k): [v.start, v.stop] for k, v in units.items()}, "unit_counts": [i.num_slices for i in infos],
+    "f32": [float(f32[0].real), float(f32[1].imag)], "bad": bad}), flush=True)
 dist.barrier()
 torch.distributed.destroy_process_group()

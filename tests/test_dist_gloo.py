@@ -59,3 +59,11 @@ def test_sliced_contraction_over_ranks(world):
     for r in outs:                                                        # all-reduce: every rank has the sum
         assert abs(complex(*r["sum"]["NCCL"]) - want) < 1e-12
     assert abs(complex(*outs[0]["sum"]["MPI"]) - want) < 1e-12             # reduce: root has the sum
+    # Hamiltonian: every (term, slice) unit is owned by exactly one rank and the reduced sum is right
+    counts = outs[0]["unit_counts"]
+    owned = sorted((int(t), s) for r in outs for t, (a, b) in r["units"].items() for s in range(a, b))
+    assert owned == [(t, s) for t, c in enumerate(counts) for s in range(c)]
+    for r in outs:
+        assert r["unit_counts"] == counts
+        assert abs(r["ham"][0] - r["ham"][1]) < 1e-10
+

@@ -173,3 +173,20 @@ def test_header_symbols_are_exported_and_structs_match():
     assert b"sm_100a" in h.qtn_version()
     with pytest.raises(lib.QtnError):
         lib.set_option("no_such_option", 1)
+
+
+def test_partition_units_covers_every_term_slice_once():
+    """dist.partition_units: the flattened (term, slice) list cut by the reference's slice rule
+    (eval.py:197-205) -- contiguous, complete, disjoint, low ranks take the remainder."""
+    from qibotn_b200 import dist
+    for counts in ([1] * 60, [1, 4, 1, 1, 32, 1, 2], [64], [], [3, 0, 5]):
+        for size in (1, 2, 3, 8, 70):
+            seen, sizes = [], []
+            for r in range(size):
+                mine = dist.partition_units(counts, r, size)
+                units = [(t, s) for t, rg in mine.items() for s in rg]
+                sizes.append(len(units))
+                seen += units
+            assert seen == [(t, s) for t, c in enumerate(counts) for s in range(c)]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
