@@ -190,3 +190,42 @@ def test_partition_units_covers_every_term_slice_once():
             assert seen == [(t, s) for t, c in enumerate(counts) for s in range(c)]
             assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
 
+
+def test_plan_store_round_trip(tmp_path, monkeypatch):
+    """engine.PLAN_STORE: a plan found for a network structure is written to disk and a fresh cache reads
+    it back instead of searching again (offline planning of many-term observables, scripts/plan_c5.py)."""
+    from qibotn_b200 import circuits, engine
+    from qibotn_b200 import planner
+    from qibotn_b200.network import QiboCircuitToEinsum
+    from qibotn_b200.observables import get_ham_gates
+    circ, edges = circuits.qaoa_maxcut(8, 2, seed=1)
+    conv = QiboCircuitToEinsum(circ, "complex64")
+    net = conv.expectation_network(get_ham_gates([(edges[0][0], "Z", 1.0), (edges[0][1], "Z", 1.0)], dtype="complex64"),
+                                   hyper=True)
+    monkeypatch.setattr(engine, "PLAN_STORE", str(tmp_path))
+    engine.clear_caches()
+    info = engine.find_info(net, "complex64", samples=2)
+    files = list(tmp_path.iterdir())
+    assert len(files) == 1 and files[0].name.endswith("_w31_s1.json")
+    engine.clear_caches()
+    calls = []
+    monkeypatch.setattr(engine, "find_path", lambda *a, **k: calls.append(1))
+    again = engine.find_info(net, "complex64", samples=2)
+    assert not calls and again.path == info.path and again.sliced_labels == info.sliced_labels
+    # the committed plans of config 5 at p = 3 belong to the networks the converter builds today
+    import os
+    store = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "plans", "c5_p3")
+    if os.path.isdir(store):
+        from qibotn_b200 import eval as ev
+        monkeypatch.setattr(engine, "PLAN_STORE", store)
+        circ, edges = circuits.qaoa_maxcut(40, 3, seed=0)
+        nets = list(ev._term_networks(circ, "complex64", circuits.zz_terms(edges)))
+        assert len(nets) == 60
+        for net in nets[:5]:
+            stored = engine._stored_plan(net, engine.default_width("complex64"), 1)
+            assert stored is not None
+            cost, width, _, _ = planner.path_cost(planner.SymbolicNetwork(net.modes, net.out), stored.path,
+                                                  planner.SymbolicNetwork(net.modes, net.out).to_mask(stored.sliced_labels)
+                                                  if stored.sliced_labels else 0)
+            assert width <= 31 and abs(cost - stored.opt_cost) <= 1e-6 * stored.opt_cost
+
