@@ -144,8 +144,15 @@ typedef struct {
    * split and laid out as shared-memory stage images, into the workspace at byte offset
    * tc_prepack_off; the main kernel then fetches a whole B stage with one cp.async.bulk. */
   int32_t tc_prepack;
-  int32_t tc_pair;               /* 1: CTA-pair kernel (tcgen05 cta_group::2), tc_reserved even ("tc_pair") */
+  int32_t tc_pair;               /* 1: CTA-pair kernel (tcgen05 cta_group::2), tc_reserved even ("tc_pair");
+                                  * 2: staggered CTA-pair kernel for 128-column tiles ("tc_stagger") */
   int64_t tc_prepack_off;
+  /* 0: error-compensated 3xTF32 split (12 kind::tf32 MMAs per 8 contracted complex values);
+   * 1: scaled 3xFP16 split (12 kind::f16 MMAs per 16 values: half the tensor-pipe cycles, the same
+   *    22 significant bits): operands are scaled by a power of two taken from the run-time magnitude
+   *    bound of each tensor, so the plan must be run with qtn_pair_run_scaled ("tc_fp16"). */
+  int32_t tc_kind;
+  int32_t tc_reserved2;
 } qtn_pair_plan_t;
 
 /* Library-wide switches (thread-unsafe, meant for tests and A/B measurements):
@@ -158,6 +165,11 @@ typedef struct {
  *   "tc_pair"      5 (default): tiles of 2^5 .. 128 columns with a pre-packed B run on CTA pairs
  *                  (tcgen05 cta_group::2: two m tiles share one B tile, each SM stages half of it);
  *                  n = 6, 7 raises the smallest paired tile to 2^n columns, 0 turns pairs off;
+ *   "tc_stagger"   1 (default): 128-column paired tiles run as two 64-column halves with their own accumulators
+ *                  that share every A stage (plan value tc_pair = 2): the TMEM drain of one half overlaps the
+ *                  MMAs of the other; 0: the round-1 pair kernel (tile and accumulators as one unit);
+ *   "tc_fp16"      1 (default): staggered tiles split their operands into scaled fp16 pieces (tc_kind = 1,
+ *                  half the tensor-pipe work of the TF32 split; run through qtn_pair_run_scaled); 0: TF32 split;
  *   "tc_persistent" 1 (default): one CTA per SM streams over the tiles with loads, MMAs and
  *                  epilogue of neighbouring tiles overlapped; 0: one CTA per tile.
  *   "svd_wide"     1 (default): qtn_svd_rows runs 512-thread CTAs holding twice the block rows (200 KB of
@@ -188,6 +200,19 @@ int qtn_pair_plan(qtn_pair_desc *desc, int sm_count, qtn_pair_plan_t *plan);
  * graph be replayed for every slice.  `workspace` must hold plan->workspace_bytes. */
 int qtn_pair_run(const qtn_pair_plan_t *plan, const void *a, const void *b, void *c,
                  void *workspace, const int32_t *slice_id, void *stream);
+
+/* qtn_pair_run with magnitude tracking.  Every tensor may carry a DEVICE word `amax`: the bit pattern
+ * of a non-negative float that bounds max(|re|, |im|) over the tensor (0 = unknown/empty).  Plans with
+ * tc_kind == 1 need amax_a and amax_b (the operands are scaled into the fp16 range by
+ * 2^(14 - exponent(amax))); any plan updates *amax_c (atomic max over the words it was given) when
+ * amax_c is not NULL -- inside the epilogue of the tensor-core kernels, by one extra streaming pass over C
+ * for the others.  complex128 plans ignore all three.  The caller zeroes a word before its tensor is
+ * (re)computed; a stale larger bound only costs precision below 2^-28 of that bound. */
+int qtn_pair_run_scaled(const qtn_pair_plan_t *plan, const void *a, const void *b, void *c, void *workspace,
+                        const int32_t *slice_id, const uint32_t *amax_a, const uint32_t *amax_b,
+                        uint32_t *amax_c, void *stream);
+/* *amax = max(*amax, bits(max over x of max(|re|, |im|))) for a complex64 vector of n elements. */
+int qtn_absmax(int dtype, int64_t n, const void *x, uint32_t *amax, void *stream);
 
 /* ------------------------------------------------------------------------
  * Bit-tensor permute: out[label -> pos_out] = in[label -> pos_in].

@@ -23,6 +23,8 @@ int g_tc_terms = 3;
 int g_tc_accum_split = 1;
 int g_tc_prepack = 1;
 int g_tc_pair = 5;
+int g_tc_stagger = 1;
+int g_tc_fp16 = 1;
 int g_svd_wide = 1;
 int g_svd_group_mb = 0;
 int g_svd_reg = 4;
@@ -35,6 +37,8 @@ extern "C" int qtn_option_tc_terms(void) { return g_tc_terms; }
 extern "C" int qtn_option_tc_accum_split(void) { return g_tc_accum_split; }
 extern "C" int qtn_option_tc_prepack(void) { return g_tc_prepack; }
 extern "C" int qtn_option_tc_pair(void) { return g_tc_pair; }
+extern "C" int qtn_option_tc_stagger(void) { return g_tc_stagger; }
+extern "C" int qtn_option_tc_fp16(void) { return g_tc_fp16; }
 extern "C" int qtn_option_svd_wide(void) { return g_svd_wide; }
 extern "C" int qtn_option_svd_group_mb(void) { return g_svd_group_mb; }
 extern "C" int qtn_option_svd_reg(void) { return g_svd_reg; }
@@ -48,6 +52,8 @@ extern "C" int qtn_set_option(const char *name, int value) {
   if (!std::strcmp(name, "tc_accum_split")) { g_tc_accum_split = value != 0; return QTN_OK; }
   if (!std::strcmp(name, "tc_prepack")) { g_tc_prepack = value != 0; return QTN_OK; }
   if (!std::strcmp(name, "tc_pair")) { g_tc_pair = value < 0 ? 0 : value; return QTN_OK; }
+  if (!std::strcmp(name, "tc_stagger")) { g_tc_stagger = value != 0; return QTN_OK; }
+  if (!std::strcmp(name, "tc_fp16")) { g_tc_fp16 = value != 0; return QTN_OK; }
   if (!std::strcmp(name, "svd_wide")) { g_svd_wide = value != 0; return QTN_OK; }
   if (!std::strcmp(name, "svd_group_mb")) { g_svd_group_mb = value < 0 ? 0 : value; return QTN_OK; }
   if (!std::strcmp(name, "svd_reg")) { g_svd_reg = value < 0 ? 0 : (value > 5 ? 5 : value); return QTN_OK; }
@@ -63,6 +69,8 @@ extern "C" int qtn_get_option(const char *name, int *value) {
   if (!std::strcmp(name, "tc_accum_split")) { *value = g_tc_accum_split; return QTN_OK; }
   if (!std::strcmp(name, "tc_prepack")) { *value = g_tc_prepack; return QTN_OK; }
   if (!std::strcmp(name, "tc_pair")) { *value = g_tc_pair; return QTN_OK; }
+  if (!std::strcmp(name, "tc_stagger")) { *value = g_tc_stagger; return QTN_OK; }
+  if (!std::strcmp(name, "tc_fp16")) { *value = g_tc_fp16; return QTN_OK; }
   if (!std::strcmp(name, "svd_wide")) { *value = g_svd_wide; return QTN_OK; }
   if (!std::strcmp(name, "svd_group_mb")) { *value = g_svd_group_mb; return QTN_OK; }
   if (!std::strcmp(name, "svd_reg")) { *value = g_svd_reg; return QTN_OK; }

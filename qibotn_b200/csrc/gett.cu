@@ -595,26 +595,92 @@ int qtn_launch_splitk_sum(int dtype, void *c, const void *ws, long long n, int n
   return QTN_OK;
 }
 
-extern "C" int qtn_pair_run(const qtn_pair_plan_t *plan, const void *a, const void *b, void *c,
-                            void *workspace, const int32_t *slice_id, void *stream) {
+// max(|re|, |im|) over a complex64 vector as an fp32 bit pattern, atomically merged into *amax
+// (non-negative floats order like unsigned integers).  Streaming, 16-byte loads, grid-stride.
+__global__ void __launch_bounds__(256) absmax_kernel(const float4 *__restrict__ x, long long n4, const float2 *__restrict__ tail,
+                                                     int ntail, uint32_t *__restrict__ amax) {
+  uint32_t m = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    m = max(max(m, __float_as_uint(v.x) & 0x7fffffffu), max(__float_as_uint(v.y) & 0x7fffffffu,
+            max(__float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu)));
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) {
+    const float2 v = tail[threadIdx.x];
+    m = max(m, max(__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu));
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(amax, m);
+}
+
+int qtn_launch_absmax(const void *x, long long n, uint32_t *amax, cudaStream_t st) {
+  if (n <= 0) return QTN_OK;
+  const long long n4 = n / 2;                       // float4 = two complex64 values
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float4 *)x, n4, (const float2 *)x + 2 * n4, (int)(n - 2 * n4), amax);
+  QTN_LAUNCH_CHECK();
+  return QTN_OK;
+}
+
+extern "C" int qtn_absmax(int dtype, int64_t n, const void *x, uint32_t *amax, void *stream) {
+  if (dtype != QTN_C64) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_absmax: complex64 only");
+  if (n < 0 || (n > 0 && !x) || !amax) return qtn_fail(QTN_ERR_ARG, "qtn_absmax: bad argument");
+  return qtn_launch_absmax(x, n, amax, (cudaStream_t)stream);
+}
+
+extern "C" int qtn_pair_run_scaled(const qtn_pair_plan_t *plan, const void *a, const void *b, void *c,
+                                   void *workspace, const int32_t *slice_id, const uint32_t *amax_a,
+                                   const uint32_t *amax_b, uint32_t *amax_c, void *stream) {
   if (!plan || !a || !b || !c) return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: null argument");
   if (plan->workspace_bytes > 0 && !workspace)
     return qtn_fail(QTN_ERR_WORKSPACE, "qtn_pair_run: plan needs a workspace");
   if ((plan->n_slice_a || plan->n_slice_b) && !slice_id)
     return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: plan has sliced labels but slice_id is NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  if (plan->swapped) { const void *tmp = a; a = b; b = tmp; }
+  if (plan->swapped) {
+    const void *tmp = a; a = b; b = tmp;
+    const uint32_t *tm = amax_a; amax_a = amax_b; amax_b = tm;
+  }
   const bool f32 = plan->dtype == QTN_C64;
-  if (plan->kernel == QTN_KERNEL_TC)
-    return qtn_launch_tc(*plan, a, b, c, workspace, slice_id, st);
+  if (!f32) amax_c = nullptr;                       // magnitude words are a complex64 device
+  if (plan->kernel == QTN_KERNEL_TC) {
+    if (plan->tc_kind == 1 && (!amax_a || !amax_b)) {
+      // a caller without magnitude words (plain qtn_pair_run): measure both operands here, into the two
+      // words the planner reserved at the end of the workspace -- correct, at the price of one extra
+      // pass over A and B
+      uint32_t *words = reinterpret_cast<uint32_t *>((unsigned char *)workspace + plan->workspace_bytes - 256);
+      QTN_CUDA_CHECK(cudaMemsetAsync(words, 0, 8, st));
+      long long ea = 1, eb = 1;
+      ea <<= (plan->tmb + plan->tkb + plan->n_mhi + plan->n_khi + plan->n_slice_a);
+      eb <<= (plan->tnb + plan->tkb + plan->n_nhi + plan->n_khi + plan->n_slice_b);
+      int rc = qtn_launch_absmax(a, ea, words, st);
+      if (rc != QTN_OK) return rc;
+      rc = qtn_launch_absmax(b, eb, words + 1, st);
+      if (rc != QTN_OK) return rc;
+      amax_a = words; amax_b = words + 1;
+    }
+    return qtn_launch_tc(*plan, a, b, c, workspace, slice_id, amax_a, amax_b, amax_c, st);
+  }
+  int rc;
   if (plan->kernel == QTN_KERNEL_TILE)
-    return f32 ? launch_tile<float>(*plan, a, b, c, workspace, slice_id, st)
-               : launch_tile<double>(*plan, a, b, c, workspace, slice_id, st);
-  if (plan->kernel == QTN_KERNEL_KRED)
-    return f32 ? launch_kred<float>(*plan, a, b, c, workspace, slice_id, st)
-               : launch_kred<double>(*plan, a, b, c, workspace, slice_id, st);
-  if (plan->kernel == QTN_KERNEL_REDUCE)
-    return f32 ? launch_reduce<float>(*plan, a, b, c, workspace, slice_id, st)
-               : launch_reduce<double>(*plan, a, b, c, workspace, slice_id, st);
-  return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: unknown kernel id");
+    rc = f32 ? launch_tile<float>(*plan, a, b, c, workspace, slice_id, st)
+             : launch_tile<double>(*plan, a, b, c, workspace, slice_id, st);
+  else if (plan->kernel == QTN_KERNEL_KRED)
+    rc = f32 ? launch_kred<float>(*plan, a, b, c, workspace, slice_id, st)
+             : launch_kred<double>(*plan, a, b, c, workspace, slice_id, st);
+  else if (plan->kernel == QTN_KERNEL_REDUCE)
+    rc = f32 ? launch_reduce<float>(*plan, a, b, c, workspace, slice_id, st)
+             : launch_reduce<double>(*plan, a, b, c, workspace, slice_id, st);
+  else
+    return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: unknown kernel id");
+  if (rc != QTN_OK) return rc;
+  if (amax_c) return qtn_launch_absmax(c, plan->c_elems, amax_c, st);
+  return QTN_OK;
+}
+
+extern "C" int qtn_pair_run(const qtn_pair_plan_t *plan, const void *a, const void *b, void *c,
+                            void *workspace, const int32_t *slice_id, void *stream) {
+  return qtn_pair_run_scaled(plan, a, b, c, workspace, slice_id, nullptr, nullptr, nullptr, stream);
 }

@@ -329,6 +329,69 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
       p->tc_stages = std::max(2, std::min(6, (200 * 1024) / pair_stage));
       p->smem_bytes = p->tc_stages * pair_stage + 256;
       p->tc_reserved = sm_count & ~1;
+      // 128-column tiles: the staggered variant (two 64-column halves with their own accumulators share
+      // every A stage; the drain of one half hides behind the MMAs of the other).  Per CTA a stage holds
+      // the 4 A planes and 384 rows of B (2 halves x {hi, lo} x [Br | Bi | -Br] x 32 rows); an image
+      // holds both ranks' rows.
+      if (tnb == 7 && qtn_option_tc_stagger() && p->tc_terms == 3) {
+        const int rank_b = 384 * KT * 4;
+        const int stage2 = 4 * p->tc_plane_a + rank_b;
+        const int64_t images = (int64_t)1 << (p->n_nhi + p->n_khi);
+        const int64_t base = (p->tc_prepack_off);
+        p->tc_pair = 2;
+        // shared memory: operand stages + a ring of 6 raw A chunks (128 x KT elements of 8 bytes: the
+        // cp.async gathers in flight) + barriers
+        const int raw_ring = 6 * 128 * KT * 8;
+        p->tc_stages = std::max(2, std::min(8, (227 * 1024 - 512 - raw_ring) / stage2));
+        p->smem_bytes = p->tc_stages * stage2 + raw_ring + 512;
+        p->workspace_bytes = base + images * 2 * rank_b;
+        // Scaled 3xFP16 split (tc_kind = 1): the same stage geometry in 2-byte elements.  Operand planes are
+        // K-major fp16 core matrices (8 rows x 8 values): offset in halves of row bit j / k bit i =
+        // (r&7)*8 + (k&7) + (r>>3)*(KT*8) + (k>>3)*64.  A producer thread packs two k-adjacent values
+        // into one 32-bit store, so the lowest k bit is the first ITERATION bit of the enumeration and the
+        // five lane bits own the five bank-selecting word offsets (k bits 1-2, row bits 0-2).
+        if (qtn_option_tc_fp16() && tkb == 4) {
+          p->tc_kind = 1;
+          auto row_off16 = [&](int j) { return j < 3 ? 8 << j : (KT * 8) << (j - 3); };
+          auto k_off16 = [&](int i) { return i < 3 ? 1 << i : 64 << (i - 3); };
+          std::vector<E> fa, fb;
+          for (int j = 0; j < tmb; ++j) fa.push_back({mlo[j].pa, row_off16(j)});
+          for (int i = 0; i < tkb; ++i) fa.push_back({klo[i].pa, k_off16(i)});
+          for (int j = 0; j < tnb; ++j) fb.push_back({nlo[j].pb, row_off16(j)});
+          for (int i = 0; i < tkb; ++i) fb.push_back({klo[i].pb, k_off16(i)});
+          auto cls = [](const E &x) { return x.sstr == 1 ? 2 : (x.sstr <= 32 ? 0 : 1); };   // lane, other, pair bit
+          std::stable_sort(fa.begin(), fa.end(), [&](const E &x, const E &y) {
+            if ((cls(x) == 0) != (cls(y) == 0)) return cls(x) == 0;
+            return x.pos < y.pos;
+          });
+          // the pair bit (k bit 0) becomes enumeration bit 8 = iteration bit 0
+          for (size_t q = 0; q < fa.size(); ++q)
+            if (fa[q].sstr == 1) { E e = fa[q]; fa.erase(fa.begin() + q); fa.insert(fa.begin() + 8, e); break; }
+          std::stable_sort(fb.begin(), fb.end(), [&](const E &x, const E &y) { return x.pos < y.pos; });
+          for (int i = 0; i < p->na_lo; ++i) { p->a_lo_pos[i] = (uint8_t)fa[i].pos; p->a_lo_sstr[i] = (uint16_t)fa[i].sstr; }
+          for (int i = 0; i < p->nb_lo; ++i) { p->b_lo_pos[i] = (uint8_t)fb[i].pos; p->b_lo_sstr[i] = (uint16_t)fb[i].sstr; }
+          for (int it = 0; it < 8; ++it) {
+            int64_t g = 0; int32_t so = 0;
+            for (int j = 8; j < p->na_lo; ++j)
+              if ((it >> (j - 8)) & 1) { g |= (int64_t)1 << p->a_lo_pos[j]; so += p->a_lo_sstr[j]; }
+            p->tc_a_it_g[it] = g; p->tc_a_it_s[it] = so;
+          }
+          for (int it = 0; it < 16; ++it) {
+            int64_t g = 0; int32_t so = 0;
+            for (int j = 8; j < p->nb_lo; ++j)
+              if ((it >> (j - 8)) & 1) { g |= (int64_t)1 << p->b_lo_pos[j]; so += p->b_lo_sstr[j]; }
+            p->tc_b_it_g[it] = g; p->tc_b_it_s[it] = so;
+          }
+          p->tc_plane_a = 128 * KT * 2;
+          p->tc_plane_b = TN * KT * 2;
+          const int rank_h = 384 * KT * 2;
+          const int stage_h = 4 * p->tc_plane_a + rank_h;
+          p->tc_stages = std::max(2, std::min(8, (227 * 1024 - 512 - raw_ring) / stage_h));
+          p->smem_bytes = p->tc_stages * stage_h + raw_ring + 512;
+          // + 256 bytes: two magnitude words for callers that come through plain qtn_pair_run
+          p->workspace_bytes = base + images * 2 * rank_h + 256;
+        }
+      }
     }
     p->sa_stride = 0; p->sb_stride = 0;
   } else {

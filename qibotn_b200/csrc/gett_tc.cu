@@ -22,6 +22,8 @@
 //              releases the stage with tcgen05.commit.
 // C's layout is chosen by the planner (m bits 0-4 | n bits | m bits 5-6 | tile index),
 // which makes the epilogue's stores contiguous straight out of the TMEM registers.
+#include <cuda_fp16.h>
+
 #include <cstdint>
 
 #include "qtn_internal.h"
@@ -70,6 +72,17 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void *src
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+
+// Ampere-style asynchronous copy, 8 bytes, global -> shared (LDGSTS): no register staging
+__device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+constexpr int kRawDepth = 6;   // chunks of A gathers in flight per CTA in the staggered kernel (16 KB each)
 
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -180,6 +193,17 @@ __device__ __forceinline__ float round_tf32(float x) {
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
   hi = round_tf32(x);
   lo = round_tf32(x - hi);
+}
+
+// running max of |re|, |im| as fp32 bit patterns (non-negative floats order like unsigned integers)
+__device__ __forceinline__ void amax_acc(uint32_t &m, float2 v) {
+  m = max(m, max(__float_as_uint(v.x) & 0x7fffffffu, __float_as_uint(v.y) & 0x7fffffffu));
+}
+// publish a warp's running maximum (see qtn_pair_run_scaled)
+__device__ __forceinline__ void amax_publish(uint32_t *amax, uint32_t m) {
+  if (amax == nullptr) return;
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(amax, m);
 }
 
 __device__ __forceinline__ long long deposit(unsigned long long idx, const uint8_t *pos, int n) {
@@ -455,7 +479,8 @@ template <int TNB, int TKB, bool SEP, bool PRE>
 __global__ void __launch_bounds__(kThreadsP, 1)
 gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ A,
                           const float2 *__restrict__ B, float2 *__restrict__ C,
-                          float2 *__restrict__ ws, const int32_t *__restrict__ slice_id) {
+                          float2 *__restrict__ ws, const int32_t *__restrict__ slice_id,
+                          uint32_t *__restrict__ amax_c) {
   constexpr int TN = 1 << TNB, KT = 1 << TKB;
   constexpr int PLANE_A = 128 * KT, PLANE_B = TN * KT;
   constexpr int STAGE = 4 * (PLANE_A + PLANE_B);
@@ -621,6 +646,7 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
     const int r = q * 32 + lane;
     const long long row_off = (r & 31) + ((long long)(r >> 5) << (5 + TNB));
     constexpr int CH = TN < 16 ? TN : 16;
+    uint32_t cmax = 0;
     unsigned long long it = 0;
     for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int buf = (int)(it % NBUF);
@@ -646,19 +672,26 @@ gett_tc_persistent_kernel(const __grid_constant__ qtn_pair_plan_t P, const float
           tmem_ld<CH>::run(trow + (uint32_t)(3 * TN + c0), xi);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < CH; ++j)
-            out[(long long)(c0 + j) << 5] = make_float2(__uint_as_float(re[j]) + __uint_as_float(xr[j]),
-                                                        __uint_as_float(im[j]) + __uint_as_float(xi[j]));
+          for (int j = 0; j < CH; ++j) {
+            const float2 v = make_float2(__uint_as_float(re[j]) + __uint_as_float(xr[j]),
+                                         __uint_as_float(im[j]) + __uint_as_float(xi[j]));
+            amax_acc(cmax, v);
+            out[(long long)(c0 + j) << 5] = v;
+          }
         } else {
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < CH; ++j)
-            out[(long long)(c0 + j) << 5] = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+          for (int j = 0; j < CH; ++j) {
+            const float2 v = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+            amax_acc(cmax, v);
+            out[(long long)(c0 + j) << 5] = v;
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));                 // accumulator buffer may be overwritten
     }
+    if (P.split_bits == 0) amax_publish(amax_c, cmax);
   } else {
     // ================= MMA issuer: the whole warp walks the loops, one elected lane issues =================
     int s = 0;
@@ -817,7 +850,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32_m256(int n, int neg_a) {
 template <int TNB, int TKB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP, 1)
 gett_tc_pair_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ A,
-                    float2 *__restrict__ C, float2 *__restrict__ ws, const int32_t *__restrict__ slice_id) {
+                    float2 *__restrict__ C, float2 *__restrict__ ws, const int32_t *__restrict__ slice_id,
+                    uint32_t *__restrict__ amax_c) {
   constexpr int TN = 1 << TNB, KT = 1 << TKB;
   constexpr int PLANE_A = 128 * KT, PLANE_B = TN * KT, PLANE_BH = PLANE_B / 2;
   constexpr int STAGE = 4 * (PLANE_A + PLANE_BH);
@@ -962,6 +996,7 @@ gett_tc_pair_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__r
     const int r = q * 32 + lane;
     const long long row_off = (r & 31) + ((long long)(r >> 5) << (5 + TNB));
     constexpr int CH = 16;
+    uint32_t cmax = 0;
     unsigned long long it = 0;
     for (unsigned long long u = pair0; u < nsuper; u += npairs, ++it) {
       const int buf = (int)(it % NBUF);
@@ -983,14 +1018,18 @@ gett_tc_pair_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__r
         tmem_ld<CH>::run(trow + (uint32_t)(3 * TN + c0), xi);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < CH; ++j)
-          out[(long long)(c0 + j) << 5] = make_float2(__uint_as_float(re[j]) + __uint_as_float(xr[j]),
-                                                      __uint_as_float(im[j]) + __uint_as_float(xi[j]));
+        for (int j = 0; j < CH; ++j) {
+          const float2 v = make_float2(__uint_as_float(re[j]) + __uint_as_float(xr[j]),
+                                       __uint_as_float(im[j]) + __uint_as_float(xi[j]));
+          amax_acc(cmax, v);
+          out[(long long)(c0 + j) << 5] = v;
+        }
       }
       tc_fence_before();
       if (rank == 0) mbar_arrive(tempty_bar(buf));
       else mbar_arrive_remote(tempty_bar(buf), 0);
     }
+    if (P.split_bits == 0) amax_publish(amax_c, cmax);
   } else if (rank == 0) {
     // ================= MMA issuer (leader CTA): whole warp walks the loops, one elected lane issues =================
     int s = 0;
@@ -1073,6 +1112,509 @@ gett_tc_pair_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__r
 }
 
 
+// --------------------------------------------------------------------------------------------
+// Staggered CTA-pair variant for 128-column tiles ("tc_pair" plan value 2, the default for them).
+//
+// A 128 x 128 tile with split accumulators fills TMEM (4 regions x 128 columns), so the pair kernel
+// above cannot double-buffer it: the tensor pipe idles while the epilogue drains 256 KB of TMEM per
+// tile (ncu, round 1: tensor pipe active 61.7 %, = exactly the MMA cycles / elapsed cycles).  Here the
+// tile is treated as two 64-column HALVES that share every A stage but own their accumulators:
+//     TMEM columns  [h*256, h*256+128)      HH_h : hi*hi sums         (half h = n columns h*64 .. h*64+63)
+//                   [h*256+128, h*256+256)  XX_h : the cross terms
+// and the MMA warp walks the flat (tile, k chunk) stream with TWO cursors: half 0 runs ahead of half 1
+// by up to the depth of the shared-memory ring.  When half 0 finishes a tile its accumulators drain
+// while the tensor pipe still has the lagging half-1 chunks of that tile to do, and half 0 starts the
+// next tile while half 1 drains -- the drain of one half hides behind the MMAs of the other.
+//
+// Re and Im of a product are produced by ONE MMA of 128 columns: the B operand of half h is the row
+// concatenation [Br | Bi] (for Ar) or [Bi | -Br] (for Ai, issued with the negate-A bit), so the 64
+// columns of a half cost the same 12 MMAs of N = 128 per 8 contracted values as before and A is not
+// read from shared memory more often.  In cta_group::2 CTA r supplies rows [r*64, r*64+64) of every
+// B operand; with n = h*64 + r*32 + j (j < 32) a region's 128 columns are
+//     [ re(r=0) 32 | im(r=0) 32 | re(r=1) 32 | im(r=1) 32 ].
+// B images (tc_prepack_b2_kernel) per (n tile, k chunk) and per rank r:
+//     half h: hi sequence [Br_hi | Bi_hi | -Br_hi], lo sequence [Br_lo | Bi_lo | -Br_lo], 32 rows each,
+// 384 rows x KT per rank = one cp.async.bulk per stage and CTA.
+// --------------------------------------------------------------------------------------------
+// Non-blocking probes (mbarrier.test_wait): the MMA warp of the staggered kernel polls several barriers
+// and must not be put to sleep on one of them (try_wait suspends the thread for a system-dependent
+// time when the phase is not complete) while the other half has chunks ready to issue.
+// Relaxed semantics on purpose: an .acquire.cluster probe makes ptxas emit CCTL.IVALL (an L1 flush) on
+// every success and a .release.cluster arrive emits MEMBAR.ALL.GPU + ERRBAR, which stalls the arriving
+// thread until all its global stores are performed (ncu, round 2: 7 % of the epilogue's and 16 % of
+// the forwarder's samples, and ~500 cycles per pass of the issue loop).  What the barriers order here
+// is tensor-core traffic: shared-memory operands are published by fence.proxy.async + the local full
+// barrier before the forwarder arrives, TMEM reads are closed by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync before the epilogue arrives, and the MMA warp runs
+// tcgen05.fence::after_thread_sync after every successful probe.
+__device__ __forceinline__ bool mbar_test_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {     // acquire at CTA scope
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+
+// ---- scaled 3xFP16 split (plan tc_kind = 1) ------------------------------------------------------
+// x * 2^s = h1 + h2 / 2^11 (+ error <= 2^-24 |x| 2^s), h1 = fp16(x 2^s), h2 = fp16((x 2^s - h1) 2^11),
+// with s = 14 - exponent(amax) so that the largest magnitude of the tensor lands in [2^14, 2^15): every
+// value within 2^-28 of the largest keeps 22 significant bits (fp16 normals span 2^-14 .. 2^15, the
+// residual is rescaled into the same range), smaller ones degrade gradually instead of vanishing.
+// HH accumulates h1*h1, XX accumulates h1*h2 + h2*h1 (scaled by 2^11); the epilogue forms
+// (HH + XX / 2^11) / 2^(sa+sb).  fp16 carries the same 11 significant bits as tf32, and kind::f16
+// MMAs contract 16 values in the cycles kind::tf32 needs for 8: half the tensor-pipe work.
+__device__ __forceinline__ int amax_scale_exp(const uint32_t *amax) {
+  const uint32_t bits = amax ? *reinterpret_cast<const volatile uint32_t *>(amax) : 0u;
+  int e = (int)((bits >> 23) & 0xffu) - 127;
+  if ((bits & 0x7fffffffu) == 0u) e = 0;
+  int s = 14 - e;
+  return s < -100 ? -100 : (s > 100 ? 100 : s);
+}
+__device__ __forceinline__ float exp2_int(int s) { return __uint_as_float((uint32_t)(s + 127) << 23); }
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t &h1, uint32_t &h2) {
+  const __half2 a = __floats2half2_rn(x0, x1);                       // x0 -> low half (lower k)
+  const float2 af = __half22float2(a);
+  const __half2 b = __floats2half2_rn((x0 - af.x) * 2048.f, (x1 - af.y) * 2048.f);
+  h1 = *reinterpret_cast<const uint32_t *>(&a);
+  h2 = *reinterpret_cast<const uint32_t *>(&b);
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 instruction descriptor: D fp32, A/B fp16 (format 0), both K-major, M = 256
+__host__ __device__ constexpr uint32_t umma_idesc_f16_m256(int n, int neg_a) {
+  return (1u << 4) | ((uint32_t)neg_a << 13) | ((uint32_t)(n >> 3) << 17) | ((256u >> 4) << 24);
+}
+
+template <int TKB, bool F16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP, 1)
+gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ A,
+                     float2 *__restrict__ C, float2 *__restrict__ ws, const int32_t *__restrict__ slice_id,
+                     const uint32_t *__restrict__ amax_a, const uint32_t *__restrict__ amax_b,
+                     uint32_t *__restrict__ amax_c) {
+  constexpr int TNB = 7, TN = 128, KT = 1 << TKB;
+  constexpr int EB = F16 ? 2 : 4;                       // bytes per operand-plane element
+  constexpr int PLANE_A = 128 * KT * EB;                // bytes
+  constexpr int CHUNK = 32 * KT * EB, SEQ = 3 * CHUNK, HALF = 2 * SEQ, RANK_B = 2 * HALF;
+  constexpr int STAGE = 4 * PLANE_A + RANK_B;
+  constexpr int NA = 128 * KT / kProducerThreads;
+  constexpr int TMEM_COLS = 512;
+  constexpr int KSTEPS = KT * EB / 32;                  // MMAs of one operand pair per stage (32 bytes of K each)
+  constexpr uint32_t LBO = 128, SBO = KT * EB * 8;
+  constexpr uint32_t IDESC = F16 ? umma_idesc_f16_m256(TN, 0) : umma_idesc_tf32_m256(TN, 0);
+  constexpr uint32_t IDESC_NEG = F16 ? umma_idesc_f16_m256(TN, 1) : umma_idesc_tf32_m256(TN, 1);
+  static_assert(!F16 || TKB == 4, "the fp16 split packs k pairs: 16 values per stage");
+
+  // A travels global -> shared memory with cp.async (8 bytes per thread and element) into a ring of kRawDepth
+  // raw chunks, and only then through registers into the operand planes: the gathers of kRawDepth chunks
+  // (96 KB per SM) are in flight without holding registers, where a register ring of 3 chunks (48 KB)
+  // left the producers waiting on DRAM for a third of their time (ncu, round 2: long-scoreboard stalls at
+  // the first use of the loaded values; read latency behind the 16 GB of C writes is ~3 us).
+  constexpr int RAW = NA * kProducerThreads * 8;        // bytes of one raw chunk (the tile's A elements, 8 B each)
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int S = P.tc_stages;
+  unsigned char *raw_ring = smem_raw + (size_t)S * STAGE;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(raw_ring + (size_t)kRawDepth * RAW);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + 4);
+  unsigned long long *img_ring = reinterpret_cast<unsigned long long *>(bars + 3 * S + 4 + 2);   // thread 0 only
+  const int t = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0), lane = t & 31;   // provably warp-uniform
+  const uint32_t rank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto pfull_bar = [&](int s) { return bar0 + 8u * (2 * S + s); };
+  auto tfull_bar = [&](int h) { return bar0 + 8u * (3 * S + h); };
+  auto tempty_bar = [&](int h) { return bar0 + 8u * (3 * S + 2 + h); };
+
+  const unsigned long long nsuper = (unsigned long long)P.grid >> 1;
+  const unsigned long long pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int k_iters_bits = P.n_khi - P.split_bits;
+  const unsigned long long k_iters = 1ull << k_iters_bits;
+  const long long a_slice = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
+  auto decode = [&](unsigned long long u, unsigned &split, unsigned long long &nh, unsigned long long &mh) {
+    split = (unsigned)(u & ((1ull << P.split_bits) - 1));
+    u >>= P.split_bits;
+    nh = u & ((1ull << P.n_nhi) - 1);
+    mh = ((u >> P.n_nhi) << 1) | rank;
+  };
+
+  if (t == 32) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), kProducerThreads + 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(pfull_bar(s), 1);
+    }
+    for (int h = 0; h < 2; ++h) { mbar_init(tfull_bar(h), 1); mbar_init(tempty_bar(h), 2 * kEpilogueThreads); }
+    fence_proxy_async_smem();
+    fence_mbar_init();
+  }
+  if (warp == 12) tmem_alloc_pair<TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ================= producers: this CTA's A rows (split in registers), its B image (one bulk copy) =================
+    long long a_t_g = 0;
+    int a_t_s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!((t >> j) & 1)) continue;
+      if (j < P.na_lo) { a_t_g |= 1ll << P.a_lo_pos[j]; a_t_s += P.a_lo_sstr[j]; }
+    }
+    const float sgn_a = P.conj_a ? -1.f : 1.f;
+    const float sc_re = F16 ? exp2_int(amax_scale_exp(amax_a)) : 1.f, sc_im = sc_re * sgn_a;
+    unsigned long long u = pair0, kk = 0;
+    long long a_k = 0;
+    constexpr uint32_t kRankBytes = RANK_B, kImageBytes = 2u * kRankBytes;
+    const unsigned char *images = reinterpret_cast<const unsigned char *>(ws) + P.tc_prepack_off + (size_t)rank * kRankBytes;
+    unsigned long long image0 = 0;
+    auto enter_tile = [&]() {
+      unsigned split;
+      unsigned long long nh, mh;
+      decode(u, split, nh, mh);
+      const unsigned long long kh0 = (unsigned long long)split << k_iters_bits;
+      a_k = a_slice | deposit_warp(mh, P.a_mhi, P.n_mhi) | deposit_warp(kh0, P.a_khi, P.n_khi);
+      image0 = (nh << P.n_khi) | kh0;
+      kk = 0;
+    };
+    auto advance = [&]() {
+      if (kk + 1 == k_iters) { u += npairs; if (u < nsuper) enter_tile(); return; }
+      const unsigned long long flip = kk ^ (kk + 1);
+      const int nflip = 64 - __clzll(flip);
+      for (int i = 0; i < nflip && i < k_iters_bits; ++i) a_k ^= 1ll << P.a_khi[i];
+      ++kk;
+    };
+    const uint32_t raw_t = smem_u32(raw_ring) + (uint32_t)t * 8u;
+    auto load = [&](int slot) {                       // this thread's NA elements of the current chunk -> raw slot
+      const uint32_t dst = raw_t + (uint32_t)slot * (uint32_t)RAW;
+#pragma unroll
+      for (int i = 0; i < NA; ++i)
+        cp_async8(dst + (uint32_t)i * (kProducerThreads * 8u), A + (a_k | a_t_g | P.tc_a_it_g[i]));
+      if (t == 0) img_ring[slot] = image0 + kk;
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    auto store = [&](int slot) {
+      float2 va[NA];
+      {
+        const float2 *src = reinterpret_cast<const float2 *>(raw_ring + (size_t)slot * RAW) + t;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) va[i] = src[i * kProducerThreads];
+      }
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      unsigned char *sA = smem_raw + (size_t)s * STAGE;
+      if (t == 0) {
+        mbar_arrive_expect_tx(full_bar(s), kRankBytes);
+        bulk_copy_g2s(smem_u32(sA + 4 * PLANE_A), images + img_ring[slot] * kImageBytes, kRankBytes, full_bar(s));
+      }
+      if constexpr (F16) {
+        // elements 2p and 2p+1 of a thread differ in the lowest k bit: one packed 32-bit store per plane
+        uint32_t *w = reinterpret_cast<uint32_t *>(sA);
+        constexpr int PW = PLANE_A / 4;
+#pragma unroll
+        for (int p = 0; p < NA / 2; ++p) {
+          const int o = (a_t_s + P.tc_a_it_s[2 * p]) >> 1;
+          uint32_t h1, h2;
+          split_f16x2(va[2 * p].x * sc_re, va[2 * p + 1].x * sc_re, h1, h2);
+          w[o] = h1; w[PW + o] = h2;
+          split_f16x2(va[2 * p].y * sc_im, va[2 * p + 1].y * sc_im, h1, h2);
+          w[2 * PW + o] = h1; w[3 * PW + o] = h2;
+        }
+      } else {
+        float *f = reinterpret_cast<float *>(sA);
+        constexpr int PF = PLANE_A / 4;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          const int o = a_t_s + P.tc_a_it_s[i];
+          float h, l;
+          split_tf32(va[i].x, h, l);
+          f[o] = h; f[PF + o] = l;
+          split_tf32(va[i].y * sgn_a, h, l);
+          f[2 * PF + o] = h; f[3 * PF + o] = l;
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(full_bar(s));
+      if (++s == S) { s = 0; ph ^= 1u; }
+    };
+    // every ring slot owns one cp.async group per lap (an empty one once the stream has ended), so that
+    // "all but the kRawDepth - 1 youngest groups are complete" always means "the oldest slot has landed"
+    const unsigned long long my_tiles = pair0 < nsuper ? (nsuper - pair0 + npairs - 1) / npairs : 0;
+    unsigned long long remaining = my_tiles * k_iters;   // chunks still to be stored
+    if (u < nsuper) enter_tile();
+#pragma unroll 1
+    for (int d = 0; d < kRawDepth; ++d) {
+      if (u < nsuper) { load(d); advance(); }
+      cp_async_commit();
+    }
+    int slot = 0;
+#pragma unroll 1
+    while (remaining) {
+      cp_async_wait<kRawDepth - 1>();
+      store(slot);
+      if (u < nsuper) { load(slot); advance(); }
+      cp_async_commit();
+      if (++slot == kRawDepth) slot = 0;
+      --remaining;
+    }
+  } else if (warp < 12) {
+    // ================= epilogue: half 0 then half 1 of every tile, each as soon as its MMAs are complete =================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const long long row_off = (r & 31) + ((long long)(r >> 5) << (5 + TNB));
+    constexpr int CH = 16;
+    // fp16 split: undo the operand scales (two factors: their product may leave the fp32 range)
+    const float inv_a = F16 ? exp2_int(-amax_scale_exp(amax_a)) : 1.f;
+    const float inv_b = F16 ? exp2_int(-amax_scale_exp(amax_b)) : 1.f;
+    const float xs = F16 ? (1.f / 2048.f) : 1.f;
+    uint32_t cmax = 0;
+    unsigned long long it = 0;
+    for (unsigned long long u = pair0; u < nsuper; u += npairs, ++it) {
+      const uint32_t tph = (uint32_t)(it & 1);
+      unsigned split;
+      unsigned long long nh, mh;
+      decode(u, split, nh, mh);
+      const long long c_base = deposit_warp(mh, P.c_mhi, P.n_mhi) | deposit_warp(nh, P.c_nhi, P.n_nhi);
+      float2 *out = (P.split_bits ? ws + (long long)split * P.c_elems : C) + c_base + row_off;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(tfull_bar(h), tph);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256);
+#pragma unroll 2
+        for (int rc = 0; rc < 4; ++rc) {
+          const uint32_t col = (uint32_t)((rc >> 1) * 64 + (rc & 1) * CH);
+          uint32_t re[CH], im[CH], xr[CH], xi[CH];
+          tmem_ld<CH>::run(trow + col, re);
+          tmem_ld<CH>::run(trow + col + 32u, im);
+          tmem_ld<CH>::run(trow + 128u + col, xr);
+          tmem_ld<CH>::run(trow + 160u + col, xi);
+          tmem_ld_wait();
+          float2 *o = out + ((long long)(h * 64 + (rc >> 1) * 32 + (rc & 1) * CH) << 5);
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            float2 v;
+            if constexpr (F16) {
+              v.x = fmaf(__uint_as_float(xr[j]), xs, __uint_as_float(re[j])) * inv_a * inv_b;
+              v.y = fmaf(__uint_as_float(xi[j]), xs, __uint_as_float(im[j])) * inv_a * inv_b;
+            } else {
+              v.x = __uint_as_float(re[j]) + __uint_as_float(xr[j]);
+              v.y = __uint_as_float(im[j]) + __uint_as_float(xi[j]);
+            }
+            amax_acc(cmax, v);
+            o[(long long)j << 5] = v;
+          }
+        }
+        tc_fence_before();
+        if (rank == 0) mbar_arrive_relaxed(tempty_bar(h));
+        else mbar_arrive_remote_relaxed(tempty_bar(h), 0);
+      }
+    }
+    if (P.split_bits == 0) amax_publish(amax_c, cmax);
+  } else if (rank == 0) {
+    // ================= MMA issuer (leader CTA): two cursors over the flat (tile, k chunk) stream =================
+    const uint32_t tmem_b = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t stage0 = smem_u32(smem_raw);
+    const unsigned long long my_tiles = pair0 < nsuper ? (nsuper - pair0 + npairs - 1) / npairs : 0;
+    const unsigned long long total = my_tiles * k_iters;
+    unsigned long long t0 = 0, t1 = 0;                  // chunks issued for half 0 / half 1
+    unsigned long long kk0 = 0, kk1 = 0, it0 = 0, it1 = 0;
+    int s0 = 0, s1 = 0;
+    uint32_t ph0 = 0;
+    bool acc0 = false, acc1 = false, stage0_ok = false;  // accumulators drained / stage known to be full
+    auto issue = [&](int h, int s, unsigned long long kk) {
+      if (elect_one()) {
+        const uint32_t sa = stage0 + (uint32_t)s * (uint32_t)STAGE;
+        const uint32_t sb = sa + 4u * PLANE_A + (uint32_t)h * (uint32_t)HALF;
+        const uint32_t hh = tmem_b + (uint32_t)(h * 256), xx = hh + 128u;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint32_t ko = (uint32_t)ks * 2u * LBO;
+          const uint64_t arh = umma_desc(sa + ko, LBO, SBO);
+          const uint64_t arl = umma_desc(sa + PLANE_A + ko, LBO, SBO);
+          const uint64_t aih = umma_desc(sa + 2u * PLANE_A + ko, LBO, SBO);
+          const uint64_t ail = umma_desc(sa + 3u * PLANE_A + ko, LBO, SBO);
+          const uint64_t bh0 = umma_desc(sb + ko, LBO, SBO);                       // [Br_hi | Bi_hi]
+          const uint64_t bh1 = umma_desc(sb + CHUNK + ko, LBO, SBO);               // [Bi_hi | -Br_hi]
+          const uint64_t bl0 = umma_desc(sb + SEQ + ko, LBO, SBO);                 // [Br_lo | Bi_lo]
+          const uint64_t bl1 = umma_desc(sb + SEQ + CHUNK + ko, LBO, SBO);         // [Bi_lo | -Br_lo]
+          const uint32_t acc = (kk | (unsigned)ks) ? 1u : 0u;
+          if constexpr (F16) {
+            umma_f16_pair(xx, arl, bh0, IDESC, acc);
+            umma_f16_pair(xx, ail, bh1, IDESC_NEG, 1u);
+            umma_f16_pair(xx, arh, bl0, IDESC, 1u);
+            umma_f16_pair(xx, aih, bl1, IDESC_NEG, 1u);
+            umma_f16_pair(hh, arh, bh0, IDESC, acc);
+            umma_f16_pair(hh, aih, bh1, IDESC_NEG, 1u);
+          } else {
+            umma_tf32_pair(xx, arl, bh0, IDESC, acc);
+            umma_tf32_pair(xx, ail, bh1, IDESC_NEG, 1u);
+            umma_tf32_pair(xx, arh, bl0, IDESC, 1u);
+            umma_tf32_pair(xx, aih, bl1, IDESC_NEG, 1u);
+            umma_tf32_pair(hh, arh, bh0, IDESC, acc);
+            umma_tf32_pair(hh, aih, bh1, IDESC_NEG, 1u);
+          }
+        }
+        if (h == 1) umma_commit_pair(empty_bar(s));     // both halves have read the stage
+        if (kk + 1 == k_iters) umma_commit_pair(tfull_bar(h));
+      }
+      __syncwarp();
+    };
+    // One pass issues at most one chunk per half.  The probes of a pass are independent of each other and are
+    // launched together; a barrier that has been seen complete is not probed again.
+    auto all_lanes = [](bool v) { return __all_sync(0xffffffffu, v) != 0; };
+    unsigned idle = 0;
+    while (t1 < total) {
+      const bool want1 = t1 < t0, want0 = t0 < total;
+      const bool probe_a1 = want1 && kk1 == 0 && !acc1;
+      const bool probe_a0 = want0 && kk0 == 0 && !acc0;
+      const bool probe_s0 = want0 && !stage0_ok;
+      bool r_a1 = true, r_a0 = true, r_f = true, r_p = true;
+      if (probe_a1) r_a1 = mbar_test_relaxed(tempty_bar(1), (uint32_t)((it1 & 1) ^ 1));
+      if (probe_a0) r_a0 = mbar_test_relaxed(tempty_bar(0), (uint32_t)((it0 & 1) ^ 1));
+      if (probe_s0) { r_f = mbar_test(full_bar(s0), ph0); r_p = mbar_test_relaxed(pfull_bar(s0), ph0); }
+      if (probe_a1) acc1 = all_lanes(r_a1);
+      if (probe_a0) acc0 = all_lanes(r_a0);
+      if (probe_s0) stage0_ok = all_lanes(r_f & r_p);
+      tc_fence_after();
+      bool did = false;
+      if (want1 && (kk1 != 0 || acc1)) {                // half 1: its stage is resident (half 0 saw it full)
+        issue(1, s1, kk1);
+        if (++kk1 == k_iters) { kk1 = 0; ++it1; acc1 = false; }
+        if (++s1 == S) s1 = 0;
+        ++t1;
+        did = true;
+      }
+      if (want0 && (kk0 != 0 || acc0) && stage0_ok) {
+        issue(0, s0, kk0);
+        if (++kk0 == k_iters) { kk0 = 0; ++it0; acc0 = false; }
+        if (++s0 == S) { s0 = 0; ph0 ^= 1u; }
+        ++t0;
+        stage0_ok = false;
+        did = true;
+      }
+      if (did) idle = 0;
+      else if (++idle > (1u << 26)) __trap();
+    }
+  } else {
+    // ================= forwarder (peer CTA): "my stage is full" -> the leader =================
+    int s = 0;
+    uint32_t ph = 0;
+    for (unsigned long long u = pair0; u < nsuper; u += npairs) {
+      for (unsigned long long kk = 0; kk < k_iters; ++kk) {
+        mbar_wait(full_bar(s), ph);
+        if (lane == 0) mbar_arrive_remote_relaxed(pfull_bar(s), 0);
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+  }
+}
+
+// B images of the staggered kernel: see the layout above.  One CTA per (n tile, k chunk); the tile
+// enumeration (global address, logical position) is the planner's, the logical (n, k) of an element
+// is decoded from its offset in the canonical plane layout (tf32: 8 rows x 4 values per core matrix,
+// fp16: 8 rows x 8 values).
+template <int TKB, bool F16>
+__global__ void __launch_bounds__(kProducerThreads)
+tc_prepack_b2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ B,
+                     unsigned char *__restrict__ images, const int32_t *__restrict__ slice_id,
+                     const uint32_t *__restrict__ amax_b) {
+  constexpr int TN = 128, KT = 1 << TKB;
+  constexpr int RG = KT * 8;                                      // elements per 8-row group of a plane
+  constexpr int CHUNK = 32 * KT, SEQ = 3 * CHUNK, HALF = 2 * SEQ, RANK_B = 2 * HALF;   // elements
+  constexpr int NB = TN * KT / kProducerThreads;
+  const int t = threadIdx.x;
+  const unsigned long long nh = (unsigned long long)blockIdx.x >> P.n_khi;
+  const unsigned long long kh = (unsigned long long)blockIdx.x & ((1ull << P.n_khi) - 1);
+  const long long b_k = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b) |
+                        deposit(nh, P.b_nhi, P.n_nhi) | deposit(kh, P.b_khi, P.n_khi);
+  long long b_t_g = 0;
+  int b_t_s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (((t >> j) & 1) && j < P.nb_lo) { b_t_g |= 1ll << P.b_lo_pos[j]; b_t_s += P.b_lo_sstr[j]; }
+  const float sgn_b = P.conj_b ? -1.f : 1.f;
+  const float sc = F16 ? exp2_int(amax_scale_exp(amax_b)) : 1.f;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const float2 v = __ldg(B + (b_k | b_t_g | P.tc_b_it_g[i]));
+    const int o = b_t_s + P.tc_b_it_s[i];                       // offset in the canonical 128 x KT plane
+    int k, n, inner;
+    if constexpr (F16) {
+      k = (o & 7) | (((o % RG) >> 6) << 3);
+      n = ((o >> 3) & 7) | ((o / RG) << 3);
+      inner = ((n & 31) >> 3) * RG + (k >> 3) * 64 + (n & 7) * 8 + (k & 7);
+    } else {
+      k = (o & 3) | (((o % RG) >> 5) << 2);
+      n = ((o >> 2) & 7) | ((o / RG) << 3);
+      inner = ((n & 31) >> 3) * RG + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
+    }
+    const size_t at = (size_t)blockIdx.x * 2 * RANK_B + ((n >> 5) & 1) * RANK_B + (n >> 6) * HALF + inner;
+    if constexpr (F16) {
+      __half *dst = reinterpret_cast<__half *>(images) + at;
+      float x = v.x * sc;
+      __half h1 = __float2half_rn(x), h2 = __float2half_rn((x - __half2float(h1)) * 2048.f);
+      dst[0] = h1; dst[2 * CHUNK] = __hneg(h1);
+      dst[SEQ] = h2; dst[SEQ + 2 * CHUNK] = __hneg(h2);
+      x = v.y * sgn_b * sc;
+      h1 = __float2half_rn(x); h2 = __float2half_rn((x - __half2float(h1)) * 2048.f);
+      dst[CHUNK] = h1; dst[SEQ + CHUNK] = h2;
+    } else {
+      float *dst = reinterpret_cast<float *>(images) + at;
+      float h, l;
+      split_tf32(v.x, h, l);
+      dst[0] = h; dst[2 * CHUNK] = -h;
+      dst[SEQ] = l; dst[SEQ + 2 * CHUNK] = -l;
+      split_tf32(v.y * sgn_b, h, l);
+      dst[CHUNK] = h; dst[SEQ + CHUNK] = l;
+    }
+  }
+}
+
 // B pre-pack: one CTA per (n tile, k chunk) writes that B stage -- split into hi/lo re/im planes
 // and laid out exactly as the main kernel's shared-memory stage -- to the workspace.
 template <int TNB, int TKB>
@@ -1109,9 +1651,44 @@ tc_prepack_b_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__r
 
 template <int TNB, int TKB>
 int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
-                   const int32_t *slice_id, cudaStream_t st) {
+                   const int32_t *slice_id, const uint32_t *amax_a, const uint32_t *amax_b, uint32_t *amax_c,
+                   bool &amax_done, cudaStream_t st) {
+  amax_done = P.split_bits == 0;                // the persistent kernels publish max |C| from their epilogue
   if (P.tc_reserved > 0) {                      // persistent variant: tc_reserved = CTAs to launch
     const long long ctas = P.grid < P.tc_reserved ? P.grid : P.tc_reserved;
+    if (P.tc_pair == 2) {                         // staggered CTA pairs: 128-column tiles only
+      if constexpr (TNB == 7) {
+        const long long images = 1ll << (P.n_nhi + P.n_khi);
+        if (!P.tc_pad || !P.tc_prepack || (P.grid & 1) || (ctas & 1) || images > 0x7fffffffLL)
+          return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: malformed staggered CTA-pair plan");
+        auto go2 = [&](auto prepack, auto kernel, int &smem_set) -> int {
+          prepack<<<(unsigned)images, kProducerThreads, 0, st>>>(P, (const float2 *)b,
+                                                                 (unsigned char *)ws + P.tc_prepack_off, slice_id, amax_b);
+          QTN_LAUNCH_CHECK();
+          if (smem_set < P.smem_bytes) {
+            QTN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+            smem_set = P.smem_bytes;
+          }
+          kernel<<<(unsigned)ctas, kThreadsP, P.smem_bytes, st>>>(P, (const float2 *)a, (float2 *)c, (float2 *)ws, slice_id,
+                                                                 amax_a, amax_b, amax_c);
+          QTN_LAUNCH_CHECK();
+          return QTN_OK;
+        };
+        static int set_t = 0, set_h = 0;
+        if (P.tc_kind == 1) {
+          if constexpr (TKB == 4) {
+            if (!amax_a || !amax_b)
+              return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: an fp16-split plan needs the operands' magnitude words");
+            return go2(tc_prepack_b2_kernel<TKB, true>, gett_tc_pair2_kernel<TKB, true>, set_h);
+          } else {
+            return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: the fp16 split needs 16 contracted values per stage");
+          }
+        }
+        return go2(tc_prepack_b2_kernel<TKB, false>, gett_tc_pair2_kernel<TKB, false>, set_t);
+      } else {
+        return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: staggered CTA pairs need a 128-column tile");
+      }
+    }
     if (P.tc_prepack) {
       const long long images = 1ll << (P.n_nhi + P.n_khi);
       if (images > 0x7fffffffLL) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_run: too many B images");
@@ -1125,7 +1702,7 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
         smem_set = P.smem_bytes;
       }
       kernel<<<(unsigned)ctas, kThreadsP, P.smem_bytes, st>>>(P, (const float2 *)a, (const float2 *)b, (float2 *)c,
-                                                             (float2 *)ws, slice_id);
+                                                             (float2 *)ws, slice_id, amax_c);
       QTN_LAUNCH_CHECK();
       return QTN_OK;
     };
@@ -1141,7 +1718,7 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
           set_pair = P.smem_bytes;
         }
         gett_tc_pair_kernel<TNB, TKB><<<(unsigned)ctas, kThreadsP, P.smem_bytes, st>>>(P, (const float2 *)a, (float2 *)c,
-                                                                                    (float2 *)ws, slice_id);
+                                                                                    (float2 *)ws, slice_id, amax_c);
         QTN_LAUNCH_CHECK();
         return QTN_OK;
       } else {
@@ -1159,6 +1736,7 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
     return P.tc_prepack ? go(gett_tc_persistent_kernel<TNB, TKB, false, true>, set_p)
                         : go(gett_tc_persistent_kernel<TNB, TKB, false, false>, set_0);
   }
+  amax_done = false;                            // one CTA per tile: no magnitude tracking in the kernel
   static int smem_set = 0;
   if (smem_set < P.smem_bytes) {
     QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tc_kernel<TNB, TKB>,
@@ -1174,22 +1752,27 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
 }  // namespace
 
 int qtn_launch_tc(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
-                  const int32_t *slice_id, cudaStream_t st) {
+                  const int32_t *slice_id, const uint32_t *amax_a, const uint32_t *amax_b, uint32_t *amax_c,
+                  cudaStream_t st) {
   if (P.dtype != QTN_C64) return qtn_fail(QTN_ERR_UNSUPPORTED, "tensor-core kernel is complex64 only");
   if (P.grid <= 0 || P.grid > 0x7fffffffLL) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_run: grid too large");
   if (P.tmb != 7 || P.tc_stages < 1 || P.tc_stages > 8)
     return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: malformed tensor-core plan");
   int rc;
+  bool amax_done = false;
   switch (P.tnb * 8 + P.tkb) {
 #define QTN_TC_CASE(NB, KB) \
-  case NB * 8 + KB: rc = launch_tc_inst<NB, KB>(P, a, b, c, ws, slice_id, st); break;
+  case NB * 8 + KB: rc = launch_tc_inst<NB, KB>(P, a, b, c, ws, slice_id, amax_a, amax_b, amax_c, amax_done, st); break;
     QTN_TC_CASE(4, 3) QTN_TC_CASE(4, 4) QTN_TC_CASE(5, 3) QTN_TC_CASE(5, 4) QTN_TC_CASE(6, 3)
     QTN_TC_CASE(6, 4) QTN_TC_CASE(7, 3) QTN_TC_CASE(7, 4) QTN_TC_CASE(8, 3) QTN_TC_CASE(8, 4)
 #undef QTN_TC_CASE
     default: return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: unsupported tensor-core tile");
   }
   if (rc != QTN_OK) return rc;
-  if (P.split_bits)
-    return qtn_launch_splitk_sum(QTN_C64, c, ws, P.c_elems, 1 << P.split_bits, P.accumulate, st);
+  if (P.split_bits) {
+    rc = qtn_launch_splitk_sum(QTN_C64, c, ws, P.c_elems, 1 << P.split_bits, P.accumulate, st);
+    if (rc != QTN_OK) return rc;
+  }
+  if (amax_c && !amax_done) return qtn_launch_absmax(c, P.c_elems, amax_c, st);
   return QTN_OK;
 }

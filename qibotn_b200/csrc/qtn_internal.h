@@ -15,6 +15,8 @@ int qtn_option_tc_terms(void);
 int qtn_option_tc_accum_split(void);
 int qtn_option_tc_prepack(void);
 int qtn_option_tc_pair(void);
+int qtn_option_tc_stagger(void);
+int qtn_option_tc_fp16(void);
 int qtn_option_svd_wide(void);
 int qtn_option_svd_group_mb(void);
 int qtn_option_svd_reg(void);
@@ -30,8 +32,12 @@ int qtn_option_svd_reg(void);
     if (_e != cudaSuccess) return qtn_fail(QTN_ERR_CUDA, cudaGetErrorString(_e));   \
   } while (0)
 // gett_tc.cu: tcgen05 kernel launch (plan->kernel == QTN_KERNEL_TC)
+// amax_*: device words bounding max(|re|, |im|) of each tensor (see qtn_pair_run_scaled); may be NULL
 int qtn_launch_tc(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
-                  const int32_t *slice_id, cudaStream_t st);
+                  const int32_t *slice_id, const uint32_t *amax_a, const uint32_t *amax_b, uint32_t *amax_c,
+                  cudaStream_t st);
+// gett.cu: *amax = max(*amax, bits of max(|re|, |im|)) over n complex64 elements
+int qtn_launch_absmax(const void *x, long long n, uint32_t *amax, cudaStream_t st);
 // gett.cu: C (+)= sum of `nsplit` split-K partials of `n` elements each
 int qtn_launch_splitk_sum(int dtype, void *c, const void *ws, long long n, int nsplit, int accumulate,
                           cudaStream_t st);

@@ -67,6 +67,7 @@ class PairPlan(C.Structure):
         ("tc_a_it_s", C.c_int32 * 8), ("tc_b_it_s", C.c_int32 * 16),
         ("tc_terms", C.c_int32), ("tc_pad", C.c_int32),
         ("tc_prepack", C.c_int32), ("tc_pair", C.c_int32), ("tc_prepack_off", C.c_int64),
+        ("tc_kind", C.c_int32), ("tc_reserved2", C.c_int32),
     ]
 
 
@@ -101,6 +102,9 @@ _SIGNATURES = {
     "qtn_pair_plan": (C.c_int, [C.POINTER(PairDesc), C.c_int, C.POINTER(PairPlan)]),
     "qtn_pair_run": (C.c_int, [C.POINTER(PairPlan), C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qtn_pair_run_scaled": (C.c_int, [C.POINTER(PairPlan), C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qtn_absmax": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qtn_permute_bits": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8),
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "qtn_permute": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32),

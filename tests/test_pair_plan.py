@@ -164,13 +164,41 @@ def test_cta_pair_plans_are_well_formed(shape):
         lib.set_option("tc_pair", 5)
     assert plan.kernel == lib.KERNEL_TC and single.kernel == lib.KERNEL_TC and single.tc_pair == 0
     eligible = plan.tc_prepack == 1 and plan.tc_pad == 1 and 5 <= plan.tnb <= 7
-    assert plan.tc_pair == (1 if eligible else 0)
+    # 128-column tiles take the staggered variant (plan value 2): two 64-column halves per tile
+    assert plan.tc_pair == ((2 if plan.tnb == 7 else 1) if eligible else 0)
     assert (m >= 10 and n >= 5) == bool(plan.tc_pair)
     if plan.tc_pair:
         assert plan.grid % 2 == 0 and plan.tc_reserved % 2 == 0 and plan.tc_reserved > 0
+        # same tiling and C layout as the single-CTA plan: the kernels are interchangeable
+        assert (plan.tmb, plan.tnb, plan.tkb, plan.split_bits) == (single.tmb, single.tnb, single.tkb, single.split_bits)
+        assert plan.c_elems == single.c_elems
+    if plan.tc_pair == 1:
         stage = 4 * (plan.tc_plane_a + plan.tc_plane_b // 2)
         assert plan.smem_bytes == plan.tc_stages * stage + 256 <= 227 * 1024
         assert 2 <= plan.tc_stages <= 6 and plan.tc_stages >= single.tc_stages
-        # same tiling and C layout as the single-CTA plan: the two kernels are interchangeable
-        assert (plan.tmb, plan.tnb, plan.tkb, plan.split_bits) == (single.tmb, single.tnb, single.tkb, single.split_bits)
-        assert plan.c_elems == single.c_elems and plan.workspace_bytes == single.workspace_bytes
+        assert plan.workspace_bytes == single.workspace_bytes
+    if plan.tc_pair == 2:
+        kt = 1 << plan.tkb
+        assert plan.tc_kind == (1 if plan.tkb == 4 else 0)      # scaled 3xFP16 split: 2-byte operand planes
+        eb = 2 if plan.tc_kind else 4
+        assert plan.tc_plane_a == 128 * kt * eb
+        rank_b = 384 * kt * eb         # per CTA: 2 halves x {hi, lo} x [Br | Bi | -Br] x 32 rows x kt values
+        stage = 4 * plan.tc_plane_a + rank_b
+        raw_ring = 6 * 128 * kt * 8    # cp.async gathers of A in flight: 6 chunks of 8-byte elements
+        assert plan.smem_bytes == plan.tc_stages * stage + raw_ring + 512 <= 227 * 1024
+        assert 2 <= plan.tc_stages <= 8
+        images = 1 << (plan.n_nhi + plan.n_khi)
+        assert plan.workspace_bytes == plan.tc_prepack_off + images * 2 * rank_b + (256 if plan.tc_kind else 0)
+        if plan.tc_kind:
+            # the lowest k label is the first iteration bit (a thread packs two k-adjacent fp16 values per
+            # store) and the five lane bits own the bank-selecting word offsets
+            assert plan.a_lo_sstr[8] == 1 and sorted(plan.a_lo_sstr[:5]) == [2, 4, 8, 16, 32]
+            assert all(plan.tc_a_it_s[2 * q + 1] == plan.tc_a_it_s[2 * q] + 1 for q in range(4))
+        lib.set_option("tc_min_log2", 0)
+        lib.set_option("tc_stagger", 0)
+        try:
+            old = lib.pair_plan(lib.make_pair_desc("complex64", la, lb))
+        finally:
+            lib.set_option("tc_min_log2", 18)
+            lib.set_option("tc_stagger", 1)
+        assert old.tc_pair == 1 and old.tc_prepack_off == plan.tc_prepack_off
