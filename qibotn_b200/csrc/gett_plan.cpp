@@ -329,12 +329,11 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
       p->tc_stages = std::max(2, std::min(6, (200 * 1024) / pair_stage));
       p->smem_bytes = p->tc_stages * pair_stage + 256;
       p->tc_reserved = sm_count & ~1;
-      // 128-column tiles: the staggered variant (two 64-column halves with their own accumulators share
-      // every A stage; the drain of one half hides behind the MMAs of the other).  Per CTA a stage holds
-      // the 4 A planes and 384 rows of B (2 halves x {hi, lo} x [Br | Bi | -Br] x 32 rows); an image
-      // holds both ranks' rows.
-      if (tnb == 7 && qtn_option_tc_stagger() && p->tc_terms == 3) {
-        const int rank_b = 384 * KT * 4;
+      // The staggered variant: two half-width halves with their own accumulators share every A stage; the
+      // drain of one half hides behind the MMAs of the other.  Per CTA a stage holds the 4 A planes and
+      // 3 * TN rows of B (2 halves x {hi, lo} x [Br | Bi | -Br] x TN / 4 rows); an image holds both ranks' rows.
+      if (qtn_option_tc_stagger() && p->tc_terms == 3) {
+        const int rank_b = 3 * TN * KT * 4;
         const int stage2 = 4 * p->tc_plane_a + rank_b;
         const int64_t images = (int64_t)1 << (p->n_nhi + p->n_khi);
         const int64_t base = (p->tc_prepack_off);
@@ -384,7 +383,7 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
           }
           p->tc_plane_a = 128 * KT * 2;
           p->tc_plane_b = TN * KT * 2;
-          const int rank_h = 384 * KT * 2;
+          const int rank_h = 3 * TN * KT * 2;
           const int stage_h = 4 * p->tc_plane_a + rank_h;
           p->tc_stages = std::max(2, std::min(8, (227 * 1024 - 512 - raw_ring) / stage_h));
           p->smem_bytes = p->tc_stages * stage_h + raw_ring + 512;

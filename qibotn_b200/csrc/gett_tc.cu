@@ -1113,7 +1113,8 @@ gett_tc_pair_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__r
 
 
 // --------------------------------------------------------------------------------------------
-// Staggered CTA-pair variant for 128-column tiles ("tc_pair" plan value 2, the default for them).
+// Staggered CTA-pair variant ("tc_pair" plan value 2, the default for paired tiles; written for TN = 128
+// columns below, the same with TN / 2-column halves and TN / 4-row chunks for 64 and 32).
 //
 // A 128 x 128 tile with split accumulators fills TMEM (4 regions x 128 columns), so the pair kernel
 // above cannot double-buffer it: the tensor pipe idles while the epilogue drains 256 KB of TMEM per
@@ -1218,19 +1219,21 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_m256(int n, int neg_a) {
   return (1u << 4) | ((uint32_t)neg_a << 13) | ((uint32_t)(n >> 3) << 17) | ((256u >> 4) << 24);
 }
 
-template <int TKB, bool F16>
+template <int TNB, int TKB, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP, 1)
 gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ A,
                      float2 *__restrict__ C, float2 *__restrict__ ws, const int32_t *__restrict__ slice_id,
                      const uint32_t *__restrict__ amax_a, const uint32_t *__restrict__ amax_b,
                      uint32_t *__restrict__ amax_c) {
-  constexpr int TNB = 7, TN = 128, KT = 1 << TKB;
+  constexpr int TN = 1 << TNB, KT = 1 << TKB;
+  constexpr int Q = TN / 4;                             // B rows per chunk = columns of one [re] or [im] block
   constexpr int EB = F16 ? 2 : 4;                       // bytes per operand-plane element
   constexpr int PLANE_A = 128 * KT * EB;                // bytes
-  constexpr int CHUNK = 32 * KT * EB, SEQ = 3 * CHUNK, HALF = 2 * SEQ, RANK_B = 2 * HALF;
+  constexpr int CHUNK = Q * KT * EB, SEQ = 3 * CHUNK, HALF = 2 * SEQ, RANK_B = 2 * HALF;
   constexpr int STAGE = 4 * PLANE_A + RANK_B;
   constexpr int NA = 128 * KT / kProducerThreads;
-  constexpr int TMEM_COLS = 512;
+  constexpr int TMEM_COLS = 4 * TN;                     // two halves x (HH, XX) x TN columns
+  static_assert(TNB >= 5 && TNB <= 7, "staggered pair tiles have 32, 64 or 128 columns");
   constexpr int KSTEPS = KT * EB / 32;                  // MMAs of one operand pair per stage (32 bytes of K each)
   constexpr uint32_t LBO = 128, SBO = KT * EB * 8;
   constexpr uint32_t IDESC = F16 ? umma_idesc_f16_m256(TN, 0) : umma_idesc_tf32_m256(TN, 0);
@@ -1398,7 +1401,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const long long row_off = (r & 31) + ((long long)(r >> 5) << (5 + TNB));
-    constexpr int CH = 16;
+    constexpr int CH = Q < 16 ? Q : 16, NCH = Q / CH;  // column chunks of one [re] block
     // fp16 split: undo the operand scales (two factors: their product may leave the fp32 range)
     const float inv_a = F16 ? exp2_int(-amax_scale_exp(amax_a)) : 1.f;
     const float inv_b = F16 ? exp2_int(-amax_scale_exp(amax_b)) : 1.f;
@@ -1416,17 +1419,18 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
       for (int h = 0; h < 2; ++h) {
         mbar_wait(tfull_bar(h), tph);
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256);
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 2 * TN);
 #pragma unroll 2
-        for (int rc = 0; rc < 4; ++rc) {
-          const uint32_t col = (uint32_t)((rc >> 1) * 64 + (rc & 1) * CH);
+        for (int rc = 0; rc < 2 * NCH; ++rc) {
+          const int rr = rc / NCH, cc = (rc % NCH) * CH;    // rank block, first column inside it
+          const uint32_t col = (uint32_t)(rr * 2 * Q + cc);
           uint32_t re[CH], im[CH], xr[CH], xi[CH];
           tmem_ld<CH>::run(trow + col, re);
-          tmem_ld<CH>::run(trow + col + 32u, im);
-          tmem_ld<CH>::run(trow + 128u + col, xr);
-          tmem_ld<CH>::run(trow + 160u + col, xi);
+          tmem_ld<CH>::run(trow + col + (uint32_t)Q, im);
+          tmem_ld<CH>::run(trow + (uint32_t)TN + col, xr);
+          tmem_ld<CH>::run(trow + (uint32_t)(TN + Q) + col, xi);
           tmem_ld_wait();
-          float2 *o = out + ((long long)(h * 64 + (rc >> 1) * 32 + (rc & 1) * CH) << 5);
+          float2 *o = out + ((long long)(h * (TN / 2) + rr * Q + cc) << 5);
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
             float2 v;
@@ -1462,7 +1466,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
       if (elect_one()) {
         const uint32_t sa = stage0 + (uint32_t)s * (uint32_t)STAGE;
         const uint32_t sb = sa + 4u * PLANE_A + (uint32_t)h * (uint32_t)HALF;
-        const uint32_t hh = tmem_b + (uint32_t)(h * 256), xx = hh + 128u;
+        const uint32_t hh = tmem_b + (uint32_t)(h * 2 * TN), xx = hh + (uint32_t)TN;
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
           const uint32_t ko = (uint32_t)ks * 2u * LBO;
@@ -1558,15 +1562,15 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
 // enumeration (global address, logical position) is the planner's, the logical (n, k) of an element
 // is decoded from its offset in the canonical plane layout (tf32: 8 rows x 4 values per core matrix,
 // fp16: 8 rows x 8 values).
-template <int TKB, bool F16>
+template <int TNB, int TKB, bool F16>
 __global__ void __launch_bounds__(kProducerThreads)
 tc_prepack_b2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ B,
                      unsigned char *__restrict__ images, const int32_t *__restrict__ slice_id,
                      const uint32_t *__restrict__ amax_b) {
-  constexpr int TN = 128, KT = 1 << TKB;
+  constexpr int TN = 1 << TNB, KT = 1 << TKB, Q = TN / 4;
   constexpr int RG = KT * 8;                                      // elements per 8-row group of a plane
-  constexpr int CHUNK = 32 * KT, SEQ = 3 * CHUNK, HALF = 2 * SEQ, RANK_B = 2 * HALF;   // elements
-  constexpr int NB = TN * KT / kProducerThreads;
+  constexpr int CHUNK = Q * KT, SEQ = 3 * CHUNK, HALF = 2 * SEQ, RANK_B = 2 * HALF;   // elements
+  constexpr int NB = (TN * KT + kProducerThreads - 1) / kProducerThreads;
   const int t = threadIdx.x;
   const unsigned long long nh = (unsigned long long)blockIdx.x >> P.n_khi;
   const unsigned long long kh = (unsigned long long)blockIdx.x & ((1ull << P.n_khi) - 1);
@@ -1579,6 +1583,7 @@ tc_prepack_b2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     if (((t >> j) & 1) && j < P.nb_lo) { b_t_g |= 1ll << P.b_lo_pos[j]; b_t_s += P.b_lo_sstr[j]; }
   const float sgn_b = P.conj_b ? -1.f : 1.f;
   const float sc = F16 ? exp2_int(amax_scale_exp(amax_b)) : 1.f;
+  if (!(P.nb_lo >= 8 || t < (1 << P.nb_lo))) return;
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
     const float2 v = __ldg(B + (b_k | b_t_g | P.tc_b_it_g[i]));
@@ -1587,13 +1592,13 @@ tc_prepack_b2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     if constexpr (F16) {
       k = (o & 7) | (((o % RG) >> 6) << 3);
       n = ((o >> 3) & 7) | ((o / RG) << 3);
-      inner = ((n & 31) >> 3) * RG + (k >> 3) * 64 + (n & 7) * 8 + (k & 7);
+      inner = ((n % Q) >> 3) * RG + (k >> 3) * 64 + (n & 7) * 8 + (k & 7);
     } else {
       k = (o & 3) | (((o % RG) >> 5) << 2);
       n = ((o >> 2) & 7) | ((o / RG) << 3);
-      inner = ((n & 31) >> 3) * RG + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
+      inner = ((n % Q) >> 3) * RG + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
     }
-    const size_t at = (size_t)blockIdx.x * 2 * RANK_B + ((n >> 5) & 1) * RANK_B + (n >> 6) * HALF + inner;
+    const size_t at = (size_t)blockIdx.x * 2 * RANK_B + ((n / Q) & 1) * RANK_B + (n / (2 * Q)) * HALF + inner;
     if constexpr (F16) {
       __half *dst = reinterpret_cast<__half *>(images) + at;
       float x = v.x * sc;
@@ -1656,8 +1661,8 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
   amax_done = P.split_bits == 0;                // the persistent kernels publish max |C| from their epilogue
   if (P.tc_reserved > 0) {                      // persistent variant: tc_reserved = CTAs to launch
     const long long ctas = P.grid < P.tc_reserved ? P.grid : P.tc_reserved;
-    if (P.tc_pair == 2) {                         // staggered CTA pairs: 128-column tiles only
-      if constexpr (TNB == 7) {
+    if (P.tc_pair == 2) {                         // staggered CTA pairs: tiles of 32, 64 or 128 columns
+      if constexpr (TNB >= 5 && TNB <= 7) {
         const long long images = 1ll << (P.n_nhi + P.n_khi);
         if (!P.tc_pad || !P.tc_prepack || (P.grid & 1) || (ctas & 1) || images > 0x7fffffffLL)
           return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: malformed staggered CTA-pair plan");
@@ -1679,14 +1684,14 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
           if constexpr (TKB == 4) {
             if (!amax_a || !amax_b)
               return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: an fp16-split plan needs the operands' magnitude words");
-            return go2(tc_prepack_b2_kernel<TKB, true>, gett_tc_pair2_kernel<TKB, true>, set_h);
+            return go2(tc_prepack_b2_kernel<TNB, TKB, true>, gett_tc_pair2_kernel<TNB, TKB, true>, set_h);
           } else {
             return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: the fp16 split needs 16 contracted values per stage");
           }
         }
-        return go2(tc_prepack_b2_kernel<TKB, false>, gett_tc_pair2_kernel<TKB, false>, set_t);
+        return go2(tc_prepack_b2_kernel<TNB, TKB, false>, gett_tc_pair2_kernel<TNB, TKB, false>, set_t);
       } else {
-        return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: staggered CTA pairs need a 128-column tile");
+        return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: staggered CTA pairs need a tile of 32 to 128 columns");
       }
     }
     if (P.tc_prepack) {

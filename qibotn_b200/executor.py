@@ -236,6 +236,25 @@ class ContractionRunner:
         self.ws = torch.empty(max(lowered.workspace_bytes, 256), dtype=u8, device=self.device)
         self.out = torch.zeros(1 << self._live_out_rank(), dtype=self.cdtype, device=self.device)
         self.slice_id = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # Magnitude words (qtn_pair_run_scaled): one device word per tensor that an fp16-split plan reads,
+        # bounding max(|re|, |im|) of that tensor.  Leaves are measured after every upload, intermediates
+        # by the kernel that produces them; the words of per-slice tensors are cleared at the start of
+        # every slice (inside the captured graph), so a slice's result does not depend on its predecessors.
+        self._amax_slot = {}
+        needs = set()
+        for node in lowered.nodes:
+            if node.plan.kernel == lib.KERNEL_TC and node.plan.tc_kind == 1:
+                needs.update((node.a, node.b))
+        groups = {"leaf": [], "hoist": [], "slice": [], "out": []}
+        for tid in sorted(needs):
+            groups[lowered.tensors[tid].where].append(tid)
+        self._amax = {}
+        for where, tids in groups.items():
+            self._amax[where] = torch.zeros(max(len(tids), 1), dtype=torch.int32, device=self.device)
+            for k, tid in enumerate(tids):
+                self._amax_slot[tid] = self._amax[where].data_ptr() + 4 * k
+        self._amax_leaves = groups["leaf"]
+        self._amax_used = {where: bool(tids) for where, tids in groups.items()}
         self.use_graph = use_graph
         self._graph = None
         self._graph_hoist = None
@@ -277,14 +296,60 @@ class ContractionRunner:
     def _run_nodes(self, depends):
         st = self.torch.cuda.current_stream().cuda_stream
         n = 0
+        slot = self._amax_slot
+        where = "slice" if depends else "hoist"
+        if self._amax_used[where]:
+            self._amax[where].zero_()
         for node in self.low.nodes:
             if node.depends != depends:
                 continue
-            lib.check(self.lib.qtn_pair_run(C.byref(node.plan), self._ptr(node.a), self._ptr(node.b),
-                                            self._ptr(node.c), self.ws.data_ptr(),
-                                            self.slice_id.data_ptr(), st))
+            lib.check(self.lib.qtn_pair_run_scaled(C.byref(node.plan), self._ptr(node.a), self._ptr(node.b),
+                                                   self._ptr(node.c), self.ws.data_ptr(),
+                                                   self.slice_id.data_ptr(), slot.get(node.a), slot.get(node.b),
+                                                   slot.get(node.c), st))
             n += 2 if (node.plan.split_bits or node.plan.kernel == lib.KERNEL_REDUCE) else 1
         return n
+
+    def time_nodes(self, slice_id=0, reps=3):
+        """Per-node device times (ms, CUDA events on the launch stream) of one slice, nodes run in order.
+        Measurement helper for bench.py / scripts: returns [(node, ms)] for the per-slice nodes."""
+        torch = self.torch
+        st = torch.cuda.current_stream().cuda_stream
+        slot = self._amax_slot
+        self._measure_leaves()
+        self._run_hoisted()
+        lib.check(self.lib.qtn_set_i32(self.slice_id.data_ptr(), slice_id, st))
+        out = []
+        if self._amax_used["slice"]:
+            self._amax["slice"].zero_()
+        for node in self.low.nodes:
+            if not node.depends:
+                continue
+            best = None
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                lib.check(self.lib.qtn_pair_run_scaled(C.byref(node.plan), self._ptr(node.a), self._ptr(node.b),
+                                                       self._ptr(node.c), self.ws.data_ptr(),
+                                                       self.slice_id.data_ptr(), slot.get(node.a), slot.get(node.b),
+                                                       slot.get(node.c), st))
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+            out.append((node, best))
+        return out
+
+    def _measure_leaves(self):
+        """Magnitude words of the leaves that an fp16-split plan reads directly (rare: such plans mostly
+        read intermediates); one small streaming kernel per leaf, after every upload."""
+        if not self._amax_leaves:
+            return
+        st = self.torch.cuda.current_stream().cuda_stream
+        self._amax["leaf"].zero_()
+        for tid in self._amax_leaves:
+            t = self.low.tensors[tid]
+            lib.check(self.lib.qtn_absmax(lib.QTN_C64, t.nbytes // 8, self._ptr(tid), self._amax_slot[tid], st))
 
     def run(self, slice_ids=None):
         """Hoisted nodes once, then the per-slice nodes for every id in ``slice_ids``
@@ -301,6 +366,7 @@ class ContractionRunner:
         any_dep = any(n.depends for n in low.nodes)
         if any_dep:
             self.out.zero_()
+        self._measure_leaves()
         launches += self._run_hoisted()
         if any_dep and slice_ids:
             contiguous = slice_ids == list(range(slice_ids[0], slice_ids[0] + len(slice_ids)))

@@ -127,8 +127,9 @@ elif sys.argv[1] == "check":
     # one tile per pair; several n tiles; deep k (32 chunks); split-K; many tiles per CTA pair (the stagger
     # crosses tile boundaries); k of one chunk only
     for (m, n, k), seed in (((10, 7, 7), 1), ((11, 9, 5), 2), ((10, 7, 9), 3), ((10, 7, 4), 4), ((17, 7, 6), 5),
-                            ((15, 8, 5), 6), ((13, 7, 3), 7), ((18, 8, 7), 8)):
+                            ((15, 8, 5), 6), ((13, 7, 3), 7), ((18, 8, 7), 8), ((12, 6, 6), 9), ((18, 6, 5), 10),
+                            ((12, 5, 7), 11), ((19, 5, 4), 12), ((13, 6, 3), 13), ((13, 5, 3), 14)):
         check(m, n, k, seed)
 else:
-    for m, n, k in ((21, 10, 7), (24, 7, 7), (22, 7, 7), (19, 8, 8), (20, 7, 10), (23, 7, 5)):
+    for m, n, k in ((21, 10, 7), (24, 7, 7), (23, 7, 8), (25, 6, 6), (24, 6, 6), (23, 5, 7), (20, 7, 10)):
         time_case(m, n, k)

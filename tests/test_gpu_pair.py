@@ -168,8 +168,8 @@ def test_tensor_core_variants_agree_with_einsum(shape):
         want_pair = opts.get("tc_pair", 5)
         paired = (want_pair and n >= want_pair and opts.get("tc_persistent", 1) and opts.get("tc_prepack", 1)
                   and opts.get("tc_accum_split", 1))
-        # 128-column tiles take the staggered pair kernel (two 64-column halves, plan value 2)
-        staggered = paired and n >= 7 and opts.get("tc_stagger", 1) and opts.get("tc_terms", 3) == 3
+        # paired tiles take the staggered kernel (two half-width halves per tile, plan value 2)
+        staggered = paired and opts.get("tc_stagger", 1) and opts.get("tc_terms", 3) == 3
         assert plan.tc_pair == (2 if staggered else 1 if paired else 0), (shape, opts)
         # ... and, with 16 contracted values per stage, the scaled 3xFP16 split (plain qtn_pair_run then measures
         # the operands' magnitudes itself)

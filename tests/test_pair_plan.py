@@ -164,8 +164,8 @@ def test_cta_pair_plans_are_well_formed(shape):
         lib.set_option("tc_pair", 5)
     assert plan.kernel == lib.KERNEL_TC and single.kernel == lib.KERNEL_TC and single.tc_pair == 0
     eligible = plan.tc_prepack == 1 and plan.tc_pad == 1 and 5 <= plan.tnb <= 7
-    # 128-column tiles take the staggered variant (plan value 2): two 64-column halves per tile
-    assert plan.tc_pair == ((2 if plan.tnb == 7 else 1) if eligible else 0)
+    # paired tiles take the staggered variant (plan value 2): two half-width halves per tile
+    assert plan.tc_pair == (2 if eligible else 0)
     assert (m >= 10 and n >= 5) == bool(plan.tc_pair)
     if plan.tc_pair:
         assert plan.grid % 2 == 0 and plan.tc_reserved % 2 == 0 and plan.tc_reserved > 0
@@ -182,7 +182,7 @@ def test_cta_pair_plans_are_well_formed(shape):
         assert plan.tc_kind == (1 if plan.tkb == 4 else 0)      # scaled 3xFP16 split: 2-byte operand planes
         eb = 2 if plan.tc_kind else 4
         assert plan.tc_plane_a == 128 * kt * eb
-        rank_b = 384 * kt * eb         # per CTA: 2 halves x {hi, lo} x [Br | Bi | -Br] x 32 rows x kt values
+        rank_b = 3 * (1 << plan.tnb) * kt * eb   # per CTA: 2 halves x {hi, lo} x [Br | Bi | -Br] x TN/4 rows x kt values
         stage = 4 * plan.tc_plane_a + rank_b
         raw_ring = 6 * 128 * kt * 8    # cp.async gathers of A in flight: 6 chunks of 8-byte elements
         assert plan.smem_bytes == plan.tc_stages * stage + raw_ring + 512 <= 227 * 1024
