@@ -346,6 +346,15 @@ int qtn_svd_emit(int dtype, const void *w, int32_t m, const int32_t *perm, const
 int qtn_pauli_expectation(int dtype, int nqubits, const void *state, int nterms, const uint64_t *xmask,
                           const uint64_t *zmask, const int32_t *ny, void *out, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Measurement helper (bench.py): achieved rate of the FP32 (is_double = 0) or FP64 FMA pipe with 16
+ * independent FMA chains per thread, 2 flops per FMA, in TFLOP/s -- the roofline denominator of the kernels
+ * that run on those pipes (Jacobi rotations, FFMA/DFMA contractions).  `scratch`: >= 148*8*256*8 device
+ * bytes.  Synchronises `stream`.
+ * ------------------------------------------------------------------------ */
+int qtn_microbench_fma(int is_double, int iters, void *scratch, int64_t scratch_bytes, double *tflops,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

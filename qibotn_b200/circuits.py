@@ -103,6 +103,17 @@ def tfim_trotter(nqubits, steps, j_dt=0.4, h_dt=0.6):
     return c
 
 
+# BASELINE config 3 (64-site TFIM Trotter brickwork, 20 steps, bond <= 256).  Angles chosen by a scan on
+# the engine (scripts/c3_scan.py, profiles/r02_c3_angle_scan.jsonl): every bulk bond reaches 256 AND the
+# truncated state keeps <psi|psi> = 0.914 (8.6 % discarded weight) -- the round-1 angles (0.4, 0.6) left a
+# state of norm 9e-6, i.e. nothing physical to check at full size.
+C3_ANGLES = {"j_dt": 0.2, "h_dt": 0.3}
+
+
+def tfim_c3(nqubits=64, steps=20):
+    return tfim_trotter(nqubits, steps, **C3_ANGLES)
+
+
 # --------------------------------------------------------------- Sycamore-like
 def sycamore_qubits(drop=((3, 2),)):
     """The 54-site diamond of Google's Sycamore as (row, col) grid points, minus

@@ -99,3 +99,55 @@ extern "C" int qtn_device_info(int device, int *sm_count, int *max_smem_optin, i
   if (cc_minor) *cc_minor = prop.minor;
   return QTN_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Measured FMA-pipe peak (bench.py's roofline denominator for the kernels that run on the FP32 / FP64
+// FMA pipes: MEASURED_PEAKS.json only carries HBM and bf16 tensor numbers).  Every thread runs 16
+// independent FMA chains for `iters` rounds; returns 2 * FMAs / elapsed in TFLOP/s.
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) fma_peak_kernel(R *out, int iters, R b, R c) {
+  R a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = (R)(threadIdx.x + j) * (R)1e-3;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = fma(a[j], b, c);
+  }
+  R s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += a[j];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int qtn_microbench_fma(int is_double, int iters, void *scratch, int64_t scratch_bytes, double *tflops,
+                                  void *stream) {
+  if (!scratch || !tflops || iters < 1) return qtn_fail(QTN_ERR_ARG, "qtn_microbench_fma: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  QTN_CUDA_CHECK(cudaGetDevice(&dev));
+  QTN_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, threads = 256;
+  if (scratch_bytes < (int64_t)blocks * threads * 8)
+    return qtn_fail(QTN_ERR_WORKSPACE, "qtn_microbench_fma: scratch too small (148 * 8 * 256 * 8 bytes)");
+  cudaEvent_t e0, e1;
+  QTN_CUDA_CHECK(cudaEventCreate(&e0));
+  QTN_CUDA_CHECK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    QTN_CUDA_CHECK(cudaEventRecord(e0, st));
+    if (is_double) fma_peak_kernel<double><<<blocks, threads, 0, st>>>((double *)scratch, iters, 0.999999, 1e-7);
+    else fma_peak_kernel<float><<<blocks, threads, 0, st>>>((float *)scratch, iters, 0.999999f, 1e-7f);
+    QTN_CUDA_CHECK(cudaEventRecord(e1, st));
+    QTN_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    QTN_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  QTN_LAUNCH_CHECK();
+  *tflops = 2.0 * 16.0 * (double)iters * (double)blocks * threads / ((double)best * 1e-3) / 1e12;
+  return QTN_OK;
+}

@@ -108,13 +108,14 @@ def _store_file(net, width, min_slices):
 def _stored_plan(net, width, min_slices):
     import os
 
-    if not PLAN_STORE:
-        return None
-    path = _store_file(net, width, min_slices)
-    if not os.path.exists(path):
-        return None
-    with open(path) as f:
-        return PathInfo.from_json(f.read())
+    if PLAN_STORE:
+        path = _store_file(net, width, min_slices)
+        if os.path.exists(path):
+            with open(path) as f:
+                return PathInfo.from_json(f.read())
+    # plans committed under plans/ for named workloads, matched by network structure
+    from .plans import find_by_structure
+    return find_by_structure(net.modes, net.out, max_log2_width=width, min_slices=min_slices)
 
 
 def _store_plan(net, width, min_slices, info):
@@ -178,7 +179,9 @@ def contract(net: TensorNetwork, dtype="complex64", samples=32, seed=0, min_slic
     info, lowered = plan(net, dtype, samples, seed, min_slices, target_log2_width, info)
     run = runner_for(lowered, use_graph)
     LAST.h2d_bytes = run.upload(net.tensors)
-    out = run.run(slice_ids)
+    # the runner owns ONE output buffer, reused by every later run of the same structure (parametrised
+    # circuits): the caller gets its own copy, as the reference's `contract` returns a fresh array
+    out = run.run(slice_ids).clone()
     ns = info.num_slices if slice_ids is None else len(list(slice_ids))
     LAST.launches = run.launches
     LAST.flops = lowered.flops_hoisted + ns * lowered.flops_per_slice

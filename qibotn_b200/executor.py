@@ -310,9 +310,11 @@ class ContractionRunner:
             n += 2 if (node.plan.split_bits or node.plan.kernel == lib.KERNEL_REDUCE) else 1
         return n
 
-    def time_nodes(self, slice_id=0, reps=3):
-        """Per-node device times (ms, CUDA events on the launch stream) of one slice, nodes run in order.
-        Measurement helper for bench.py / scripts: returns [(node, ms)] for the per-slice nodes."""
+    def time_nodes(self, slice_id=0, reps=3, flush=None):
+        """Per-node device times (ms, CUDA events on the launch stream) of one slice, nodes run in tree order so
+        that every node sees its real inputs; each node is launched ``reps`` times in place and the mean of
+        all but the first launch is reported (``flush``: a device buffer larger than L2, zeroed before every
+        launch).  Measurement helper for bench.py / scripts: returns [(node, ms)] for the per-slice nodes."""
         torch = self.torch
         st = torch.cuda.current_stream().cuda_stream
         slot = self._amax_slot
@@ -325,8 +327,10 @@ class ContractionRunner:
         for node in self.low.nodes:
             if not node.depends:
                 continue
-            best = None
+            ts = []
             for _ in range(reps):
+                if flush is not None:
+                    flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 lib.check(self.lib.qtn_pair_run_scaled(C.byref(node.plan), self._ptr(node.a), self._ptr(node.b),
@@ -335,9 +339,8 @@ class ContractionRunner:
                                                        slot.get(node.c), st))
                 e1.record()
                 torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1)
-                best = ms if best is None else min(best, ms)
-            out.append((node, best))
+                ts.append(e0.elapsed_time(e1))
+            out.append((node, sum(ts[1:]) / (len(ts) - 1) if len(ts) > 1 else ts[0]))
         return out
 
     def _measure_leaves(self):

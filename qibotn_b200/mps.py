@@ -48,16 +48,31 @@ def _torch():
 
 
 def parse_algorithm(algorithm):
-    """``gate_algo`` dict -> (SvdTrunc, partition code).  Keys as cuQuantum's
-    ``ContractDecomposeAlgorithm`` (``qr_method``, ``svd_method{...}``).  ``svd_method: False``
-    (pure QR) is served by the same Jacobi kernel as an untruncated orthogonal factorisation
-    theta = Q R' with Q^H Q = 1 (R' is not triangular: the MPS gauge differs, the state does not)."""
+    """``gate_algo`` dict -> (SvdTrunc, partition code, qr_only, qr_assist).  Keys and defaults as cuQuantum's
+    ``ContractDecomposeAlgorithm`` (the reference forwards the dict verbatim, mps_utils.py:32-37,78-84):
+
+    * ``svd_method`` missing or ``False``: **QR split** (cuQuantum's default, ``qr_method={}``): exact,
+      untruncated; the left factor is an isometry and the right one upper triangular (blocks with more
+      columns than rows are split as L.Q instead: lower-triangular left factor, isometric right factor);
+    * ``svd_method`` a dict: truncated SVD with cuTensorNet ``SVDMethod`` semantics.  ``partition`` must say
+      where the singular values go ("U", "V" or "UV"): with ``None`` cuTensorNet returns S separately and the
+      reference's ``a, _, b = contract_decompose(...)`` drops it -- that is refused here instead of silently
+      corrupting the state;
+    * ``qr_method`` (``{}`` or a dict) together with ``svd_method``: QR-assisted SVD -- every block is reduced
+      to its triangular factor (``qtn_svd_lq``) before the Jacobi sweeps; ``False``: the engine decides
+      (blocks of >= LQ_MIN_ROWS rows are reduced).  Same factors either way."""
     algorithm = algorithm or {}
-    svd = algorithm.get("svd_method", {})
+    unknown = set(algorithm) - {"qr_method", "svd_method"}
+    if unknown:
+        raise ValueError(f"unknown gate_algo key(s): {sorted(unknown)}")
+    svd = algorithm.get("svd_method", False)
+    qr = algorithm.get("qr_method", {})
     tr = lib.SvdTrunc(0.0, 0.0, 0.0, 0, 0)
-    if svd is False:
-        return tr, _PARTITION["V"], True
-    svd = svd or {}
+    if svd is False or svd is None:
+        if qr is False:
+            raise ValueError("gate_algo disables both qr_method and svd_method")
+        return tr, _PARTITION["V"], True, False
+    svd = {} if svd is True else dict(svd)
     unknown = set(svd) - {"abs_cutoff", "rel_cutoff", "discarded_weight_cutoff", "max_extent", "partition",
                           "normalization", "algorithm", "gesvdj_tol", "gesvdj_max_sweeps",
                           "gesvdr_oversampling", "gesvdr_niters"}
@@ -72,7 +87,10 @@ def parse_algorithm(algorithm):
         part = _PARTITION[svd.get("partition")]
     except KeyError as exc:
         raise ValueError(f"unknown svd_method value {exc}") from None
-    return tr, part, False
+    if part == 0:
+        raise ValueError("svd_method needs partition 'U', 'V' or 'UV': with partition=None the singular values are "
+                         "returned separately and the MPS update (mps_utils.py:78-84) would drop them")
+    return tr, part, False, qr is not False
 
 
 # Two-site blocks with at least this many rows are LQ-preconditioned before the Jacobi sweeps
@@ -95,7 +113,8 @@ class MPSEngine:
         self.code = lib.dtype_code(self.dtype)
         self.cdtype = torch.complex64 if self.dtype == "complex64" else torch.complex128
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.trunc, self.partition, self.qr_only = parse_algorithm(algorithm)
+        self.trunc, self.partition, self.qr_only, self.qr_assist = parse_algorithm(algorithm)
+        self._svd_events = []          # (start, stop) CUDA events of every decomposition batch
         self.tol = float(tol) if tol else 0.0
         self.max_sweeps = int(max_sweeps)
         zero = torch.zeros(1, 2, 1, dtype=self.cdtype, device=self.device)
@@ -221,6 +240,8 @@ class MPSEngine:
             transposed = p > q
             w = self._transpose(theta, p, q) if transposed else theta.clone()
             work.append((i, l, r, p, q, theta, w, transposed))
+        if self.qr_only:
+            return self._split_qr(work)
         nb = len(work)
         items = (lib.SvdItem * nb)()
         ld = 1
@@ -236,9 +257,12 @@ class MPSEngine:
         scales = (C.c_double * nb)()
         sweeps = C.c_int32(0)
         import time as _time
-        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        if PROFILE_PHASES:
+            torch.cuda.synchronize()
         t_svd = _time.perf_counter()
-        precond = LQ_MIN_ROWS > 0 and ld >= LQ_MIN_ROWS
+        precond = self.qr_assist or (LQ_MIN_ROWS > 0 and ld >= LQ_MIN_ROWS)
         xs = []
         if precond:
             # W = L Q (rows, modified Gram-Schmidt), Jacobi on X = L^H: rows converge to sigma_i z_i^H,
@@ -260,7 +284,12 @@ class MPSEngine:
         lib.check(self.lib.qtn_svd_rows(self.code, nb, items, self.tol, self.max_sweeps, C.byref(self.trunc),
                                         sigma.data_ptr(), perm.data_ptr(), ld, ranks, scales,
                                         C.byref(sweeps), ws.data_ptr(), ws_bytes, self._stream()))
-        self.stats["svd_seconds"] = self.stats.get("svd_seconds", 0.0) + _time.perf_counter() - t_svd
+        ev1.record()
+        self._svd_events.append((ev0, ev1))
+        if int(sweeps.value) >= self.max_sweeps:
+            import warnings
+            warnings.warn(f"qtn_svd_rows stopped at max_sweeps={self.max_sweeps} with rows still rotating: "
+                          "the factors of this layer may not be orthogonal to working precision", RuntimeWarning)
         self.stats["svd_batches"] += 1
         # credited work, SURVEY 8(d): thin complex SVD with vectors of a p x q block (p >= q) = 4 (14 p q^2 + 8 q^3)
         self.stats["svd_credited_flops"] = self.stats.get("svd_credited_flops", 0.0) + sum(
@@ -312,6 +341,51 @@ class MPSEngine:
             self.sites[i + 1] = right.view(kk, 2, r)
             self.stats["max_bond"] = max(self.stats["max_bond"], kk)
         self._gemm_batched(post)
+
+    def _split_qr(self, work):
+        """Exact QR split of every block of a layer (``svd_method: False``): modified Gram-Schmidt through
+        ``qtn_svd_lq``.  theta (p x q) with p >= q: theta^T = L Q'  =>  theta = Q'^T L^T (isometry times upper
+        triangular); p < q: theta = L Q'' (lower triangular times isometric rows)."""
+        torch = self.torch
+        nb = len(work)
+        items, xitems = (lib.SvdItem * nb)(), (lib.SvdItem * nb)()
+        xs = []
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for k, (_, _, _, p, q, _, w, transposed) in enumerate(work):
+            # work[k].w already is theta^T (q x p) when p > q, theta (p x q) otherwise; square blocks: QR
+            if p == q:
+                w = self._transpose(w, p, q)
+                work[k] = work[k][:6] + (w, True)
+            n_k, m_k = (q, p) if p >= q else (p, q)
+            x = torch.empty(n_k * n_k, dtype=self.cdtype, device=self.device)
+            xs.append(x)
+            items[k].w, items[k].n, items[k].m = w.data_ptr(), n_k, m_k
+            xitems[k].w, xitems[k].n, xitems[k].m = x.data_ptr(), n_k, n_k
+        lq_bytes = int(self.lib.qtn_svd_lq_workspace_bytes(nb))
+        lq_ws = torch.empty(lq_bytes, dtype=torch.uint8, device=self.device)
+        lib.check(self.lib.qtn_svd_lq(self.code, nb, items, xitems, lq_ws.data_ptr(), lq_bytes, self._stream()))
+        self.stats["launches"] += 1
+        for k, (i, l, r, p, q, _, w, _) in enumerate(work):
+            if p >= q:
+                left = self._transpose(w, q, p)                           # Q'^T: p x q, orthonormal columns
+                right = xs[k].view(q, q).conj().resolve_conj().contiguous()     # L^T = conj(L^H): upper triangular
+                kk = q
+            else:
+                left = xs[k].view(p, p).conj().t().contiguous()           # L = (L^H)^H: lower triangular
+                right = w                                                 # Q'': p x q, orthonormal rows
+                kk = p
+            self.sites[i] = left.reshape(l, 2, kk)
+            self.sites[i + 1] = right.reshape(kk, 2, r)
+            self.stats["max_bond"] = max(self.stats["max_bond"], kk)
+        ev1.record()
+        self._svd_events.append((ev0, ev1))
+        self.stats["svd_batches"] += 1
+
+    def decomposition_seconds(self):
+        """Device time spent in the decompositions so far (CUDA events; synchronises)."""
+        self.torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in self._svd_events) * 1e-3
 
     def bond_dimensions(self):
         self.flush()
@@ -366,6 +440,7 @@ class QiboCircuitToMPS:
         self.engine.flush()
         self.mps_tensors = self.engine.sites
         self.stats = self.engine.stats
+        self.stats["svd_seconds"] = self.engine.decomposition_seconds()
 
 
 class MPSContractionHelper:

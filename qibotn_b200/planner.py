@@ -667,6 +667,7 @@ def find_path(modes, out, samples=32, seed=0, target_log2_width=30, min_slices=1
 def compute_slices(num_slices, rank, size):
     """Contiguous slice-id range of ``rank``; the remainder goes to the low ranks.
     Same partition as ``compute_slices`` in ``/root/reference/src/qibotn/eval.py:197-205``."""
+    num_slices = int(getattr(num_slices, "num_slices", num_slices))     # the reference passes its `info` object
     chunk, extra = divmod(num_slices, size)
     begin = rank * chunk + min(rank, extra)
     end = num_slices if rank == size - 1 else (rank + 1) * chunk + min(rank + 1, extra)

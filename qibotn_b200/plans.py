@@ -42,3 +42,35 @@ def load_plan(name, modes, out):
     if info.extra.get("structure") != structure_hash(modes, out):
         return None
     return info
+
+
+_BY_STRUCTURE = None
+
+
+def find_by_structure(modes, out, max_log2_width=None, min_slices=1):
+    """A committed plan (``plans/*.json``) made for exactly this network structure, or None: lets the public
+    entry points (``eval.amplitude_tn`` ...) pick up the plans that ``scripts/search_plan.py`` /
+    ``scripts/anneal_plan.py`` produced offline instead of searching for minutes (the cheapest match wins)."""
+    global _BY_STRUCTURE
+    if _BY_STRUCTURE is None:
+        _BY_STRUCTURE = {}
+        if os.path.isdir(PLAN_DIR):
+            for fn in sorted(os.listdir(PLAN_DIR)):
+                if not fn.endswith(".json"):
+                    continue
+                try:
+                    info = PathInfo.from_json(open(os.path.join(PLAN_DIR, fn)).read())
+                except (OSError, ValueError, KeyError, TypeError):
+                    continue
+                key = info.extra.get("structure")
+                if key:
+                    _BY_STRUCTURE.setdefault(key, []).append(info)
+    best = None
+    for info in _BY_STRUCTURE.get(structure_hash(modes, out), []):
+        if max_log2_width is not None and info.log2_width > max_log2_width:
+            continue
+        if info.num_slices < min_slices:
+            continue
+        if best is None or info.flops < best.flops:
+            best = info
+    return best

@@ -32,6 +32,39 @@ _OPS = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, as
 _FUNCS = {"sin": math.sin, "cos": math.cos, "tan": math.tan, "exp": math.exp, "ln": math.log, "sqrt": math.sqrt}
 
 
+def _split_statement(st):
+    """``name(params) args`` -> (name, params or None, args); the parameter list is taken by matching
+    balanced parentheses, so that ``rz(cos(pi/4)) q[0]`` keeps its inner call."""
+    m = re.match(r"\s*(\w+)\s*", st)
+    if not m:
+        raise ValueError(f"cannot parse statement {st!r}")
+    name, rest = m.group(1).lower(), st[m.end():]
+    if not rest.startswith("("):
+        return name, None, rest.strip()
+    depth = 0
+    for pos, ch in enumerate(rest):
+        depth += ch == "("
+        depth -= ch == ")"
+        if depth == 0:
+            return name, rest[1:pos], rest[pos + 1:].strip()
+    raise ValueError(f"unbalanced parentheses in {st!r}")
+
+
+def _split_top_level(params):
+    """Split a parameter list at the commas outside any parentheses."""
+    out, depth, cur = [], 0, []
+    for ch in params:
+        depth += ch == "("
+        depth -= ch == ")"
+        if ch == "," and depth == 0:
+            out.append("".join(cur))
+            cur = []
+        else:
+            cur.append(ch)
+    out.append("".join(cur))
+    return out
+
+
 def _eval(expr: str) -> float:
     """Arithmetic in gate parameters: numbers, pi, + - * / ^ and the QASM math functions."""
     def ev(node):
@@ -48,7 +81,11 @@ def _eval(expr: str) -> float:
         if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in _FUNCS:
             return _FUNCS[node.func.id](*[ev(a) for a in node.args])
         raise ValueError(f"unsupported expression in QASM parameter: {expr!r}")
-    return ev(ast.parse(expr.replace("^", "**"), mode="eval"))
+    try:
+        tree = ast.parse(expr.strip().replace("^", "**"), mode="eval")
+    except SyntaxError:
+        raise ValueError(f"cannot parse QASM parameter {expr!r}") from None
+    return ev(tree)
 
 
 def _u3(theta, phi, lam):
@@ -94,15 +131,14 @@ def from_openqasm2_str(text: str):
     two = {"cx": gates.CNOT, "cz": gates.CZ, "swap": gates.SWAP}
     rot2 = {"crz": gates.CRZ, "cu1": gates.CU1, "cp": gates.CU1, "rzz": gates.RZZ, "rxx": gates.RXX}
     for st in ops:
-        m = re.fullmatch(r"(\w+)\s*(?:\(([^)]*)\))?\s*(.*)", st, flags=re.S)
-        name, params, args = m.group(1).lower(), m.group(2), m.group(3)
+        name, params, args = _split_statement(st)
         if name == "barrier":
             continue
         if name == "measure":
             src = args.split("->")[0].strip()
             circ.add(gates.M(*qubits_of(src)))
             continue
-        par = [_eval(p) for p in params.split(",")] if params else []
+        par = [_eval(p) for p in _split_top_level(params)] if params else []
         lists = [qubits_of(a.strip()) for a in args.split(",")]
         width = max(len(q) for q in lists)
         for i in range(width):                            # register broadcast, as qelib semantics

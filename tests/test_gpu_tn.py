@@ -14,7 +14,18 @@ from qibotn_b200.network import QiboCircuitToEinsum
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
+# BASELINE.json north_star: results within 1e-5 (complex64) / 1e-10 (complex128) RELATIVE of the CPU path.
+# The norm each comparison uses, with no extra multipliers:
+#   state vectors      ||got - want||_2 / ||want||_2                      (rel2)
+#   single amplitudes  |got - want| / |want|
+#   expectation values |got - want| / sum_i |c_i|  -- the operator-norm bound of H = sum_i c_i P_i, which is
+#                      what the rounding of a sandwich <psi|H|psi> scales with (<H> itself may be ~0)
 TOL = {"complex64": 1e-5, "complex128": 1e-10}
+
+
+def rel2(got, want):
+    got, want = np.asarray(got).reshape(-1), np.asarray(want).reshape(-1)
+    return float(np.linalg.norm(got - want) / np.linalg.norm(want))
 
 
 def _backend(dtype):
@@ -44,7 +55,7 @@ def test_random_circuit_state_vs_oracle(nqubits, layers, dtype):
     circ = circuits.ry_rz_cnot_ring(nqubits, layers, seed=42)
     want = osv.simulate(circ)
     got = ev.dense_vector_tn(circ, dtype).flatten().get()
-    assert np.abs(got - want).max() < TOL[dtype] * max(1.0, np.abs(want).max()) * 4
+    assert rel2(got, want) <= TOL[dtype]
 
 
 @pytest.mark.parametrize("dtype", ["complex128", "complex64"])
@@ -64,8 +75,11 @@ def test_expectation_three_runcard_forms(nqubits, dtype):
             b.configure_tn_simulation({"MPI_enabled": False, "MPS_enabled": False,
                                        "NCCL_enabled": False, "expectation_enabled": value})
             res = b.execute_circuit(circuit=circ)
-            assert math.isclose(want, res.real.get().item(), abs_tol=1e-7 if dtype == "complex128" else 2e-5)
-            assert math.isclose(want, float(res[0]), abs_tol=1e-7 if dtype == "complex128" else 2e-5)
+            # the reference's own bound (abs 1e-7, tests/test_cuquantum_cutensor_backend.py:10) in double;
+            # 1e-5 of the operator-norm bound n * 0.5 in single
+            bound = 1e-7 if dtype == "complex128" else TOL[dtype] * 0.5 * nqubits
+            assert math.isclose(want, res.real.get().item(), abs_tol=bound)
+            assert math.isclose(want, float(res[0]), abs_tol=bound)
 
 
 def test_pauli_string_pattern_runcard():
@@ -93,18 +107,19 @@ def test_amplitude_sliced_equals_unsliced_and_oracle(dtype):
         out = engine.contract(net, dtype, samples=4, min_slices=min_slices, use_graph=graph)
         vals.append(complex(out.cpu().numpy().reshape(-1)[0]))
     for v in vals:
-        assert abs(v - want) < TOL[dtype] * max(abs(want), 1e-3) * 10
+        assert abs(v - want) <= TOL[dtype] * abs(want), (v, want)
     # partial slice ranges add up (what each rank of a multi-GPU run computes)
     engine.clear_caches()
     info, low = engine.plan(net, dtype, samples=4, min_slices=8)
     parts = [engine.contract(net, dtype, info=info, slice_ids=ev.compute_slices(info.num_slices, r, 3))
              .cpu().numpy().reshape(-1)[0] for r in range(3)]
-    assert abs(sum(parts) - want) < TOL[dtype] * max(abs(want), 1e-3) * 10
+    assert abs(sum(parts) - want) <= TOL[dtype] * abs(want)
     # and each partial equals the oracle's sum over the same slice ids on the same path
     r1 = ev.compute_slices(info.num_slices, 1, 3)
     o = ocontract.contract_sliced(net.interleaved(), info.path, info.sliced_labels, r1,
                                   dtype=np.complex128)
-    assert abs(parts[1] - o) < TOL[dtype] * max(abs(o), 1e-3) * 10
+    # a partial sum is not an amplitude: its error is relative to the terms it adds up, bounded by |want| + |o|
+    assert abs(parts[1] - o) <= TOL[dtype] * (abs(o) + abs(want))
 
 
 def test_dense_output_drops_inactive_qubits_and_initial_state_rejected():
@@ -131,12 +146,12 @@ def test_against_committed_golden_vectors(dtype):
     for n, layers in ((5, 2), (8, 3), (12, 3)):
         circ = circuits.ry_rz_cnot_ring(n, layers, seed=42)
         got = ev.dense_vector_tn(circ, dtype).flatten().get()
-        assert np.abs(got - GOLD[f"ring_state_{n}_{layers}"]).max() < TOL[dtype] * 4
+        assert rel2(got, GOLD[f"ring_state_{n}_{layers}"]) <= TOL[dtype]
         exp = float(ev.expectation_tn(circ, dtype, None)[0])
-        assert abs(exp - float(GOLD[f"ring_xz_{n}_{layers}"])) < TOL[dtype] * 10
+        assert abs(exp - float(GOLD[f"ring_xz_{n}_{layers}"])) <= TOL[dtype] * 0.5 * n
     circ = circuits.brickwork(12, 6, seed=0)
     z = float(ev.expectation_tn(circ, dtype, {"pauli_string_pattern": "Z"})[0])
-    assert abs(z - float(GOLD["brick12x6_zall"])) < TOL[dtype] * 10
+    assert abs(z - float(GOLD["brick12x6_zall"])) <= TOL[dtype]
     # 53-qubit Sycamore-like circuit, 4 cycles: single amplitudes (the C4 code path at reduced depth)
     circ = circuits.sycamore_rqc(4, seed=0)
     for bits in ("0" * 53, "01" * 26 + "1"):
@@ -197,7 +212,7 @@ def test_fused_pauli_kernel_route_equals_network_route(dtype):
         finally:
             ev.EXPECTATION_ROUTE = "auto"
     for route, v in vals.items():
-        assert abs(v - want) < TOL[dtype] * 20, (route, v, want)
+        assert abs(v - want) <= TOL[dtype] * sum(abs(c) for c, _ in terms), (route, v, want)
     # inactive qubits stay |0>: Z acts as +1, X kills the term
     from qibotn_b200.qibo_compat import Circuit, H, CNOT
     c = Circuit(5)
@@ -211,7 +226,7 @@ def test_fused_pauli_kernel_route_equals_network_route(dtype):
             v = complex(ev.expectation_tn(c, dtype, obs).get()[0])
         finally:
             ev.EXPECTATION_ROUTE = "auto"
-        assert abs(v - 1.5) < TOL[dtype] * 10, (route, v)
+        assert abs(v - 1.5) <= TOL[dtype] * 6.5, (route, v)
 
 
 def test_c4_full_amplitude_within_tolerance_of_complex128():
@@ -284,7 +299,7 @@ def test_edge_cases(dtype):
     c.add(H(0)); c.add(CNOT(0, 3))
     got = b.execute_circuit(c).statevector.flatten().get()                          # qubits 0, 2, 3 active
     want = osv.simulate(c).reshape(2, 2, 2, 2)[:, 0, :, :].reshape(-1)
-    assert np.abs(got - want).max() < TOL[dtype] * 4
+    assert rel2(got, want) <= TOL[dtype]
     # expectation of Z0 on an empty circuit is <0|Z|0> = 1, X0 gives 0
     for letter, want in (("Z", 1.0), ("X", 0.0)):
         b.configure_tn_simulation({"MPI_enabled": False, "MPS_enabled": False, "NCCL_enabled": False,
@@ -296,7 +311,7 @@ def test_edge_cases(dtype):
     got = b.execute_circuit(Circuit(3)).statevector.flatten().get()
     assert np.allclose(got, np.eye(8)[0])
     got = b.execute_circuit(c).statevector.flatten().get()
-    assert np.abs(got - osv.simulate(c)).max() < TOL[dtype] * 10
+    assert rel2(got, osv.simulate(c)) <= TOL[dtype]
 
 
 @pytest.mark.parametrize("ansatz", ["mps", None])
@@ -343,7 +358,7 @@ def test_light_cone_cancellation_changes_no_value(dtype):
         b = complex(engine.contract(cone, dtype, samples=4).cpu().numpy().reshape(-1)[0])
         coeff = np.prod([c for _, _, c in term])
         want = coeff * osv.pauli_expectation(psi, [(1.0, [(l, q) for q, l, _ in term])], n)
-        assert abs(a - want) < TOL[dtype] * 10 and abs(b - want) < TOL[dtype] * 10
+        assert abs(a - want) <= TOL[dtype] * abs(coeff) and abs(b - want) <= TOL[dtype] * abs(coeff)
 
 
 @pytest.mark.parametrize("dtype", ["complex128", "complex64"])
@@ -366,4 +381,32 @@ def test_qaoa_maxcut_expectation(dtype):
             got = float(ev.expectation_tn(circ, dtype, circuits.zz_terms(edges)).real.get().reshape(-1)[0])
         finally:
             ev.EXPECTATION_ROUTE, ev.PLAN_SAMPLES, ev.HYPER_DIAGONAL = "auto", samples, hyper_default
-        assert abs(got - want) < TOL[dtype] * 50, (route, hyper, got, want)
+        assert abs(got - want) <= TOL[dtype] * len(edges), (route, hyper, got, want)     # sum_i |c_i| = #edges
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_results_survive_a_second_run_of_the_same_structure(dtype):
+    """A parametrised circuit run twice reuses the plan, the runner and its output buffer: the first result
+    must be the caller's own copy (the reference's `contract` returns a fresh array every time)."""
+    from qibotn_b200.qibo_compat import Circuit, H, CNOT, RY
+
+    def circuit(theta):
+        c = Circuit(6)
+        for q in range(6):
+            c.add(H(q))
+        for q in range(5):
+            c.add(CNOT(q, q + 1))
+            c.add(RY(q + 1, theta=theta * (q + 1)))
+        return c
+
+    first = ev.dense_vector_tn(circuit(0.3), dtype)
+    keep = first.flatten().get().copy()
+    second = ev.dense_vector_tn(circuit(1.1), dtype)
+    assert rel2(first.flatten().get(), keep) == 0.0
+    assert rel2(first.flatten().get(), osv.simulate(circuit(0.3))) <= TOL[dtype]
+    assert rel2(second.flatten().get(), osv.simulate(circuit(1.1))) <= TOL[dtype]
+    b = _backend(dtype)
+    r1 = b.execute_circuit(circuit(0.3))
+    r2 = b.execute_circuit(circuit(1.1))
+    assert rel2(r1.statevector.flatten().get(), keep) <= TOL[dtype]
+    assert rel2(r2.statevector.flatten().get(), osv.simulate(circuit(1.1))) <= TOL[dtype]

@@ -229,3 +229,25 @@ def test_plan_store_round_trip(tmp_path, monkeypatch):
                                                   if stored.sliced_labels else 0)
             assert width <= 31 and abs(cost - stored.opt_cost) <= 1e-6 * stored.opt_cost
 
+
+
+def test_gate_algo_rules():
+    """``gate_algo`` follows cuQuantum's ContractDecomposeAlgorithm: QR split by default, SVD needs a
+    partition (the reference's ``a, _, b = contract_decompose(...)`` would drop separate singular values)."""
+    from qibotn_b200 import mps
+
+    for algo in (None, {}, {"qr_method": {}}, {"qr_method": {}, "svd_method": False}):
+        tr, part, qr_only, assist = mps.parse_algorithm(algo)
+        assert qr_only and not assist and tr.max_extent == 0
+    tr, part, qr_only, assist = mps.parse_algorithm({"qr_method": False,
+                                                     "svd_method": {"partition": "UV", "abs_cutoff": 1e-12}})
+    assert (part, qr_only, assist, tr.abs_cutoff) == (3, False, False, 1e-12)
+    assert mps.parse_algorithm({"svd_method": {"partition": "U", "max_extent": 8}})[3] is True     # qr_method default {}
+    with pytest.raises(ValueError):
+        mps.parse_algorithm({"qr_method": False, "svd_method": False})
+    with pytest.raises(ValueError):
+        mps.parse_algorithm({"svd_method": {"abs_cutoff": 1e-12}})            # partition None
+    with pytest.raises(ValueError):
+        mps.parse_algorithm({"svd_method": {"partition": "UV", "cutoff": 1}})
+    with pytest.raises(ValueError):
+        mps.parse_algorithm({"svd": {}})

@@ -60,3 +60,20 @@ def test_unsupported_statements_raise():
         from_openqasm2_str("OPENQASM 2.0; qreg q[3]; ccx q[0],q[1],q[2];")
     with pytest.raises(ValueError):
         from_openqasm2_str("OPENQASM 2.0; h q[0];")
+
+
+def test_function_calls_in_parameters():
+    """Parameters are cut at balanced parentheses: ``rz(cos(pi/4))`` keeps its inner call, a list may mix
+    calls and commas, and a malformed expression is a ValueError."""
+    import math
+
+    from qibotn_b200 import qasm
+
+    src = 'OPENQASM 2.0;\ninclude "qelib1.inc";\nqreg q[2];\nrz(cos(pi/4)) q[0];\nu3(sin(pi/2), ln(exp(1)), sqrt(4)/2) q[1];\n'
+    circ = qasm.from_openqasm2_str(src)
+    g0, g1 = circ.queue[0], circ.queue[1]
+    want = np.diag([np.exp(-0.5j * math.cos(math.pi / 4)), np.exp(0.5j * math.cos(math.pi / 4))])
+    assert np.allclose(g0.matrix(), want)
+    assert np.allclose(g1.matrix(), qasm._u3(1.0, 1.0, 1.0))
+    with pytest.raises(ValueError):
+        qasm.from_openqasm2_str('OPENQASM 2.0;\nqreg q[1];\nrz(cos(pi/4) q[0];\n')
