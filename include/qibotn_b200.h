@@ -155,6 +155,19 @@ typedef struct {
   int32_t tc_reserved2;
 } qtn_pair_plan_t;
 
+/* Per-call options.  Every switch below can be handed to the planner / the SVD driver explicitly
+ * (qtn_pair_plan_opts, qtn_svd_rows_opts): nothing a caller plans or runs that way reads process-wide state,
+ * so concurrent callers with different settings do not interfere.  qtn_options_default fills in the library
+ * defaults; the plain entry points (qtn_pair_plan, qtn_svd_rows) use the process-wide copy that qtn_set_option
+ * edits (a convenience for tests and A/B runs: set it before threads start). */
+typedef struct {
+  int32_t tc_enable, tc_min_log2, tc_persistent, tc_terms, tc_accum_split, tc_prepack, tc_pair, tc_stagger, tc_fp16;
+  int32_t svd_wide, svd_group_mb, svd_reg;
+  int32_t reserved[4];
+} qtn_options;
+void qtn_options_default(qtn_options *opt);     /* the built-in defaults */
+void qtn_options_current(qtn_options *opt);     /* the process-wide copy (defaults + qtn_set_option edits) */
+
 /* Library-wide switches (thread-unsafe, meant for tests and A/B measurements):
  *   "tc_enable"    1 (default) lets qtn_pair_plan choose QTN_KERNEL_TC, 0 forbids it;
  *   "tc_min_log2"  smallest m+n+k (log2 of the MAC count) for which TC is chosen (default 18);
@@ -187,13 +200,15 @@ typedef struct {
 int qtn_set_option(const char *name, int value);
 int qtn_get_option(const char *name, int *value);
 /* sizeof() of a public struct by name ("qtn_pair_desc", "qtn_pair_plan_t", "qtn_svd_item",
- * "qtn_svd_trunc"), -1 if unknown: lets a foreign-language binding verify its mirror. */
+ * "qtn_svd_trunc", "qtn_gemm_item", "qtn_options"), -1 if unknown: lets a foreign-language binding verify its mirror. */
 int64_t qtn_sizeof(const char *struct_name);
 
 /* Host-only: derive roles, tile shape, coalescing-driven label placement and,
  * when desc->c_layout_free, C's layout (written back to desc->pos_c).
  * `sm_count` sizes split-K (pass 148 for B200; <=0 means 148). */
 int qtn_pair_plan(qtn_pair_desc *desc, int sm_count, qtn_pair_plan_t *plan);
+/* The same with explicit options (NULL = the process-wide copy). */
+int qtn_pair_plan_opts(qtn_pair_desc *desc, int sm_count, const qtn_options *opt, qtn_pair_plan_t *plan);
 
 /* Launch.  `slice_id` is a DEVICE pointer to one int32 (may be NULL when the
  * plan has no sliced labels): keeping it on the device lets a captured CUDA
@@ -322,6 +337,11 @@ int qtn_svd_rows(int dtype, int batch, qtn_svd_item *items, double tol, int max_
                  const qtn_svd_trunc *trunc, double *sigma, int32_t *perm, int64_t ld,
                  int32_t *rank_host, double *scale_host, int32_t *sweeps_host, void *workspace,
                  int64_t workspace_bytes, void *stream);
+/* qtn_svd_rows with explicit options (svd_wide, svd_reg, svd_group_mb; NULL = the process-wide copy). */
+int qtn_svd_rows_opts(int dtype, int batch, qtn_svd_item *items, double tol, int max_sweeps,
+                      const qtn_svd_trunc *trunc, double *sigma, int32_t *perm, int64_t ld,
+                      int32_t *rank_host, double *scale_host, int32_t *sweeps_host, void *workspace,
+                      int64_t workspace_bytes, const qtn_options *opt, void *stream);
 /* Scaled copies of the k leading rows (sorted order) of an orthogonalised W (m columns):
  * with s = sigma[c], sn = s*scale and (fa, fb) the share of sn absorbed by the left / right factor
  * (partition 0 none: (1,1); 1 "U": (sn,1); 2 "V": (1,sn); 3 "UV": (sqrt sn, sqrt sn)):

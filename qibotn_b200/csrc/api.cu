@@ -16,64 +16,54 @@ extern "C" int qtn_fail(int code, const char *msg) {
 extern "C" const char *qtn_last_error(void) { return g_last_error.c_str(); }
 
 namespace {
-int g_tc_enable = 1;
-int g_tc_min_log2 = 18;
-int g_tc_persistent = 1;
-int g_tc_terms = 3;
-int g_tc_accum_split = 1;
-int g_tc_prepack = 1;
-int g_tc_pair = 5;
-int g_tc_stagger = 1;
-int g_tc_fp16 = 1;
-int g_svd_wide = 1;
-int g_svd_group_mb = 0;
-int g_svd_reg = 4;
+constexpr qtn_options kDefaults = {1, 18, 1, 3, 1, 1, 5, 1, 1, 1, 0, 4, {0, 0, 0, 0}};
+qtn_options g_opt = kDefaults;
+
+struct Field { const char *name; int32_t qtn_options::*member; };
+const Field kFields[] = {
+    {"tc_enable", &qtn_options::tc_enable},       {"tc_min_log2", &qtn_options::tc_min_log2},
+    {"tc_persistent", &qtn_options::tc_persistent}, {"tc_terms", &qtn_options::tc_terms},
+    {"tc_accum_split", &qtn_options::tc_accum_split}, {"tc_prepack", &qtn_options::tc_prepack},
+    {"tc_pair", &qtn_options::tc_pair},           {"tc_stagger", &qtn_options::tc_stagger},
+    {"tc_fp16", &qtn_options::tc_fp16},           {"svd_wide", &qtn_options::svd_wide},
+    {"svd_group_mb", &qtn_options::svd_group_mb}, {"svd_reg", &qtn_options::svd_reg},
+};
+
+// the value ranges every option is clamped to, wherever it comes from
+void normalise(qtn_options &o) {
+  o.tc_enable = o.tc_enable != 0;
+  o.tc_persistent = o.tc_persistent != 0;
+  o.tc_terms = o.tc_terms >= 4 ? 4 : 3;
+  o.tc_accum_split = o.tc_accum_split != 0;
+  o.tc_prepack = o.tc_prepack != 0;
+  o.tc_pair = o.tc_pair < 0 ? 0 : o.tc_pair;
+  o.tc_stagger = o.tc_stagger != 0;
+  o.tc_fp16 = o.tc_fp16 != 0;
+  o.svd_wide = o.svd_wide != 0;
+  o.svd_group_mb = o.svd_group_mb < 0 ? 0 : o.svd_group_mb;
+  o.svd_reg = o.svd_reg < 0 ? 0 : (o.svd_reg > 5 ? 5 : o.svd_reg);
+}
 }  // namespace
 
-extern "C" int qtn_option_tc_enable(void) { return g_tc_enable; }
-extern "C" int qtn_option_tc_min_log2(void) { return g_tc_min_log2; }
-extern "C" int qtn_option_tc_persistent(void) { return g_tc_persistent; }
-extern "C" int qtn_option_tc_terms(void) { return g_tc_terms; }
-extern "C" int qtn_option_tc_accum_split(void) { return g_tc_accum_split; }
-extern "C" int qtn_option_tc_prepack(void) { return g_tc_prepack; }
-extern "C" int qtn_option_tc_pair(void) { return g_tc_pair; }
-extern "C" int qtn_option_tc_stagger(void) { return g_tc_stagger; }
-extern "C" int qtn_option_tc_fp16(void) { return g_tc_fp16; }
-extern "C" int qtn_option_svd_wide(void) { return g_svd_wide; }
-extern "C" int qtn_option_svd_group_mb(void) { return g_svd_group_mb; }
-extern "C" int qtn_option_svd_reg(void) { return g_svd_reg; }
+extern "C" void qtn_options_default(qtn_options *opt) { if (opt) *opt = kDefaults; }
+extern "C" void qtn_options_current(qtn_options *opt) { if (opt) *opt = g_opt; }
+// internal: the options a call runs with (a normalised copy of the caller's, or of the process-wide set)
+extern "C" void qtn_options_resolve(const qtn_options *given, qtn_options *out) {
+  *out = given ? *given : g_opt;
+  normalise(*out);
+}
 
 extern "C" int qtn_set_option(const char *name, int value) {
   if (!name) return qtn_fail(QTN_ERR_ARG, "qtn_set_option: null name");
-  if (!std::strcmp(name, "tc_enable")) { g_tc_enable = value != 0; return QTN_OK; }
-  if (!std::strcmp(name, "tc_min_log2")) { g_tc_min_log2 = value; return QTN_OK; }
-  if (!std::strcmp(name, "tc_persistent")) { g_tc_persistent = value != 0; return QTN_OK; }
-  if (!std::strcmp(name, "tc_terms")) { g_tc_terms = value >= 4 ? 4 : 3; return QTN_OK; }
-  if (!std::strcmp(name, "tc_accum_split")) { g_tc_accum_split = value != 0; return QTN_OK; }
-  if (!std::strcmp(name, "tc_prepack")) { g_tc_prepack = value != 0; return QTN_OK; }
-  if (!std::strcmp(name, "tc_pair")) { g_tc_pair = value < 0 ? 0 : value; return QTN_OK; }
-  if (!std::strcmp(name, "tc_stagger")) { g_tc_stagger = value != 0; return QTN_OK; }
-  if (!std::strcmp(name, "tc_fp16")) { g_tc_fp16 = value != 0; return QTN_OK; }
-  if (!std::strcmp(name, "svd_wide")) { g_svd_wide = value != 0; return QTN_OK; }
-  if (!std::strcmp(name, "svd_group_mb")) { g_svd_group_mb = value < 0 ? 0 : value; return QTN_OK; }
-  if (!std::strcmp(name, "svd_reg")) { g_svd_reg = value < 0 ? 0 : (value > 5 ? 5 : value); return QTN_OK; }
+  for (const Field &f : kFields)
+    if (!std::strcmp(name, f.name)) { g_opt.*(f.member) = value; normalise(g_opt); return QTN_OK; }
   return qtn_fail(QTN_ERR_ARG, "qtn_set_option: unknown option");
 }
 
 extern "C" int qtn_get_option(const char *name, int *value) {
   if (!name || !value) return qtn_fail(QTN_ERR_ARG, "qtn_get_option: null argument");
-  if (!std::strcmp(name, "tc_enable")) { *value = g_tc_enable; return QTN_OK; }
-  if (!std::strcmp(name, "tc_min_log2")) { *value = g_tc_min_log2; return QTN_OK; }
-  if (!std::strcmp(name, "tc_persistent")) { *value = g_tc_persistent; return QTN_OK; }
-  if (!std::strcmp(name, "tc_terms")) { *value = g_tc_terms; return QTN_OK; }
-  if (!std::strcmp(name, "tc_accum_split")) { *value = g_tc_accum_split; return QTN_OK; }
-  if (!std::strcmp(name, "tc_prepack")) { *value = g_tc_prepack; return QTN_OK; }
-  if (!std::strcmp(name, "tc_pair")) { *value = g_tc_pair; return QTN_OK; }
-  if (!std::strcmp(name, "tc_stagger")) { *value = g_tc_stagger; return QTN_OK; }
-  if (!std::strcmp(name, "tc_fp16")) { *value = g_tc_fp16; return QTN_OK; }
-  if (!std::strcmp(name, "svd_wide")) { *value = g_svd_wide; return QTN_OK; }
-  if (!std::strcmp(name, "svd_group_mb")) { *value = g_svd_group_mb; return QTN_OK; }
-  if (!std::strcmp(name, "svd_reg")) { *value = g_svd_reg; return QTN_OK; }
+  for (const Field &f : kFields)
+    if (!std::strcmp(name, f.name)) { *value = g_opt.*(f.member); return QTN_OK; }
   return qtn_fail(QTN_ERR_ARG, "qtn_get_option: unknown option");
 }
 
@@ -84,6 +74,7 @@ extern "C" int64_t qtn_sizeof(const char *name) {
   if (!std::strcmp(name, "qtn_svd_item")) return (int64_t)sizeof(qtn_svd_item);
   if (!std::strcmp(name, "qtn_svd_trunc")) return (int64_t)sizeof(qtn_svd_trunc);
   if (!std::strcmp(name, "qtn_gemm_item")) return (int64_t)sizeof(qtn_gemm_item);
+  if (!std::strcmp(name, "qtn_options")) return (int64_t)sizeof(qtn_options);
   return -1;
 }
 

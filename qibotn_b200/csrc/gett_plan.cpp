@@ -30,7 +30,13 @@ constexpr int kPhantom = 255;
 }  // namespace
 
 extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p) {
+  return qtn_pair_plan_opts(d, sm_count, nullptr, p);
+}
+
+extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_options *given, qtn_pair_plan_t *p) {
   if (!d || !p) return qtn_fail(QTN_ERR_ARG, "qtn_pair_plan: null argument");
+  qtn_options opt;
+  qtn_options_resolve(given, &opt);
   if (d->dtype != QTN_C64 && d->dtype != QTN_C128)
     return qtn_fail(QTN_ERR_ARG, "qtn_pair_plan: dtype must be QTN_C64 or QTN_C128");
   if (d->rank_a < 0 || d->rank_b < 0 || d->rank_c < 0 || d->rank_a > QTN_MAX_RANK ||
@@ -183,12 +189,12 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     // max(2 buffers x (A + B) chunk, 16 x 256 partials)
     p->smem_bytes = std::max(2 * 2 * (1 << tkb) * 18 * esz, 16 * 256 * esz);
   } else if (d->dtype == QTN_C64 && d->c_layout_free && bbits == 0 && mbits >= 7 && nbits >= 4 &&
-             kbits >= 3 && mbits + nbits + kbits >= qtn_option_tc_min_log2() && qtn_option_tc_enable()) {
+             kbits >= 3 && mbits + nbits + kbits >= opt.tc_min_log2 && opt.tc_enable) {
     // ---- tensor-core kernel (gett_tc.cu) ----------------------------------------
     // Tile = 128 rows of A x 2^tnb rows of B, 2^tkb contracted values per pipeline stage.
     p->kernel = QTN_KERNEL_TC;
     // separate accumulators for the cross terms need 4 TMEM regions per tile: 128 columns at most
-    const int sep = qtn_option_tc_accum_split() && qtn_option_tc_persistent();
+    const int sep = opt.tc_accum_split && opt.tc_persistent;
     const int tmb = 7, tnb = std::min(nbits, sep ? 7 : 8), tkb = std::min(kbits, 4);
     const int KT = 1 << tkb, TN = 1 << tnb;
     p->tmb = tmb; p->tnb = tnb; p->tkb = tkb;
@@ -297,10 +303,10 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     const int budget = (tnb <= 6 && 2 * stage_bytes <= 110 * 1024) ? 110 * 1024 : 200 * 1024;
     int stages = std::max(1, std::min(4, budget / stage_bytes));
     if ((int64_t)stages > k_iters) stages = (int)k_iters;
-    p->tc_terms = qtn_option_tc_terms();
+    p->tc_terms = opt.tc_terms;
     p->tc_pad = sep;
     p->tc_reserved = 0;
-    if (qtn_option_tc_persistent()) {
+    if (opt.tc_persistent) {
       // persistent kernel: one CTA per SM streams over tiles, so the pipeline may be deeper than
       // one tile's k loop; tc_reserved carries the number of CTAs to launch
       stages = std::max(2, std::min(6, (200 * 1024) / stage_bytes));
@@ -314,7 +320,7 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     {
       const int64_t images = (int64_t)1 << (p->n_nhi + p->n_khi);
       const int64_t image_bytes = 4 * (int64_t)p->tc_plane_b;
-      if (qtn_option_tc_prepack() && p->tc_reserved > 0 && p->n_mhi >= 3 && images * image_bytes <= ((int64_t)1 << 30)) {
+      if (opt.tc_prepack && p->tc_reserved > 0 && p->n_mhi >= 3 && images * image_bytes <= ((int64_t)1 << 30)) {
         p->tc_prepack = 1;
         p->tc_prepack_off = (p->workspace_bytes + 255) & ~(int64_t)255;
         p->workspace_bytes = p->tc_prepack_off + images * image_bytes;
@@ -323,7 +329,7 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
     // CTA pairs (cta_group::2): two m tiles that share a B tile run on the two SMs of a TPC, each
     // staging half of B -- for the tiles whose MMAs saturate shared-memory bandwidth on one SM
     p->tc_pair = 0;
-    if (qtn_option_tc_pair() && p->tc_prepack && sep && tnb >= qtn_option_tc_pair() && tnb <= 7 && p->n_mhi >= 1) {
+    if (opt.tc_pair && p->tc_prepack && sep && tnb >= opt.tc_pair && tnb <= 7 && p->n_mhi >= 1) {
       p->tc_pair = 1;
       const int pair_stage = 4 * (p->tc_plane_a + p->tc_plane_b / 2);
       p->tc_stages = std::max(2, std::min(6, (200 * 1024) / pair_stage));
@@ -332,7 +338,7 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
       // The staggered variant: two half-width halves with their own accumulators share every A stage; the
       // drain of one half hides behind the MMAs of the other.  Per CTA a stage holds the 4 A planes and
       // 3 * TN rows of B (2 halves x {hi, lo} x [Br | Bi | -Br] x TN / 4 rows); an image holds both ranks' rows.
-      if (qtn_option_tc_stagger() && p->tc_terms == 3) {
+      if (opt.tc_stagger && p->tc_terms == 3) {
         const int rank_b = 3 * TN * KT * 4;
         const int stage2 = 4 * p->tc_plane_a + rank_b;
         const int64_t images = (int64_t)1 << (p->n_nhi + p->n_khi);
@@ -349,7 +355,7 @@ extern "C" int qtn_pair_plan(qtn_pair_desc *d, int sm_count, qtn_pair_plan_t *p)
         // (r&7)*8 + (k&7) + (r>>3)*(KT*8) + (k>>3)*64.  A producer thread packs two k-adjacent values
         // into one 32-bit store, so the lowest k bit is the first ITERATION bit of the enumeration and the
         // five lane bits own the five bank-selecting word offsets (k bits 1-2, row bits 0-2).
-        if (qtn_option_tc_fp16() && tkb == 4) {
+        if (opt.tc_fp16 && tkb == 4) {
           p->tc_kind = 1;
           auto row_off16 = [&](int j) { return j < 3 ? 8 << j : (KT * 8) << (j - 3); };
           auto k_off16 = [&](int i) { return i < 3 ? 1 << i : 64 << (i - 3); };

@@ -7,19 +7,8 @@ extern "C" {
 #endif
 // Records `msg` as the thread-local last error and returns `code`.
 int qtn_fail(int code, const char *msg);
-// Library-wide switches (api.cu); read by the host planner.
-int qtn_option_tc_enable(void);
-int qtn_option_tc_min_log2(void);
-int qtn_option_tc_persistent(void);
-int qtn_option_tc_terms(void);
-int qtn_option_tc_accum_split(void);
-int qtn_option_tc_prepack(void);
-int qtn_option_tc_pair(void);
-int qtn_option_tc_stagger(void);
-int qtn_option_tc_fp16(void);
-int qtn_option_svd_wide(void);
-int qtn_option_svd_group_mb(void);
-int qtn_option_svd_reg(void);
+// The options a call runs with: a normalised copy of `given`, or of the process-wide set when NULL (api.cu).
+void qtn_options_resolve(const qtn_options *given, qtn_options *out);
 #ifdef __cplusplus
 }
 #endif

@@ -1230,6 +1230,16 @@ extern "C" int qtn_svd_rows(int dtype, int batch, qtn_svd_item *items, double to
                             const qtn_svd_trunc *trunc, double *sigma, int32_t *perm, int64_t ld,
                             int32_t *rank_host, double *scale_host, int32_t *sweeps_host, void *workspace,
                             int64_t workspace_bytes, void *stream) {
+  return qtn_svd_rows_opts(dtype, batch, items, tol, max_sweeps, trunc, sigma, perm, ld, rank_host, scale_host,
+                           sweeps_host, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int qtn_svd_rows_opts(int dtype, int batch, qtn_svd_item *items, double tol, int max_sweeps,
+                                 const qtn_svd_trunc *trunc, double *sigma, int32_t *perm, int64_t ld,
+                                 int32_t *rank_host, double *scale_host, int32_t *sweeps_host, void *workspace,
+                                 int64_t workspace_bytes, const qtn_options *given, void *stream) {
+  qtn_options opt;
+  qtn_options_resolve(given, &opt);
   if (dtype != QTN_C64 && dtype != QTN_C128) return qtn_fail(QTN_ERR_ARG, "qtn_svd_rows: bad dtype");
   if (batch < 1 || !items || !trunc || !sigma || !perm || !rank_host || !scale_host || !workspace)
     return qtn_fail(QTN_ERR_ARG, "qtn_svd_rows: null argument");
@@ -1245,9 +1255,9 @@ extern "C" int qtn_svd_rows(int dtype, int batch, qtn_svd_item *items, double to
   // "svd_group_mb": matrices are swept in groups whose rows fit that many MiB, so that a group stays in L2 over
   // the ~n/b launches of a sweep (0 = the whole batch at once)
   const int64_t esz = dtype == QTN_C64 ? 8 : 16;
-  const int64_t group_bytes = (int64_t)qtn_option_svd_group_mb() << 20;
-  const bool wide = qtn_option_svd_wide() != 0;
-  const int reg_variant = qtn_option_svd_reg();
+  const int64_t group_bytes = (int64_t)opt.svd_group_mb << 20;
+  const bool wide = opt.svd_wide != 0;
+  const int reg_variant = opt.svd_reg;
   int sweeps_max = 0;
   for (int g0 = 0; g0 < batch;) {
     int g1 = g0;

@@ -71,6 +71,13 @@ class PairPlan(C.Structure):
     ]
 
 
+class Options(C.Structure):
+    """``qtn_options``: per-call switches of the planner and the SVD driver (include/qibotn_b200.h)."""
+    _fields_ = [(n, C.c_int32) for n in ("tc_enable", "tc_min_log2", "tc_persistent", "tc_terms", "tc_accum_split",
+                                         "tc_prepack", "tc_pair", "tc_stagger", "tc_fp16", "svd_wide",
+                                         "svd_group_mb", "svd_reg")] + [("reserved", C.c_int32 * 4)]
+
+
 class GemmItem(C.Structure):
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p), ("m", C.c_int32), ("n", C.c_int32),
                 ("k", C.c_int32), ("lda", C.c_int32), ("ldb", C.c_int32), ("ldc", C.c_int32),
@@ -100,6 +107,13 @@ _SIGNATURES = {
     "qtn_last_error": (C.c_char_p, []),
     "qtn_device_info": (C.c_int, [C.c_int] + [C.POINTER(C.c_int)] * 4),
     "qtn_pair_plan": (C.c_int, [C.POINTER(PairDesc), C.c_int, C.POINTER(PairPlan)]),
+    "qtn_pair_plan_opts": (C.c_int, [C.POINTER(PairDesc), C.c_int, C.POINTER(Options), C.POINTER(PairPlan)]),
+    "qtn_options_default": (None, [C.POINTER(Options)]),
+    "qtn_options_current": (None, [C.POINTER(Options)]),
+    "qtn_svd_rows_opts": (C.c_int, [C.c_int, C.c_int, C.POINTER(SvdItem), C.c_double, C.c_int,
+                                    C.POINTER(SvdTrunc), C.c_void_p, C.c_void_p, C.c_int64,
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                    C.c_void_p, C.c_int64, C.POINTER(Options), C.c_void_p]),
     "qtn_pair_run": (C.c_int, [C.POINTER(PairPlan), C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "qtn_pair_run_scaled": (C.c_int, [C.POINTER(PairPlan), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -222,7 +236,24 @@ def make_pair_desc(dtype, a, b, c=None, accumulate=False, conj_a=False, conj_b=F
     return d
 
 
-def pair_plan(desc, sm_count=148):
+def options(**overrides):
+    """The library's default ``qtn_options`` with ``overrides`` applied (e.g. ``options(tc_fp16=0)``): handed to
+    ``pair_plan`` / ``qtn_svd_rows_opts`` it takes the place of the process-wide switches for that call."""
+    opt = Options()
+    load().qtn_options_default(C.byref(opt))
+    for key, val in overrides.items():
+        if not hasattr(opt, key) or key == "reserved":
+            raise QtnError(f"unknown option {key!r}")
+        setattr(opt, key, int(val))
+    return opt
+
+
+def pair_plan(desc, sm_count=148, options=None):
+    """Launch-ready plan of one pairwise contraction; ``options``: a ``qtn_options`` (see ``lib.options``) for this
+    call only, None = the process-wide switches."""
     plan = PairPlan()
-    check(load().qtn_pair_plan(C.byref(desc), sm_count, C.byref(plan)))
+    if options is None:
+        check(load().qtn_pair_plan(C.byref(desc), sm_count, C.byref(plan)))
+    else:
+        check(load().qtn_pair_plan_opts(C.byref(desc), sm_count, C.byref(options), C.byref(plan)))
     return plan

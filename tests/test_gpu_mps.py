@@ -460,3 +460,29 @@ def test_mps_sampling_at_48_qubits_through_the_quimb_platform():
     for state, p in res.probabilities().items():
         assert abs(p - 0.5) < 1e-10
 
+
+
+def test_c3_full_size_against_the_cpu_oracle_fixture():
+    """BASELINE config 3 at FULL size (64-site TFIM Trotter, 20 steps, bond <= 256, abs_cutoff 1e-12,
+    complex128) against tests/golden/c3_mps.json, produced by scripts/make_golden_c3.py from the CPU oracle
+    (numpy.linalg.svd gate loop, minutes of CPU): identical bond profile, <psi|psi> (0.914: 8.6 % of the weight
+    is truncated away, so the truncation itself is under test) and <Z_i Z_{i+1}> at three bonds."""
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "c3_mps.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/c3_mps.json not generated yet (scripts/make_golden_c3.py)")
+    ref = json.load(open(path))
+    circ = circuits.tfim_c3(ref["n"], ref["steps"])
+    algo = {"qr_method": False, "svd_method": {"partition": "UV", "abs_cutoff": 1e-12, "max_extent": ref["chi"]}}
+    conv = gmps.QiboCircuitToMPS(circ, algo, dtype="complex128")
+    helper = gmps.MPSContractionHelper(ref["n"])
+    bonds = [int(t.shape[2]) for t in conv.mps_tensors[:-1]]
+    assert bonds == ref["bonds"]
+    norm = float(helper.contract_norm(conv.mps_tensors).cpu())
+    assert abs(norm - ref["norm"]) <= 1e-10 * ref["norm"], (norm, ref["norm"])
+    for i, (re, im) in ref["zz"].items():
+        i = int(i)
+        got = complex(helper.pauli_expectation(conv.mps_tensors, {i: "Z", i + 1: "Z"}).cpu())
+        assert abs(got - complex(re, im)) <= 1e-10, (i, got, re, im)

@@ -202,3 +202,25 @@ def test_cta_pair_plans_are_well_formed(shape):
             lib.set_option("tc_min_log2", 18)
             lib.set_option("tc_stagger", 1)
         assert old.tc_pair == 1 and old.tc_prepack_off == plan.tc_prepack_off
+
+
+def test_options_per_call_do_not_touch_process_state():
+    """``qtn_pair_plan_opts``: the switches travel with the call (a ``qtn_options`` struct); the process-wide
+    copy that ``qtn_set_option`` edits is neither read nor written."""
+    import ctypes as C
+
+    la = [(i, i) for i in range(12 + 7)]
+    lb = [(12 + i, i) for i in range(7)] + [(19 + j, 7 + j) for j in range(7)]
+    before = {k: lib.get_option(k) for k in ("tc_enable", "tc_min_log2", "tc_pair", "tc_stagger", "tc_fp16")}
+    assert lib.load().qtn_sizeof(b"qtn_options") == C.sizeof(lib.Options)
+    plans = {}
+    for tag, opt in (("default", lib.options(tc_min_log2=0)), ("tf32", lib.options(tc_min_log2=0, tc_fp16=0)),
+                     ("pair1", lib.options(tc_min_log2=0, tc_stagger=0)), ("ffma", lib.options(tc_enable=0))):
+        plans[tag] = lib.pair_plan(lib.make_pair_desc("complex64", la, lb), options=opt)
+    assert (plans["default"].kernel, plans["default"].tc_pair, plans["default"].tc_kind) == (lib.KERNEL_TC, 2, 1)
+    assert (plans["tf32"].tc_pair, plans["tf32"].tc_kind) == (2, 0)
+    assert (plans["pair1"].tc_pair, plans["pair1"].tc_kind) == (1, 0)
+    assert plans["ffma"].kernel == lib.KERNEL_TILE
+    assert before == {k: lib.get_option(k) for k in before}
+    with pytest.raises(lib.QtnError):
+        lib.options(no_such_switch=1)
