@@ -365,6 +365,12 @@ int qtn_svd_emit(int dtype, const void *w, int32_t m, const int32_t *perm, const
  * ------------------------------------------------------------------------ */
 int qtn_pauli_expectation(int dtype, int nqubits, const void *state, int nterms, const uint64_t *xmask,
                           const uint64_t *zmask, const int32_t *ny, void *out, void *stream);
+/* The same with the masks in HOST memory (xmask, zmask, ny: host arrays; state, out: device): terms that share
+ * an xmask are evaluated up to 16 at a time in ONE pass over psi (the pair product conj(psi[x ^ xmask]) psi[x]
+ * is formed once, only the Z sign differs per term), so a sum of ZZ terms reads psi ceil(nterms / 16) times
+ * instead of nterms times.  Algorithmic traffic per pass as above. */
+int qtn_pauli_expectation_host(int dtype, int nqubits, const void *state, int nterms, const uint64_t *xmask,
+                               const uint64_t *zmask, const int32_t *ny, void *out, void *stream);
 
 /* ------------------------------------------------------------------------
  * Measurement helper (bench.py): achieved rate of the FP32 (is_double = 0) or FP64 FMA pipe with 16

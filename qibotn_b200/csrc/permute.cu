@@ -63,6 +63,93 @@ permute_bits_kernel(const __grid_constant__ BitPermParams P, const T *__restrict
   }
 }
 
+// Vectorised variant for full tiles (12 labels, 4096 elements) of dense layouts, where the label at input
+// address bit 0 and the label at output address bit 0 are tile labels by construction: every global access
+// moves 16 bytes (two complex64 values / one complex128 value), all 8 loads of a thread are in flight before
+// the first shared-memory store, and the write side reads its pairs with one 16-byte shared-memory load.
+// Staging index = rank in output order, so an output pair is adjacent in the stage; the XOR swizzle leaves
+// bit 0 alone to keep it so.
+__device__ __forceinline__ int swz2(int s) { return s ^ (((s >> 6) & 31) << 1); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+permute_bits_vec_kernel(const __grid_constant__ BitPermParams P, const T *__restrict__ in, T *__restrict__ out) {
+  constexpr int PER = sizeof(T) == 8 ? 2 : 1;          // elements per 16-byte access
+  constexpr int NV = 4096 / PER / 256;                 // 16-byte accesses per thread
+  struct __align__(16) V { T e[PER]; };
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *stage = reinterpret_cast<T *>(smem_raw);
+  const int t = threadIdx.x;
+  constexpr int LOW = PER == 2 ? 1 : 0;                // enumeration starts above the pair bit
+  long long ti = 0, to = 0; int ts = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if ((t >> j) & 1) { ti |= 1ll << P.in_pos[j + LOW]; ts += P.in_sidx[j + LOW]; to |= 1ll << P.out_pos[j + LOW]; }
+  long long base_in = 0, base_out = 0;
+  {
+    unsigned long long id = blockIdx.x;
+    for (int i = 0; i < P.nhi; ++i)
+      if ((id >> i) & 1ull) { base_in |= 1ll << P.hi_in[i]; base_out |= 1ll << P.hi_out[i]; }
+  }
+  V v[NV];
+#pragma unroll
+  for (int it = 0; it < NV; ++it) {
+    long long gi = 0;
+#pragma unroll
+    for (int j = 8 + LOW; j < 12; ++j)
+      if ((it >> (j - 8 - LOW)) & 1) gi |= 1ll << P.in_pos[j];
+    v[it] = *reinterpret_cast<const V *>(in + base_in + (ti | gi));
+  }
+  const int pair_s = PER == 2 ? P.in_sidx[0] : 0;      // staging step of the label at input bit 0
+#pragma unroll
+  for (int it = 0; it < NV; ++it) {
+    int s = ts;
+#pragma unroll
+    for (int j = 8 + LOW; j < 12; ++j)
+      if ((it >> (j - 8 - LOW)) & 1) s += P.in_sidx[j];
+    stage[swz2(s)] = v[it].e[0];
+    if constexpr (PER == 2) stage[swz2(s + pair_s)] = v[it].e[1];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < NV; ++it) {
+    long long go = 0;
+#pragma unroll
+    for (int j = 8 + LOW; j < 12; ++j)
+      if ((it >> (j - 8 - LOW)) & 1) go |= 1ll << P.out_pos[j];
+    const int e = (t + it * 256) * PER;                // staging index of the (first) element
+    V w = *reinterpret_cast<const V *>(stage + swz2(e));
+    V *dst = reinterpret_cast<V *>(out + base_out + (to | go));
+    if (P.accumulate) {
+      const V o = *dst;
+#pragma unroll
+      for (int q = 0; q < PER; ++q) { w.e[q].x += o.e[q].x; w.e[q].y += o.e[q].y; }
+    }
+    *dst = w;
+  }
+}
+
+// Rank-2 transpose (the MPS path's only permute: theta <-> theta^T, factor transposes): 32 x 32 tiles through
+// padded shared memory, both sides coalesced -- the general kernel below gathers with a div/mod chain per element.
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_kernel(long long rows, long long cols, const T *__restrict__ in, T *__restrict__ out) {
+  __shared__ T tile[32][33];
+  const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const long long r = r0 + ty + k, c = c0 + tx;
+    if (r < rows && c < cols) tile[ty + k][tx] = in[r * cols + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const long long c = c0 + ty + k, r = r0 + tx;
+    if (r < rows && c < cols) out[c * rows + r] = tile[tx][ty + k];
+  }
+}
+
 struct PermParams {
   int rank;
   long long n;
@@ -140,6 +227,26 @@ extern "C" int qtn_permute_bits(int dtype, int rank, const uint8_t *pos_in, cons
   for (int i = 0; i < P.nhi; ++i) { P.hi_in[i] = pos_in[hi[i]]; P.hi_out[i] = pos_out[hi[i]]; }
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = 1u << P.nhi;
+  // full tiles of dense layouts: 16-byte accesses on both sides (the pair bit is the label at address bit 0)
+  const bool vec = P.nt == 12 && P.in_pos[0] == 0 && P.out_pos[0] == 0 &&
+                   ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (vec) {
+    // in the vector kernel a thread's 16-byte output access covers staging indices e, e + 1: the enumeration of
+    // the write side is by output order, whose bit 0 is the label at output address bit 0
+    if (dtype == QTN_C64) {
+      permute_bits_vec_kernel<float2><<<grid, 256, 4096 * sizeof(float2), st>>>(P, (const float2 *)in, (float2 *)out);
+    } else {
+      static bool attr_v = false;
+      if (!attr_v) {
+        QTN_CUDA_CHECK(cudaFuncSetAttribute(permute_bits_vec_kernel<double2>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int)sizeof(double2)));
+        attr_v = true;
+      }
+      permute_bits_vec_kernel<double2><<<grid, 256, 4096 * sizeof(double2), st>>>(P, (const double2 *)in, (double2 *)out);
+    }
+    QTN_LAUNCH_CHECK();
+    return QTN_OK;
+  }
   if (dtype == QTN_C64) {
     permute_bits_kernel<float2><<<grid, 256, 4096 * sizeof(float2), st>>>(P, (const float2 *)in,
                                                                         (float2 *)out);
@@ -178,6 +285,15 @@ extern "C" int qtn_permute(int dtype, int rank, const int64_t *extent_in, const 
   }
   if (P.n == 0) return QTN_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (rank == 2 && perm[0] == 1 && perm[1] == 0 && extent_in[1] <= 0x7fffffffLL * 32 && (extent_in[0] + 31) / 32 <= 65535) {
+    const dim3 tgrid((unsigned)((extent_in[1] + 31) / 32), (unsigned)((extent_in[0] + 31) / 32));
+    if (dtype == QTN_C64)
+      transpose_kernel<float2><<<tgrid, 256, 0, st>>>(extent_in[0], extent_in[1], (const float2 *)in, (float2 *)out);
+    else
+      transpose_kernel<double2><<<tgrid, 256, 0, st>>>(extent_in[0], extent_in[1], (const double2 *)in, (double2 *)out);
+    QTN_LAUNCH_CHECK();
+    return QTN_OK;
+  }
   const unsigned grid = (unsigned)std::min<long long>((P.n + 255) / 256, 148 * 16);
   if (dtype == QTN_C64)
     permute_general_kernel<float2><<<grid, 256, 0, st>>>(P, (const float2 *)in, (float2 *)out);

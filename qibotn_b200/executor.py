@@ -256,6 +256,7 @@ class ContractionRunner:
         self._amax_leaves = groups["leaf"]
         self._amax_used = {where: bool(tids) for where, tids in groups.items()}
         self.use_graph = use_graph
+        self._hoist_valid = False
         self._graph = None
         self._graph_hoist = None
         self._copied = None
@@ -281,6 +282,7 @@ class ContractionRunner:
         self.leaf_buf.copy_(self.host_buf, non_blocking=True)
         self._copied = self.torch.cuda.Event()
         self._copied.record()
+        self._hoist_valid = False            # the slice-independent intermediates belong to the previous leaves
         return low.leaf_bytes
 
     def _ptr(self, tid):
@@ -320,6 +322,7 @@ class ContractionRunner:
         slot = self._amax_slot
         self._measure_leaves()
         self._run_hoisted()
+        self._hoist_valid = True
         lib.check(self.lib.qtn_set_i32(self.slice_id.data_ptr(), slice_id, st))
         out = []
         if self._amax_used["slice"]:
@@ -369,8 +372,12 @@ class ContractionRunner:
         any_dep = any(n.depends for n in low.nodes)
         if any_dep:
             self.out.zero_()
-        self._measure_leaves()
-        launches += self._run_hoisted()
+        if not self._hoist_valid or not any_dep:
+            # slice-independent nodes: once per upload (their results stay valid while the leaves do -- every
+            # rank of a sliced run would otherwise replay the same sub-tree at every call)
+            self._measure_leaves()
+            launches += self._run_hoisted()
+            self._hoist_valid = True
         if any_dep and slice_ids:
             contiguous = slice_ids == list(range(slice_ids[0], slice_ids[0] + len(slice_ids)))
             if self.use_graph and contiguous and len(slice_ids) > 1:

@@ -144,6 +144,8 @@ _SIGNATURES = {
                                C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qtn_pauli_expectation": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qtn_pauli_expectation_host": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]),
     "qtn_microbench_fma": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_void_p]),
     "qtn_sizeof": (C.c_int64, [C.c_char_p]),
     "qtn_set_option": (C.c_int, [C.c_char_p, C.c_int]),

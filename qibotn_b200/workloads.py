@@ -57,7 +57,7 @@ def build(name: str) -> Workload:
         n, steps = 64, 20
         if opt:
             n, steps = (int(x) for x in opt.split("x"))
-        return Workload(name, "mps", "complex128", circuits.tfim_trotter(n, steps),
+        return Workload(name, "mps", "complex128", circuits.tfim_c3(n, steps),
                         f"{n}-site TFIM Trotter, {steps} steps, MPS bond<=256, complex128")
     if base == "c4":
         d = int(opt[1:]) if opt else 14

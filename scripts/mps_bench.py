@@ -38,7 +38,7 @@ gmps.PROFILE_PHASES = a.phases
 if a.lq_min_rows >= 0:
     gmps.LQ_MIN_ROWS = a.lq_min_rows
 
-circ = circuits.tfim_trotter(a.n, a.steps)
+circ = circuits.tfim_c3(a.n, a.steps)          # config 3 angles (circuits.C3_ANGLES)
 algo = {"qr_method": False, "svd_method": {"partition": "UV", "abs_cutoff": 1e-12, "max_extent": a.chi}}
 ngates = sum(1 for g in circ.queue)
 best = None

@@ -410,3 +410,51 @@ def test_results_survive_a_second_run_of_the_same_structure(dtype):
     r2 = b.execute_circuit(circuit(1.1))
     assert rel2(r1.statevector.flatten().get(), keep) <= TOL[dtype]
     assert rel2(r2.statevector.flatten().get(), osv.simulate(circuit(1.1))) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_fused_multi_term_pauli_kernel(dtype):
+    """qtn_pauli_expectation_host: terms sharing an xmask are evaluated up to 16 per pass over psi; every term must
+    equal the one-term-per-pass kernel and the numpy value, whatever the grouping (more than 16 terms with one
+    xmask, single-term groups, identity, Y phases)."""
+    import ctypes as C
+    from qibotn_b200 import lib
+
+    n = 11
+    rng = np.random.default_rng(3)
+    psi = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    psi = (psi / np.linalg.norm(psi)).astype(dtype)
+    terms = []
+    for _ in range(37):                                   # 37 Z-only strings: one xmask, three passes
+        terms.append({q: "Z" for q in rng.choice(n, size=rng.integers(1, 5), replace=False)})
+    for _ in range(9):                                    # XX/YY/XY-type strings on a few pairs: shared xmasks
+        a, b = rng.choice(n, size=2, replace=False)
+        for letters in (("X", "X"), ("Y", "Y"), ("X", "Y")):
+            t = {int(a): letters[0], int(b): letters[1]}
+            if rng.random() < 0.5:
+                t[int((a + 3) % n)] = "Z" if (a + 3) % n not in (a, b) else t[int((a + 3) % n)]
+            terms.append(t)
+    terms.append({})                                      # identity
+    terms.append({0: "Y", 5: "Y", 7: "Y", 2: "X"})
+    xm, zm, ny = [], [], []
+    for t in terms:
+        fx = sum(1 << (n - 1 - q) for q, l in t.items() if l in "XY")
+        fz = sum(1 << (n - 1 - q) for q, l in t.items() if l in "ZY")
+        xm.append(fx); zm.append(fz); ny.append(sum(l == "Y" for l in t.values()))
+    want = [complex(osv.pauli_expectation(psi.astype(np.complex128), [(1.0, [(l, q) for q, l in t.items()])], n))
+            for t in terms]
+    h = lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    d_psi = torch.from_numpy(psi).cuda()
+    nt = len(terms)
+    out_h = torch.empty(nt, dtype=torch.complex128, device="cuda")
+    lib.check(h.qtn_pauli_expectation_host(lib.dtype_code(dtype), n, d_psi.data_ptr(), nt, (C.c_uint64 * nt)(*xm),
+                                           (C.c_uint64 * nt)(*zm), (C.c_int32 * nt)(*ny), out_h.data_ptr(), st))
+    out_d = torch.empty(nt, dtype=torch.complex128, device="cuda")
+    lib.check(h.qtn_pauli_expectation(lib.dtype_code(dtype), n, d_psi.data_ptr(), nt,
+                                      torch.tensor(xm, dtype=torch.int64, device="cuda").data_ptr(),
+                                      torch.tensor(zm, dtype=torch.int64, device="cuda").data_ptr(),
+                                      torch.tensor(ny, dtype=torch.int32, device="cuda").data_ptr(), out_d.data_ptr(), st))
+    got_h, got_d = out_h.cpu().numpy(), out_d.cpu().numpy()
+    assert np.abs(got_h - got_d).max() <= 1e-12
+    assert np.abs(got_h - np.array(want)).max() <= TOL[dtype]      # |<P>| <= 1: absolute = relative to the norm bound
