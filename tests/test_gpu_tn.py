@@ -451,10 +451,12 @@ def test_fused_multi_term_pauli_kernel(dtype):
     lib.check(h.qtn_pauli_expectation_host(lib.dtype_code(dtype), n, d_psi.data_ptr(), nt, (C.c_uint64 * nt)(*xm),
                                            (C.c_uint64 * nt)(*zm), (C.c_int32 * nt)(*ny), out_h.data_ptr(), st))
     out_d = torch.empty(nt, dtype=torch.complex128, device="cuda")
-    lib.check(h.qtn_pauli_expectation(lib.dtype_code(dtype), n, d_psi.data_ptr(), nt,
-                                      torch.tensor(xm, dtype=torch.int64, device="cuda").data_ptr(),
-                                      torch.tensor(zm, dtype=torch.int64, device="cuda").data_ptr(),
-                                      torch.tensor(ny, dtype=torch.int32, device="cuda").data_ptr(), out_d.data_ptr(), st))
+    # the mask arrays must outlive the launch (a temporary's block is handed to the next allocation)
+    d_xm = torch.tensor(xm, dtype=torch.int64, device="cuda")
+    d_zm = torch.tensor(zm, dtype=torch.int64, device="cuda")
+    d_ny = torch.tensor(ny, dtype=torch.int32, device="cuda")
+    lib.check(h.qtn_pauli_expectation(lib.dtype_code(dtype), n, d_psi.data_ptr(), nt, d_xm.data_ptr(),
+                                      d_zm.data_ptr(), d_ny.data_ptr(), out_d.data_ptr(), st))
     got_h, got_d = out_h.cpu().numpy(), out_d.cpu().numpy()
     assert np.abs(got_h - got_d).max() <= 1e-12
     assert np.abs(got_h - np.array(want)).max() <= TOL[dtype]      # |<P>| <= 1: absolute = relative to the norm bound
