@@ -388,8 +388,10 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   T *sA = reinterpret_cast<T *>(smem_raw);                   // [2][KC][16]
   T *sB = sA + 2 * KC * KRED_ROW;                            // [2][KC][16]
   const int t = threadIdx.x;
-  const long long a_base = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
-  const long long b_base = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
+  const long long a_base = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a) |
+                           deposit(blockIdx.y, P.a_bat, P.n_batch);      // grid.y = batch (hyper) value
+  const long long b_base = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b) |
+                           deposit(blockIdx.y, P.b_bat, P.n_batch);
   // enumeration: element index e = t + 256 * u.  Bits 0-7 come from the thread (a_t_*), bits 8-10
   // from u: their global / shared strides are three per-operand constants, so the offset of
   // iteration u is a sum of at most three registers (u is a compile-time constant below).
@@ -511,7 +513,8 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
     for (int g = 0; g < 16; ++g) { const T v = red[g * 256 + t]; s.x += v.x; s.y += v.y; }
     const int m = t >> 4, n = t & 15;
     if (m < (1 << P.m_real) && n < (1 << P.n_real)) {
-      const long long off = deposit(m, P.c_mhi, P.m_real) | deposit(n, P.c_nhi, P.n_real);
+      const long long off = deposit(m, P.c_mhi, P.m_real) | deposit(n, P.c_nhi, P.n_real) |
+                            deposit(blockIdx.y, P.c_bat, P.n_batch);
       ws[(long long)blockIdx.x * P.c_elems + off] = s;
     }
   }
@@ -550,8 +553,8 @@ int launch_kred(const qtn_pair_plan_t &P, const void *a, const void *b, void *c,
                                         80 * 1024));
     attr_set = true;
   }
-  gett_kred_kernel<R><<<(unsigned)P.grid, 256, P.smem_bytes, st>>>(P, (const T *)a, (const T *)b, (T *)ws,
-                                                                  slice_id);
+  gett_kred_kernel<R><<<dim3((unsigned)P.grid, 1u << P.n_batch), 256, P.smem_bytes, st>>>(
+      P, (const T *)a, (const T *)b, (T *)ws, slice_id);
   QTN_LAUNCH_CHECK();
   return qtn_launch_splitk_sum(P.dtype, c, ws, P.c_elems, (int)P.grid, P.accumulate, st);
 }

@@ -114,6 +114,19 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
   // positions below this many bits are "forced" into a tile for coalescing
   const int cforce = d->dtype == QTN_C64 ? 4 : 3;
 
+  // Batch (hyper) labels on the tensor cores: only the staggered CTA-pair kernel with pre-packed B images
+  // carries them (a batch value = one more group of m tiles for A and C, one more set of B images), so the
+  // plan must be one that lands there: >= 8 m tiles per B image, 32..128 columns, images within 1 GiB.
+  auto tc_batch_ok = [&]() {
+    if (!(opt.tc_pair && opt.tc_prepack && opt.tc_persistent && opt.tc_accum_split && opt.tc_stagger &&
+          opt.tc_terms == 3))
+      return false;
+    const int tnb = std::min(nbits, 7), tkb = std::min(kbits, 4);
+    if (mbits < 10 || tnb < opt.tc_pair || mbits - 7 + bbits > QTN_HI_MAX) return false;
+    const int64_t images = (int64_t)1 << std::min(40, (nbits - tnb) + (kbits - tkb) + bbits);
+    return images * (4 * (int64_t)(4 << (tnb + tkb))) <= ((int64_t)1 << 30);
+  };
+
   // ---- K-parallel reduction for tiny outputs --------------------------------
   if (bbits == 0 && mbits + nbits <= 4 && kbits >= 10) {
     p->kernel = QTN_KERNEL_REDUCE;
@@ -139,7 +152,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     p->grid = (int64_t)1 << (kbits - chunk);
     p->smem_bytes = 0;
     p->workspace_bytes = p->grid * 16 * esz;
-  } else if (bbits == 0 && mbits <= 4 && nbits <= 4 && kbits >= 10) {
+  } else if (bbits <= 15 && mbits <= 4 && nbits <= 4 && kbits >= 10) {
     // ---- streaming K reduction (<= 16 x 16 outputs) ----------------------------
     p->kernel = QTN_KERNEL_KRED;
     const int tkb = std::min(kbits, d->dtype == QTN_C64 ? 7 : 6);   // chunk: 128 / 64 contracted values
@@ -161,9 +174,13 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
       int next_c = 0;
       for (auto &l : N) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
       for (auto &l : M) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
+      for (auto &l : Bt) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
     }
     for (int i = 0; i < mbits; ++i) { p->a_mhi[i] = M[i].pa; p->c_mhi[i] = M[i].pc; }
     for (int i = 0; i < nbits; ++i) { p->b_nhi[i] = N[i].pb; p->c_nhi[i] = N[i].pc; }
+    // batch (hyper) labels: one independent reduction per batch value (grid.y)
+    p->n_batch = bbits;
+    for (int i = 0; i < bbits; ++i) { p->a_bat[i] = Bt[i].pa; p->b_bat[i] = Bt[i].pb; p->c_bat[i] = Bt[i].pc; }
     p->n_mhi = 0; p->n_nhi = 0; p->n_khi = (int)khi.size();
     for (int i = 0; i < p->n_khi; ++i) { p->a_khi[i] = khi[i].pa; p->b_khi[i] = khi[i].pb; }
     // shared-memory chunk: element (k, row) at k * 18 + row (padded rows: conflict-free stores
@@ -184,11 +201,11 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     // every CTA leaves one partial C in the workspace
     const int64_t ngroups = (int64_t)1 << std::max(0, p->n_khi - 3);   // groups of 8 chunks
     p->split_bits = 0;
-    p->grid = std::min<int64_t>(ngroups, (int64_t)2 * sm_count);
+    p->grid = std::min<int64_t>(ngroups, std::max<int64_t>(1, ((int64_t)2 * sm_count) >> bbits));
     p->workspace_bytes = ((int64_t)esz << d->rank_c) * p->grid;
     // max(2 buffers x (A + B) chunk, 16 x 256 partials)
     p->smem_bytes = std::max(2 * 2 * (1 << tkb) * 18 * esz, 16 * 256 * esz);
-  } else if (d->dtype == QTN_C64 && d->c_layout_free && bbits == 0 && mbits >= 7 && nbits >= 4 &&
+  } else if (d->dtype == QTN_C64 && d->c_layout_free && (bbits == 0 || tc_batch_ok()) && mbits >= 7 && nbits >= 4 &&
              kbits >= 3 && mbits + nbits + kbits >= opt.tc_min_log2 && opt.tc_enable) {
     // ---- tensor-core kernel (gett_tc.cu) ----------------------------------------
     // Tile = 128 rows of A x 2^tnb rows of B, 2^tkb contracted values per pipeline stage.
@@ -228,8 +245,13 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
       return std::max(x.pa, x.pb) < std::max(y.pa, y.pb);
     });
     p->m_real = tmb; p->n_real = tnb; p->k_real = tkb;
+    // batch labels: the top bits of the m-tile index for A and C (a_mhi / c_mhi), separate deposits for B
+    // (b_bat, read by the image pre-pack); n_batch tells the kernel how many of the m-hi bits they are
+    const int true_mhi = (int)mhi.size();
+    std::sort(Bt.begin(), Bt.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
+    for (auto &l : Bt) mhi.push_back(l);
     p->n_mhi = (int)mhi.size(); p->n_nhi = (int)nhi.size(); p->n_khi = (int)khi.size();
-    p->n_batch = 0;
+    p->n_batch = bbits;
     if (p->n_mhi > QTN_HI_MAX || p->n_nhi > QTN_HI_MAX || p->n_khi > QTN_HI_MAX)
       return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_plan: rank too large");
     // C: m bits 0-4 | n bits | m bits 5-6 | n-hi | m-hi  (the epilogue's store order)
@@ -287,6 +309,9 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     for (int i = 0; i < p->n_mhi; ++i) { p->a_mhi[i] = mhi[i].pa; p->c_mhi[i] = mhi[i].pc; }
     for (int i = 0; i < p->n_nhi; ++i) { p->b_nhi[i] = nhi[i].pb; p->c_nhi[i] = nhi[i].pc; }
     for (int i = 0; i < p->n_khi; ++i) { p->a_khi[i] = khi[i].pa; p->b_khi[i] = khi[i].pb; }
+    for (int i = 0; i < bbits; ++i) {
+      p->a_bat[i] = mhi[true_mhi + i].pa; p->b_bat[i] = mhi[true_mhi + i].pb; p->c_bat[i] = mhi[true_mhi + i].pc;
+    }
     // split-K when there are fewer tiles than SMs (one CTA owns a whole SM here)
     const double tiles = std::ldexp(1.0, p->n_mhi + p->n_nhi);
     int split = 0;
@@ -318,9 +343,9 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     p->tc_prepack = 0;
     p->tc_prepack_off = 0;
     {
-      const int64_t images = (int64_t)1 << (p->n_nhi + p->n_khi);
+      const int64_t images = (int64_t)1 << (p->n_nhi + p->n_khi + bbits);
       const int64_t image_bytes = 4 * (int64_t)p->tc_plane_b;
-      if (opt.tc_prepack && p->tc_reserved > 0 && p->n_mhi >= 3 && images * image_bytes <= ((int64_t)1 << 30)) {
+      if (opt.tc_prepack && p->tc_reserved > 0 && true_mhi >= 3 && images * image_bytes <= ((int64_t)1 << 30)) {
         p->tc_prepack = 1;
         p->tc_prepack_off = (p->workspace_bytes + 255) & ~(int64_t)255;
         p->workspace_bytes = p->tc_prepack_off + images * image_bytes;
@@ -329,7 +354,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     // CTA pairs (cta_group::2): two m tiles that share a B tile run on the two SMs of a TPC, each
     // staging half of B -- for the tiles whose MMAs saturate shared-memory bandwidth on one SM
     p->tc_pair = 0;
-    if (opt.tc_pair && p->tc_prepack && sep && tnb >= opt.tc_pair && tnb <= 7 && p->n_mhi >= 1) {
+    if (opt.tc_pair && p->tc_prepack && sep && tnb >= opt.tc_pair && tnb <= 7 && true_mhi >= 1) {
       p->tc_pair = 1;
       const int pair_stage = 4 * (p->tc_plane_a + p->tc_plane_b / 2);
       p->tc_stages = std::max(2, std::min(6, (200 * 1024) / pair_stage));
@@ -341,7 +366,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
       if (opt.tc_stagger && p->tc_terms == 3) {
         const int rank_b = 3 * TN * KT * 4;
         const int stage2 = 4 * p->tc_plane_a + rank_b;
-        const int64_t images = (int64_t)1 << (p->n_nhi + p->n_khi);
+        const int64_t images = (int64_t)1 << (p->n_nhi + p->n_khi + bbits);
         const int64_t base = (p->tc_prepack_off);
         p->tc_pair = 2;
         // shared memory: operand stages + a ring of 6 raw A chunks (128 x KT elements of 8 bytes: the
@@ -399,6 +424,8 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
       }
     }
     p->sa_stride = 0; p->sb_stride = 0;
+    if (bbits > 0 && p->tc_pair != 2)
+      return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_plan: batch labels need the staggered CTA-pair kernel");
   } else {
     // ---- shared-memory tiled kernel -----------------------------------------
     p->kernel = QTN_KERNEL_TILE;

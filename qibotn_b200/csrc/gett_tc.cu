@@ -1313,7 +1313,9 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
       decode(u, split, nh, mh);
       const unsigned long long kh0 = (unsigned long long)split << k_iters_bits;
       a_k = a_slice | deposit_warp(mh, P.a_mhi, P.n_mhi) | deposit_warp(kh0, P.a_khi, P.n_khi);
-      image0 = (nh << P.n_khi) | kh0;
+      // batch labels are the top n_batch bits of the m-tile index: one set of B images per batch value
+      const unsigned long long bt = P.n_batch ? mh >> (P.n_mhi - P.n_batch) : 0ull;
+      image0 = ((((bt << P.n_nhi) | nh) << P.n_khi)) | kh0;
       kk = 0;
     };
     auto advance = [&]() {
@@ -1572,10 +1574,12 @@ tc_prepack_b2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
   constexpr int CHUNK = Q * KT, SEQ = 3 * CHUNK, HALF = 2 * SEQ, RANK_B = 2 * HALF;   // elements
   constexpr int NB = (TN * KT + kProducerThreads - 1) / kProducerThreads;
   const int t = threadIdx.x;
-  const unsigned long long nh = (unsigned long long)blockIdx.x >> P.n_khi;
+  const unsigned long long nb = (unsigned long long)blockIdx.x >> P.n_khi;       // (batch, n tile)
+  const unsigned long long nh = nb & ((1ull << P.n_nhi) - 1), bt = nb >> P.n_nhi;
   const unsigned long long kh = (unsigned long long)blockIdx.x & ((1ull << P.n_khi) - 1);
   const long long b_k = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b) |
-                        deposit(nh, P.b_nhi, P.n_nhi) | deposit(kh, P.b_khi, P.n_khi);
+                        deposit(nh, P.b_nhi, P.n_nhi) | deposit(kh, P.b_khi, P.n_khi) |
+                        deposit(bt, P.b_bat, P.n_batch);
   long long b_t_g = 0;
   int b_t_s = 0;
 #pragma unroll
@@ -1663,7 +1667,7 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
     const long long ctas = P.grid < P.tc_reserved ? P.grid : P.tc_reserved;
     if (P.tc_pair == 2) {                         // staggered CTA pairs: tiles of 32, 64 or 128 columns
       if constexpr (TNB >= 5 && TNB <= 7) {
-        const long long images = 1ll << (P.n_nhi + P.n_khi);
+        const long long images = 1ll << (P.n_nhi + P.n_khi + P.n_batch);
         if (!P.tc_pad || !P.tc_prepack || (P.grid & 1) || (ctas & 1) || images > 0x7fffffffLL)
           return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: malformed staggered CTA-pair plan");
         auto go2 = [&](auto prepack, auto kernel, int &smem_set) -> int {
@@ -1694,6 +1698,7 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
         return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: staggered CTA pairs need a tile of 32 to 128 columns");
       }
     }
+    if (P.n_batch) return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: batch labels need the staggered CTA-pair kernel");
     if (P.tc_prepack) {
       const long long images = 1ll << (P.n_nhi + P.n_khi);
       if (images > 0x7fffffffLL) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_run: too many B images");
@@ -1741,6 +1746,7 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
     return P.tc_prepack ? go(gett_tc_persistent_kernel<TNB, TKB, false, true>, set_p)
                         : go(gett_tc_persistent_kernel<TNB, TKB, false, false>, set_0);
   }
+  if (P.n_batch) return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: batch labels need the staggered CTA-pair kernel");
   amax_done = false;                            // one CTA per tile: no magnitude tracking in the kernel
   static int smem_set = 0;
   if (smem_set < P.smem_bytes) {

@@ -227,13 +227,14 @@ def _absorb_small(net: SymbolicNetwork):
 
 
 # ------------------------------------------------------- variable elimination
-def _elimination_path(live, out, hyper, nxt, rng, temperature=0.0):
+def _elimination_path(live, out, hyper, nxt, rng, temperature=0.0, order=None):
     """Bucket (variable) elimination for networks with hyper labels: repeatedly pick the label whose
     elimination -- contracting every tensor that owns it -- yields the smallest tensor (ties and, with
     ``temperature`` > 0, near-ties broken at random), and contract its owners pairwise, smallest first.
     For circuits whose entangling gates are diagonal (QAOA) the labels are the vertices of a sparse
     "line graph" and this is the classic min-width heuristic on it; pairwise greedy on the tensors,
-    which scores one merge at a time, does far worse there.  Returns ssa pairs."""
+    which scores one merge at a time, does far worse there.  ``order`` (label bits, as single-bit masks)
+    replaces the greedy choice by a given elimination order (``elimorder.search``).  Returns ssa pairs."""
     live = dict(live)
     owners = {}
     for i, m in live.items():
@@ -251,8 +252,15 @@ def _elimination_path(live, out, hyper, nxt, rng, temperature=0.0):
         return (u & ~low).bit_count() if not (low & out) else u.bit_count()
 
     size = {low: merged_size(low) for low in owners if not (low & out)}
+    given = list(order) if order is not None else None
     while size:
-        if temperature > 0:
+        if given is not None:
+            while given and given[0] not in size:
+                given.pop(0)
+            if not given:
+                break
+            best = given.pop(0)
+        elif temperature > 0:
             best = min(size, key=lambda low: (size[low] - temperature * math.log(rng.random() + 1e-300) * -1.0, low))
         else:
             best = min(size, key=lambda low: (size[low], low))
@@ -524,10 +532,17 @@ def _partition_path(live, out, hyper, nxt, rng, imbalance=0.15, leaf_size=10):
 
 
 # --------------------------------------------------------------------- slicing
-def _slice(net: SymbolicNetwork, path, target_log2_width, min_slices, max_sliced=40):
-    sliced = 0
+def _slice_more(net: SymbolicNetwork, path, sliced, target_log2_width, max_sliced=40):
+    """Continue slicing ``path`` from the labels already in ``sliced``; returns (mask, the added single-bit masks)."""
+    n0 = sliced.bit_count()
+    sliced2, order = _slice(net, path, target_log2_width, 1, max_sliced=max(0, max_sliced - n0), sliced0=sliced)
+    return sliced2, order
+
+
+def _slice(net: SymbolicNetwork, path, target_log2_width, min_slices, max_sliced=40, sliced0=0):
+    sliced = sliced0
     order = []
-    cost, width, _, _ = path_cost(net, path, 0)
+    cost, width, _, _ = path_cost(net, path, sliced)
     want_bits = max(0, math.ceil(math.log2(max(1, min_slices))))
     while (width > target_log2_width or len(order) < want_bits) and len(order) < max_sliced:
         # candidates: labels living in the widest intermediates (or anything, when only
@@ -575,7 +590,7 @@ def find_path(modes, out, samples=32, seed=0, target_log2_width=30, min_slices=1
     """
     import time
 
-    from .treeopt import Tree
+    from .treeopt import HyperTree, Tree
 
     net = SymbolicNetwork(modes, out)
     pre, live, nxt = _absorb_small(net)
@@ -586,6 +601,26 @@ def find_path(modes, out, samples=32, seed=0, target_log2_width=30, min_slices=1
     if len(live) <= 1:
         cands.append((0.0, "trivial", []))
     else:
+        if net.hyper_mask:
+            # label-graph elimination orders (elimorder.py): randomised min-fill / min-degree restarts, the
+            # cheapest few by the order's own cost proxy become candidate trees
+            from . import elimorder
+
+            nb = elimorder.label_graph(list(live.values()))
+            orders = []
+            for s in range(max(4, 4 * samples)):
+                rule = "fill" if s % 4 != 3 else "degree"
+                noise = 0.0 if s < 4 else rng.choice([0.1, 0.3, 1.0])
+                res = elimorder.greedy_order(nb, net.out_mask, rng, noise, rule)
+                orders.append((res[2], res[1], res[0]))
+                if deadline is not None and time.time() > t0 + 0.2 * time_budget_s:
+                    break
+            orders.sort(key=lambda o: (o[0], o[1]))
+            for _c, _w, order in orders[:max(2, samples)]:
+                tail = _elimination_path(live, net.out_mask, net.hyper_mask, nxt, rng, 0.0,
+                                         order=[1 << v for v in order])
+                cost, width, _, _ = path_cost(net, pre + tail, 0)
+                cands.append((cost * (1.0 + 2.0 ** max(0, width - target_log2_width)) ** 0.5, "order", tail))
         for s in range(max(1, samples)):
             for meth in (tuple(methods) + ("eliminate",) if net.hyper_mask else methods):
                 if meth == "eliminate":
@@ -603,12 +638,17 @@ def find_path(modes, out, samples=32, seed=0, target_log2_width=30, min_slices=1
                 cands.append((cost * (1.0 + 2.0 ** max(0, width - target_log2_width)) ** 0.5, meth, tail))
             if deadline is not None and time.time() > t0 + 0.4 * time_budget_s:
                 break
+    if net.hyper_mask and len(cands) > 3 * max(1, refine):
+        # polishing a hyper tree is cheap but not free: only the more promising candidates get it
+        cands.sort(key=lambda c: c[0])
+        cands = cands[:3 * max(1, refine)]
+    TreeCls = HyperTree if net.hyper_mask else Tree
     # every candidate gets a cheap polish (small subtrees); ranking happens after it
     polished = []
-    can_refine = not net.hyper_mask and len(live) >= 3
+    can_refine = len(live) >= 3
     for score, meth, tail in cands:
         if can_refine and meth != "trivial":
-            tree = Tree(live, tail, nxt, net.out_mask)
+            tree = TreeCls(live, tail, nxt, net.out_mask)
             tree.reconfigure(rounds=reconf_rounds, k=min(8, subtree_size), deadline=deadline)
             w = tree.width()
             score = tree.total_cost() * (1.0 + 2.0 ** max(0, w - target_log2_width)) ** 0.5
@@ -640,8 +680,7 @@ def find_path(modes, out, samples=32, seed=0, target_log2_width=30, min_slices=1
             if steps > 0:
                 # annealing moves single subtrees across the tree, which reconfiguration (bounded
                 # subtrees) cannot; the result is kept only if the sliced total really went down
-                snap = (dict(tree.children), dict(tree.mask), dict(tree.parent), tree.next_id,
-                        list(order), sliced)
+                snap = (tree.snapshot(), list(order), sliced)
                 before = tree.total_cost(sliced) * (1 << len(order))
                 tree.anneal(steps, rng, removed=sliced, max_width=target_log2_width, deadline=deadline)
                 tree.reconfigure(rounds=2, k=min(8, subtree_size), removed=sliced, deadline=deadline)
@@ -649,8 +688,8 @@ def find_path(modes, out, samples=32, seed=0, target_log2_width=30, min_slices=1
                     more, sliced = tree.slice_greedy(target_log2_width, 1, removed=sliced, reconf_every=0)
                     order = order + more
                 if tree.total_cost(sliced) * (1 << len(order)) >= before:
-                    tree.children, tree.mask, tree.parent, tree.next_id = snap[0], snap[1], snap[2], snap[3]
-                    order, sliced = snap[4], snap[5]
+                    tree.restore(snap[0])
+                    order, sliced = snap[1], snap[2]
             path = pre + tree.ssa_pairs(nxt)
         cost, width, per_slice, hoisted = path_cost(net, path, sliced)
         if best is None or cost < best[0]:

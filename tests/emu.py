@@ -156,12 +156,26 @@ def _canonical_kmajor(plane, rows, kt):
     return out
 
 
+def _canonical_kmajor16(plane, rows, kt):
+    """The fp16 planes of the scaled 3xFP16 split: 8-row x 8-value core matrices of 64 halves; K-neighbours
+    64 halves apart, 8-row groups ``kt * 8`` halves apart."""
+    out = np.zeros((rows, kt), dtype=plane.dtype)
+    for r in range(rows):
+        for k in range(kt):
+            out[r, k] = plane[(r & 7) * 8 + (k & 7) + (r >> 3) * (kt * 8) + (k >> 3) * 64]
+    return out
+
+
 def _run_tc(P, a, b, c, sa, sb):
     """Emulate gett_tc.cu: gather into canonical-layout planes, tile product, fixed C tile layout."""
     TN, KT = 1 << P.tnb, 1 << P.tkb
-    assert P.tmb == 7 and P.n_batch == 0 and not P.accumulate
-    assert P.tc_plane_a == 128 * KT * 4 and P.tc_plane_b == TN * KT * 4
-    assert P.smem_bytes >= P.tc_stages * 4 * (P.tc_plane_a + P.tc_plane_b) + 8 * (2 * P.tc_stages + 2)
+    assert P.tmb == 7 and not P.accumulate
+    f16 = P.tc_kind == 1                       # scaled 3xFP16 split: 2-byte planes, 8 x 8 core matrices
+    eb = 2 if f16 else 4
+    assert P.tc_plane_a == 128 * KT * eb and P.tc_plane_b == TN * KT * eb
+    if P.tc_pair != 2:
+        assert P.n_batch == 0                  # batch labels ride on the staggered CTA-pair kernel only
+        assert P.smem_bytes >= P.tc_stages * 4 * (P.tc_plane_a + P.tc_plane_b) + 8 * (2 * P.tc_stages + 2)
     assert P.smem_bytes <= 227 * 1024 and 1 <= P.tc_stages <= 8
     # the epilogue hard-codes C's tile layout: m bits 0-4 | n bits | m bits 5-6
     want = list(range(5)) + [5 + P.tnb, 6 + P.tnb] + [5 + j for j in range(P.tnb)]
@@ -174,8 +188,10 @@ def _run_tc(P, a, b, c, sa, sb):
         rest = cta >> P.split_bits
         nh = rest & ((1 << P.n_nhi) - 1)
         mh = rest >> P.n_nhi
+        # batch labels = the top n_batch bits of the m-tile index (A, C) and their own deposits in B
+        bt = mh >> (P.n_mhi - P.n_batch) if P.n_batch else 0
         a_base = dep(mh, P.a_mhi, P.n_mhi) | sa
-        b_base = dep(nh, P.b_nhi, P.n_nhi) | sb
+        b_base = dep(nh, P.b_nhi, P.n_nhi) | dep(bt, P.b_bat, P.n_batch) | sb
         c_base = dep(mh, P.c_mhi, P.n_mhi) | dep(nh, P.c_nhi, P.n_nhi)
         acc = np.zeros((128, TN), dtype=np.complex128)
         for kk in range(1 << kbits):
@@ -187,7 +203,8 @@ def _run_tc(P, a, b, c, sa, sb):
                     (P.nb_lo, P.b_lo_pos, P.b_lo_sstr, TN * KT, b, b_base | b_k)):
                 assert (1 << n_lo) == size
                 # the five lane bits own the five bank-selecting offsets (1, 2, 4, 8, 16 floats)
-                assert sorted(lo_sstr[j] for j in range(5)) == [1, 2, 4, 8, 16]
+                if not f16:
+                    assert sorted(lo_sstr[j] for j in range(5)) == [1, 2, 4, 8, 16]
                 plane = np.full(size, np.nan, dtype=np.complex128)
                 for e in range(size):
                     g = s = 0
@@ -198,7 +215,8 @@ def _run_tc(P, a, b, c, sa, sb):
                     assert np.isnan(plane[s])           # every slot written exactly once
                     plane[s] = src[base | g]
                 planes.append(plane)
-            acc += _canonical_kmajor(planes[0], 128, KT) @ _canonical_kmajor(planes[1], TN, KT).T
+            cm = _canonical_kmajor16 if f16 else _canonical_kmajor
+            acc += cm(planes[0], 128, KT) @ cm(planes[1], TN, KT).T
         out = ws[split] if P.split_bits else c
         for r in range(128):
             for n in range(TN):
@@ -212,18 +230,18 @@ def _run_kred(P, a, b, c, sa, sb):
     """Emulate gett_kred_kernel: per CTA a range of k chunks, 16 x 16 (padded) outputs, one partial
     per CTA summed at the end."""
     KC = 1 << P.tkb
-    assert P.tmb == 4 and P.tnb == 4 and P.n_batch == 0 and P.n_mhi == 0 and P.n_nhi == 0
+    assert P.tmb == 4 and P.tnb == 4 and 0 <= P.n_batch <= 15 and P.n_mhi == 0 and P.n_nhi == 0
     ib = min(3, P.n_khi)
     ngroups = 1 << (P.n_khi - ib)
     assert P.smem_bytes >= 2 * 2 * KC * 18 * c.itemsize and 1 <= P.grid <= ngroups and P.smem_bytes <= 80 * 1024
     assert P.na_lo <= 11 and P.nb_lo <= 11
     ws = np.zeros((P.grid, P.c_elems), dtype=np.complex128)
-    for cta in range(P.grid):
+    for cta, bt in ((x, y) for x in range(P.grid) for y in range(1 << P.n_batch)):      # grid.y = batch value
         acc = np.zeros((16, 16), dtype=np.complex128)
         # groups of 2^ib consecutive chunks; neighbouring CTAs take neighbouring groups
         for kh in (g << ib | i for g in range(cta, ngroups, P.grid) for i in range(1 << ib)):
-            a_k = sa | dep(kh, P.a_khi, P.n_khi)
-            b_k = sb | dep(kh, P.b_khi, P.n_khi)
+            a_k = sa | dep(kh, P.a_khi, P.n_khi) | dep(bt, P.a_bat, P.n_batch)
+            b_k = sb | dep(kh, P.b_khi, P.n_khi) | dep(bt, P.b_bat, P.n_batch)
             chunks = []
             for (n_lo, lo_pos, lo_sstr, src, base) in ((P.na_lo, P.a_lo_pos, P.a_lo_sstr, a, a_k),
                                                        (P.nb_lo, P.b_lo_pos, P.b_lo_sstr, b, b_k)):
@@ -239,7 +257,7 @@ def _run_kred(P, a, b, c, sa, sb):
             acc += chunks[0].T @ chunks[1]
         for m in range(1 << P.m_real):
             for n in range(1 << P.n_real):
-                ws[cta, dep(m, P.c_mhi, P.m_real) | dep(n, P.c_nhi, P.n_real)] = acc[m, n]
+                ws[cta, dep(m, P.c_mhi, P.m_real) | dep(n, P.c_nhi, P.n_real) | dep(bt, P.c_bat, P.n_batch)] = acc[m, n]
     tot = ws.sum(0)
     if P.accumulate:
         c[: P.c_elems] += tot

@@ -176,3 +176,41 @@ def test_tensor_core_variants_agree_with_einsum(shape):
         assert plan.tc_kind == (1 if staggered and k >= 4 and opts.get("tc_fp16", 1) else 0), (shape, opts)
         want = np.einsum(A, la, B, lb, lc_used)
         assert np.abs(got - want).max() / np.abs(want).max() < 4e-6 * max(1, k), (shape, opts)
+
+
+@pytest.mark.parametrize("case", [
+    # kind, m, n, k, batch: batch (hyper) labels -- the diagonal gates of QAOA networks (BASELINE config 5) -- on the
+    # staggered tcgen05 pair kernel (one set of B images per batch value) and on the streaming K reduction (grid.y)
+    ("tc", 10, 5, 4, 2), ("tc", 11, 7, 5, 3), ("tc", 10, 6, 3, 1), ("tc", 12, 7, 6, 2), ("tc", 10, 5, 8, 4),
+    ("kred", 4, 4, 12, 3), ("kred", 2, 3, 14, 6), ("kred", 0, 1, 16, 1), ("kred", 4, 3, 10, 9),
+])
+def test_batch_labels_on_tensor_core_and_kred_kernels(case):
+    kind, m, n, k, batch = case
+    rng = np.random.default_rng(31 * m + 17 * n + 5 * k + batch)
+    labels = list(range(m + n + k + batch))
+    M, N, K, Bt = labels[:m], labels[m:m + n], labels[m + n:m + n + k], labels[m + n + k:]
+    la, lb, lc = M + K + Bt, K + N + Bt, M + N + Bt
+    rng.shuffle(la); rng.shuffle(lb); rng.shuffle(lc)
+    pa_all = [int(x) for x in rng.permutation(len(la) + 1)]
+    pa, sa = pa_all[:-1], [(0, pa_all[-1])]                   # one sliced label on A, slice id 1
+    pb = [int(x) for x in rng.permutation(len(lb))]
+    a = (rng.normal(size=1 << (len(la) + 1)) + 1j * rng.normal(size=1 << (len(la) + 1))).astype(np.complex64)
+    b = (rng.normal(size=1 << len(lb)) + 1j * rng.normal(size=1 << len(lb))).astype(np.complex64)
+    A = _dense(a.astype(np.complex128), la, pa, off=1 << pa_all[-1])
+    B = _dense(b.astype(np.complex128), lb, pb)
+    dtypes = ["complex64"] if kind == "tc" else ["complex64", "complex128"]
+    for dtype in dtypes:
+        try:
+            lib.set_option("tc_min_log2", 0)
+            got, lc_used, plan = run_pair(dtype, la, pa, lb, pb, lc, None, a.astype(dtype), b.astype(dtype),
+                                          slice_a=sa, slice_id=1)
+        finally:
+            lib.set_option("tc_min_log2", 18)
+        assert plan.n_batch == batch
+        if kind == "tc":
+            assert plan.kernel == lib.KERNEL_TC and plan.tc_pair == 2 and plan.tc_kind == (1 if k >= 4 else 0)
+        else:
+            assert plan.kernel == lib.KERNEL_KRED
+        want = np.einsum(A, la, B, lb, lc_used, optimize=True)
+        tol = 4e-6 if dtype == "complex64" else 1e-13
+        assert np.abs(got - want).max() / np.abs(want).max() < tol * max(1, k), (case, dtype)

@@ -224,3 +224,49 @@ def test_options_per_call_do_not_touch_process_state():
     assert before == {k: lib.get_option(k) for k in before}
     with pytest.raises(lib.QtnError):
         lib.options(no_such_switch=1)
+
+
+BATCH_CASES = [
+    # m, n, k, batch, slices a/b: batch (hyper) labels on the tensor-core kernel (staggered CTA pairs only) and on
+    # the streaming K reduction
+    ("tc", 10, 5, 3, 2, 0, 0), ("tc", 10, 5, 4, 1, 1, 0), ("tc", 11, 6, 5, 2, 0, 1), ("tc", 10, 7, 4, 3, 0, 0),
+    ("kred", 2, 3, 10, 2, 0, 0), ("kred", 4, 4, 10, 1, 1, 1), ("kred", 0, 1, 11, 3, 0, 0),
+    ("tile", 9, 5, 4, 2, 0, 0), ("tile", 10, 4, 4, 1, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", BATCH_CASES)
+def test_batch_labels_in_tensor_core_and_kred_plans(case):
+    kind, m, n, k, batch, nsa, nsb = case
+    lib.set_option("tc_min_log2", 0)
+    try:
+        rng = np.random.default_rng(abs(hash(case)) % 2**32)
+        la, pa, sa_pos, lb, pb, sb_pos, lc, _ = random_case(rng, m, n, k, batch, nsa, nsb)
+        ra, rb = len(la) + nsa, len(lb) + nsb
+        a = (rng.normal(size=1 << ra) + 1j * rng.normal(size=1 << ra)).astype(np.complex64)
+        b = (rng.normal(size=1 << rb) + 1j * rng.normal(size=1 << rb)).astype(np.complex64)
+        bits_a = list(range(nsa)); bits_b = list(range(1, 1 + nsb))
+        desc = lib.make_pair_desc("complex64", list(zip(la, pa)), list(zip(lb, pb)), lc,
+                                  slice_a=list(zip(bits_a, sa_pos)), slice_b=list(zip(bits_b, sb_pos)))
+        plan = lib.pair_plan(desc, 4)
+    finally:
+        lib.set_option("tc_min_log2", 18)
+    assert plan.n_batch == batch
+    if kind == "tc":
+        # m >= 10 (8 m tiles per B image), n >= 5: the staggered pair kernel; fp16 split when 16 k values fill a stage
+        assert plan.kernel == lib.KERNEL_TC and plan.tc_pair == 2 and plan.tc_prepack == 1
+        assert plan.tc_kind == (1 if k >= 4 else 0)
+        assert plan.n_mhi == m - 7 + batch and plan.grid == (1 << (plan.n_mhi + plan.n_nhi + plan.split_bits))
+    elif kind == "kred":
+        assert plan.kernel == lib.KERNEL_KRED and plan.grid >= 1
+    else:
+        assert plan.kernel == lib.KERNEL_TILE          # too few m tiles (or columns) for the pair kernel
+    pc_used = [desc.pos_c[i] for i in range(len(lc))]
+    lc_used = [desc.label_c[i] for i in range(len(lc))]
+    assert sorted(pc_used) == list(range(len(lc)))
+    for slice_id in ([0] if nsa + nsb == 0 else [0, 3]):
+        c = np.zeros(1 << len(lc), dtype=np.complex64)
+        emu.run_plan(plan, a, b, c, slice_id)
+        got = emu.dense_from_flat(c, lc_used, pc_used)
+        want = reference(a, la, pa, sa_pos, b, lb, pb, sb_pos, lc_used, slice_id, bits_a, bits_b)
+        assert np.allclose(got, want, rtol=1e-4, atol=1e-4 * (1 << (k // 2)))
