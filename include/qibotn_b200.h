@@ -152,7 +152,17 @@ typedef struct {
    *    22 significant bits): operands are scaled by a power of two taken from the run-time magnitude
    *    bound of each tensor, so the plan must be run with qtn_pair_run_scaled ("tc_fp16"). */
   int32_t tc_kind;
-  int32_t tc_reserved2;
+  /* 1: the staggered kernel gathers A in ascending ADDRESS order of the tile's labels (a warp's 32 copies of
+   * 8 bytes cover the 5 lowest address bits among them: runs of up to 256 contiguous bytes) into the raw
+   * shared-memory ring and the conversion to operand planes reads the ring across threads ("tc_gather");
+   * 0: every thread gathers the elements it converts itself (lanes own the bank-selecting plane offsets,
+   * whatever their addresses).  tc_a_gbit[r] = address bit of the tile label of rank r in address order,
+   * tc_a_rank[j] = that rank for enumeration bit j of a_lo_pos; tc_a_it_gg / tc_a_it_raw = global offset and
+   * raw-ring element index of iteration i in the gather order / of the converted element. */
+  int32_t tc_gather;
+  uint8_t tc_a_gbit[QTN_LO_MAX], tc_a_rank[QTN_LO_MAX];
+  int64_t tc_a_it_gg[8];
+  int32_t tc_a_it_raw[8];
 } qtn_pair_plan_t;
 
 /* Per-call options.  Every switch below can be handed to the planner / the SVD driver explicitly
@@ -163,7 +173,8 @@ typedef struct {
 typedef struct {
   int32_t tc_enable, tc_min_log2, tc_persistent, tc_terms, tc_accum_split, tc_prepack, tc_pair, tc_stagger, tc_fp16;
   int32_t svd_wide, svd_group_mb, svd_reg;
-  int32_t reserved[4];
+  int32_t tc_gather;
+  int32_t reserved[3];
 } qtn_options;
 void qtn_options_default(qtn_options *opt);     /* the built-in defaults */
 void qtn_options_current(qtn_options *opt);     /* the process-wide copy (defaults + qtn_set_option edits) */
@@ -183,6 +194,9 @@ void qtn_options_current(qtn_options *opt);     /* the process-wide copy (defaul
  *                  MMAs of the other; 0: the round-1 pair kernel (tile and accumulators as one unit);
  *   "tc_fp16"      1 (default): staggered tiles split their operands into scaled fp16 pieces (tc_kind = 1,
  *                  half the tensor-pipe work of the TF32 split; run through qtn_pair_run_scaled); 0: TF32 split;
+ *   "tc_gather"    1 (default): the staggered kernel gathers A in ascending address order (contiguous runs per
+ *                  warp) and hands the raw elements across threads through shared memory; 0: every thread
+ *                  gathers the elements it converts (round-2 first version);
  *   "tc_persistent" 1 (default): one CTA per SM streams over the tiles with loads, MMAs and
  *                  epilogue of neighbouring tiles overlapped; 0: one CTA per tile.
  *   "svd_wide"     1 (default): qtn_svd_rows runs 512-thread CTAs holding twice the block rows (200 KB of

@@ -423,6 +423,22 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
         }
       }
     }
+    // address-ordered gather of A for the staggered kernel (see tc_gather in the header)
+    p->tc_gather = 0;
+    if (p->tc_pair == 2 && opt.tc_gather) {
+      const int n = p->na_lo;
+      std::vector<int> idx(n);
+      for (int j = 0; j < n; ++j) idx[j] = j;
+      std::sort(idx.begin(), idx.end(), [&](int x, int y) { return p->a_lo_pos[x] < p->a_lo_pos[y]; });
+      for (int r = 0; r < n; ++r) { p->tc_a_gbit[r] = p->a_lo_pos[idx[r]]; p->tc_a_rank[idx[r]] = (uint8_t)r; }
+      for (int it = 0; it < 8; ++it) {
+        int64_t g = 0; int32_t raw = 0;
+        for (int j = 8; j < n; ++j)
+          if ((it >> (j - 8)) & 1) { g |= (int64_t)1 << p->tc_a_gbit[j]; raw += 1 << p->tc_a_rank[j]; }
+        p->tc_a_it_gg[it] = g; p->tc_a_it_raw[it] = raw;
+      }
+      p->tc_gather = 1;
+    }
     p->sa_stride = 0; p->sb_stride = 0;
     if (bbits > 0 && p->tc_pair != 2)
       return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_plan: batch labels need the staggered CTA-pair kernel");

@@ -78,6 +78,11 @@ __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// arrive on `bar` once all cp.async copies this thread has issued so far have landed (no pending-count increment:
+// the arrival is one of the barrier's expected count)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -1253,6 +1258,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
   uint64_t *bars = reinterpret_cast<uint64_t *>(raw_ring + (size_t)kRawDepth * RAW);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + 4);
   unsigned long long *img_ring = reinterpret_cast<unsigned long long *>(bars + 3 * S + 4 + 2);   // thread 0 only
+  uint64_t *raw_bars = reinterpret_cast<uint64_t *>(img_ring + kRawDepth);   // "raw chunk landed" (tc_gather)
   const int t = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, t >> 5, 0), lane = t & 31;   // provably warp-uniform
   const uint32_t rank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
@@ -1282,6 +1288,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
       mbar_init(pfull_bar(s), 1);
     }
     for (int h = 0; h < 2; ++h) { mbar_init(tfull_bar(h), 1); mbar_init(tempty_bar(h), 2 * kEpilogueThreads); }
+    for (int d = 0; d < kRawDepth; ++d) mbar_init(smem_u32(raw_bars + d), kProducerThreads);
     fence_proxy_async_smem();
     fence_mbar_init();
   }
@@ -1299,6 +1306,20 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     for (int j = 0; j < 8; ++j) {
       if (!((t >> j) & 1)) continue;
       if (j < P.na_lo) { a_t_g |= 1ll << P.a_lo_pos[j]; a_t_s += P.a_lo_sstr[j]; }
+    }
+    // tc_gather: the copies of a chunk are issued in ascending ADDRESS order of the tile's labels (bit r of the
+    // element index e = i * 256 + t walks the label of rank r), element e lands at raw[e]; the thread that
+    // converts an element finds it at the index built from the ranks of its own enumeration bits.
+    const bool gather = P.tc_gather != 0;
+    long long g_t_g = 0;
+    int r_t = 0;
+    if (gather) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!((t >> j) & 1)) continue;
+        g_t_g |= 1ll << P.tc_a_gbit[j];
+        r_t += 1 << P.tc_a_rank[j];
+      }
     }
     const float sgn_a = P.conj_a ? -1.f : 1.f;
     const float sc_re = F16 ? exp2_int(amax_scale_exp(amax_a)) : 1.f, sc_im = sc_re * sgn_a;
@@ -1328,16 +1349,30 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     const uint32_t raw_t = smem_u32(raw_ring) + (uint32_t)t * 8u;
     auto load = [&](int slot) {                       // this thread's NA elements of the current chunk -> raw slot
       const uint32_t dst = raw_t + (uint32_t)slot * (uint32_t)RAW;
+      if (gather) {
 #pragma unroll
-      for (int i = 0; i < NA; ++i)
-        cp_async8(dst + (uint32_t)i * (kProducerThreads * 8u), A + (a_k | a_t_g | P.tc_a_it_g[i]));
+        for (int i = 0; i < NA; ++i)
+          cp_async8(dst + (uint32_t)i * (kProducerThreads * 8u), A + (a_k | g_t_g | P.tc_a_it_gg[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+          cp_async8(dst + (uint32_t)i * (kProducerThreads * 8u), A + (a_k | a_t_g | P.tc_a_it_g[i]));
+      }
       if (t == 0) img_ring[slot] = image0 + kk;
     };
     int s = 0;
     uint32_t ph = 0;
     auto store = [&](int slot) {
       float2 va[NA];
-      {
+      if (gather) {
+        const float2 *src = reinterpret_cast<const float2 *>(raw_ring + (size_t)slot * RAW) + r_t;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) va[i] = src[P.tc_a_it_raw[i]];
+        // every producer has taken its elements out of the slot: it may be refilled (by other threads' copies)
+        asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
+        if (u < nsuper) { load(slot); advance(); }
+        cp_async_mbar_arrive(smem_u32(raw_bars + slot));
+      } else {
         const float2 *src = reinterpret_cast<const float2 *>(raw_ring + (size_t)slot * RAW) + t;
 #pragma unroll
         for (int i = 0; i < NA; ++i) va[i] = src[i * kProducerThreads];
@@ -1383,20 +1418,39 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     const unsigned long long my_tiles = pair0 < nsuper ? (nsuper - pair0 + npairs - 1) / npairs : 0;
     unsigned long long remaining = my_tiles * k_iters;   // chunks still to be stored
     if (u < nsuper) enter_tile();
+    if (gather) {
+      // every thread arrives on a slot's barrier once per lap, when its own copies into the slot (possibly none)
+      // have landed: 256 arrivals = the chunk is complete, whoever copied which element
 #pragma unroll 1
-    for (int d = 0; d < kRawDepth; ++d) {
-      if (u < nsuper) { load(d); advance(); }
-      cp_async_commit();
-    }
-    int slot = 0;
+      for (int d = 0; d < kRawDepth; ++d) {
+        if (u < nsuper) { load(d); advance(); }
+        cp_async_mbar_arrive(smem_u32(raw_bars + d));
+      }
+      int slot = 0;
+      uint32_t rph = 0;
 #pragma unroll 1
-    while (remaining) {
-      cp_async_wait<kRawDepth - 1>();
-      store(slot);
-      if (u < nsuper) { load(slot); advance(); }
-      cp_async_commit();
-      if (++slot == kRawDepth) slot = 0;
-      --remaining;
+      while (remaining) {
+        mbar_wait(smem_u32(raw_bars + slot), rph);
+        store(slot);                                     // refills the slot itself, behind the named barrier
+        if (++slot == kRawDepth) { slot = 0; rph ^= 1u; }
+        --remaining;
+      }
+    } else {
+#pragma unroll 1
+      for (int d = 0; d < kRawDepth; ++d) {
+        if (u < nsuper) { load(d); advance(); }
+        cp_async_commit();
+      }
+      int slot = 0;
+#pragma unroll 1
+      while (remaining) {
+        cp_async_wait<kRawDepth - 1>();
+        store(slot);
+        if (u < nsuper) { load(slot); advance(); }
+        cp_async_commit();
+        if (++slot == kRawDepth) slot = 0;
+        --remaining;
+      }
     }
   } else if (warp < 12) {
     // ================= epilogue: half 0 then half 1 of every tile, each as soon as its MMAs are complete =================

@@ -28,12 +28,36 @@ __all__ = ["initialize", "rank_size", "vote_best", "reduce_result", "compute_sli
 _STATE = {"initialized": False, "rank": 0, "size": 1, "device_id": 0, "backend": None}
 
 
-def partition_units(counts, rank, size):
+def partition_units(counts, rank, size, weights=None):
     """Work of a many-term observable is the flat list of (term, slice) units, term-major; rank ``rank``
     takes the contiguous range ``compute_slices(sum(counts), rank, size)`` of it (the reference's
     partition rule, eval.py:197-205, applied to the flattened list instead of once per term as
     eval.py:352-380 does).  ``counts[t]`` = number of slices of term t.  Returns ``{term: range}`` with the
-    slice ids of each term this rank owns (terms it does not touch are absent)."""
+    slice ids of each term this rank owns (terms it does not touch are absent).
+
+    ``weights[t]`` = cost of ONE slice of term t: the list is then cut where the cumulative cost crosses
+    multiples of total / size instead of by unit count (light-cone terms of one observable differ by
+    orders of magnitude in cost: QAOA p = 4 on 40 qubits spans 10^8 .. 10^15 flops per term).  A unit
+    belongs to the rank in whose share its cost midpoint falls: still contiguous, every unit owned once."""
+    if weights is not None:
+        total = float(sum(float(w) * int(c) for w, c in zip(weights, counts)))
+        if total <= 0.0:
+            return partition_units(counts, rank, size)
+        share = total / size
+        out, before = {}, 0.0
+        for t, (c, w) in enumerate(zip(counts, weights)):
+            c, w = int(c), float(w)
+            lo = hi = None
+            for s in range(c):
+                owner = min(size - 1, int((before + (s + 0.5) * w) / share))
+                if owner == rank:
+                    if lo is None:
+                        lo = s
+                    hi = s + 1
+            if lo is not None:
+                out[t] = range(lo, hi)
+            before += c * w
+        return out
     total = int(sum(counts))
     mine = compute_slices(total, rank, size) if total else range(0)
     out, begin = {}, 0

@@ -230,7 +230,9 @@ def _expectation_distributed(qibo_circ, datatype, observable, n_samples, method)
             info = engine.find_info(net, datatype, samples=n_samples, seed=rk, min_slices=forced)
             plans[key], _winner = dist.vote_best(info.opt_cost, info)   # lowered by its owners only
         infos.append(plans[key])
-    mine = dist.partition_units([info.num_slices for info in infos], rank, size)
+    # cut by cost, not by unit count: the light cones of one observable differ by orders of magnitude
+    mine = dist.partition_units([info.num_slices for info in infos], rank, size,
+                                weights=[info.opt_cost / max(1, info.num_slices) for info in infos])
     cdtype = torch.complex64 if str(datatype) == "complex64" else torch.complex128
     partials = torch.zeros(len(nets), dtype=cdtype, device="cuda")
     for t, slices in mine.items():

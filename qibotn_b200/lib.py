@@ -67,7 +67,9 @@ class PairPlan(C.Structure):
         ("tc_a_it_s", C.c_int32 * 8), ("tc_b_it_s", C.c_int32 * 16),
         ("tc_terms", C.c_int32), ("tc_pad", C.c_int32),
         ("tc_prepack", C.c_int32), ("tc_pair", C.c_int32), ("tc_prepack_off", C.c_int64),
-        ("tc_kind", C.c_int32), ("tc_reserved2", C.c_int32),
+        ("tc_kind", C.c_int32), ("tc_gather", C.c_int32),
+        ("tc_a_gbit", C.c_uint8 * QTN_LO_MAX), ("tc_a_rank", C.c_uint8 * QTN_LO_MAX),
+        ("tc_a_it_gg", C.c_int64 * 8), ("tc_a_it_raw", C.c_int32 * 8),
     ]
 
 
@@ -75,7 +77,7 @@ class Options(C.Structure):
     """``qtn_options``: per-call switches of the planner and the SVD driver (include/qibotn_b200.h)."""
     _fields_ = [(n, C.c_int32) for n in ("tc_enable", "tc_min_log2", "tc_persistent", "tc_terms", "tc_accum_split",
                                          "tc_prepack", "tc_pair", "tc_stagger", "tc_fp16", "svd_wide",
-                                         "svd_group_mb", "svd_reg")] + [("reserved", C.c_int32 * 4)]
+                                         "svd_group_mb", "svd_reg", "tc_gather")] + [("reserved", C.c_int32 * 3)]
 
 
 class GemmItem(C.Structure):
@@ -166,6 +168,13 @@ def load():
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
+    # the ctypes mirrors must be the structs this build of the library was compiled with
+    for cname, mirror in (("qtn_pair_desc", PairDesc), ("qtn_pair_plan_t", PairPlan), ("qtn_options", Options),
+                          ("qtn_gemm_item", GemmItem)):
+        want = int(lib.qtn_sizeof(cname.encode()))
+        if want != C.sizeof(mirror):
+            raise QtnError(f"{LIB_PATH} is stale: sizeof({cname}) = {want} there, {C.sizeof(mirror)} in lib.py; "
+                           "rebuild it (`make -C qibotn_b200/csrc`)")
     return lib
 
 

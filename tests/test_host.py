@@ -191,6 +191,53 @@ def test_partition_units_covers_every_term_slice_once():
             assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
 
 
+def test_partition_units_by_cost():
+    """With per-slice costs the flattened list is cut where the cumulative cost crosses multiples of total / size:
+    still contiguous, complete and disjoint, and no rank carries more than its share plus one unit."""
+    from qibotn_b200 import dist
+    rng = np.random.default_rng(5)
+    for counts in ([1] * 60, [1, 4, 1, 1, 32, 1, 2], [64], [3, 0, 5], [1, 128, 1, 512, 2]):
+        weights = [float(10.0 ** rng.uniform(-3, 3)) for _ in counts]
+        total = sum(c * w for c, w in zip(counts, weights))
+        for size in (1, 2, 3, 8):
+            seen, loads = [], []
+            for r in range(size):
+                mine = dist.partition_units(counts, r, size, weights)
+                units = [(t, s) for t, rg in mine.items() for s in rg]
+                loads.append(sum(weights[t] for t, _ in units))
+                seen += units
+            assert seen == [(t, s) for t, c in enumerate(counts) for s in range(c)]
+            assert max(loads) <= total / size + max(weights) * (1 + 1e-9)
+    assert dist.partition_units([2, 3], 1, 2, [0.0, 0.0]) == dist.partition_units([2, 3], 1, 2)
+
+
+def test_hyper_tree_legs_match_the_path_walk():
+    """treeopt.HyperTree keeps a label open until ALL its owners are inside a subtree (owner counts as bit-sliced
+    counters); its costs must be those planner.path_cost computes for the same pairs, before and after subtree
+    reconfiguration and annealing, and find_path must use it for hyper-indexed (QAOA) networks."""
+    import random
+    from qibotn_b200 import circuits, planner
+    from qibotn_b200 import eval as ev
+    from qibotn_b200.treeopt import HyperTree
+    circ, edges = circuits.qaoa_maxcut(12, 2, seed=0)
+    net = list(ev._term_networks(circ, "complex64", circuits.zz_terms(edges)))[3]
+    sn = planner.SymbolicNetwork(net.modes, net.out)
+    assert sn.hyper_mask
+    pre, live, nxt = planner._absorb_small(sn)
+    tail = planner._elimination_path(live, sn.out_mask, sn.hyper_mask, nxt, random.Random(0), 0.0)
+    pre_cost = planner.path_cost(sn, pre + tail, 0)[0] - HyperTree(live, tail, nxt, sn.out_mask).total_cost()
+    tree = HyperTree(live, tail, nxt, sn.out_mask)
+    start = tree.total_cost()
+    tree.reconfigure(rounds=4, k=8)
+    tree.anneal(5000, random.Random(1))
+    path = pre + tree.ssa_pairs(nxt)
+    cost, width, _, _ = planner.path_cost(sn, path, 0)
+    assert abs(cost - pre_cost - tree.total_cost()) <= 1e-9 * cost and width == max(width, tree.width())
+    assert tree.total_cost() <= start
+    info = planner.find_path(net.modes, net.out, samples=2, seed=0, target_log2_width=30)
+    assert info.opt_cost <= cost * 1.5 and info.log2_width <= 30
+
+
 def test_plan_store_round_trip(tmp_path, monkeypatch):
     """engine.PLAN_STORE: a plan found for a network structure is written to disk and a fresh cache reads
     it back instead of searching again (offline planning of many-term observables, scripts/plan_c5.py)."""

@@ -189,6 +189,20 @@ def test_cta_pair_plans_are_well_formed(shape):
         assert 2 <= plan.tc_stages <= 8
         images = 1 << (plan.n_nhi + plan.n_khi)
         assert plan.workspace_bytes == plan.tc_prepack_off + images * 2 * rank_b + (256 if plan.tc_kind else 0)
+        # address-ordered gather ("tc_gather", default): bit r of the gathered element index walks the tile label
+        # of rank r in address order, and the element a thread converts -- enumeration (t, i) of a_lo_pos -- sits
+        # in the raw ring at the index built from the ranks of its bits: both must name the same address
+        assert plan.tc_gather == 1
+        n_lo = plan.na_lo
+        gbit, rank = list(plan.tc_a_gbit[:n_lo]), list(plan.tc_a_rank[:n_lo])
+        assert gbit == sorted(plan.a_lo_pos[:n_lo]) and sorted(rank) == list(range(n_lo))
+        for e in range(0, 1 << n_lo, 37):
+            t_, i_ = e & 255, e >> 8
+            addr_s = sum(1 << plan.a_lo_pos[j] for j in range(8) if (t_ >> j) & 1) | plan.tc_a_it_g[i_]
+            raw = sum(1 << rank[j] for j in range(8) if (t_ >> j) & 1) + plan.tc_a_it_raw[i_]
+            tg, ig = raw & 255, raw >> 8
+            addr_g = sum(1 << gbit[j] for j in range(8) if (tg >> j) & 1) | plan.tc_a_it_gg[ig]
+            assert addr_s == addr_g
         if plan.tc_kind:
             # the lowest k label is the first iteration bit (a thread packs two k-adjacent fp16 values per
             # store) and the five lane bits own the bank-selecting word offsets
