@@ -194,9 +194,12 @@ void qtn_options_current(qtn_options *opt);     /* the process-wide copy (defaul
  *                  MMAs of the other; 0: the round-1 pair kernel (tile and accumulators as one unit);
  *   "tc_fp16"      1 (default): staggered tiles split their operands into scaled fp16 pieces (tc_kind = 1,
  *                  half the tensor-pipe work of the TF32 split; run through qtn_pair_run_scaled); 0: TF32 split;
- *   "tc_gather"    1 (default): the staggered kernel gathers A in ascending address order (contiguous runs per
- *                  warp) and hands the raw elements across threads through shared memory; 0: every thread
- *                  gathers the elements it converts (round-2 first version);
+ *   "tc_gather"    0 (default): every producer thread of the staggered kernel gathers the elements it converts;
+ *                  1: A is gathered in ascending address order (contiguous runs per warp) and the raw elements
+ *                  change hands across threads through shared memory (an mbarrier per raw chunk + one named
+ *                  barrier per chunk).  Measured 5-20 % slower (profiles/r02_gather_ab.jsonl): fewer LSU
+ *                  wavefronts, but the producers are bound by their serial wait -> convert -> store chain, which
+ *                  the extra hand-off lengthens;
  *   "tc_persistent" 1 (default): one CTA per SM streams over the tiles with loads, MMAs and
  *                  epilogue of neighbouring tiles overlapped; 0: one CTA per tile.
  *   "svd_wide"     1 (default): qtn_svd_rows runs 512-thread CTAs holding twice the block rows (200 KB of

@@ -1364,6 +1364,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     uint32_t ph = 0;
     auto store = [&](int slot) {
       float2 va[NA];
+      const unsigned long long img = t == 0 ? img_ring[slot] : 0ull;   // before a refill of the slot replaces it
       if (gather) {
         const float2 *src = reinterpret_cast<const float2 *>(raw_ring + (size_t)slot * RAW) + r_t;
 #pragma unroll
@@ -1381,7 +1382,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
       unsigned char *sA = smem_raw + (size_t)s * STAGE;
       if (t == 0) {
         mbar_arrive_expect_tx(full_bar(s), kRankBytes);
-        bulk_copy_g2s(smem_u32(sA + 4 * PLANE_A), images + img_ring[slot] * kImageBytes, kRankBytes, full_bar(s));
+        bulk_copy_g2s(smem_u32(sA + 4 * PLANE_A), images + img * kImageBytes, kRankBytes, full_bar(s));
       }
       if constexpr (F16) {
         // elements 2p and 2p+1 of a thread differ in the lowest k bit: one packed 32-bit store per plane

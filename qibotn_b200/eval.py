@@ -208,6 +208,19 @@ def expectation_tn(qibo_circ, datatype, observable):
     return DeviceArray(total)
 
 
+def unit_seconds(nets, infos, datatype):
+    """Estimated seconds of ONE (term, slice) unit of every term (planner.estimate_seconds; the slice-independent
+    part of a term is charged to its slices in equal parts: a rank that owns any slice of a term runs it once)."""
+    from .planner import SymbolicNetwork, estimate_seconds
+
+    out = []
+    for net, info in zip(nets, infos):
+        sn = SymbolicNetwork(net.modes, net.out)
+        per_slice, hoisted = estimate_seconds(sn, info.path, sn.to_mask(info.sliced_labels), datatype)
+        out.append(per_slice + hoisted / max(1, info.num_slices))
+    return out
+
+
 def _expectation_distributed(qibo_circ, datatype, observable, n_samples, method):
     """Terms AND slices are sharded: the unit of work is (term, slice), the flat list is cut into ``size``
     contiguous ranges (``dist.partition_units``), each rank contracts its units and ONE all-reduce of the
@@ -230,9 +243,10 @@ def _expectation_distributed(qibo_circ, datatype, observable, n_samples, method)
             info = engine.find_info(net, datatype, samples=n_samples, seed=rk, min_slices=forced)
             plans[key], _winner = dist.vote_best(info.opt_cost, info)   # lowered by its owners only
         infos.append(plans[key])
-    # cut by cost, not by unit count: the light cones of one observable differ by orders of magnitude
+    # cut by estimated device time, not by unit count: the light cones of one observable differ by orders of
+    # magnitude in cost and in how memory-bound their nodes are
     mine = dist.partition_units([info.num_slices for info in infos], rank, size,
-                                weights=[info.opt_cost / max(1, info.num_slices) for info in infos])
+                                weights=unit_seconds(nets, infos, datatype))
     cdtype = torch.complex64 if str(datatype) == "complex64" else torch.complex128
     partials = torch.zeros(len(nets), dtype=cdtype, device="cuda")
     for t, slices in mine.items():

@@ -175,6 +175,11 @@ def load():
         if want != C.sizeof(mirror):
             raise QtnError(f"{LIB_PATH} is stale: sizeof({cname}) = {want} there, {C.sizeof(mirror)} in lib.py; "
                            "rebuild it (`make -C qibotn_b200/csrc`)")
+    # A/B runs of whole scripts: QTN_OPTIONS="tc_gather=0,svd_reg=5" edits the process-wide option set once
+    for item in filter(None, os.environ.get("QTN_OPTIONS", "").split(",")):
+        key, _, val = item.partition("=")
+        if lib.qtn_set_option(key.strip().encode(), int(val)) != 0:
+            raise QtnError(f"QTN_OPTIONS: unknown option {key!r}")
     return lib
 
 

@@ -29,7 +29,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-__all__ = ["SymbolicNetwork", "PathInfo", "find_path", "path_cost", "compute_slices"]
+__all__ = ["SymbolicNetwork", "PathInfo", "find_path", "path_cost", "estimate_seconds", "compute_slices"]
 
 
 class SymbolicNetwork:
@@ -160,6 +160,39 @@ def path_cost(net: SymbolicNetwork, path, sliced_mask=0):
         width = max(width, c.bit_count(), a.bit_count(), b.bit_count())
     ns = 2.0 ** sliced_mask.bit_count()
     return per_slice * ns + hoisted, width, per_slice, hoisted
+
+
+def estimate_seconds(net: SymbolicNetwork, path, sliced_mask=0, dtype="complex64"):
+    """Rough device time of a plan, (seconds of one slice, seconds of the hoisted part): every pairwise contraction
+    costs max(flops / rate, bytes / bandwidth) + a launch, with the rates the kernels reach on a B200
+    (`profiles/`: tcgen05 kernel ~280 TFLOP/s or ~4.2 TB/s, FFMA tile kernel ~25 TFLOP/s or ~1.8 TB/s, K reduction
+    ~2.5 TB/s; complex128 on the DFMA kernels).  Symbolic, no lowering: used to cut many-term observables into
+    equal TIME shares (eval._expectation_distributed) -- flops alone misjudge light cones whose nodes are
+    memory-bound."""
+    esz = 8.0 if str(dtype) == "complex64" else 16.0
+    c64 = esz == 8.0
+    per_slice = hoisted = 0.0
+    for _, a, b, c, d in _walk(net, path, sliced_mask):
+        ra, rb, rc = a.bit_count(), b.bit_count(), c.bit_count()
+        batch = (a & b & c).bit_count()
+        k = (a & b & ~c).bit_count()
+        m, n = ra - k - batch, rb - k - batch
+        if n > m:
+            m, n = n, m
+        flops = 8.0 * 2.0 ** (m + n + k + batch)
+        nbytes = esz * (2.0 ** ra + 2.0 ** rb + 2.0 ** rc)
+        if c64 and m >= (10 if batch else 7) and n >= (5 if batch else 4) and k >= 3 and m + n + k >= 18:
+            t = max(flops / 280e12, nbytes / 4.2e12)
+        elif m <= 4 and n <= 4 and k >= 10 and batch <= 15:
+            t = nbytes / 2.5e12
+        else:
+            t = max(flops / (25e12 if c64 else 8e12), nbytes / (1.8e12 if c64 else 1.0e12))
+        t += 4e-6
+        if d:
+            per_slice += t
+        else:
+            hoisted += t
+    return per_slice, hoisted
 
 
 # --------------------------------------------------------------- simplification

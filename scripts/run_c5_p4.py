@@ -48,8 +48,8 @@ for k, net in enumerate(nets):
         raise SystemExit(f"no stored plan for term {k} in {a.plan_store}: run scripts/plan_c5.py first")
     infos.append(info)
 counts = [infos[k].num_slices if k in only else 0 for k in range(len(nets))]
-weights = [infos[k].opt_cost / max(1, infos[k].num_slices) for k in range(len(nets))]
-mine = dist.partition_units(counts, rank, world, weights)
+weights = [infos[k].opt_cost / max(1, infos[k].num_slices) for k in range(len(nets))]          # MACs per unit
+mine = dist.partition_units(counts, rank, world, ev.unit_seconds(nets, infos, dtype))          # cut by est. time
 my_flops = sum(8.0 * weights[t] * len(rg) for t, rg in mine.items())
 torch.cuda.synchronize()
 dist.barrier()

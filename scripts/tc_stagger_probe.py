@@ -16,7 +16,7 @@ from qibotn_b200 import lib  # noqa: E402
 
 h = lib.load()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-DEFAULTS = dict(tc_pair=5, tc_stagger=1, tc_fp16=1, tc_min_log2=18)
+DEFAULTS = dict(tc_pair=5, tc_stagger=1, tc_fp16=1, tc_min_log2=18, tc_gather=lib.get_option("tc_gather"))
 
 
 def plan_for(la, pa, lb, pb, lc, **opts):
@@ -79,7 +79,8 @@ def check(m, n, k, seed):
     b = torch.randn(1 << len(lb), dtype=torch.complex64, device="cuda", generator=g)
     out = {}
     res = {"mode": "check", "m": m, "n": n, "k": k, "seed": seed}
-    for tag, opts in (("pair", dict(tc_stagger=0)), ("stagger", dict(tc_fp16=0)), ("fp16", dict())):
+    for tag, opts in (("pair", dict(tc_stagger=0)), ("stagger", dict(tc_fp16=0)), ("fp16", dict()),
+                      ("fp16_own", dict(tc_gather=0))):
         desc, plan = plan_for(la, pa, lb, pb, lc, **opts)
         dc, _ = launch(plan, a, b, len(lc))
         lcu = [desc.label_c[i] for i in range(len(lc))]
@@ -90,7 +91,7 @@ def check(m, n, k, seed):
         want = torch.einsum(f"{sym(oa)},{sym(ob)}->{sym(oc)}", ta, tb)
         err = float((tc_ - want).abs().max() / want.abs().max())
         out[tag] = dc
-        res[tag] = {"kernel": plan.kernel, "pair": plan.tc_pair, "kind": plan.tc_kind, "tile": [plan.tmb, plan.tnb, plan.tkb],
+        res[tag] = {"kernel": plan.kernel, "pair": plan.tc_pair, "kind": plan.tc_kind, "gather": plan.tc_gather, "tile": [plan.tmb, plan.tnb, plan.tkb],
                     "split": plan.split_bits, "stages": plan.tc_stages, "grid": int(plan.grid), "rel_err": err,
                     "amax_abc": launch.amax, "true_cmax": launch.cmax}
         del ta, tb, tc_, want
@@ -104,11 +105,12 @@ def time_case(m, n, k):
     a = torch.randn(1 << len(la), dtype=torch.complex64, device="cuda")
     b = torch.randn(1 << len(lb), dtype=torch.complex64, device="cuda")
     res = {"mode": "time", "m": m, "n": n, "k": k}
-    for tag, opts in (("pair", dict(tc_stagger=0)), ("stagger", dict(tc_fp16=0)), ("fp16", dict()),
-                      ("pair_again", dict(tc_stagger=0)), ("fp16_again", dict())):
+    for tag, opts in (("fp16_own", dict(tc_gather=0)), ("fp16_gather", dict(tc_gather=1)),
+                      ("fp16_own_again", dict(tc_gather=0)), ("fp16_gather_again", dict(tc_gather=1)),
+                      ("tf32_gather", dict(tc_fp16=0, tc_gather=1))):
         _, plan = plan_for(la, pa, lb, pb, lc, **opts)
         _, ms = launch(plan, a, b, len(lc), reps=5)
-        res[tag] = {"pair": plan.tc_pair, "kind": plan.tc_kind, "tile": [plan.tmb, plan.tnb, plan.tkb], "stages": plan.tc_stages,
+        res[tag] = {"pair": plan.tc_pair, "kind": plan.tc_kind, "gather": plan.tc_gather, "tile": [plan.tmb, plan.tnb, plan.tkb], "stages": plan.tc_stages,
                     "ms": ms, "TFs": plan.flops / ms / 1e9, "GBs": plan.bytes / ms / 1e6}
     print(json.dumps(res), flush=True)
 

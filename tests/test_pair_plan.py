@@ -192,7 +192,16 @@ def test_cta_pair_plans_are_well_formed(shape):
         # address-ordered gather ("tc_gather", default): bit r of the gathered element index walks the tile label
         # of rank r in address order, and the element a thread converts -- enumeration (t, i) of a_lo_pos -- sits
         # in the raw ring at the index built from the ranks of its bits: both must name the same address
-        assert plan.tc_gather == 1
+        assert plan.tc_gather == 0                          # off by default (measured slower, see the header)
+        lib.set_option("tc_min_log2", 0)
+        lib.set_option("tc_gather", 1)
+        try:
+            gplan = lib.pair_plan(lib.make_pair_desc("complex64", la, lb))
+        finally:
+            lib.set_option("tc_min_log2", 18)
+            lib.set_option("tc_gather", 0)
+        assert gplan.tc_gather == 1 and list(gplan.a_lo_pos) == list(plan.a_lo_pos)
+        plan_own, plan = plan, gplan
         n_lo = plan.na_lo
         gbit, rank = list(plan.tc_a_gbit[:n_lo]), list(plan.tc_a_rank[:n_lo])
         assert gbit == sorted(plan.a_lo_pos[:n_lo]) and sorted(rank) == list(range(n_lo))
@@ -203,6 +212,7 @@ def test_cta_pair_plans_are_well_formed(shape):
             tg, ig = raw & 255, raw >> 8
             addr_g = sum(1 << gbit[j] for j in range(8) if (tg >> j) & 1) | plan.tc_a_it_gg[ig]
             assert addr_s == addr_g
+        plan = plan_own
         if plan.tc_kind:
             # the lowest k label is the first iteration bit (a thread packs two k-adjacent fp16 values per
             # store) and the five lane bits own the bank-selecting word offsets
