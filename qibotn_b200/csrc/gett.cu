@@ -39,6 +39,14 @@ __device__ __forceinline__ long long deposit(unsigned long long idx, const uint8
   return off;
 }
 
+// the same for label lists in which position 255 marks a label the operand does not carry
+__device__ __forceinline__ long long deposit_present(unsigned long long idx, const uint8_t *pos, int n) {
+  long long off = 0;
+  for (int i = 0; i < n; ++i)
+    if (pos[i] != 255) off |= (long long)((idx >> i) & 1ull) << pos[i];
+  return off;
+}
+
 __device__ __forceinline__ long long slice_offset(const int32_t *slice_id, int n, const uint8_t *bit,
                                                   const uint8_t *pos) {
   if (n == 0) return 0;
@@ -389,9 +397,9 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   T *sB = sA + 2 * KC * KRED_ROW;                            // [2][KC][16]
   const int t = threadIdx.x;
   const long long a_base = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a) |
-                           deposit(blockIdx.y, P.a_bat, P.n_batch);      // grid.y = batch (hyper) value
+                           deposit_present(blockIdx.y, P.a_bat, P.n_batch);   // grid.y = batch (hyper) value
   const long long b_base = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b) |
-                           deposit(blockIdx.y, P.b_bat, P.n_batch);
+                           deposit_present(blockIdx.y, P.b_bat, P.n_batch);
   // enumeration: element index e = t + 256 * u.  Bits 0-7 come from the thread (a_t_*), bits 8-10
   // from u: their global / shared strides are three per-operand constants, so the offset of
   // iteration u is a sum of at most three registers (u is a compile-time constant below).

@@ -26,6 +26,10 @@ int find_label(const int32_t *labels, int n, int label) {
 }
 
 constexpr int kPhantom = 255;
+// Largest set of pre-packed B images (bytes of the 3xTF32 form; the fp16 form is 3/4 of it): B is re-laid once per
+// launch at 1.5-2x its size, which pays whenever >= 8 m tiles read every image -- also for a B of many GB (the deep
+// hyper-indexed nodes of QAOA light cones: both operands 2^31 elements).  The workspace is sized by the plan.
+constexpr int64_t kMaxImageBytes = (int64_t)1 << 35;
 
 }  // namespace
 
@@ -124,7 +128,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     const int tnb = std::min(nbits, 7), tkb = std::min(kbits, 4);
     if (mbits < 10 || tnb < opt.tc_pair || mbits - 7 + bbits > QTN_HI_MAX) return false;
     const int64_t images = (int64_t)1 << std::min(40, (nbits - tnb) + (kbits - tkb) + bbits);
-    return images * (4 * (int64_t)(4 << (tnb + tkb))) <= ((int64_t)1 << 30);
+    return images * (4 * (int64_t)(4 << (tnb + tkb))) <= kMaxImageBytes;
   };
 
   // ---- K-parallel reduction for tiny outputs --------------------------------
@@ -152,14 +156,22 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     p->grid = (int64_t)1 << (kbits - chunk);
     p->smem_bytes = 0;
     p->workspace_bytes = p->grid * 16 * esz;
-  } else if (bbits <= 15 && mbits <= 4 && nbits <= 4 && kbits >= 10) {
+  } else if (mbits <= 5 && nbits <= 5 && kbits >= 10 &&
+             bbits + std::max(0, mbits - 4) + std::max(0, nbits - 4) <= 15) {
     // ---- streaming K reduction (<= 16 x 16 outputs) ----------------------------
     p->kernel = QTN_KERNEL_KRED;
     const int tkb = std::min(kbits, d->dtype == QTN_C64 ? 7 : 6);   // chunk: 128 / 64 contracted values
     p->tmb = 4; p->tnb = 4; p->tkb = tkb;
-    p->m_real = mbits; p->n_real = nbits; p->k_real = tkb;
     std::sort(M.begin(), M.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
     std::sort(N.begin(), N.end(), [](const Lab &x, const Lab &y) { return x.pb < y.pb; });
+    // a fifth m (n) label -- the one with the highest address -- is enumerated by grid.y next to the batch labels:
+    // it is absent from B (A), which is simply read once per value of it
+    std::vector<Lab> Mx, Nx;
+    while ((int)M.size() > 4) { Mx.push_back(M.back()); M.pop_back(); }
+    while ((int)N.size() > 4) { Nx.push_back(N.back()); N.pop_back(); }
+    const int mt = (int)M.size(), nt = (int)N.size();
+    const int ybits = bbits + (int)Mx.size() + (int)Nx.size();      // labels enumerated by grid.y
+    p->m_real = mt; p->n_real = nt; p->k_real = tkb;
     // chunk labels = the K labels with the lowest addresses (in either operand): contiguous runs
     std::sort(K.begin(), K.end(), [](const Lab &x, const Lab &y) {
       return std::min(x.pa, x.pb) != std::min(y.pa, y.pb) ? std::min(x.pa, x.pb) < std::min(y.pa, y.pb)
@@ -174,22 +186,29 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
       int next_c = 0;
       for (auto &l : N) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
       for (auto &l : M) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
-      for (auto &l : Bt) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
+      for (auto *v : {&Nx, &Mx, &Bt})
+        for (auto &l : *v) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
     }
-    for (int i = 0; i < mbits; ++i) { p->a_mhi[i] = M[i].pa; p->c_mhi[i] = M[i].pc; }
-    for (int i = 0; i < nbits; ++i) { p->b_nhi[i] = N[i].pb; p->c_nhi[i] = N[i].pc; }
-    // batch (hyper) labels: one independent reduction per batch value (grid.y)
-    p->n_batch = bbits;
-    for (int i = 0; i < bbits; ++i) { p->a_bat[i] = Bt[i].pa; p->b_bat[i] = Bt[i].pb; p->c_bat[i] = Bt[i].pc; }
+    for (int i = 0; i < mt; ++i) { p->a_mhi[i] = M[i].pa; p->c_mhi[i] = M[i].pc; }
+    for (int i = 0; i < nt; ++i) { p->b_nhi[i] = N[i].pb; p->c_nhi[i] = N[i].pc; }
+    // grid.y: batch (hyper) labels -- one independent reduction per value -- and the surplus m / n labels
+    // (position 255 = the operand does not carry the label)
+    p->n_batch = ybits;
+    {
+      int i = 0;
+      for (auto &l : Bt) { p->a_bat[i] = l.pa; p->b_bat[i] = l.pb; p->c_bat[i] = l.pc; ++i; }
+      for (auto &l : Mx) { p->a_bat[i] = l.pa; p->b_bat[i] = kPhantom; p->c_bat[i] = l.pc; ++i; }
+      for (auto &l : Nx) { p->a_bat[i] = kPhantom; p->b_bat[i] = l.pb; p->c_bat[i] = l.pc; ++i; }
+    }
     p->n_mhi = 0; p->n_nhi = 0; p->n_khi = (int)khi.size();
     for (int i = 0; i < p->n_khi; ++i) { p->a_khi[i] = khi[i].pa; p->b_khi[i] = khi[i].pb; }
     // shared-memory chunk: element (k, row) at k * 18 + row (padded rows: conflict-free stores
     // when a warp's lanes walk k); enumerations in address order
     struct E { int pos; int sstr; };
     std::vector<E> ea, eb;
-    for (int i = 0; i < mbits; ++i) ea.push_back({M[i].pa, 1 << i});
+    for (int i = 0; i < mt; ++i) ea.push_back({M[i].pa, 1 << i});
     for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, 18 << i});
-    for (int i = 0; i < nbits; ++i) eb.push_back({N[i].pb, 1 << i});
+    for (int i = 0; i < nt; ++i) eb.push_back({N[i].pb, 1 << i});
     for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, 18 << i});
     auto by_pos = [](const E &x, const E &y) { return x.pos < y.pos; };
     std::sort(ea.begin(), ea.end(), by_pos);
@@ -201,7 +220,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     // every CTA leaves one partial C in the workspace
     const int64_t ngroups = (int64_t)1 << std::max(0, p->n_khi - 3);   // groups of 8 chunks
     p->split_bits = 0;
-    p->grid = std::min<int64_t>(ngroups, std::max<int64_t>(1, ((int64_t)2 * sm_count) >> bbits));
+    p->grid = std::min<int64_t>(ngroups, std::max<int64_t>(1, ((int64_t)2 * sm_count) >> ybits));
     p->workspace_bytes = ((int64_t)esz << d->rank_c) * p->grid;
     // max(2 buffers x (A + B) chunk, 16 x 256 partials)
     p->smem_bytes = std::max(2 * 2 * (1 << tkb) * 18 * esz, 16 * 256 * esz);
@@ -345,7 +364,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     {
       const int64_t images = (int64_t)1 << (p->n_nhi + p->n_khi + bbits);
       const int64_t image_bytes = 4 * (int64_t)p->tc_plane_b;
-      if (opt.tc_prepack && p->tc_reserved > 0 && true_mhi >= 3 && images * image_bytes <= ((int64_t)1 << 30)) {
+      if (opt.tc_prepack && p->tc_reserved > 0 && true_mhi >= 3 && images * image_bytes <= kMaxImageBytes) {
         p->tc_prepack = 1;
         p->tc_prepack_off = (p->workspace_bytes + 255) & ~(int64_t)255;
         p->workspace_bytes = p->tc_prepack_off + images * image_bytes;

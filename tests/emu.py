@@ -19,6 +19,12 @@ def dep(idx, pos, n):
     return off
 
 
+def dep_present(idx, pos, n):
+    """``dep`` for label lists where position 255 marks a label the operand does not carry."""
+    return dep(idx, [p if p != 255 else 0 for p in pos], n) if all(p != 255 for p in pos[:n]) else \
+        sum(((idx >> i) & 1) << pos[i] for i in range(n) if pos[i] != 255)
+
+
 def slice_off(slice_id, n, bits, pos):
     off = 0
     for i in range(n):
@@ -240,8 +246,8 @@ def _run_kred(P, a, b, c, sa, sb):
         acc = np.zeros((16, 16), dtype=np.complex128)
         # groups of 2^ib consecutive chunks; neighbouring CTAs take neighbouring groups
         for kh in (g << ib | i for g in range(cta, ngroups, P.grid) for i in range(1 << ib)):
-            a_k = sa | dep(kh, P.a_khi, P.n_khi) | dep(bt, P.a_bat, P.n_batch)
-            b_k = sb | dep(kh, P.b_khi, P.n_khi) | dep(bt, P.b_bat, P.n_batch)
+            a_k = sa | dep(kh, P.a_khi, P.n_khi) | dep_present(bt, P.a_bat, P.n_batch)
+            b_k = sb | dep(kh, P.b_khi, P.n_khi) | dep_present(bt, P.b_bat, P.n_batch)
             chunks = []
             for (n_lo, lo_pos, lo_sstr, src, base) in ((P.na_lo, P.a_lo_pos, P.a_lo_sstr, a, a_k),
                                                        (P.nb_lo, P.b_lo_pos, P.b_lo_sstr, b, b_k)):

@@ -187,6 +187,7 @@ def test_tensor_core_variants_agree_with_einsum(shape):
     # staggered tcgen05 pair kernel (one set of B images per batch value) and on the streaming K reduction (grid.y)
     ("tc", 10, 5, 4, 2), ("tc", 11, 7, 5, 3), ("tc", 10, 6, 3, 1), ("tc", 12, 7, 6, 2), ("tc", 10, 5, 8, 4),
     ("kred", 4, 4, 12, 3), ("kred", 2, 3, 14, 6), ("kred", 0, 1, 16, 1), ("kred", 4, 3, 10, 9),
+    ("kred", 5, 3, 14, 4), ("kred", 5, 5, 12, 0), ("kred", 2, 5, 13, 2),
 ])
 def test_batch_labels_on_tensor_core_and_kred_kernels(case):
     kind, m, n, k, batch = case
@@ -210,7 +211,7 @@ def test_batch_labels_on_tensor_core_and_kred_kernels(case):
                                           slice_a=sa, slice_id=1)
         finally:
             lib.set_option("tc_min_log2", 18)
-        assert plan.n_batch == batch
+        assert plan.n_batch == batch + (max(0, m - 4) + max(0, n - 4) if kind == "kred" else 0)
         if kind == "tc":
             assert plan.kernel == lib.KERNEL_TC and plan.tc_pair == 2 and plan.tc_kind == (1 if k >= 4 else 0)
         else:

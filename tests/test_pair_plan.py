@@ -255,6 +255,7 @@ BATCH_CASES = [
     # the streaming K reduction
     ("tc", 10, 5, 3, 2, 0, 0), ("tc", 10, 5, 4, 1, 1, 0), ("tc", 11, 6, 5, 2, 0, 1), ("tc", 10, 7, 4, 3, 0, 0),
     ("kred", 2, 3, 10, 2, 0, 0), ("kred", 4, 4, 10, 1, 1, 1), ("kred", 0, 1, 11, 3, 0, 0),
+    ("kred", 5, 3, 10, 2, 0, 0), ("kred", 5, 5, 10, 0, 1, 0), ("kred", 3, 5, 11, 1, 0, 1),
     ("tile", 9, 5, 4, 2, 0, 0), ("tile", 10, 4, 4, 1, 0, 0),
 ]
 
@@ -275,7 +276,7 @@ def test_batch_labels_in_tensor_core_and_kred_plans(case):
         plan = lib.pair_plan(desc, 4)
     finally:
         lib.set_option("tc_min_log2", 18)
-    assert plan.n_batch == batch
+    assert plan.n_batch == batch + (max(0, m - 4) + max(0, n - 4) if kind == "kred" else 0)
     if kind == "tc":
         # m >= 10 (8 m tiles per B image), n >= 5: the staggered pair kernel; fp16 split when 16 k values fill a stage
         assert plan.kernel == lib.KERNEL_TC and plan.tc_pair == 2 and plan.tc_prepack == 1
