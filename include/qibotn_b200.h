@@ -163,6 +163,10 @@ typedef struct {
   uint8_t tc_a_gbit[QTN_LO_MAX], tc_a_rank[QTN_LO_MAX];
   int64_t tc_a_it_gg[8];
   int32_t tc_a_it_raw[8];
+  /* QTN_KERNEL_TILE: shared-memory stages of (A tile, B tile); 2 = the next k step is copied (cp.async) while the
+   * current one is multiplied */
+  int32_t tile_stages;
+  int32_t reserved_tail;
 } qtn_pair_plan_t;
 
 /* Per-call options.  Every switch below can be handed to the planner / the SVD driver explicitly

@@ -59,6 +59,17 @@ __device__ __forceinline__ long long slice_offset(const int32_t *slice_id, int n
 // --------------------------------------------------------------------------
 // Tiled kernel
 // --------------------------------------------------------------------------
+// cp.async of one element (8 bytes complex64 / 16 bytes complex128); `valid` false = zero fill (phantom rows)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_elem(void *dst_smem, const void *src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int n = valid ? BYTES : 0;
+  if constexpr (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
 template <typename R>
 __global__ void __launch_bounds__(256)
 gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restrict__ A,
@@ -66,8 +77,9 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
                  const int32_t *__restrict__ slice_id) {
   using T = cx<R>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *sA = reinterpret_cast<T *>(smem_raw);
-  T *sB = sA + (P.sa_stride << P.tkb);
+  // P.tile_stages (1 or 2) stages of [A tile | B tile]; the epilogue's staging buffer aliases them
+  const int stage_elems = (P.sa_stride + P.sb_stride) << P.tkb;
+  T *stages = reinterpret_cast<T *>(smem_raw);
   T *sC = reinterpret_cast<T *>(smem_raw);
   // per-iteration parts of the tile enumerations (bits 8.. of the element index)
   __shared__ long long a_it_g[16], b_it_g[16], c_it_g[16];
@@ -143,66 +155,66 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
     for (int j = 0; j < 4; ++j) acc[i][j] = cx_zero<R>();
 
   // ---- K loop -----------------------------------------------------------------
+  // The (A, B) tiles of k step kk+1 travel global -> shared memory by cp.async while step kk is being multiplied
+  // (two stages); every element is its own copy, in ascending address order of its operand (phantom rows are
+  // zero-filled copies), the conjugation flags are applied when the values are read back.
   const int k_iters_bits = P.n_khi - P.split_bits;
   const unsigned long long k_iters = 1ull << k_iters_bits;
   const unsigned long long kh0 = (unsigned long long)split << k_iters_bits;
   long long a_k = deposit(kh0, P.a_khi, P.n_khi);
   long long b_k = deposit(kh0, P.b_khi, P.n_khi);
+  const R sgn_a = P.conj_a ? (R)-1 : (R)1, sgn_b = P.conj_b ? (R)-1 : (R)1;
+  const bool two = P.tile_stages >= 2;
   __syncthreads();
 
-  for (unsigned long long kk = 0; kk < k_iters; ++kk) {
-    // global -> shared, ascending address order of each operand; loads are issued in
-    // batches of 8 before any shared-memory store so that many requests are in flight
+  auto issue = [&](int buf) {                  // this thread's copies of the step at (a_k, b_k) into stage `buf`
+    T *sA = stages + (size_t)buf * stage_elems;
+    T *sB = sA + (P.sa_stride << P.tkb);
     if (a_act) {
-#pragma unroll 1
-      for (int it0 = 0; it0 < a_nit; it0 += 8) {
-        T v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          v[u] = cx_zero<R>();
-          if (it0 + u < a_nit) {
-            const long long g = a_it_g[it0 + u];
-            if (a_t_g >= 0 && g >= 0) v[u] = A[a_base + a_k + (a_t_g | g)];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (it0 + u < a_nit) {
-            if (P.conj_a) v[u].y = -v[u].y;
-            sA[a_t_s + a_it_s[it0 + u]] = v[u];
-          }
+      for (int it = 0; it < a_nit; ++it) {
+        const long long g = a_it_g[it];
+        const bool ok = a_t_g >= 0 && g >= 0;
+        cp_async_elem<(int)sizeof(T)>(sA + a_t_s + a_it_s[it], A + (ok ? a_base + a_k + (a_t_g | g) : 0), ok);
       }
     }
     if (b_act) {
-#pragma unroll 1
-      for (int it0 = 0; it0 < b_nit; it0 += 4) {
-        T v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          v[u] = cx_zero<R>();
-          if (it0 + u < b_nit) {
-            const long long g = b_it_g[it0 + u];
-            if (b_t_g >= 0 && g >= 0) v[u] = B[b_base + b_k + (b_t_g | g)];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (it0 + u < b_nit) {
-            if (P.conj_b) v[u].y = -v[u].y;
-            sB[b_t_s + b_it_s[it0 + u]] = v[u];
-          }
+      for (int it = 0; it < b_nit; ++it) {
+        const long long g = b_it_g[it];
+        const bool ok = b_t_g >= 0 && g >= 0;
+        cp_async_elem<(int)sizeof(T)>(sB + b_t_s + b_it_s[it], B + (ok ? b_base + b_k + (b_t_g | g) : 0), ok);
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto next_k = [&](unsigned long long kk) {   // flip the trailing bits that change between kk and kk+1
+    const unsigned long long flip = kk ^ (kk + 1);
+    const int nflip = 64 - __clzll(flip);
+    for (int i = 0; i < nflip && i < k_iters_bits; ++i) {
+      a_k ^= 1ll << P.a_khi[i];
+      b_k ^= 1ll << P.b_khi[i];
+    }
+  };
+
+  issue(0);
+  for (unsigned long long kk = 0; kk < k_iters; ++kk) {
+    const int buf = two ? (int)(kk & 1) : 0;
+    if (two && kk + 1 < k_iters) {
+      next_k(kk);
+      issue(buf ^ 1);                          // stage buf^1 was released by the barrier that ended step kk-1
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
-    const T *pa = sA + tm * 4;
-    const T *pb = sB + tn * 4;
+    const T *pa = stages + (size_t)buf * stage_elems + tm * 4;
+    const T *pb = stages + (size_t)buf * stage_elems + (P.sa_stride << P.tkb) + tn * 4;
 #pragma unroll 4
     for (int k = 0; k < TK; ++k) {
       T a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = pa[i];
+      for (int i = 0; i < 4; ++i) { a[i] = pa[i]; a[i].y *= sgn_a; }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = pb[j];
+      for (int j = 0; j < 4; ++j) { b[j] = pb[j]; b[j].y *= sgn_b; }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -211,13 +223,7 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
       pb += P.sb_stride;
     }
     __syncthreads();
-    // next k_hi: flip the trailing bits that change between kk and kk+1
-    const unsigned long long flip = kk ^ (kk + 1);
-    const int nflip = 64 - __clzll(flip);
-    for (int i = 0; i < nflip && i < k_iters_bits; ++i) {
-      a_k ^= 1ll << P.a_khi[i];
-      b_k ^= 1ll << P.b_khi[i];
-    }
+    if (!two && kk + 1 < k_iters) { next_k(kk); issue(0); }
   }
 
   // ---- epilogue: registers -> staging (C address order) -> global ---------------
@@ -535,7 +541,7 @@ int launch_tile(const qtn_pair_plan_t &P, const void *a, const void *b, void *c,
   static bool attr_set = false;
   if (!attr_set) {
     QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tile_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        4608 * (int)sizeof(T)));
+                                        2 * 4608 * (int)sizeof(float2)));
     attr_set = true;
   }
   if (P.grid <= 0 || P.grid > 0x7fffffffLL) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_run: grid too large");

@@ -469,8 +469,10 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     else if (nbits < 6) { tnb = std::max(nbits, 2); tmb = 12 - tnb; }
     else { tmb = std::max(mbits, 2); tnb = 12 - tmb; }   // unreachable after swap, kept for safety
     const int TM = 1 << tmb, TN = 1 << tnb;
+    // two stages of (A, B) tiles (the next k step is copied while this one is multiplied) within ~68 KB of shared
+    // memory, so that three CTAs share an SM: 4224 elements per stage in complex64, 2112 in complex128
     int tkb = 4;
-    while (tkb > 0 && (1 << tkb) * (TM + TN + 4) > 4224) --tkb;
+    while (tkb > 0 && (1 << tkb) * (TM + TN + 4) > (d->dtype == QTN_C64 ? 4224 : 2112)) --tkb;
     tkb = std::min(tkb, kbits);
     p->tmb = tmb; p->tnb = tnb; p->tkb = tkb;
     p->sa_stride = TM + 2; p->sb_stride = TN + 2;
@@ -569,7 +571,8 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     p->workspace_bytes = split ? ((int64_t)esz << (d->rank_c + split)) : 0;
     int tile_bytes = ((1 << tkb) * (p->sa_stride + p->sb_stride)) * esz;
     int stage_bytes = 4096 * esz;
-    p->smem_bytes = std::max(tile_bytes, stage_bytes);
+    p->tile_stages = (p->n_khi - split) >= 1 ? 2 : 1;          // a single k step has nothing to prefetch
+    p->smem_bytes = std::max(p->tile_stages * tile_bytes, stage_bytes);
   }
 
   // write the chosen layout of C back to the descriptor
