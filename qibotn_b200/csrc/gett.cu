@@ -71,16 +71,17 @@ __device__ __forceinline__ void cp_async_elem(void *dst_smem, const void *src, b
 }
 
 template <typename R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2)
 gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restrict__ A,
                  const cx<R> *__restrict__ B, cx<R> *__restrict__ C, cx<R> *__restrict__ ws,
                  const int32_t *__restrict__ slice_id) {
   using T = cx<R>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // P.tile_stages (1 or 2) stages of [A tile | B tile]; the epilogue's staging buffer aliases them
+  // two stages of [A tile | B tile]; the epilogue's staging buffer (4096 outputs) aliases the stage that was
+  // consumed last when it fits there (complex64: the other stage already receives the next tile), else both
   const int stage_elems = (P.sa_stride + P.sb_stride) << P.tkb;
   T *stages = reinterpret_cast<T *>(smem_raw);
-  T *sC = reinterpret_cast<T *>(smem_raw);
+  const bool xtile = stage_elems >= 4096;      // cross-tile prefetch: the staging buffer fits one stage
   // per-iteration parts of the tile enumerations (bits 8.. of the element index)
   __shared__ long long a_it_g[16], b_it_g[16], c_it_g[16];
   __shared__ int a_it_s[16], b_it_s[16];
@@ -88,24 +89,7 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   const int t = threadIdx.x;
   const int TK = 1 << P.tkb;
 
-  // ---- which tile ----------------------------------------------------------
-  unsigned long long id = blockIdx.x;
-  const unsigned split = (unsigned)(id & ((1ull << P.split_bits) - 1));
-  id >>= P.split_bits;
-  const unsigned long long mh = id & ((1ull << P.n_mhi) - 1);
-  id >>= P.n_mhi;
-  const unsigned long long nh = id & ((1ull << P.n_nhi) - 1);
-  id >>= P.n_nhi;
-  const unsigned long long bt = id;
-
-  const long long a_base = deposit(mh, P.a_mhi, P.n_mhi) | deposit(bt, P.a_bat, P.n_batch) |
-                           slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
-  const long long b_base = deposit(nh, P.b_nhi, P.n_nhi) | deposit(bt, P.b_bat, P.n_batch) |
-                           slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
-  const long long c_base = deposit(mh, P.c_mhi, P.n_mhi) | deposit(nh, P.c_nhi, P.n_nhi) |
-                           deposit(bt, P.c_bat, P.n_batch);
-
-  // ---- enumeration tables ---------------------------------------------------
+  // ---- enumeration tables (the same for every tile) -----------------------------
   if (t < 16) {
     long long g = 0; int s = 0;
     for (int j = 8; j < P.na_lo; ++j)
@@ -145,88 +129,9 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   const int a_nit = P.na_lo > 8 ? 1 << (P.na_lo - 8) : 1;
   const int b_nit = P.nb_lo > 8 ? 1 << (P.nb_lo - 8) : 1;
 
-  // ---- thread's 4x4 outputs --------------------------------------------------
+  // ---- thread's 4x4 outputs: staging indices -----------------------------------
   const int tn = t & ((1 << (P.tnb - 2)) - 1);
   const int tm = t >> (P.tnb - 2);
-  T acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = cx_zero<R>();
-
-  // ---- K loop -----------------------------------------------------------------
-  // The (A, B) tiles of k step kk+1 travel global -> shared memory by cp.async while step kk is being multiplied
-  // (two stages); every element is its own copy, in ascending address order of its operand (phantom rows are
-  // zero-filled copies), the conjugation flags are applied when the values are read back.
-  const int k_iters_bits = P.n_khi - P.split_bits;
-  const unsigned long long k_iters = 1ull << k_iters_bits;
-  const unsigned long long kh0 = (unsigned long long)split << k_iters_bits;
-  long long a_k = deposit(kh0, P.a_khi, P.n_khi);
-  long long b_k = deposit(kh0, P.b_khi, P.n_khi);
-  const R sgn_a = P.conj_a ? (R)-1 : (R)1, sgn_b = P.conj_b ? (R)-1 : (R)1;
-  const bool two = P.tile_stages >= 2;
-  __syncthreads();
-
-  auto issue = [&](int buf) {                  // this thread's copies of the step at (a_k, b_k) into stage `buf`
-    T *sA = stages + (size_t)buf * stage_elems;
-    T *sB = sA + (P.sa_stride << P.tkb);
-    if (a_act) {
-      for (int it = 0; it < a_nit; ++it) {
-        const long long g = a_it_g[it];
-        const bool ok = a_t_g >= 0 && g >= 0;
-        cp_async_elem<(int)sizeof(T)>(sA + a_t_s + a_it_s[it], A + (ok ? a_base + a_k + (a_t_g | g) : 0), ok);
-      }
-    }
-    if (b_act) {
-      for (int it = 0; it < b_nit; ++it) {
-        const long long g = b_it_g[it];
-        const bool ok = b_t_g >= 0 && g >= 0;
-        cp_async_elem<(int)sizeof(T)>(sB + b_t_s + b_it_s[it], B + (ok ? b_base + b_k + (b_t_g | g) : 0), ok);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  auto next_k = [&](unsigned long long kk) {   // flip the trailing bits that change between kk and kk+1
-    const unsigned long long flip = kk ^ (kk + 1);
-    const int nflip = 64 - __clzll(flip);
-    for (int i = 0; i < nflip && i < k_iters_bits; ++i) {
-      a_k ^= 1ll << P.a_khi[i];
-      b_k ^= 1ll << P.b_khi[i];
-    }
-  };
-
-  issue(0);
-  for (unsigned long long kk = 0; kk < k_iters; ++kk) {
-    const int buf = two ? (int)(kk & 1) : 0;
-    if (two && kk + 1 < k_iters) {
-      next_k(kk);
-      issue(buf ^ 1);                          // stage buf^1 was released by the barrier that ended step kk-1
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const T *pa = stages + (size_t)buf * stage_elems + tm * 4;
-    const T *pb = stages + (size_t)buf * stage_elems + (P.sa_stride << P.tkb) + tn * 4;
-#pragma unroll 4
-    for (int k = 0; k < TK; ++k) {
-      T a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = pa[i]; a[i].y *= sgn_a; }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { b[j] = pb[j]; b[j].y *= sgn_b; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cfma<R>(acc[i][j], a[i], b[j]);
-      pa += P.sa_stride;
-      pb += P.sb_stride;
-    }
-    __syncthreads();
-    if (!two && kk + 1 < k_iters) { next_k(kk); issue(0); }
-  }
-
-  // ---- epilogue: registers -> staging (C address order) -> global ---------------
   int mi[4], nj[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -237,25 +142,141 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
     mi[i] = sm; nj[i] = sn;
   }
   const int c_count = 1 << P.nc_lo;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int idx = mi[i] + nj[j];
-      if (idx < c_count) sC[idx] = acc[i][j];
-    }
-  __syncthreads();
-  T *out = C;
-  long long out_off = c_base;
-  if (P.split_bits) { out = ws; out_off += (long long)split * P.c_elems; }
+  const int k_iters_bits = P.n_khi - P.split_bits;
+  const unsigned long long k_iters = 1ull << k_iters_bits;
+  const R sgn_a = P.conj_a ? (R)-1 : (R)1, sgn_b = P.conj_b ? (R)-1 : (R)1;
+  const long long a_slice = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
+  const long long b_slice = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
   const bool acc_out = P.accumulate && !P.split_bits;
+
+  // ---- a persistent CTA walks tiles blockIdx.x, + gridDim.x, ... -------------------
+  // Copies (cp.async, one per element, ascending address order of the operand, zero fill for phantom rows) run
+  // one k step ahead of the multiplication -- across tile boundaries too, so the first step of the next tile
+  // arrives while this tile is multiplied and stored.  Conjugation flags are applied when the values are read.
+  long long a_k = 0, b_k = 0;                  // operand offsets of the step to be COPIED next
+  auto enter = [&](unsigned long long tile) {
+    unsigned long long id = tile;
+    const unsigned split = (unsigned)(id & ((1ull << P.split_bits) - 1));
+    id >>= P.split_bits;
+    const unsigned long long mh = id & ((1ull << P.n_mhi) - 1);
+    id >>= P.n_mhi;
+    const unsigned long long nh = id & ((1ull << P.n_nhi) - 1);
+    id >>= P.n_nhi;
+    const unsigned long long kh0 = (unsigned long long)split << k_iters_bits;
+    a_k = a_slice | deposit(mh, P.a_mhi, P.n_mhi) | deposit(id, P.a_bat, P.n_batch) | deposit(kh0, P.a_khi, P.n_khi);
+    b_k = b_slice | deposit(nh, P.b_nhi, P.n_nhi) | deposit(id, P.b_bat, P.n_batch) | deposit(kh0, P.b_khi, P.n_khi);
+  };
+  auto issue = [&](int buf) {                  // this thread's copies of the step at (a_k, b_k) into stage `buf`
+    T *sA = stages + (size_t)buf * stage_elems;
+    T *sB = sA + (P.sa_stride << P.tkb);
+    if (a_act) {
+      for (int it = 0; it < a_nit; ++it) {
+        const long long g = a_it_g[it];
+        const bool ok = a_t_g >= 0 && g >= 0;
+        cp_async_elem<(int)sizeof(T)>(sA + a_t_s + a_it_s[it], A + (ok ? a_k + (a_t_g | g) : 0), ok);
+      }
+    }
+    if (b_act) {
+      for (int it = 0; it < b_nit; ++it) {
+        const long long g = b_it_g[it];
+        const bool ok = b_t_g >= 0 && g >= 0;
+        cp_async_elem<(int)sizeof(T)>(sB + b_t_s + b_it_s[it], B + (ok ? b_k + (b_t_g | g) : 0), ok);
+      }
+    }
+  };
+  auto next_k = [&](unsigned long long kk) {   // flip the trailing bits that change between kk and kk+1
+    const unsigned long long flip = kk ^ (kk + 1);
+    const int nflip = 64 - __clzll(flip);
+    for (int i = 0; i < nflip && i < k_iters_bits; ++i) {
+      a_k ^= 1ll << P.a_khi[i];
+      b_k ^= 1ll << P.b_khi[i];
+    }
+  };
+
+  const unsigned long long ntiles = (unsigned long long)P.grid;
+  unsigned long long tile = blockIdx.x;
+  __syncthreads();                             // the iteration tables are in shared memory
+  if (tile < ntiles) { enter(tile); issue(0); }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int buf = 0;                                 // stage holding the step to be multiplied next
+  for (; tile < ntiles; tile += gridDim.x) {
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = cx_zero<R>();
+    const unsigned long long next_tile = tile + gridDim.x;
+    bool pending_next = false;                 // the next tile's first step still has to be issued (no cross-tile room)
+    for (unsigned long long kk = 0; kk < k_iters; ++kk) {
+      // one group per step, possibly empty: "all but the newest group complete" = this step has landed
+      if (kk + 1 < k_iters) { next_k(kk); issue(buf ^ 1); }
+      else if (next_tile < ntiles) {
+        if (xtile) { enter(next_tile); issue(buf ^ 1); } else pending_next = true;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncthreads();
+      const T *pa = stages + (size_t)buf * stage_elems + tm * 4;
+      const T *pb = stages + (size_t)buf * stage_elems + (P.sa_stride << P.tkb) + tn * 4;
 #pragma unroll 4
-  for (int e = t, it = 0; e < c_count; e += 256, ++it) {
-    const long long g = out_off + (c_t_g | c_it_g[it]);
-    T v = sC[e];
-    if (acc_out) { const T o = out[g]; v.x += o.x; v.y += o.y; }
-    out[g] = v;
+      for (int k = 0; k < TK; ++k) {
+        T a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = pa[i]; a[i].y *= sgn_a; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { b[j] = pb[j]; b[j].y *= sgn_b; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cfma<R>(acc[i][j], a[i], b[j]);
+        pa += P.sa_stride;
+        pb += P.sb_stride;
+      }
+      __syncthreads();
+      buf ^= 1;
+    }
+
+    // ---- epilogue: registers -> staging (C address order) -> global ---------------
+    // the stage consumed last (buf ^ 1) is free; without cross-tile prefetch nothing is in flight and the
+    // staging buffer may span both stages
+    T *sC = xtile ? stages + (size_t)(buf ^ 1) * stage_elems : stages;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = mi[i] + nj[j];
+        if (idx < c_count) sC[idx] = acc[i][j];
+      }
+    __syncthreads();
+    {
+      unsigned long long id = tile;
+      const unsigned split = (unsigned)(id & ((1ull << P.split_bits) - 1));
+      id >>= P.split_bits;
+      const unsigned long long mh = id & ((1ull << P.n_mhi) - 1);
+      id >>= P.n_mhi;
+      const unsigned long long nh = id & ((1ull << P.n_nhi) - 1);
+      id >>= P.n_nhi;
+      const long long c_base = deposit(mh, P.c_mhi, P.n_mhi) | deposit(nh, P.c_nhi, P.n_nhi) |
+                               deposit(id, P.c_bat, P.n_batch);
+      T *out = C;
+      long long out_off = c_base;
+      if (P.split_bits) { out = ws; out_off += (long long)split * P.c_elems; }
+#pragma unroll 4
+      for (int e = t, it = 0; e < c_count; e += 256, ++it) {
+        const long long g = out_off + (c_t_g | c_it_g[it]);
+        T v = sC[e];
+        if (acc_out) { const T o = out[g]; v.x += o.x; v.y += o.y; }
+        out[g] = v;
+      }
+    }
+    __syncthreads();                           // the staging buffer becomes a stage again
+    if (pending_next) {                        // complex128: the next tile's first step, into the stage `buf`
+      enter(next_tile);
+      issue(buf);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // C (+)= sum over split-K partials, elementwise (C dense: c_elems contiguous elements)
@@ -538,14 +559,19 @@ template <typename R>
 int launch_tile(const qtn_pair_plan_t &P, const void *a, const void *b, void *c, void *ws,
                 const int32_t *slice_id, cudaStream_t st) {
   using T = cx<R>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int ctas_max = 0;
+  if (!ctas_max) {
     QTN_CUDA_CHECK(cudaFuncSetAttribute(gett_tile_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         2 * 4608 * (int)sizeof(float2)));
-    attr_set = true;
+    int dev = 0, sms = 0;
+    QTN_CUDA_CHECK(cudaGetDevice(&dev));
+    QTN_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ctas_max = (sizeof(R) == 4 ? 3 : 2) * sms; // resident CTAs per SM (registers, ~68 KB of shared memory each)
   }
   if (P.grid <= 0 || P.grid > 0x7fffffffLL) return qtn_fail(QTN_ERR_UNSUPPORTED, "qtn_pair_run: grid too large");
-  gett_tile_kernel<R><<<(unsigned)P.grid, 256, P.smem_bytes, st>>>(
+  // persistent CTAs: the tile-independent set-up is paid once per CTA and copies run ahead across tiles
+  const long long ctas = P.grid < ctas_max ? P.grid : ctas_max;
+  gett_tile_kernel<R><<<(unsigned)ctas, 256, P.smem_bytes, st>>>(
       P, (const T *)a, (const T *)b, (T *)c, (T *)ws, slice_id);
   QTN_LAUNCH_CHECK();
   if (P.split_bits) {

@@ -571,7 +571,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     p->workspace_bytes = split ? ((int64_t)esz << (d->rank_c + split)) : 0;
     int tile_bytes = ((1 << tkb) * (p->sa_stride + p->sb_stride)) * esz;
     int stage_bytes = 4096 * esz;
-    p->tile_stages = (p->n_khi - split) >= 1 ? 2 : 1;          // a single k step has nothing to prefetch
+    p->tile_stages = 2;                                        // copies run one k step ahead, across tiles too
     p->smem_bytes = std::max(p->tile_stages * tile_bytes, stage_bytes);
   }
 
