@@ -85,11 +85,36 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   // per-iteration parts of the tile enumerations (bits 8.. of the element index)
   __shared__ long long a_it_g[16], b_it_g[16], c_it_g[16];
   __shared__ int a_it_s[16], b_it_s[16];
+  // Staging swizzle.  A thread owns outputs m = tm + i TM/4, n = tn + j TN/4; for fixed (i, j) the 16 lanes of a
+  // half warp store to staging indices that differ in the bits their lane bits own, wherever the C layout puts
+  // them -- often far apart (stride 4..1024 elements: up to 16-way bank conflicts, which made this kernel
+  // shared-memory bound: ncu, round 2).  The low nibble of the staging index (the 8-byte slot inside a 128-byte
+  // row) is XORed with a linear function G of the bits above it, chosen so that the four lane-owned bits land on
+  // four different nibble bits: conflict-free stores, and the read-out (consecutive indices per half warp, their
+  // high bits equal) stays conflict-free under any such G.
+  __shared__ unsigned char swz_col[12];
+  __shared__ unsigned char c_it_swz[16];
 
   const int t = threadIdx.x;
   const int TK = 1 << P.tkb;
 
   // ---- enumeration tables (the same for every tile) -----------------------------
+  if (t == 32) {
+    int pos[4];
+    unsigned used = 0;
+    for (int b = 0; b < 4; ++b) {
+      const int sidx = b < P.tnb - 2 ? P.c_n_sidx[b] : P.c_m_sidx[b - (P.tnb - 2)];
+      pos[b] = __ffs(sidx) - 1;
+      if (pos[b] >= 0 && pos[b] < 4) used |= 1u << pos[b];
+    }
+    for (int b = 0; b < 12; ++b) swz_col[b] = 0;
+    for (int b = 0; b < 4; ++b)
+      if (pos[b] >= 4 && pos[b] < 12) {
+        int u = 0;
+        while (u < 4 && ((used >> u) & 1u)) ++u;
+        if (u < 4) { swz_col[pos[b]] = (unsigned char)(1u << u); used |= 1u << u; }
+      }
+  }
   if (t < 16) {
     long long g = 0; int s = 0;
     for (int j = 8; j < P.na_lo; ++j)
@@ -132,10 +157,11 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   // ---- thread's 4x4 outputs: staging indices -----------------------------------
   const int tn = t & ((1 << (P.tnb - 2)) - 1);
   const int tm = t >> (P.tnb - 2);
+  const int qm = 1 << (P.tmb - 2), qn = 1 << (P.tnb - 2);          // a thread's rows / columns are qm / qn apart
   int mi[4], nj[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int m = tm * 4 + i, n = tn * 4 + i;
+    const int m = tm + i * qm, n = tn + i * qn;
     int sm = 0, sn = 0;
     for (int b = 0; b < P.tmb; ++b) if ((m >> b) & 1) sm += P.c_m_sidx[b];
     for (int b = 0; b < P.tnb; ++b) if ((n >> b) & 1) sn += P.c_n_sidx[b];
@@ -196,6 +222,19 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   const unsigned long long ntiles = (unsigned long long)P.grid;
   unsigned long long tile = blockIdx.x;
   __syncthreads();                             // the iteration tables are in shared memory
+  auto swz_of = [&](int x) {                   // G(x): XOR of the columns of the set bits 4..11
+    int g = 0;
+    for (int b = 4; b < 12; ++b) if ((x >> b) & 1) g ^= swz_col[b];
+    return g;
+  };
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {                // staging index (12 bits) and its swizzle nibble share a register
+    mi[i] |= swz_of(mi[i]) << 12;
+    nj[i] |= swz_of(nj[i]) << 12;
+  }
+  const int g_t = swz_of(t);
+  if (t < 16) c_it_swz[t] = (unsigned char)swz_of(t << 8);
+  __syncthreads();
   if (tile < ntiles) { enter(tile); issue(0); }
   asm volatile("cp.async.commit_group;" ::: "memory");
   int buf = 0;                                 // stage holding the step to be multiplied next
@@ -216,15 +255,15 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncthreads();
-      const T *pa = stages + (size_t)buf * stage_elems + tm * 4;
-      const T *pb = stages + (size_t)buf * stage_elems + (P.sa_stride << P.tkb) + tn * 4;
+      const T *pa = stages + (size_t)buf * stage_elems + tm;
+      const T *pb = stages + (size_t)buf * stage_elems + (P.sa_stride << P.tkb) + tn;
 #pragma unroll 4
       for (int k = 0; k < TK; ++k) {
         T a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { a[i] = pa[i]; a[i].y *= sgn_a; }
+        for (int i = 0; i < 4; ++i) { a[i] = pa[i * qm]; a[i].y *= sgn_a; }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { b[j] = pb[j]; b[j].y *= sgn_b; }
+        for (int j = 0; j < 4; ++j) { b[j] = pb[j * qn]; b[j].y *= sgn_b; }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -244,8 +283,8 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int idx = mi[i] + nj[j];
-        if (idx < c_count) sC[idx] = acc[i][j];
+        const int idx = (mi[i] & 0xfff) + (nj[j] & 0xfff);
+        if (idx < c_count) sC[idx ^ ((mi[i] ^ nj[j]) >> 12)] = acc[i][j];
       }
     __syncthreads();
     {
@@ -264,7 +303,7 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
 #pragma unroll 4
       for (int e = t, it = 0; e < c_count; e += 256, ++it) {
         const long long g = out_off + (c_t_g | c_it_g[it]);
-        T v = sC[e];
+        T v = sC[e ^ g_t ^ c_it_swz[it]];
         if (acc_out) { const T o = out[g]; v.x += o.x; v.y += o.y; }
         out[g] = v;
       }

@@ -31,15 +31,28 @@ pauli_expectation_kernel(int nqubits, const typename cx_of<R>::type *__restrict_
   const uint64_t fx = xmask[term], fz = zmask[term];
   const uint64_t total = 1ull << nqubits;
   double sr = 0, si = 0;
-  for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total;
-       x += (uint64_t)gridDim.x * blockDim.x) {
-    const T a = psi[x];
-    const T b = fx ? psi[x ^ fx] : a;
+  auto add = [&](uint64_t x, const T a, const T b) {
     // conj(b) * a
     double pr = (double)b.x * a.x + (double)b.y * a.y;
     double pi = (double)b.x * a.y - (double)b.y * a.x;
     if (__popcll(x & fz) & 1) { pr = -pr; pi = -pi; }
     sr += pr; si += pi;
+  };
+  constexpr int U = 4;                         // independent loads in flight per thread
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t x0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; x0 + (U - 1) * stride < total; x0 += U * stride) {
+    T a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = psi[x0 + u * stride];
+#pragma unroll
+    for (int u = 0; u < U; ++u) b[u] = fx ? psi[(x0 + u * stride) ^ fx] : a[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) add(x0 + u * stride, a[u], b[u]);
+  }
+  for (; x0 < total; x0 += stride) {
+    const T a = psi[x0];
+    add(x0, a, fx ? psi[x0 ^ fx] : a);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -77,35 +90,67 @@ struct PauliGroup {
   int32_t count;
 };
 
-template <typename R>
+// Sign of a term on basis state x as a mask for the SIGN BIT of a double: parity of popcount(x & zmask) moved to
+// bit 31 of the high word (no select, no conversion; the accumulation is then one integer XOR and one DADD).
+template <bool W32>
+__device__ __forceinline__ uint32_t sign_word(uint64_t x, uint64_t z) {
+  if constexpr (W32) return (uint32_t)__popc((uint32_t)x & (uint32_t)z) << 31;
+  else return (uint32_t)__popcll(x & z) << 31;
+}
+__device__ __forceinline__ double flip_sign(double v, uint32_t sw) {
+  return __hiloint2double(__double2hiint(v) ^ (int)sw, __double2loint(v));
+}
+
+// ZONLY: xmask == 0, the pair product is |psi[x]|^2 (real): half the accumulators.  W32: at most 32 qubits, masks
+// and basis states fit 32-bit words.  U independent 16-byte loads per thread are in flight before the first use
+// (the first version of this kernel had one 8-byte load in flight per thread and ran at 0.47 TB/s:
+// profiles/r02_ncu_hbm_kernels.txt).
+template <typename R, bool ZONLY, bool W32>
 __global__ void __launch_bounds__(256)
 pauli_group_kernel(int nqubits, const typename cx_of<R>::type *__restrict__ psi, const __grid_constant__ PauliGroup G,
                    double2 *__restrict__ out) {
   using T = typename cx_of<R>::type;
-  __shared__ double red[8][2 * kGroup];
+  constexpr int NACC = ZONLY ? kGroup : 2 * kGroup;
+  constexpr int U = 4;
+  __shared__ double red[8][NACC];
   const uint64_t fx = G.xmask;
   const uint64_t total = 1ull << nqubits;
-  double acc[2 * kGroup];
+  double acc[NACC];
 #pragma unroll
-  for (int j = 0; j < 2 * kGroup; ++j) acc[j] = 0.0;
-  for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total;
-       x += (uint64_t)gridDim.x * blockDim.x) {
-    const T a = psi[x];
-    const T b = fx ? psi[x ^ fx] : a;
+  for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
+  auto add = [&](uint64_t x, const T a, const T b) {
     const double pr = (double)b.x * a.x + (double)b.y * a.y;      // conj(b) * a
-    const double pi = (double)b.x * a.y - (double)b.y * a.x;
+    double pi = 0.0;
+    if constexpr (!ZONLY) pi = (double)b.x * a.y - (double)b.y * a.x;
 #pragma unroll
     for (int j = 0; j < kGroup; ++j) {
       if (j < G.count) {
-        const bool neg = __popcll(x & G.zmask[j]) & 1;
-        acc[2 * j] += neg ? -pr : pr;
-        acc[2 * j + 1] += neg ? -pi : pi;
+        const uint32_t sw = sign_word<W32>(x, G.zmask[j]);
+        if constexpr (ZONLY) acc[j] += flip_sign(pr, sw);
+        else { acc[2 * j] += flip_sign(pr, sw); acc[2 * j + 1] += flip_sign(pi, sw); }
       }
     }
+  };
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t x0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; x0 + (U - 1) * stride < total; x0 += U * stride) {
+    T a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = psi[x0 + u * stride];
+    if constexpr (!ZONLY) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) b[u] = psi[(x0 + u * stride) ^ fx];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) add(x0 + u * stride, a[u], ZONLY ? a[u] : b[u]);
+  }
+  for (; x0 < total; x0 += stride) {
+    const T a = psi[x0];
+    add(x0, a, ZONLY ? a : psi[x0 ^ fx]);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int j = 0; j < 2 * kGroup; ++j) {
+  for (int j = 0; j < NACC; ++j) {
     double v = acc[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -115,7 +160,10 @@ pauli_group_kernel(int nqubits, const typename cx_of<R>::type *__restrict__ psi,
   if (threadIdx.x < G.count) {
     const int j = threadIdx.x;
     double r = 0, i = 0;
-    for (int w = 0; w < 8; ++w) { r += red[w][2 * j]; i += red[w][2 * j + 1]; }
+    for (int w = 0; w < 8; ++w) {
+      if constexpr (ZONLY) r += red[w][j];
+      else { r += red[w][2 * j]; i += red[w][2 * j + 1]; }
+    }
     double fr = r, fi = i;                                        // times i^ny
     switch (G.ny[j] & 3) {
       case 1: fr = -i; fi = r; break;
@@ -126,6 +174,16 @@ pauli_group_kernel(int nqubits, const typename cx_of<R>::type *__restrict__ psi,
     atomicAdd(&out[G.index[j]].x, fr);
     atomicAdd(&out[G.index[j]].y, fi);
   }
+}
+
+template <typename R>
+void launch_group(unsigned blocks, cudaStream_t st, int nqubits, const void *state, const PauliGroup &G, double2 *out) {
+  using T = typename cx_of<R>::type;
+  const bool z = G.xmask == 0, w32 = nqubits <= 32;
+  if (z && w32) pauli_group_kernel<R, true, true><<<blocks, 256, 0, st>>>(nqubits, (const T *)state, G, out);
+  else if (z) pauli_group_kernel<R, true, false><<<blocks, 256, 0, st>>>(nqubits, (const T *)state, G, out);
+  else if (w32) pauli_group_kernel<R, false, true><<<blocks, 256, 0, st>>>(nqubits, (const T *)state, G, out);
+  else pauli_group_kernel<R, false, false><<<blocks, 256, 0, st>>>(nqubits, (const T *)state, G, out);
 }
 
 }  // namespace
@@ -139,9 +197,9 @@ extern "C" int qtn_pauli_expectation_host(int dtype, int nqubits, const void *st
   cudaStream_t st = (cudaStream_t)stream;
   QTN_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)nterms * sizeof(double2), st));
   const uint64_t total = 1ull << nqubits;
-  uint64_t blocks = (total + 256 * 8 - 1) / (256 * 8);
+  uint64_t blocks = (total + 256 * 16 - 1) / (256 * 16);
   if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 6) blocks = 148 * 6;
   // group the terms by xmask (stable: the order inside a group is the caller's)
   std::vector<int> order(nterms);
   for (int i = 0; i < nterms; ++i) order[i] = i;
@@ -155,10 +213,8 @@ extern "C" int qtn_pauli_expectation_host(int dtype, int nqubits, const void *st
       G.index[G.count] = order[i];
       ++G.count; ++i;
     }
-    if (dtype == QTN_C64)
-      pauli_group_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(nqubits, (const float2 *)state, G, (double2 *)out);
-    else
-      pauli_group_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(nqubits, (const double2 *)state, G, (double2 *)out);
+    if (dtype == QTN_C64) launch_group<float>((unsigned)blocks, st, nqubits, state, G, (double2 *)out);
+    else launch_group<double>((unsigned)blocks, st, nqubits, state, G, (double2 *)out);
     QTN_LAUNCH_CHECK();
   }
   return QTN_OK;

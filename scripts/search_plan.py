@@ -12,13 +12,15 @@ from qibotn_b200 import plans, workloads  # noqa: E402
 from qibotn_b200.planner import find_path  # noqa: E402
 
 
-def modeled_seconds(info, net, dtype, tc_tflops=280.0, ffma_tflops=25.0, hbm_tbs=3.5, launch_us=3.0,
-                    tile_us=3.2, sms=148):
+def modeled_seconds(info, net, dtype, tc_tflops=320.0, ffma_tflops=25.0, hbm_tbs=4.1, launch_us=3.0,
+                    tile_us=0.5, sms=148):
     """Time model of a plan on one B200: per tree node max(compute, bytes / HBM rate, launch), summed over
     slices (hoisted nodes once).  For the tcgen05 kernel compute = flops / 280 TFLOP/s + 3.2 us per
     128 x 2^tnb tile per SM (accumulator hand-off; with split accumulators a 128-column tile has no second
     TMEM buffer): fitted to profiles/r01_tc_issue_and_pair_ab.jsonl (m24n7k7 10.7 ms, m20n7k10 4.1 ms,
-    m19n8k8 1.2 ms); HBM-bound nodes stream at ~3.5 TB/s (m24n5k5, m24n6k6)."""
+    m19n8k8 1.2 ms); HBM-bound nodes stream at ~3.5 TB/s (m24n5k5, m24n6k6).  Round 2 (staggered fp16 kernel,
+    profiles/r02_gather_ab.jsonl): 320 TFLOP/s on tensor-bound nodes (m21n10k7 6.4 ms), 4.1 TB/s on HBM-bound ones
+    (m24n7k7 7.9 ms, m25n6k6 9.0 ms), the accumulator hand-off hidden by the half tiles (0.5 us kept)."""
     from qibotn_b200 import executor, lib
 
     low = executor.lower(net.modes, net.out, info, dtype)
