@@ -171,6 +171,7 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   const int k_iters_bits = P.n_khi - P.split_bits;
   const unsigned long long k_iters = 1ull << k_iters_bits;
   const R sgn_a = P.conj_a ? (R)-1 : (R)1, sgn_b = P.conj_b ? (R)-1 : (R)1;
+  const bool any_conj = P.conj_a || P.conj_b;
   const long long a_slice = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a);
   const long long b_slice = slice_offset(slice_id, P.n_slice_b, P.slice_bit_b, P.slice_pos_b);
   const bool acc_out = P.accumulate && !P.split_bits;
@@ -257,19 +258,36 @@ gett_tile_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
       __syncthreads();
       const T *pa = stages + (size_t)buf * stage_elems + tm;
       const T *pb = stages + (size_t)buf * stage_elems + (P.sa_stride << P.tkb) + tn;
+      if (any_conj) {
 #pragma unroll 4
-      for (int k = 0; k < TK; ++k) {
-        T a[4], b[4];
+        for (int k = 0; k < TK; ++k) {
+          T a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { a[i] = pa[i * qm]; a[i].y *= sgn_a; }
+          for (int i = 0; i < 4; ++i) { a[i] = pa[i * qm]; a[i].y *= sgn_a; }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { b[j] = pb[j * qn]; b[j].y *= sgn_b; }
+          for (int j = 0; j < 4; ++j) { b[j] = pb[j * qn]; b[j].y *= sgn_b; }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) cfma<R>(acc[i][j], a[i], b[j]);
-        pa += P.sa_stride;
-        pb += P.sb_stride;
+            for (int j = 0; j < 4; ++j) cfma<R>(acc[i][j], a[i], b[j]);
+          pa += P.sa_stride;
+          pb += P.sb_stride;
+        }
+      } else {
+#pragma unroll 4
+        for (int k = 0; k < TK; ++k) {
+          T a[4], b[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = pa[i * qm];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] = pb[j * qn];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cfma<R>(acc[i][j], a[i], b[j]);
+          pa += P.sa_stride;
+          pb += P.sb_stride;
+        }
       }
       __syncthreads();
       buf ^= 1;
@@ -446,9 +464,11 @@ reduce_final_kernel(const __grid_constant__ qtn_pair_plan_t P, cx<R> *__restrict
 // C (256 values) to the workspace; qtn_launch_splitk_sum adds the partials.
 // HBM-bound by design: 16 KiB of operands per 64K real FMAs.
 // --------------------------------------------------------------------------
-constexpr int KRED_ROW = 18;        // row stride (elements) of the A / B chunk in shared memory: 16 rows + 2
-                                    // pad: lanes walking k spread over the banks when they store, and rows
-                                    // stay 16-byte aligned for 128-bit loads
+constexpr int KRED_ROW = 16;        // rows of the A / B chunk in shared memory: element (k, row) of a chunk sits at
+                                    // k * 16 + (row ^ 2 (k & 7)).  The XOR spreads lanes that walk k over the banks
+                                    // (a padded row stride of 18 left 3 of 4 store wavefronts conflicted: ncu, round 1)
+                                    // and keeps row pairs adjacent and 16-byte aligned for the 128-bit loads.
+__device__ __forceinline__ int kred_swz(int idx) { return idx ^ (((idx >> 4) & 7) << 1); }
 
 template <typename R>
 __global__ void __launch_bounds__(256, 2)
@@ -529,16 +549,16 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
     }
   };
   auto stash = [&](int buf) {
-    T *da = sA + buf * KC * KRED_ROW + a_t_s, *db = sB + buf * KC * KRED_ROW + b_t_s;
+    T *da = sA + buf * KC * KRED_ROW, *db = sB + buf * KC * KRED_ROW;
 #pragma unroll
     for (int u = 0; u < NIT; ++u) {
       if (a_act && u < a_nit) {
         T v = va[u]; if (P.conj_a) v.y = -v.y;
-        da[((u & 1) ? as_[0] : 0) + ((u & 2) ? as_[1] : 0) + ((u & 4) ? as_[2] : 0)] = v;
+        da[kred_swz(a_t_s + ((u & 1) ? as_[0] : 0) + ((u & 2) ? as_[1] : 0) + ((u & 4) ? as_[2] : 0))] = v;
       }
       if (b_act && u < b_nit) {
         T v = vb[u]; if (P.conj_b) v.y = -v.y;
-        db[((u & 1) ? bs_[0] : 0) + ((u & 2) ? bs_[1] : 0) + ((u & 4) ? bs_[2] : 0)] = v;
+        db[kred_swz(b_t_s + ((u & 1) ? bs_[0] : 0) + ((u & 2) ? bs_[1] : 0) + ((u & 4) ? bs_[2] : 0))] = v;
       }
     }
   };
@@ -548,23 +568,23 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   for (int buf = 0; have; buf ^= 1) {
     const bool more = group < ngroups;            // the stream position after the current chunk
     if (more) { load(); advance(); }              // next chunk in flight while this one is used
-    const T *pa = sA + buf * KC * KRED_ROW + mi, *pb = sB + buf * KC * KRED_ROW + ni;
+    const T *pa = sA + buf * KC * KRED_ROW, *pb = sB + buf * KC * KRED_ROW;
     for (int k = kg; k < KC; k += 16) {
       T a[4], b[4];
+      const int sk = (k & 7) << 1;              // this k row's XOR (kred_swz)
       if constexpr (sizeof(R) == 4) {           // two complex64 per 128-bit shared-memory load
-        const float4 *qa = reinterpret_cast<const float4 *>(pa + k * KRED_ROW);
-        const float4 *qb = reinterpret_cast<const float4 *>(pb + k * KRED_ROW);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const float4 u = qa[i], v = qb[i];
+          const float4 u = *reinterpret_cast<const float4 *>(pa + k * KRED_ROW + ((mi + 2 * i) ^ sk));
+          const float4 v = *reinterpret_cast<const float4 *>(pb + k * KRED_ROW + ((ni + 2 * i) ^ sk));
           a[2 * i].x = u.x; a[2 * i].y = u.y; a[2 * i + 1].x = u.z; a[2 * i + 1].y = u.w;
           b[2 * i].x = v.x; b[2 * i].y = v.y; b[2 * i + 1].x = v.z; b[2 * i + 1].y = v.w;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = pa[k * KRED_ROW + i];
+        for (int i = 0; i < 4; ++i) a[i] = pa[k * KRED_ROW + ((mi + i) ^ sk)];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = pb[k * KRED_ROW + j];
+        for (int j = 0; j < 4; ++j) b[j] = pb[k * KRED_ROW + ((ni + j) ^ sk)];
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)

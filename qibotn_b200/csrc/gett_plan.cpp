@@ -202,14 +202,14 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     }
     p->n_mhi = 0; p->n_nhi = 0; p->n_khi = (int)khi.size();
     for (int i = 0; i < p->n_khi; ++i) { p->a_khi[i] = khi[i].pa; p->b_khi[i] = khi[i].pb; }
-    // shared-memory chunk: element (k, row) at k * 18 + row (padded rows: conflict-free stores
-    // when a warp's lanes walk k); enumerations in address order
+    // shared-memory chunk: element (k, row) at k * 16 + row before the kernel's bank swizzle; enumerations in
+    // address order
     struct E { int pos; int sstr; };
     std::vector<E> ea, eb;
     for (int i = 0; i < mt; ++i) ea.push_back({M[i].pa, 1 << i});
-    for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, 18 << i});
+    for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, 16 << i});
     for (int i = 0; i < nt; ++i) eb.push_back({N[i].pb, 1 << i});
-    for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, 18 << i});
+    for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, 16 << i});
     auto by_pos = [](const E &x, const E &y) { return x.pos < y.pos; };
     std::sort(ea.begin(), ea.end(), by_pos);
     std::sort(eb.begin(), eb.end(), by_pos);
@@ -223,7 +223,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     p->grid = std::min<int64_t>(ngroups, std::max<int64_t>(1, ((int64_t)2 * sm_count) >> ybits));
     p->workspace_bytes = ((int64_t)esz << d->rank_c) * p->grid;
     // max(2 buffers x (A + B) chunk, 16 x 256 partials)
-    p->smem_bytes = std::max(2 * 2 * (1 << tkb) * 18 * esz, 16 * 256 * esz);
+    p->smem_bytes = std::max(2 * 2 * (1 << tkb) * 16 * esz, 16 * 256 * esz);
   } else if (d->dtype == QTN_C64 && d->c_layout_free && (bbits == 0 || tc_batch_ok()) && mbits >= 7 && nbits >= 4 &&
              kbits >= 3 && mbits + nbits + kbits >= opt.tc_min_log2 && opt.tc_enable) {
     // ---- tensor-core kernel (gett_tc.cu) ----------------------------------------
@@ -469,10 +469,11 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     else if (nbits < 6) { tnb = std::max(nbits, 2); tmb = 12 - tnb; }
     else { tmb = std::max(mbits, 2); tnb = 12 - tmb; }   // unreachable after swap, kept for safety
     const int TM = 1 << tmb, TN = 1 << tnb;
-    // two stages of (A, B) tiles (the next k step is copied while this one is multiplied) within ~68 KB of shared
-    // memory, so that three CTAs share an SM: 4224 elements per stage in complex64, 2112 in complex128
+    // two stages of (A, B) tiles (the next k step is copied while this one is multiplied) within 72 KB of shared
+    // memory, so that three CTAs share an SM: 4224 elements per stage in complex64 (16 k values per step on a
+    // 256 x 16 tile were measured slower than 8), 2304 in complex128
     int tkb = 4;
-    while (tkb > 0 && (1 << tkb) * (TM + TN + 4) > (d->dtype == QTN_C64 ? 4224 : 2112)) --tkb;
+    while (tkb > 0 && (1 << tkb) * (TM + TN + 4) > (d->dtype == QTN_C64 ? 4224 : 2304)) --tkb;
     tkb = std::min(tkb, kbits);
     p->tmb = tmb; p->tnb = tnb; p->tkb = tkb;
     p->sa_stride = TM + 2; p->sb_stride = TN + 2;

@@ -239,7 +239,7 @@ def _run_kred(P, a, b, c, sa, sb):
     assert P.tmb == 4 and P.tnb == 4 and 0 <= P.n_batch <= 15 and P.n_mhi == 0 and P.n_nhi == 0
     ib = min(3, P.n_khi)
     ngroups = 1 << (P.n_khi - ib)
-    assert P.smem_bytes >= 2 * 2 * KC * 18 * c.itemsize and 1 <= P.grid <= ngroups and P.smem_bytes <= 80 * 1024
+    assert P.smem_bytes >= 2 * 2 * KC * 16 * c.itemsize and 1 <= P.grid <= ngroups and P.smem_bytes <= 80 * 1024
     assert P.na_lo <= 11 and P.nb_lo <= 11
     ws = np.zeros((P.grid, P.c_elems), dtype=np.complex128)
     for cta, bt in ((x, y) for x in range(P.grid) for y in range(1 << P.n_batch)):      # grid.y = batch value
@@ -251,7 +251,7 @@ def _run_kred(P, a, b, c, sa, sb):
             chunks = []
             for (n_lo, lo_pos, lo_sstr, src, base) in ((P.na_lo, P.a_lo_pos, P.a_lo_sstr, a, a_k),
                                                        (P.nb_lo, P.b_lo_pos, P.b_lo_sstr, b, b_k)):
-                buf = np.zeros(KC * 18, dtype=np.complex128)
+                buf = np.zeros(KC * 16, dtype=np.complex128)
                 for e in range(1 << n_lo):
                     g = s = 0
                     for j in range(n_lo):
@@ -259,7 +259,7 @@ def _run_kred(P, a, b, c, sa, sb):
                             g |= 1 << lo_pos[j]
                             s += lo_sstr[j]
                     buf[s] = src[base | g]
-                chunks.append(buf.reshape(KC, 18)[:, :16])
+                chunks.append(buf.reshape(KC, 16))
             acc += chunks[0].T @ chunks[1]
         for m in range(1 << P.m_real):
             for n in range(1 << P.n_real):

@@ -249,6 +249,31 @@ def test_c4_full_amplitude_within_tolerance_of_complex128():
     assert abs(got - want) <= 1e-5 * abs(want), (got, want, abs(got - want) / abs(want))
 
 
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_c4_full_circuit_slices_against_the_cpu_oracle_fixture(dtype):
+    """Engine-independent parity on the benchmark circuit itself: single slices of the CPU-sized plan
+    (plans/c4_cpu.json, width 2^24, 2^21 slices) of the 53-qubit depth-14 amplitude, against the partial sums the
+    numpy oracle produced for the same slices in complex128 (tests/golden/c4_slice_partials.json, written by
+    scripts/make_golden_c4_slices.py).  Tolerance 1e-10 (complex128) / 1e-5 (complex64) relative to the largest
+    |partial| of the fixture (the partials are within a factor 4 of each other; each is itself a sum with
+    cancellations, so its own magnitude is not the scale of its rounding error)."""
+    import json
+    from qibotn_b200 import engine, plans, workloads
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c4_slice_partials.json")))
+    wl = workloads.build("c4")
+    net = QiboCircuitToEinsum(wl.circuit, dtype=dtype).amplitude_network(wl.bitstring)
+    info = plans.load_plan("c4_cpu", net.modes, net.out)
+    assert info is not None and info.num_slices == gold["num_slices"]
+    scale = max(abs(complex(re, im)) for re, im in gold["slices"].values())
+    for sid, (re, im) in gold["slices"].items():
+        want = complex(re, im)
+        got = complex(engine.contract(net, dtype, info=info, slice_ids=[int(sid)]).reshape(-1)[0].item())
+        assert abs(got - want) <= TOL[dtype] * scale, (dtype, sid, got, want, abs(got - want) / scale)
+    want = complex(*gold["sum_0_to_3"])
+    got = complex(engine.contract(net, dtype, info=info, slice_ids=range(4)).reshape(-1)[0].item())
+    assert abs(got - want) <= TOL[dtype] * scale
+
+
 def test_c2_full_size_expectation_properties():
     """BASELINE config 2 at full size (30-qubit brickwork depth 12, <Z...Z>, one closed sandwich
     network of 1158 tensors): no dense oracle reaches 30 qubits here, so the value is checked through
