@@ -166,7 +166,13 @@ typedef struct {
   /* QTN_KERNEL_TILE: shared-memory stages of (A tile, B tile); 2 = the next k step is copied (cp.async) while the
    * current one is multiplied */
   int32_t tile_stages;
-  int32_t reserved_tail;
+  /* 1: the staggered fp16 kernel reads A as pre-packed stage images too ("tc_prepack_a"): a pre-kernel gathers,
+   * scales and splits A once per launch into images laid out exactly as the four A planes of a shared-memory stage
+   * (one image per m tile and k chunk, 128 x 16 complex values = 16 KB: as large as A itself), at workspace offset
+   * tc_prepack_a_off; the main kernel's producers shrink to one thread issuing two bulk copies per stage.  Chosen
+   * when >= 4 n tiles read every A tile (A would otherwise be gathered and converted once per n tile). */
+  int32_t tc_prepack_a;
+  int64_t tc_prepack_a_off;
 } qtn_pair_plan_t;
 
 /* Per-call options.  Every switch below can be handed to the planner / the SVD driver explicitly
@@ -178,7 +184,8 @@ typedef struct {
   int32_t tc_enable, tc_min_log2, tc_persistent, tc_terms, tc_accum_split, tc_prepack, tc_pair, tc_stagger, tc_fp16;
   int32_t svd_wide, svd_group_mb, svd_reg;
   int32_t tc_gather;
-  int32_t reserved[3];
+  int32_t tc_prepack_a;
+  int32_t reserved[2];
 } qtn_options;
 void qtn_options_default(qtn_options *opt);     /* the built-in defaults */
 void qtn_options_current(qtn_options *opt);     /* the process-wide copy (defaults + qtn_set_option edits) */
@@ -204,6 +211,8 @@ void qtn_options_current(qtn_options *opt);     /* the process-wide copy (defaul
  *                  barrier per chunk).  Measured 5-20 % slower (profiles/r02_gather_ab.jsonl): fewer LSU
  *                  wavefronts, but the producers are bound by their serial wait -> convert -> store chain, which
  *                  the extra hand-off lengthens;
+ *   "tc_prepack_a" 1 (default): staggered fp16 plans whose A tiles are read by >= 4 n tiles pre-pack A into stage
+ *                  images as well (see tc_prepack_a above); 0: A is always gathered by the producers;
  *   "tc_persistent" 1 (default): one CTA per SM streams over the tiles with loads, MMAs and
  *                  epilogue of neighbouring tiles overlapped; 0: one CTA per tile.
  *   "svd_wide"     1 (default): qtn_svd_rows runs 512-thread CTAs holding twice the block rows (200 KB of

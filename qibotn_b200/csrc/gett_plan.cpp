@@ -442,9 +442,22 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
         }
       }
     }
+    // A as pre-packed stage images (see tc_prepack_a in the header): worth one more pass over A when every A tile
+    // is read by at least four n tiles
+    p->tc_prepack_a = 0;
+    p->tc_prepack_a_off = 0;
+    if (p->tc_pair == 2 && p->tc_kind == 1 && opt.tc_prepack_a && p->n_nhi >= 2) {
+      const int64_t a_images = (int64_t)1 << (p->n_mhi + p->n_khi);
+      const int64_t a_bytes = a_images * 4 * (int64_t)p->tc_plane_a;
+      if (a_bytes <= kMaxImageBytes && a_images <= 0x7fffffffLL) {
+        p->tc_prepack_a = 1;
+        p->tc_prepack_a_off = (p->workspace_bytes + 255) & ~(int64_t)255;
+        p->workspace_bytes = p->tc_prepack_a_off + a_bytes + 256;   // the magnitude words stay the last 256 bytes
+      }
+    }
     // address-ordered gather of A for the staggered kernel (see tc_gather in the header)
     p->tc_gather = 0;
-    if (p->tc_pair == 2 && opt.tc_gather) {
+    if (p->tc_pair == 2 && opt.tc_gather && !p->tc_prepack_a) {
       const int n = p->na_lo;
       std::vector<int> idx(n);
       for (int j = 0; j < n; ++j) idx[j] = j;

@@ -1283,7 +1283,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
 
   if (t == 32) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), kProducerThreads + 1);
+      mbar_init(full_bar(s), P.tc_prepack_a ? 1 : kProducerThreads + 1);
       mbar_init(empty_bar(s), 1);
       mbar_init(pfull_bar(s), 1);
     }
@@ -1298,7 +1298,35 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 8) {
+  if (warp < 8 && P.tc_prepack_a) {
+    // ================= producer (one thread): A and B arrive as pre-packed stage images, two bulk copies per stage ======
+    if constexpr (F16) {
+      if (t == 0) {
+        constexpr uint32_t kRankBytes = RANK_B, kImageBytes = 2u * kRankBytes, kImageA = 4u * PLANE_A;
+        const unsigned char *images = reinterpret_cast<const unsigned char *>(ws) + P.tc_prepack_off + (size_t)rank * kRankBytes;
+        const unsigned char *images_a = reinterpret_cast<const unsigned char *>(ws) + P.tc_prepack_a_off;
+        int s = 0;
+        uint32_t ph = 0;
+        for (unsigned long long u = pair0; u < nsuper; u += npairs) {
+          unsigned split;
+          unsigned long long nh, mh;
+          decode(u, split, nh, mh);
+          const unsigned long long kh0 = (unsigned long long)split << k_iters_bits;
+          const unsigned long long bt = P.n_batch ? mh >> (P.n_mhi - P.n_batch) : 0ull;
+          const unsigned long long img_b0 = ((((bt << P.n_nhi) | nh) << P.n_khi)) | kh0;
+          const unsigned long long img_a0 = (mh << P.n_khi) | kh0;
+          for (unsigned long long kk = 0; kk < k_iters; ++kk) {
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            unsigned char *sA = smem_raw + (size_t)s * STAGE;
+            mbar_arrive_expect_tx(full_bar(s), kImageA + kRankBytes);
+            bulk_copy_g2s(smem_u32(sA), images_a + (img_a0 + kk) * kImageA, kImageA, full_bar(s));
+            bulk_copy_g2s(smem_u32(sA + 4 * PLANE_A), images + (img_b0 + kk) * kImageBytes, kRankBytes, full_bar(s));
+            if (++s == S) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
     // ================= producers: this CTA's A rows (split in registers), its B image (one bulk copy) =================
     long long a_t_g = 0;
     int a_t_s = 0;
@@ -1679,6 +1707,44 @@ tc_prepack_b2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
   }
 }
 
+// A images of the staggered fp16 kernel ("tc_prepack_a"): one CTA per (m tile, k chunk) gathers the 128 x 16 values of
+// that stage with the producers' own enumeration (a_lo_pos / tc_a_it_g: the same addresses, the same plane offsets),
+// scales, splits and writes the four planes [re h1 | re h2 | im h1 | im h2] as one 16 KB image.
+template <int TKB>
+__global__ void __launch_bounds__(kProducerThreads)
+tc_prepack_a2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ A,
+                     unsigned char *__restrict__ images, const int32_t *__restrict__ slice_id,
+                     const uint32_t *__restrict__ amax_a) {
+  constexpr int KT = 1 << TKB;
+  constexpr int PLANE_A = 128 * KT * 2;                 // bytes
+  constexpr int NA = 128 * KT / kProducerThreads;
+  const int t = threadIdx.x;
+  const unsigned long long mh = (unsigned long long)blockIdx.x >> P.n_khi;
+  const unsigned long long kh = (unsigned long long)blockIdx.x & ((1ull << P.n_khi) - 1);
+  const long long a_k = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a) |
+                        deposit(mh, P.a_mhi, P.n_mhi) | deposit(kh, P.a_khi, P.n_khi);
+  long long a_t_g = 0;
+  int a_t_s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (((t >> j) & 1) && j < P.na_lo) { a_t_g |= 1ll << P.a_lo_pos[j]; a_t_s += P.a_lo_sstr[j]; }
+  const float sc_re = exp2_int(amax_scale_exp(amax_a)), sc_im = P.conj_a ? -sc_re : sc_re;
+  float2 va[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) va[i] = __ldg(A + (a_k | a_t_g | P.tc_a_it_g[i]));
+  uint32_t *w = reinterpret_cast<uint32_t *>(images + (size_t)blockIdx.x * 4 * PLANE_A);
+  constexpr int PW = PLANE_A / 4;
+#pragma unroll
+  for (int p = 0; p < NA / 2; ++p) {                    // elements 2p, 2p+1 differ in the lowest k bit: one packed word
+    const int o = (a_t_s + P.tc_a_it_s[2 * p]) >> 1;
+    uint32_t h1, h2;
+    split_f16x2(va[2 * p].x * sc_re, va[2 * p + 1].x * sc_re, h1, h2);
+    w[o] = h1; w[PW + o] = h2;
+    split_f16x2(va[2 * p].y * sc_im, va[2 * p + 1].y * sc_im, h1, h2);
+    w[2 * PW + o] = h1; w[3 * PW + o] = h2;
+  }
+}
+
 // B pre-pack: one CTA per (n tile, k chunk) writes that B stage -- split into hi/lo re/im planes
 // and laid out exactly as the main kernel's shared-memory stage -- to the workspace.
 template <int TNB, int TKB>
@@ -1729,6 +1795,18 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
           prepack<<<(unsigned)images, kProducerThreads, 0, st>>>(P, (const float2 *)b,
                                                                  (unsigned char *)ws + P.tc_prepack_off, slice_id, amax_b);
           QTN_LAUNCH_CHECK();
+          if (P.tc_prepack_a) {
+            if constexpr (TKB == 4) {
+              const long long a_images = 1ll << (P.n_mhi + P.n_khi);
+              if (P.tc_kind != 1 || a_images > 0x7fffffffLL)
+                return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: malformed A pre-pack plan");
+              tc_prepack_a2_kernel<TKB><<<(unsigned)a_images, kProducerThreads, 0, st>>>(
+                  P, (const float2 *)a, (unsigned char *)ws + P.tc_prepack_a_off, slice_id, amax_a);
+              QTN_LAUNCH_CHECK();
+            } else {
+              return qtn_fail(QTN_ERR_ARG, "qtn_pair_run: the A pre-pack needs 16 contracted values per stage");
+            }
+          }
           if (smem_set < P.smem_bytes) {
             QTN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
             smem_set = P.smem_bytes;

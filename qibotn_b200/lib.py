@@ -70,7 +70,7 @@ class PairPlan(C.Structure):
         ("tc_kind", C.c_int32), ("tc_gather", C.c_int32),
         ("tc_a_gbit", C.c_uint8 * QTN_LO_MAX), ("tc_a_rank", C.c_uint8 * QTN_LO_MAX),
         ("tc_a_it_gg", C.c_int64 * 8), ("tc_a_it_raw", C.c_int32 * 8),
-        ("tile_stages", C.c_int32), ("reserved_tail", C.c_int32),
+        ("tile_stages", C.c_int32), ("tc_prepack_a", C.c_int32), ("tc_prepack_a_off", C.c_int64),
     ]
 
 
@@ -78,7 +78,7 @@ class Options(C.Structure):
     """``qtn_options``: per-call switches of the planner and the SVD driver (include/qibotn_b200.h)."""
     _fields_ = [(n, C.c_int32) for n in ("tc_enable", "tc_min_log2", "tc_persistent", "tc_terms", "tc_accum_split",
                                          "tc_prepack", "tc_pair", "tc_stagger", "tc_fp16", "svd_wide",
-                                         "svd_group_mb", "svd_reg", "tc_gather")] + [("reserved", C.c_int32 * 3)]
+                                         "svd_group_mb", "svd_reg", "tc_gather", "tc_prepack_a")] + [("reserved", C.c_int32 * 2)]
 
 
 class GemmItem(C.Structure):

@@ -133,7 +133,8 @@ def test_general_permute():
     assert np.array_equal(dy.cpu().numpy(), x.transpose(perm))
 
 
-@pytest.mark.parametrize("shape", [(11, 7, 5), (10, 8, 4), (12, 5, 7), (10, 4, 3), (10, 7, 3), (15, 7, 7)])
+@pytest.mark.parametrize("shape", [(11, 7, 5), (10, 8, 4), (12, 5, 7), (10, 4, 3), (10, 7, 3), (15, 7, 7), (12, 9, 5),
+                                   (14, 10, 7)])
 def test_tensor_core_variants_agree_with_einsum(shape):
     """Every switch of the tcgen05 path (persistent or one CTA per tile, pre-packed B or gathered B,
     split or single accumulators, 3 or 4 split terms) against a complex128 einsum, with a sliced
@@ -153,9 +154,9 @@ def test_tensor_core_variants_agree_with_einsum(shape):
     B = _dense(b.astype(np.complex128), lb, pb, off=1 << pb_all[-1])          # slice id 1
     variants = [dict(), dict(tc_persistent=0), dict(tc_prepack=0), dict(tc_accum_split=0),
                 dict(tc_terms=4), dict(tc_prepack=0, tc_accum_split=0), dict(tc_pair=0), dict(tc_pair=0, tc_terms=4), dict(tc_pair=7),
-                dict(tc_stagger=0), dict(tc_fp16=0), dict(tc_gather=1), dict(tc_gather=1, tc_fp16=0)]
+                dict(tc_stagger=0), dict(tc_fp16=0), dict(tc_gather=1), dict(tc_gather=1, tc_fp16=0), dict(tc_prepack_a=0)]
     defaults = dict(tc_persistent=1, tc_prepack=1, tc_accum_split=1, tc_terms=3, tc_min_log2=18, tc_pair=5, tc_stagger=1,
-                    tc_fp16=1, tc_gather=0)
+                    tc_fp16=1, tc_gather=0, tc_prepack_a=1)
     wants = {}
     for opts in variants:
         try:
@@ -175,7 +176,9 @@ def test_tensor_core_variants_agree_with_einsum(shape):
         # ... and, with 16 contracted values per stage, the scaled 3xFP16 split (plain qtn_pair_run then measures
         # the operands' magnitudes itself)
         assert plan.tc_kind == (1 if staggered and k >= 4 and opts.get("tc_fp16", 1) else 0), (shape, opts)
-        assert plan.tc_gather == (1 if staggered and opts.get("tc_gather", 0) else 0), (shape, opts)
+        prepack_a = plan.tc_kind == 1 and n >= 9 and opts.get("tc_prepack_a", 1)      # >= 4 n tiles per A tile
+        assert plan.tc_prepack_a == (1 if prepack_a else 0), (shape, opts)
+        assert plan.tc_gather == (1 if staggered and opts.get("tc_gather", 0) and not prepack_a else 0), (shape, opts)
         if tuple(lc_used) not in wants:
             wants[tuple(lc_used)] = np.einsum(A, la, B, lb, lc_used, optimize=True)
         want = wants[tuple(lc_used)]

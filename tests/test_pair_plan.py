@@ -188,18 +188,29 @@ def test_cta_pair_plans_are_well_formed(shape):
         assert plan.smem_bytes == plan.tc_stages * stage + raw_ring + 512 <= 227 * 1024
         assert 2 <= plan.tc_stages <= 8
         images = 1 << (plan.n_nhi + plan.n_khi)
-        assert plan.workspace_bytes == plan.tc_prepack_off + images * 2 * rank_b + (256 if plan.tc_kind else 0)
+        b_end = plan.tc_prepack_off + images * 2 * rank_b + (256 if plan.tc_kind else 0)
+        # A is pre-packed too when at least four n tiles read every A tile (fp16 split only): one 16 KB image per
+        # (m tile, k chunk) behind the B images, the magnitude words stay the last 256 bytes of the workspace
+        assert plan.tc_prepack_a == (1 if plan.tc_kind and plan.n_nhi >= 2 else 0)
+        if plan.tc_prepack_a:
+            a_images = 1 << (plan.n_mhi + plan.n_khi)
+            assert plan.tc_prepack_a_off == (b_end + 255) // 256 * 256
+            assert plan.workspace_bytes == plan.tc_prepack_a_off + a_images * 4 * plan.tc_plane_a + 256
+        else:
+            assert plan.workspace_bytes == b_end
         # address-ordered gather ("tc_gather", default): bit r of the gathered element index walks the tile label
         # of rank r in address order, and the element a thread converts -- enumeration (t, i) of a_lo_pos -- sits
         # in the raw ring at the index built from the ranks of its bits: both must name the same address
         assert plan.tc_gather == 0                          # off by default (measured slower, see the header)
         lib.set_option("tc_min_log2", 0)
         lib.set_option("tc_gather", 1)
+        lib.set_option("tc_prepack_a", 0)                   # a pre-packed A is not gathered by the main kernel at all
         try:
             gplan = lib.pair_plan(lib.make_pair_desc("complex64", la, lb))
         finally:
             lib.set_option("tc_min_log2", 18)
             lib.set_option("tc_gather", 0)
+            lib.set_option("tc_prepack_a", 1)
         assert gplan.tc_gather == 1 and list(gplan.a_lo_pos) == list(plan.a_lo_pos)
         plan_own, plan = plan, gplan
         n_lo = plan.na_lo
