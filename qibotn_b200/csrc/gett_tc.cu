@@ -479,6 +479,10 @@ gett_tc_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restri
 // --------------------------------------------------------------------------------------------
 constexpr int kThreadsP = 416;
 constexpr int kEpilogueThreads = 128;
+// the staggered kernel: 8 producer warps, 8 epilogue warps, 1 MMA-issue / forwarder warp
+constexpr int kThreadsP2 = 544;
+constexpr int kEpilogueThreads2 = 256;
+constexpr int kMmaWarp2 = 16;
 
 template <int TNB, int TKB, bool SEP, bool PRE>
 __global__ void __launch_bounds__(kThreadsP, 1)
@@ -1225,7 +1229,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_m256(int n, int neg_a) {
 }
 
 template <int TNB, int TKB, bool F16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP2, 1)
 gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restrict__ A,
                      float2 *__restrict__ C, float2 *__restrict__ ws, const int32_t *__restrict__ slice_id,
                      const uint32_t *__restrict__ amax_a, const uint32_t *__restrict__ amax_b,
@@ -1287,12 +1291,12 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
       mbar_init(empty_bar(s), 1);
       mbar_init(pfull_bar(s), 1);
     }
-    for (int h = 0; h < 2; ++h) { mbar_init(tfull_bar(h), 1); mbar_init(tempty_bar(h), 2 * kEpilogueThreads); }
+    for (int h = 0; h < 2; ++h) { mbar_init(tfull_bar(h), 1); mbar_init(tempty_bar(h), 2 * kEpilogueThreads2); }
     for (int d = 0; d < kRawDepth; ++d) mbar_init(smem_u32(raw_bars + d), kProducerThreads);
     fence_proxy_async_smem();
     fence_mbar_init();
   }
-  if (warp == 12) tmem_alloc_pair<TMEM_COLS>(smem_u32(tmem_slot));
+  if (warp == kMmaWarp2) tmem_alloc_pair<TMEM_COLS>(smem_u32(tmem_slot));
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -1481,9 +1485,14 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
         --remaining;
       }
     }
-  } else if (warp < 12) {
+  } else if (warp < kMmaWarp2) {
     // ================= epilogue: half 0 then half 1 of every tile, each as soon as its MMAs are complete =================
+    // EIGHT warps: a warp reads the TMEM lanes of its quarter (warp & 3) only, so two warps share a quarter and take
+    // one rank block of columns each.  With four warps the drain of a half tile (TMEM load latency + 64 stores per
+    // thread) took longer than the other half's MMAs: ncu with both operands pre-packed -- no producer work left --
+    // still showed the tensor pipe at 52 % (profiles/r02_ncu_pair2_prepack_a_m21n10k7.txt).
     const int q = warp & 3;
+    const int eh = (warp - 8) >> 2;                     // which rank block of every half this warp drains
     const int r = q * 32 + lane;
     const long long row_off = (r & 31) + ((long long)(r >> 5) << (5 + TNB));
     constexpr int CH = Q < 16 ? Q : 16, NCH = Q / CH;  // column chunks of one [re] block
@@ -1506,7 +1515,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 2 * TN);
 #pragma unroll 2
-        for (int rc = 0; rc < 2 * NCH; ++rc) {
+        for (int rc = eh * NCH; rc < (eh + 1) * NCH; ++rc) {
           const int rr = rc / NCH, cc = (rc % NCH) * CH;    // rank block, first column inside it
           const uint32_t col = (uint32_t)(rr * 2 * Q + cc);
           uint32_t re[CH], im[CH], xr[CH], xi[CH];
@@ -1637,7 +1646,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
   __syncwarp();
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 12) {
+  if (warp == kMmaWarp2) {
     tc_fence_after();
     tmem_dealloc_pair<TMEM_COLS>(tmem_base);
   }
@@ -1811,8 +1820,8 @@ int launch_tc_inst(const qtn_pair_plan_t &P, const void *a, const void *b, void 
             QTN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
             smem_set = P.smem_bytes;
           }
-          kernel<<<(unsigned)ctas, kThreadsP, P.smem_bytes, st>>>(P, (const float2 *)a, (float2 *)c, (float2 *)ws, slice_id,
-                                                                 amax_a, amax_b, amax_c);
+          kernel<<<(unsigned)ctas, kThreadsP2, P.smem_bytes, st>>>(P, (const float2 *)a, (float2 *)c, (float2 *)ws, slice_id,
+                                                                  amax_a, amax_b, amax_c);
           QTN_LAUNCH_CHECK();
           return QTN_OK;
         };

@@ -1156,8 +1156,27 @@ int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, co
                                         (int)std::max(smem, (size_t)kBudget)));
     smem_set = std::max(smem, (size_t)kBudget);
   }
-  std::vector<int> rot(batch);
+  // Convergence is read back ONE SWEEP LATE: the counters of sweep s travel to pinned host memory behind an event
+  // while sweep s + 1 is already being launched (its kernels return at once for matrices whose previous sweep made
+  // no rotation), so the device never waits for the host between sweeps.
+  static thread_local int *h_rot = nullptr;
+  static thread_local size_t h_cap = 0;
+  static thread_local cudaEvent_t ev[2] = {nullptr, nullptr};
+  if (h_cap < (size_t)2 * batch) {
+    if (h_rot) cudaFreeHost(h_rot);
+    h_cap = (size_t)2 * batch + 64;
+    QTN_CUDA_CHECK(cudaHostAlloc((void **)&h_rot, h_cap * sizeof(int), cudaHostAllocDefault));
+  }
+  for (int e = 0; e < 2; ++e)
+    if (!ev[e]) QTN_CUDA_CHECK(cudaEventCreateWithFlags(&ev[e], cudaEventDisableTiming));
+  auto clean = [&](int sw) {                     // did sweep `sw` leave every matrix without a rotation?
+    const int *r = h_rot + (size_t)(sw & 1) * batch;
+    for (int i = 0; i < batch; ++i)
+      if (r[i] != 0) return false;
+    return true;
+  };
   int sweep = 0;
+  bool converged = false;
   for (; sweep < max_sweeps; ++sweep) {
     int *rot_cur = d_rot + (sweep & 1) * batch, *rot_prev = d_rot + ((sweep & 1) ^ 1) * batch;
     QTN_CUDA_CHECK(cudaMemsetAsync(rot_cur, 0, (size_t)batch * sizeof(int), st));
@@ -1201,12 +1220,20 @@ int svd_rows_impl(int batch, qtn_svd_item *items, double tol, int max_sweeps, co
         QTN_LAUNCH_CHECK();
       }
     }
-    QTN_CUDA_CHECK(cudaMemcpyAsync(rot.data(), rot_cur, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, st));
-    QTN_CUDA_CHECK(cudaStreamSynchronize(st));
-    bool any = false;
-    for (int i = 0; i < batch; ++i) any = any || rot[i] != 0;
-    if (!any) { ++sweep; break; }
+    QTN_CUDA_CHECK(cudaMemcpyAsync(h_rot + (size_t)(sweep & 1) * batch, rot_cur, (size_t)batch * sizeof(int),
+                                   cudaMemcpyDeviceToHost, st));
+    QTN_CUDA_CHECK(cudaEventRecord(ev[sweep & 1], st));
+    if (sweep >= 1) {
+      QTN_CUDA_CHECK(cudaEventSynchronize(ev[(sweep - 1) & 1]));
+      if (clean(sweep - 1)) { converged = true; break; }      // sweep `sweep` was launched for nothing: all early exits
+    }
   }
+  if (!converged) {                              // ran out of sweeps (or a single sweep): the last one may be the clean one
+    const int last = sweep - 1;
+    QTN_CUDA_CHECK(cudaEventSynchronize(ev[last & 1]));
+    if (clean(last)) converged = true;
+  }
+  // sweeps executed, the clean one included (with the one-sweep lag `sweep` already is that count on a break)
   if (sweeps_host) *sweeps_host = sweep;
   finalize_kernel<R><<<batch, 256, 0, st>>>(d_items, *trunc, d_scratch, sigma, perm, ld, d_rank, d_scale);
   QTN_LAUNCH_CHECK();

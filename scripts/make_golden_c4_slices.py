@@ -17,11 +17,15 @@ sys.path.insert(0, ROOT)
 from oracle import contract as oc  # noqa: E402
 from qibotn_b200 import plans, workloads  # noqa: E402
 
+from qibotn_b200.network import QiboCircuitToEinsum  # noqa: E402
+
 wl = workloads.build("c4")
-net = wl.network()
+# gates built in complex128 (the workload's own network rounds them to complex64 first)
+net = QiboCircuitToEinsum(wl.circuit, dtype="complex128").amplitude_network(wl.bitstring)
 info = plans.load_plan("c4_cpu", net.modes, net.out)
 assert info is not None
 ops = [np.asarray(t, dtype=np.complex128) for t in net.tensors]
+assert all(np.asarray(t).dtype == np.complex128 for t in net.tensors)
 ids = [0, 1, 2, 3, 777, 123456, 1048576, info.num_slices - 1]
 out = {"plan": "plans/c4_cpu.json", "num_slices": info.num_slices, "log2_width": info.log2_width,
        "sliced_labels": len(info.sliced_labels), "dtype": "complex128", "slices": {}}
