@@ -1547,101 +1547,88 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     if (P.split_bits == 0) amax_publish(amax_c, cmax);
   } else if (rank == 0) {
     // ================= MMA issuer (leader CTA): two cursors over the flat (tile, k chunk) stream =================
-    // ONE thread runs the whole loop (probes and issue): no warp collectives per pass.  Shared-memory descriptors are
-    // built by adding the stage offset to twelve precomputed low words (the high word -- SBO, version -- is the same
-    // for every operand); with both operands pre-packed the first version of this loop (warp-wide probes, __all_sync,
-    // elect + eight full descriptors per chunk) was what kept the tensor pipe at 52 %
-    // (profiles/r02_ncu_pair2_prepack_a_m21n10k7.txt: no producer work, eight epilogue warps, still 52 %).
-    if (lane == 0) {
-      const uint32_t tmem_b = tmem_base;
-      const uint32_t stage0 = smem_u32(smem_raw);
-      const unsigned long long my_tiles = pair0 < nsuper ? (nsuper - pair0 + npairs - 1) / npairs : 0;
-      const unsigned long long total = my_tiles * k_iters;
-      constexpr uint32_t D_HI = (uint32_t)(SBO >> 4) | (1u << 14);          // bits 32.. of umma_desc: SBO, version
-      constexpr uint32_t D_LO = (uint32_t)(LBO >> 4) << 16;
-      constexpr uint32_t STEP = (uint32_t)STAGE >> 4;                      // stage s: low word + s * STEP
-      constexpr uint32_t KO = (2u * LBO) >> 4;                             // k step inside a stage
-      auto lo_of = [&](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | D_LO; };
-      const uint32_t a_rh = lo_of(stage0), a_rl = lo_of(stage0 + PLANE_A), a_ih = lo_of(stage0 + 2u * PLANE_A),
-                     a_il = lo_of(stage0 + 3u * PLANE_A);
-      const uint32_t b_base = stage0 + 4u * PLANE_A;
-      uint32_t b_h0[2], b_h1[2], b_l0[2], b_l1[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t sb = b_base + (uint32_t)h * (uint32_t)HALF;
-        b_h0[h] = lo_of(sb); b_h1[h] = lo_of(sb + CHUNK); b_l0[h] = lo_of(sb + SEQ); b_l1[h] = lo_of(sb + SEQ + CHUNK);
-      }
-      auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-        if constexpr (F16) {
-          asm volatile(
-              "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-              "setp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-              "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
-              :
-              : "r"(d), "r"(a_lo), "r"(b_lo), "r"(D_HI), "r"(idesc), "r"(acc)
-              : "memory");
-        } else {
-          asm volatile(
-              "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-              "setp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-              "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %4, p;\n\t}"
-              :
-              : "r"(d), "r"(a_lo), "r"(b_lo), "r"(D_HI), "r"(idesc), "r"(acc)
-              : "memory");
-        }
-      };
-      auto issue = [&](int h, int s, unsigned long long kk) {
-        const uint32_t so = (uint32_t)s * STEP;
+    const uint32_t tmem_b = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t stage0 = smem_u32(smem_raw);
+    const unsigned long long my_tiles = pair0 < nsuper ? (nsuper - pair0 + npairs - 1) / npairs : 0;
+    const unsigned long long total = my_tiles * k_iters;
+    unsigned long long t0 = 0, t1 = 0;                  // chunks issued for half 0 / half 1
+    unsigned long long kk0 = 0, kk1 = 0, it0 = 0, it1 = 0;
+    int s0 = 0, s1 = 0;
+    uint32_t ph0 = 0;
+    bool acc0 = false, acc1 = false, stage0_ok = false;  // accumulators drained / stage known to be full
+    auto issue = [&](int h, int s, unsigned long long kk) {
+      if (elect_one()) {
+        const uint32_t sa = stage0 + (uint32_t)s * (uint32_t)STAGE;
+        const uint32_t sb = sa + 4u * PLANE_A + (uint32_t)h * (uint32_t)HALF;
         const uint32_t hh = tmem_b + (uint32_t)(h * 2 * TN), xx = hh + (uint32_t)TN;
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
-          const uint32_t o = so + (uint32_t)ks * KO;
+          const uint32_t ko = (uint32_t)ks * 2u * LBO;
+          const uint64_t arh = umma_desc(sa + ko, LBO, SBO);
+          const uint64_t arl = umma_desc(sa + PLANE_A + ko, LBO, SBO);
+          const uint64_t aih = umma_desc(sa + 2u * PLANE_A + ko, LBO, SBO);
+          const uint64_t ail = umma_desc(sa + 3u * PLANE_A + ko, LBO, SBO);
+          const uint64_t bh0 = umma_desc(sb + ko, LBO, SBO);                       // [Br_hi | Bi_hi]
+          const uint64_t bh1 = umma_desc(sb + CHUNK + ko, LBO, SBO);               // [Bi_hi | -Br_hi]
+          const uint64_t bl0 = umma_desc(sb + SEQ + ko, LBO, SBO);                 // [Br_lo | Bi_lo]
+          const uint64_t bl1 = umma_desc(sb + SEQ + CHUNK + ko, LBO, SBO);         // [Bi_lo | -Br_lo]
           const uint32_t acc = (kk | (unsigned)ks) ? 1u : 0u;
-          mma(xx, a_rl + o, b_h0[h] + o, IDESC, acc);
-          mma(xx, a_il + o, b_h1[h] + o, IDESC_NEG, 1u);
-          mma(xx, a_rh + o, b_l0[h] + o, IDESC, 1u);
-          mma(xx, a_ih + o, b_l1[h] + o, IDESC_NEG, 1u);
-          mma(hh, a_rh + o, b_h0[h] + o, IDESC, acc);
-          mma(hh, a_ih + o, b_h1[h] + o, IDESC_NEG, 1u);
+          if constexpr (F16) {
+            umma_f16_pair(xx, arl, bh0, IDESC, acc);
+            umma_f16_pair(xx, ail, bh1, IDESC_NEG, 1u);
+            umma_f16_pair(xx, arh, bl0, IDESC, 1u);
+            umma_f16_pair(xx, aih, bl1, IDESC_NEG, 1u);
+            umma_f16_pair(hh, arh, bh0, IDESC, acc);
+            umma_f16_pair(hh, aih, bh1, IDESC_NEG, 1u);
+          } else {
+            umma_tf32_pair(xx, arl, bh0, IDESC, acc);
+            umma_tf32_pair(xx, ail, bh1, IDESC_NEG, 1u);
+            umma_tf32_pair(xx, arh, bl0, IDESC, 1u);
+            umma_tf32_pair(xx, aih, bl1, IDESC_NEG, 1u);
+            umma_tf32_pair(hh, arh, bh0, IDESC, acc);
+            umma_tf32_pair(hh, aih, bh1, IDESC_NEG, 1u);
+          }
         }
         if (h == 1) umma_commit_pair(empty_bar(s));     // both halves have read the stage
         if (kk + 1 == k_iters) umma_commit_pair(tfull_bar(h));
-      };
-      unsigned long long t0 = 0, t1 = 0;                  // chunks issued for half 0 / half 1
-      unsigned long long kk0 = 0, kk1 = 0, it0 = 0, it1 = 0;
-      int s0 = 0, s1 = 0;
-      uint32_t ph0 = 0;
-      bool acc0 = false, acc1 = false, stage0_ok = false;  // accumulators drained / stage known to be full
-      // One pass issues at most one chunk per half; a barrier that has been seen complete is not probed again.
-      unsigned idle = 0;
-      while (t1 < total) {
-        const bool want1 = t1 < t0, want0 = t0 < total;
-        if (want1 && kk1 == 0 && !acc1) acc1 = mbar_test_relaxed(tempty_bar(1), (uint32_t)((it1 & 1) ^ 1));
-        if (want0 && kk0 == 0 && !acc0) acc0 = mbar_test_relaxed(tempty_bar(0), (uint32_t)((it0 & 1) ^ 1));
-        if (want0 && !stage0_ok) {
-          const bool r_f = mbar_test(full_bar(s0), ph0), r_p = mbar_test_relaxed(pfull_bar(s0), ph0);
-          stage0_ok = r_f && r_p;
-        }
-        tc_fence_after();
-        bool did = false;
-        if (want1 && (kk1 != 0 || acc1)) {                // half 1: its stage is resident (half 0 saw it full)
-          issue(1, s1, kk1);
-          if (++kk1 == k_iters) { kk1 = 0; ++it1; acc1 = false; }
-          if (++s1 == S) s1 = 0;
-          ++t1;
-          did = true;
-        }
-        if (want0 && (kk0 != 0 || acc0) && stage0_ok) {
-          issue(0, s0, kk0);
-          if (++kk0 == k_iters) { kk0 = 0; ++it0; acc0 = false; }
-          if (++s0 == S) { s0 = 0; ph0 ^= 1u; }
-          ++t0;
-          stage0_ok = false;
-          did = true;
-        }
-        if (did) idle = 0;
-        else if (++idle > (1u << 26)) __trap();
       }
+      __syncwarp();
+    };
+    // One pass issues at most one chunk per half.  The probes of a pass are independent of each other and are
+    // launched together; a barrier that has been seen complete is not probed again.
+    auto all_lanes = [](bool v) { return __all_sync(0xffffffffu, v) != 0; };
+    unsigned idle = 0;
+    while (t1 < total) {
+      const bool want1 = t1 < t0, want0 = t0 < total;
+      const bool probe_a1 = want1 && kk1 == 0 && !acc1;
+      const bool probe_a0 = want0 && kk0 == 0 && !acc0;
+      const bool probe_s0 = want0 && !stage0_ok;
+      bool r_a1 = true, r_a0 = true, r_f = true, r_p = true;
+      if (probe_a1) r_a1 = mbar_test_relaxed(tempty_bar(1), (uint32_t)((it1 & 1) ^ 1));
+      if (probe_a0) r_a0 = mbar_test_relaxed(tempty_bar(0), (uint32_t)((it0 & 1) ^ 1));
+      if (probe_s0) { r_f = mbar_test(full_bar(s0), ph0); r_p = mbar_test_relaxed(pfull_bar(s0), ph0); }
+      if (probe_a1) acc1 = all_lanes(r_a1);
+      if (probe_a0) acc0 = all_lanes(r_a0);
+      if (probe_s0) stage0_ok = all_lanes(r_f & r_p);
+      tc_fence_after();
+      bool did = false;
+      if (want1 && (kk1 != 0 || acc1)) {                // half 1: its stage is resident (half 0 saw it full)
+        issue(1, s1, kk1);
+        if (++kk1 == k_iters) { kk1 = 0; ++it1; acc1 = false; }
+        if (++s1 == S) s1 = 0;
+        ++t1;
+        did = true;
+      }
+      if (want0 && (kk0 != 0 || acc0) && stage0_ok) {
+        issue(0, s0, kk0);
+        if (++kk0 == k_iters) { kk0 = 0; ++it0; acc0 = false; }
+        if (++s0 == S) { s0 = 0; ph0 ^= 1u; }
+        ++t0;
+        stage0_ok = false;
+        did = true;
+      }
+      if (did) idle = 0;
+      else if (++idle > (1u << 26)) __trap();
     }
   } else {
     // ================= forwarder (peer CTA): "my stage is full" -> the leader =================
