@@ -1546,39 +1546,32 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     }
     if (P.split_bits == 0) amax_publish(amax_c, cmax);
   } else if (rank == 0) {
-    // ================= MMA issuer (leader CTA): half 1 follows half 0 at a fixed distance =================
-    // The flat (tile, k chunk) stream is walked by two cursors, half 1 exactly LAG chunks behind half 0 (LAG = ring
-    // depth - 1): step i issues chunk i of half 0 and chunk i - LAG of half 1, so the accumulators of a half drain
-    // while the tensor pipe works on LAG chunks of the other one.  The order is fixed, every wait is a blocking one
-    // on the single barrier the next MMA needs, and the shared-memory descriptors are the stage's offset added to
-    // twelve constants: ~40 warp-uniform instructions per step.  The first version polled up to four barriers per
-    // pass and rebuilt eight descriptors per chunk: ~150 dependent instructions, 500 cycles per pass for 1.26 chunks
-    // on average -- the issue loop, not the producers or the epilogue, kept the tensor pipe at 48-52 % (ncu source
-    // view of round 2's first kernel; pre-packing A and doubling the epilogue warps changed nothing).
+    // ================= MMA issuer (leader CTA): two cursors over the flat (tile, k chunk) stream =================
     const uint32_t tmem_b = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t stage0 = smem_u32(smem_raw);
     const unsigned long long my_tiles = pair0 < nsuper ? (nsuper - pair0 + npairs - 1) / npairs : 0;
     const unsigned long long total = my_tiles * k_iters;
-    constexpr uint64_t D_HI = ((uint64_t)(SBO >> 4) << 32) | (1ull << 46) | ((uint64_t)(LBO >> 4) << 16);
-    constexpr uint32_t STEP = (uint32_t)STAGE >> 4;      // stage s: address field + s * STEP
-    constexpr uint32_t KO = (2u * LBO) >> 4;             // k step inside a stage
-    auto field = [&](uint32_t addr) { return (addr & 0x3FFFFu) >> 4; };
-    const uint32_t a_rh = field(stage0), a_rl = field(stage0 + PLANE_A), a_ih = field(stage0 + 2u * PLANE_A),
-                   a_il = field(stage0 + 3u * PLANE_A);
-    const uint32_t b0 = field(stage0 + 4u * PLANE_A);
-    constexpr uint32_t F_CHUNK = (uint32_t)CHUNK >> 4, F_SEQ = (uint32_t)SEQ >> 4, F_HALF = (uint32_t)HALF >> 4;
+    unsigned long long t0 = 0, t1 = 0;                  // chunks issued for half 0 / half 1
+    unsigned long long kk0 = 0, kk1 = 0, it0 = 0, it1 = 0;
+    int s0 = 0, s1 = 0;
+    uint32_t ph0 = 0;
+    bool acc0 = false, acc1 = false, stage0_ok = false;  // accumulators drained / stage known to be full
     auto issue = [&](int h, int s, unsigned long long kk) {
       if (elect_one()) {
-        const uint32_t so = (uint32_t)s * STEP;
-        const uint32_t bh = b0 + (uint32_t)h * F_HALF + so;
+        const uint32_t sa = stage0 + (uint32_t)s * (uint32_t)STAGE;
+        const uint32_t sb = sa + 4u * PLANE_A + (uint32_t)h * (uint32_t)HALF;
         const uint32_t hh = tmem_b + (uint32_t)(h * 2 * TN), xx = hh + (uint32_t)TN;
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
-          const uint32_t o = (uint32_t)ks * KO;
-          const uint64_t arh = D_HI | (a_rh + so + o), arl = D_HI | (a_rl + so + o);
-          const uint64_t aih = D_HI | (a_ih + so + o), ail = D_HI | (a_il + so + o);
-          const uint64_t bh0 = D_HI | (bh + o), bh1 = D_HI | (bh + F_CHUNK + o);          // [Br_hi | Bi_hi], [Bi_hi | -Br_hi]
-          const uint64_t bl0 = D_HI | (bh + F_SEQ + o), bl1 = D_HI | (bh + F_SEQ + F_CHUNK + o);
+          const uint32_t ko = (uint32_t)ks * 2u * LBO;
+          const uint64_t arh = umma_desc(sa + ko, LBO, SBO);
+          const uint64_t arl = umma_desc(sa + PLANE_A + ko, LBO, SBO);
+          const uint64_t aih = umma_desc(sa + 2u * PLANE_A + ko, LBO, SBO);
+          const uint64_t ail = umma_desc(sa + 3u * PLANE_A + ko, LBO, SBO);
+          const uint64_t bh0 = umma_desc(sb + ko, LBO, SBO);                       // [Br_hi | Bi_hi]
+          const uint64_t bh1 = umma_desc(sb + CHUNK + ko, LBO, SBO);               // [Bi_hi | -Br_hi]
+          const uint64_t bl0 = umma_desc(sb + SEQ + ko, LBO, SBO);                 // [Br_lo | Bi_lo]
+          const uint64_t bl1 = umma_desc(sb + SEQ + CHUNK + ko, LBO, SBO);         // [Bi_lo | -Br_lo]
           const uint32_t acc = (kk | (unsigned)ks) ? 1u : 0u;
           if constexpr (F16) {
             umma_f16_pair(xx, arl, bh0, IDESC, acc);
@@ -1601,32 +1594,41 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
       }
       __syncwarp();
     };
+    // One pass issues at most one chunk per half.  The probes of a pass are independent of each other and are
+    // launched together; a barrier that has been seen complete is not probed again.
     auto all_lanes = [](bool v) { return __all_sync(0xffffffffu, v) != 0; };
-    auto wait_relaxed = [&](uint32_t bar, uint32_t parity) {      // barriers with arrivals from the peer CTA
-      unsigned spins = 0;
-      while (!all_lanes(mbar_test_relaxed(bar, parity)))
-        if (++spins > (1u << 26)) __trap();
-    };
-    const unsigned long long lag = (unsigned long long)(S - 1);
-    unsigned long long kk0 = 0, kk1 = 0, it0 = 0, it1 = 0;
-    int s0 = 0, s1 = 0;
-    uint32_t ph0 = 0;
-    for (unsigned long long i = 0; i < total + lag; ++i) {
-      if (i < total) {                                  // half 0, chunk i
-        if (kk0 == 0) wait_relaxed(tempty_bar(0), (uint32_t)((it0 & 1) ^ 1));
-        mbar_wait(full_bar(s0), ph0);
-        wait_relaxed(pfull_bar(s0), ph0);
-        tc_fence_after();
-        issue(0, s0, kk0);
-        if (++kk0 == k_iters) { kk0 = 0; ++it0; }
-        if (++s0 == S) { s0 = 0; ph0 ^= 1u; }
-      }
-      if (i >= lag) {                                   // half 1, chunk i - lag: its stage was seen full by half 0
-        if (kk1 == 0) { wait_relaxed(tempty_bar(1), (uint32_t)((it1 & 1) ^ 1)); tc_fence_after(); }
+    unsigned idle = 0;
+    while (t1 < total) {
+      const bool want1 = t1 < t0, want0 = t0 < total;
+      const bool probe_a1 = want1 && kk1 == 0 && !acc1;
+      const bool probe_a0 = want0 && kk0 == 0 && !acc0;
+      const bool probe_s0 = want0 && !stage0_ok;
+      bool r_a1 = true, r_a0 = true, r_f = true, r_p = true;
+      if (probe_a1) r_a1 = mbar_test_relaxed(tempty_bar(1), (uint32_t)((it1 & 1) ^ 1));
+      if (probe_a0) r_a0 = mbar_test_relaxed(tempty_bar(0), (uint32_t)((it0 & 1) ^ 1));
+      if (probe_s0) { r_f = mbar_test(full_bar(s0), ph0); r_p = mbar_test_relaxed(pfull_bar(s0), ph0); }
+      if (probe_a1) acc1 = all_lanes(r_a1);
+      if (probe_a0) acc0 = all_lanes(r_a0);
+      if (probe_s0) stage0_ok = all_lanes(r_f & r_p);
+      tc_fence_after();
+      bool did = false;
+      if (want1 && (kk1 != 0 || acc1)) {                // half 1: its stage is resident (half 0 saw it full)
         issue(1, s1, kk1);
-        if (++kk1 == k_iters) { kk1 = 0; ++it1; }
+        if (++kk1 == k_iters) { kk1 = 0; ++it1; acc1 = false; }
         if (++s1 == S) s1 = 0;
+        ++t1;
+        did = true;
       }
+      if (want0 && (kk0 != 0 || acc0) && stage0_ok) {
+        issue(0, s0, kk0);
+        if (++kk0 == k_iters) { kk0 = 0; ++it0; acc0 = false; }
+        if (++s0 == S) { s0 = 0; ph0 ^= 1u; }
+        ++t0;
+        stage0_ok = false;
+        did = true;
+      }
+      if (did) idle = 0;
+      else if (++idle > (1u << 26)) __trap();
     }
   } else {
     // ================= forwarder (peer CTA): "my stage is full" -> the leader =================
