@@ -479,8 +479,9 @@ gett_tc_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__restri
 // --------------------------------------------------------------------------------------------
 constexpr int kThreadsP = 416;
 constexpr int kEpilogueThreads = 128;
-// the staggered kernel: 8 producer warps, 8 epilogue warps, 1 MMA-issue / forwarder warp
-constexpr int kThreadsP2 = 544;
+// the staggered kernel: 8 producer warps, 8 epilogue warps, 2 MMA-issue warps (one per half; the first one is the
+// forwarder in the peer CTA)
+constexpr int kThreadsP2 = 576;
 constexpr int kEpilogueThreads2 = 256;
 constexpr int kMmaWarp2 = 16;
 
@@ -1288,7 +1289,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
   if (t == 32) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), P.tc_prepack_a ? 1 : kProducerThreads + 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), 2);                    // one commit per MMA-issuing warp (half)
       mbar_init(pfull_bar(s), 1);
     }
     for (int h = 0; h < 2; ++h) { mbar_init(tfull_bar(h), 1); mbar_init(tempty_bar(h), 2 * kEpilogueThreads2); }
@@ -1546,91 +1547,77 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     }
     if (P.split_bits == 0) amax_publish(amax_c, cmax);
   } else if (rank == 0) {
-    // ================= MMA issuer (leader CTA): two cursors over the flat (tile, k chunk) stream =================
+    // ================= MMA issuers (leader CTA): one warp per half =================
+    // Warp 16 issues the MMAs of half 0, warp 17 those of half 1, each in a plain blocking loop over the flat
+    // (tile, k chunk) stream: wait for the half's accumulators at a tile start, wait for the stage, six MMAs, commit.
+    // A stage is released when BOTH warps have committed on its empty barrier (count 2).  The halves stagger by
+    // themselves: the epilogue drains half 0 first, so half 0 resumes first and half 1 works on the remaining
+    // chunks of the tile while half 0 waits for its next drain.  The first version walked both cursors in ONE warp
+    // that polled up to four barriers per pass and rebuilt eight descriptors per chunk: ~150 dependent
+    // instructions, ~500 cycles per pass for 1.26 chunk-halves on average -- the issue loop, not the producers or
+    // the epilogue, kept the tensor pipe at 48-52 % (ncu source view; pre-packing A and doubling the epilogue
+    // warps changed nothing, a one-thread loop and a fixed-lag single-warp loop were slower).
+    const int h = warp - kMmaWarp2;                     // the half this warp issues
     const uint32_t tmem_b = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t stage0 = smem_u32(smem_raw);
-    const unsigned long long my_tiles = pair0 < nsuper ? (nsuper - pair0 + npairs - 1) / npairs : 0;
-    const unsigned long long total = my_tiles * k_iters;
-    unsigned long long t0 = 0, t1 = 0;                  // chunks issued for half 0 / half 1
-    unsigned long long kk0 = 0, kk1 = 0, it0 = 0, it1 = 0;
-    int s0 = 0, s1 = 0;
-    uint32_t ph0 = 0;
-    bool acc0 = false, acc1 = false, stage0_ok = false;  // accumulators drained / stage known to be full
-    auto issue = [&](int h, int s, unsigned long long kk) {
-      if (elect_one()) {
-        const uint32_t sa = stage0 + (uint32_t)s * (uint32_t)STAGE;
-        const uint32_t sb = sa + 4u * PLANE_A + (uint32_t)h * (uint32_t)HALF;
-        const uint32_t hh = tmem_b + (uint32_t)(h * 2 * TN), xx = hh + (uint32_t)TN;
-#pragma unroll
-        for (int ks = 0; ks < KSTEPS; ++ks) {
-          const uint32_t ko = (uint32_t)ks * 2u * LBO;
-          const uint64_t arh = umma_desc(sa + ko, LBO, SBO);
-          const uint64_t arl = umma_desc(sa + PLANE_A + ko, LBO, SBO);
-          const uint64_t aih = umma_desc(sa + 2u * PLANE_A + ko, LBO, SBO);
-          const uint64_t ail = umma_desc(sa + 3u * PLANE_A + ko, LBO, SBO);
-          const uint64_t bh0 = umma_desc(sb + ko, LBO, SBO);                       // [Br_hi | Bi_hi]
-          const uint64_t bh1 = umma_desc(sb + CHUNK + ko, LBO, SBO);               // [Bi_hi | -Br_hi]
-          const uint64_t bl0 = umma_desc(sb + SEQ + ko, LBO, SBO);                 // [Br_lo | Bi_lo]
-          const uint64_t bl1 = umma_desc(sb + SEQ + CHUNK + ko, LBO, SBO);         // [Bi_lo | -Br_lo]
-          const uint32_t acc = (kk | (unsigned)ks) ? 1u : 0u;
-          if constexpr (F16) {
-            umma_f16_pair(xx, arl, bh0, IDESC, acc);
-            umma_f16_pair(xx, ail, bh1, IDESC_NEG, 1u);
-            umma_f16_pair(xx, arh, bl0, IDESC, 1u);
-            umma_f16_pair(xx, aih, bl1, IDESC_NEG, 1u);
-            umma_f16_pair(hh, arh, bh0, IDESC, acc);
-            umma_f16_pair(hh, aih, bh1, IDESC_NEG, 1u);
-          } else {
-            umma_tf32_pair(xx, arl, bh0, IDESC, acc);
-            umma_tf32_pair(xx, ail, bh1, IDESC_NEG, 1u);
-            umma_tf32_pair(xx, arh, bl0, IDESC, 1u);
-            umma_tf32_pair(xx, aih, bl1, IDESC_NEG, 1u);
-            umma_tf32_pair(hh, arh, bh0, IDESC, acc);
-            umma_tf32_pair(hh, aih, bh1, IDESC_NEG, 1u);
-          }
-        }
-        if (h == 1) umma_commit_pair(empty_bar(s));     // both halves have read the stage
-        if (kk + 1 == k_iters) umma_commit_pair(tfull_bar(h));
-      }
-      __syncwarp();
-    };
-    // One pass issues at most one chunk per half.  The probes of a pass are independent of each other and are
-    // launched together; a barrier that has been seen complete is not probed again.
+    constexpr uint64_t D_HI = ((uint64_t)(SBO >> 4) << 32) | (1ull << 46) | ((uint64_t)(LBO >> 4) << 16);
+    constexpr uint32_t STEP = (uint32_t)STAGE >> 4;      // stage s: address field + s * STEP
+    constexpr uint32_t KO = (2u * LBO) >> 4;             // k step inside a stage
+    auto field = [&](uint32_t addr) { return (addr & 0x3FFFFu) >> 4; };
+    const uint32_t a_rh = field(stage0), a_rl = field(stage0 + PLANE_A), a_ih = field(stage0 + 2u * PLANE_A),
+                   a_il = field(stage0 + 3u * PLANE_A);
+    const uint32_t bh = field(stage0 + 4u * PLANE_A + (uint32_t)h * (uint32_t)HALF);
+    constexpr uint32_t F_CHUNK = (uint32_t)CHUNK >> 4, F_SEQ = (uint32_t)SEQ >> 4;
+    const uint32_t hh = tmem_b + (uint32_t)(h * 2 * TN), xx = hh + (uint32_t)TN;
     auto all_lanes = [](bool v) { return __all_sync(0xffffffffu, v) != 0; };
-    unsigned idle = 0;
-    while (t1 < total) {
-      const bool want1 = t1 < t0, want0 = t0 < total;
-      const bool probe_a1 = want1 && kk1 == 0 && !acc1;
-      const bool probe_a0 = want0 && kk0 == 0 && !acc0;
-      const bool probe_s0 = want0 && !stage0_ok;
-      bool r_a1 = true, r_a0 = true, r_f = true, r_p = true;
-      if (probe_a1) r_a1 = mbar_test_relaxed(tempty_bar(1), (uint32_t)((it1 & 1) ^ 1));
-      if (probe_a0) r_a0 = mbar_test_relaxed(tempty_bar(0), (uint32_t)((it0 & 1) ^ 1));
-      if (probe_s0) { r_f = mbar_test(full_bar(s0), ph0); r_p = mbar_test_relaxed(pfull_bar(s0), ph0); }
-      if (probe_a1) acc1 = all_lanes(r_a1);
-      if (probe_a0) acc0 = all_lanes(r_a0);
-      if (probe_s0) stage0_ok = all_lanes(r_f & r_p);
-      tc_fence_after();
-      bool did = false;
-      if (want1 && (kk1 != 0 || acc1)) {                // half 1: its stage is resident (half 0 saw it full)
-        issue(1, s1, kk1);
-        if (++kk1 == k_iters) { kk1 = 0; ++it1; acc1 = false; }
-        if (++s1 == S) s1 = 0;
-        ++t1;
-        did = true;
+    auto wait_relaxed = [&](uint32_t bar, uint32_t parity) {      // barriers with arrivals from the peer CTA
+      unsigned spins = 0;
+      while (!all_lanes(mbar_test_relaxed(bar, parity)))
+        if (++spins > (1u << 26)) __trap();
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    unsigned long long it = 0;
+    for (unsigned long long u = pair0; u < nsuper; u += npairs, ++it) {
+      wait_relaxed(tempty_bar(h), (uint32_t)((it & 1) ^ 1));       // this half's accumulators are drained
+      for (unsigned long long kk = 0; kk < k_iters; ++kk) {
+        mbar_wait(full_bar(s), ph);
+        wait_relaxed(pfull_bar(s), ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t so = (uint32_t)s * STEP;
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks) {
+            const uint32_t o = so + (uint32_t)ks * KO;
+            const uint64_t arh = D_HI | (a_rh + o), arl = D_HI | (a_rl + o);
+            const uint64_t aih = D_HI | (a_ih + o), ail = D_HI | (a_il + o);
+            const uint64_t bh0 = D_HI | (bh + o), bh1 = D_HI | (bh + F_CHUNK + o);      // [Br_hi | Bi_hi], [Bi_hi | -Br_hi]
+            const uint64_t bl0 = D_HI | (bh + F_SEQ + o), bl1 = D_HI | (bh + F_SEQ + F_CHUNK + o);
+            const uint32_t acc = (kk | (unsigned)ks) ? 1u : 0u;
+            if constexpr (F16) {
+              umma_f16_pair(xx, arl, bh0, IDESC, acc);
+              umma_f16_pair(xx, ail, bh1, IDESC_NEG, 1u);
+              umma_f16_pair(xx, arh, bl0, IDESC, 1u);
+              umma_f16_pair(xx, aih, bl1, IDESC_NEG, 1u);
+              umma_f16_pair(hh, arh, bh0, IDESC, acc);
+              umma_f16_pair(hh, aih, bh1, IDESC_NEG, 1u);
+            } else {
+              umma_tf32_pair(xx, arl, bh0, IDESC, acc);
+              umma_tf32_pair(xx, ail, bh1, IDESC_NEG, 1u);
+              umma_tf32_pair(xx, arh, bl0, IDESC, 1u);
+              umma_tf32_pair(xx, aih, bl1, IDESC_NEG, 1u);
+              umma_tf32_pair(hh, arh, bh0, IDESC, acc);
+              umma_tf32_pair(hh, aih, bh1, IDESC_NEG, 1u);
+            }
+          }
+          umma_commit_pair(empty_bar(s));               // this half has read the stage (the barrier counts both)
+          if (kk + 1 == k_iters) umma_commit_pair(tfull_bar(h));
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
-      if (want0 && (kk0 != 0 || acc0) && stage0_ok) {
-        issue(0, s0, kk0);
-        if (++kk0 == k_iters) { kk0 = 0; ++it0; acc0 = false; }
-        if (++s0 == S) { s0 = 0; ph0 ^= 1u; }
-        ++t0;
-        stage0_ok = false;
-        did = true;
-      }
-      if (did) idle = 0;
-      else if (++idle > (1u << 26)) __trap();
     }
-  } else {
+  } else if (warp == kMmaWarp2) {
     // ================= forwarder (peer CTA): "my stage is full" -> the leader =================
     int s = 0;
     uint32_t ph = 0;
