@@ -453,6 +453,11 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
         p->tc_prepack_a = 1;
         p->tc_prepack_a_off = (p->workspace_bytes + 255) & ~(int64_t)255;
         p->workspace_bytes = p->tc_prepack_a_off + a_bytes + 256;   // the magnitude words stay the last 256 bytes
+        // no raw ring for gathered A: the shared memory goes to a deeper operand ring (the halves may drift further
+        // apart, which hides more of an accumulator drain)
+        const int stage_h = 4 * p->tc_plane_a + 3 * (1 << p->tnb) * (1 << p->tkb) * 2;
+        p->tc_stages = std::max(2, std::min(8, (227 * 1024 - 512) / stage_h));
+        p->smem_bytes = p->tc_stages * stage_h + 512;
       }
     }
     // address-ordered gather of A for the staggered kernel (see tc_gather in the header)

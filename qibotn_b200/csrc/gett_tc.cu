@@ -1260,7 +1260,8 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int S = P.tc_stages;
   unsigned char *raw_ring = smem_raw + (size_t)S * STAGE;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(raw_ring + (size_t)kRawDepth * RAW);
+  // (a pre-packed A needs no raw ring: the plan gives those bytes to more stages)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(raw_ring + (P.tc_prepack_a ? (size_t)0 : (size_t)kRawDepth * RAW));
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + 4);
   unsigned long long *img_ring = reinterpret_cast<unsigned long long *>(bars + 3 * S + 4 + 2);   // thread 0 only
   uint64_t *raw_bars = reinterpret_cast<uint64_t *>(img_ring + kRawDepth);   // "raw chunk landed" (tc_gather)

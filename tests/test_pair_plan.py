@@ -185,6 +185,8 @@ def test_cta_pair_plans_are_well_formed(shape):
         rank_b = 3 * (1 << plan.tnb) * kt * eb   # per CTA: 2 halves x {hi, lo} x [Br | Bi | -Br] x TN/4 rows x kt values
         stage = 4 * plan.tc_plane_a + rank_b
         raw_ring = 6 * 128 * kt * 8    # cp.async gathers of A in flight: 6 chunks of 8-byte elements
+        if plan.tc_prepack_a:
+            raw_ring = 0               # a pre-packed A is not gathered: the bytes go to a deeper operand ring
         assert plan.smem_bytes == plan.tc_stages * stage + raw_ring + 512 <= 227 * 1024
         assert 2 <= plan.tc_stages <= 8
         images = 1 << (plan.n_nhi + plan.n_khi)
