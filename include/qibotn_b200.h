@@ -212,7 +212,8 @@ void qtn_options_current(qtn_options *opt);     /* the process-wide copy (defaul
  *                  wavefronts, but the producers are bound by their serial wait -> convert -> store chain, which
  *                  the extra hand-off lengthens;
  *   "tc_prepack_a" 1 (default): staggered fp16 plans whose A tiles are read by >= 4 n tiles pre-pack A into stage
- *                  images as well (see tc_prepack_a above); 0: A is always gathered by the producers;
+ *                  images as well (see tc_prepack_a above); 0: A is always gathered by the producers; 2: always
+ *                  pre-packed (measurement switch: the extra pass over A does not pay with fewer n tiles);
  *   "tc_persistent" 1 (default): one CTA per SM streams over the tiles with loads, MMAs and
  *                  epilogue of neighbouring tiles overlapped; 0: one CTA per tile.
  *   "svd_wide"     1 (default): qtn_svd_rows runs 512-thread CTAs holding twice the block rows (200 KB of

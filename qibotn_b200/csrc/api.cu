@@ -41,7 +41,7 @@ void normalise(qtn_options &o) {
   o.tc_stagger = o.tc_stagger != 0;
   o.tc_fp16 = o.tc_fp16 != 0;
   o.tc_gather = o.tc_gather != 0;
-  o.tc_prepack_a = o.tc_prepack_a != 0;
+  o.tc_prepack_a = o.tc_prepack_a < 0 ? 0 : (o.tc_prepack_a > 2 ? 2 : o.tc_prepack_a);
   o.svd_wide = o.svd_wide != 0;
   o.svd_group_mb = o.svd_group_mb < 0 ? 0 : o.svd_group_mb;
   o.svd_reg = o.svd_reg < 0 ? 0 : (o.svd_reg > 5 ? 5 : o.svd_reg);

@@ -446,7 +446,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     // is read by at least four n tiles
     p->tc_prepack_a = 0;
     p->tc_prepack_a_off = 0;
-    if (p->tc_pair == 2 && p->tc_kind == 1 && opt.tc_prepack_a && p->n_nhi >= 2) {
+    if (p->tc_pair == 2 && p->tc_kind == 1 && opt.tc_prepack_a && (p->n_nhi >= 2 || opt.tc_prepack_a >= 2)) {
       const int64_t a_images = (int64_t)1 << (p->n_mhi + p->n_khi);
       const int64_t a_bytes = a_images * 4 * (int64_t)p->tc_plane_a;
       if (a_bytes <= kMaxImageBytes && a_images <= 0x7fffffffLL) {
