@@ -172,6 +172,7 @@ typedef struct {
    * tc_prepack_a_off; the main kernel's producers shrink to one thread issuing two bulk copies per stage.  Chosen
    * when >= 4 n tiles read every A tile (A would otherwise be gathered and converted once per n tile). */
   int32_t tc_prepack_a;
+  int32_t tc_run_bits;           /* tc_gather == 2: log2 of the contiguous run the tile's labels own at the bottom of A */
   int64_t tc_prepack_a_off;
 } qtn_pair_plan_t;
 
@@ -205,7 +206,10 @@ void qtn_options_current(qtn_options *opt);     /* the process-wide copy (defaul
  *                  MMAs of the other; 0: the round-1 pair kernel (tile and accumulators as one unit);
  *   "tc_fp16"      1 (default): staggered tiles split their operands into scaled fp16 pieces (tc_kind = 1,
  *                  half the tensor-pipe work of the TF32 split; run through qtn_pair_run_scaled); 0: TF32 split;
- *   "tc_gather"    0 (default): every producer thread of the staggered kernel gathers the elements it converts;
+ *   "tc_gather"    2 (default): when the labels of a tile own at least the 6 lowest address bits of A (runs of
+ *                  >= 512 contiguous bytes, the usual case: A is the output tile layout of an earlier node), a chunk
+ *                  is fetched into the raw ring by one cp.async.bulk per run (no LSU gather) and converted across
+ *                  threads; otherwise, and with 0, every producer thread gathers the elements it converts;
  *                  1: A is gathered in ascending address order (contiguous runs per warp) and the raw elements
  *                  change hands across threads through shared memory (an mbarrier per raw chunk + one named
  *                  barrier per chunk).  Measured 5-20 % slower (profiles/r02_gather_ab.jsonl): fewer LSU

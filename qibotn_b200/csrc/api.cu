@@ -16,7 +16,7 @@ extern "C" int qtn_fail(int code, const char *msg) {
 extern "C" const char *qtn_last_error(void) { return g_last_error.c_str(); }
 
 namespace {
-constexpr qtn_options kDefaults = {1, 18, 1, 3, 1, 1, 5, 1, 1, 1, 0, 4, 0, 1, {0, 0}};
+constexpr qtn_options kDefaults = {1, 18, 1, 3, 1, 1, 5, 1, 1, 1, 0, 4, 2, 1, {0, 0}};
 qtn_options g_opt = kDefaults;
 
 struct Field { const char *name; int32_t qtn_options::*member; };
@@ -40,7 +40,7 @@ void normalise(qtn_options &o) {
   o.tc_pair = o.tc_pair < 0 ? 0 : o.tc_pair;
   o.tc_stagger = o.tc_stagger != 0;
   o.tc_fp16 = o.tc_fp16 != 0;
-  o.tc_gather = o.tc_gather != 0;
+  o.tc_gather = o.tc_gather < 0 ? 0 : (o.tc_gather > 2 ? 2 : o.tc_gather);
   o.tc_prepack_a = o.tc_prepack_a < 0 ? 0 : (o.tc_prepack_a > 2 ? 2 : o.tc_prepack_a);
   o.svd_wide = o.svd_wide != 0;
   o.svd_group_mb = o.svd_group_mb < 0 ? 0 : o.svd_group_mb;

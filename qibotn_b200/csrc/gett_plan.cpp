@@ -475,6 +475,14 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
         p->tc_a_it_gg[it] = g; p->tc_a_it_raw[it] = raw;
       }
       p->tc_gather = 1;
+      if (opt.tc_gather == 2) {
+        // bulk mode: the run of address bits 0, 1, 2, ... owned by the tile; below 512 bytes a chunk would need more
+        // than 32 copies: those tiles keep the per-thread gather
+        int r = 0;
+        while (r < n && p->tc_a_gbit[r] == r) ++r;
+        if (r >= 6 && n - r <= 5) { p->tc_gather = 2; p->tc_run_bits = r; }
+        else p->tc_gather = 0;
+      }
     }
     p->sa_stride = 0; p->sb_stride = 0;
     if (bbits > 0 && p->tc_pair != 2)

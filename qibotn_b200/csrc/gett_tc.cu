@@ -1294,7 +1294,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
       mbar_init(pfull_bar(s), 1);
     }
     for (int h = 0; h < 2; ++h) { mbar_init(tfull_bar(h), 1); mbar_init(tempty_bar(h), 2 * kEpilogueThreads2); }
-    for (int d = 0; d < kRawDepth; ++d) mbar_init(smem_u32(raw_bars + d), kProducerThreads);
+    for (int d = 0; d < kRawDepth; ++d) mbar_init(smem_u32(raw_bars + d), P.tc_gather == 2 ? 1 : kProducerThreads);
     fence_proxy_async_smem();
     fence_mbar_init();
   }
@@ -1345,6 +1345,17 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     // element index e = i * 256 + t walks the label of rank r), element e lands at raw[e]; the thread that
     // converts an element finds it at the index built from the ranks of its own enumeration bits.
     const bool gather = P.tc_gather != 0;
+    // tc_gather == 2: the tile's labels own a contiguous run of 2^tc_run_bits elements at the bottom of A's address
+    // bits, so a chunk is 2^(n - run_bits) contiguous runs: lane q of warp 0 fetches run q with ONE bulk copy (the
+    // TMA engine: no LSU gather at all) into the raw slot, element e of the address order again at raw[e]
+    const bool bulk = P.tc_gather == 2;
+    const int run_bits = P.tc_run_bits;
+    const int n_runs = bulk ? 1 << (P.na_lo - run_bits) : 0;
+    long long run_g = 0;                              // global offset of this lane's run inside the chunk
+    if (bulk && t < n_runs) {
+      for (int j = run_bits; j < P.na_lo; ++j)
+        if ((t >> (j - run_bits)) & 1) run_g |= 1ll << P.tc_a_gbit[j];
+    }
     long long g_t_g = 0;
     int r_t = 0;
     if (gather) {
@@ -1383,7 +1394,16 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     const uint32_t raw_t = smem_u32(raw_ring) + (uint32_t)t * 8u;
     auto load = [&](int slot) {                       // this thread's NA elements of the current chunk -> raw slot
       const uint32_t dst = raw_t + (uint32_t)slot * (uint32_t)RAW;
-      if (gather) {
+      if (bulk) {
+        if (warp == 0) {
+          const uint32_t bar = smem_u32(raw_bars + slot);
+          if (t == 0) mbar_arrive_expect_tx(bar, (uint32_t)RAW);
+          __syncwarp();
+          if (t < n_runs)
+            bulk_copy_g2s(smem_u32(raw_ring) + (uint32_t)slot * (uint32_t)RAW + ((uint32_t)t << (run_bits + 3)),
+                          A + (a_k | run_g), 8u << run_bits, bar);
+        }
+      } else if (gather) {
 #pragma unroll
         for (int i = 0; i < NA; ++i)
           cp_async8(dst + (uint32_t)i * (kProducerThreads * 8u), A + (a_k | g_t_g | P.tc_a_it_gg[i]));
@@ -1406,7 +1426,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
         // every producer has taken its elements out of the slot: it may be refilled (by other threads' copies)
         asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
         if (u < nsuper) { load(slot); advance(); }
-        cp_async_mbar_arrive(smem_u32(raw_bars + slot));
+        if (!bulk) cp_async_mbar_arrive(smem_u32(raw_bars + slot));
       } else {
         const float2 *src = reinterpret_cast<const float2 *>(raw_ring + (size_t)slot * RAW) + t;
 #pragma unroll
@@ -1459,7 +1479,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
 #pragma unroll 1
       for (int d = 0; d < kRawDepth; ++d) {
         if (u < nsuper) { load(d); advance(); }
-        cp_async_mbar_arrive(smem_u32(raw_bars + d));
+        if (!bulk) cp_async_mbar_arrive(smem_u32(raw_bars + d));
       }
       int slot = 0;
       uint32_t rph = 0;

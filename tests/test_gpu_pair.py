@@ -154,9 +154,10 @@ def test_tensor_core_variants_agree_with_einsum(shape):
     B = _dense(b.astype(np.complex128), lb, pb, off=1 << pb_all[-1])          # slice id 1
     variants = [dict(), dict(tc_persistent=0), dict(tc_prepack=0), dict(tc_accum_split=0),
                 dict(tc_terms=4), dict(tc_prepack=0, tc_accum_split=0), dict(tc_pair=0), dict(tc_pair=0, tc_terms=4), dict(tc_pair=7),
-                dict(tc_stagger=0), dict(tc_fp16=0), dict(tc_gather=1), dict(tc_gather=1, tc_fp16=0), dict(tc_prepack_a=0)]
+                dict(tc_stagger=0), dict(tc_fp16=0), dict(tc_gather=1), dict(tc_gather=1, tc_fp16=0), dict(tc_prepack_a=0),
+                dict(tc_gather=0), dict(tc_gather=0, tc_prepack_a=0), dict(tc_gather=2, tc_fp16=0), dict(tc_prepack_a=2)]
     defaults = dict(tc_persistent=1, tc_prepack=1, tc_accum_split=1, tc_terms=3, tc_min_log2=18, tc_pair=5, tc_stagger=1,
-                    tc_fp16=1, tc_gather=0, tc_prepack_a=1)
+                    tc_fp16=1, tc_gather=2, tc_prepack_a=1)
     wants = {}
     for opts in variants:
         try:
@@ -176,9 +177,16 @@ def test_tensor_core_variants_agree_with_einsum(shape):
         # ... and, with 16 contracted values per stage, the scaled 3xFP16 split (plain qtn_pair_run then measures
         # the operands' magnitudes itself)
         assert plan.tc_kind == (1 if staggered and k >= 4 and opts.get("tc_fp16", 1) else 0), (shape, opts)
-        prepack_a = plan.tc_kind == 1 and n >= 9 and opts.get("tc_prepack_a", 1)      # >= 4 n tiles per A tile
+        want_pa = opts.get("tc_prepack_a", 1)                                         # >= 4 n tiles per A tile, or forced
+        prepack_a = plan.tc_kind == 1 and want_pa and (n >= 9 or want_pa == 2)
         assert plan.tc_prepack_a == (1 if prepack_a else 0), (shape, opts)
-        assert plan.tc_gather == (1 if staggered and opts.get("tc_gather", 0) and not prepack_a else 0), (shape, opts)
+        want_g = opts.get("tc_gather", 2)
+        if not staggered or prepack_a or want_g == 0:
+            assert plan.tc_gather == 0, (shape, opts)
+        elif want_g == 1:
+            assert plan.tc_gather == 1, (shape, opts)
+        else:
+            assert plan.tc_gather in (0, 2), (shape, opts)      # bulk copies when the tile owns >= 6 low address bits
         if tuple(lc_used) not in wants:
             wants[tuple(lc_used)] = np.einsum(A, la, B, lb, lc_used, optimize=True)
         want = wants[tuple(lc_used)]
@@ -222,3 +230,51 @@ def test_batch_labels_on_tensor_core_and_kred_kernels(case):
         want = np.einsum(A, la, B, lb, lc_used, optimize=True)
         tol = 4e-6 if dtype == "complex64" else 1e-13
         assert np.abs(got - want).max() / np.abs(want).max() < tol * max(1, k), (case, dtype)
+
+
+@pytest.mark.parametrize("shape", [(15, 7, 7, 0), (16, 6, 5, 1), (13, 5, 4, 2), (17, 7, 3, 0), (14, 8, 6, 0)])
+def test_bulk_copied_raw_chunks_of_the_staggered_kernel(shape):
+    """tc_gather = 2 (default): when the labels of a tile own the lowest address bits of A -- the usual case, A being
+    an earlier node's output tile -- a chunk reaches the raw ring by one cp.async.bulk per contiguous run and is
+    converted across threads.  Layouts built so that the run has 6, 7 or more bits (some k labels among the low bits,
+    a sliced label in the middle), against a complex128 einsum and against the per-thread gather (tc_gather = 0)."""
+    m, n, k, variant = shape
+    rng = np.random.default_rng(11 * m + 5 * n + k + variant)
+    labels = list(range(m + n + k))
+    M, N, K = labels[:m], labels[m:m + n], labels[m + n:]
+    la, lb, lc = M + K, K + N, M + N
+    # A: `low` labels at address bits 0..: variant 0 = m labels only, 1 = two k labels among them, 2 = run of 6 bits
+    low = {0: M[:8], 1: M[:4] + K[:2] + M[4:7], 2: M[:5] + K[:1]}[variant]
+    rest = [x for x in la if x not in low]
+    rng.shuffle(rest)
+    order = low + rest
+    if variant == 2:
+        order = low + [None] + rest                   # a sliced label at bit 6 ends the run
+    pa = {lab: p for p, lab in enumerate(order) if lab is not None}
+    sa = [(0, order.index(None))] if variant == 2 else []
+    ra = len(order)
+    pb = [int(x) for x in rng.permutation(len(lb))]
+    a = (rng.normal(size=1 << ra) + 1j * rng.normal(size=1 << ra)).astype(np.complex64)
+    b = (rng.normal(size=1 << len(lb)) + 1j * rng.normal(size=1 << len(lb))).astype(np.complex64)
+    pa_list = [pa[x] for x in la]
+    A = _dense(a.astype(np.complex128), la, pa_list, off=(1 << sa[0][1]) if sa else 0)
+    B = _dense(b.astype(np.complex128), lb, pb)
+    got = {}
+    for g in (2, 0):
+        try:
+            lib.set_option("tc_min_log2", 0)
+            lib.set_option("tc_gather", g)
+            got[g], lc_used, plan = run_pair("complex64", la, pa_list, lb, pb, lc, None, a, b, slice_a=sa, slice_id=1)
+        finally:
+            lib.set_option("tc_min_log2", 18)
+            lib.set_option("tc_gather", 2)
+        assert plan.kernel == lib.KERNEL_TC and plan.tc_pair == 2
+        if g == 2:
+            assert plan.tc_gather == 2 and plan.tc_run_bits == {0: 7, 1: 9, 2: 6}[variant] + (0 if variant else 0), \
+                (shape, plan.tc_gather, plan.tc_run_bits)
+        else:
+            assert plan.tc_gather == 0
+    want = np.einsum(A, la, B, lb, lc_used, optimize=True)
+    for g in (2, 0):
+        assert np.abs(got[g] - want).max() / np.abs(want).max() < 4e-6 * max(1, k), (shape, g)
+    assert np.array_equal(got[2], got[0])             # the same values reach the same planes: bit-identical results
