@@ -16,7 +16,7 @@ extern "C" int qtn_fail(int code, const char *msg) {
 extern "C" const char *qtn_last_error(void) { return g_last_error.c_str(); }
 
 namespace {
-constexpr qtn_options kDefaults = {1, 18, 1, 3, 1, 1, 5, 1, 1, 1, 0, 4, 2, 1, {0, 0}};
+constexpr qtn_options kDefaults = {1, 18, 1, 3, 1, 1, 5, 1, 1, 1, 0, 4, 2, 1, 9, {0}};
 qtn_options g_opt = kDefaults;
 
 struct Field { const char *name; int32_t qtn_options::*member; };
@@ -28,6 +28,7 @@ const Field kFields[] = {
     {"tc_fp16", &qtn_options::tc_fp16},           {"svd_wide", &qtn_options::svd_wide},
     {"svd_group_mb", &qtn_options::svd_group_mb}, {"svd_reg", &qtn_options::svd_reg},
     {"tc_gather", &qtn_options::tc_gather},       {"tc_prepack_a", &qtn_options::tc_prepack_a},
+    {"tc_gather_min_run", &qtn_options::tc_gather_min_run},
 };
 
 // the value ranges every option is clamped to, wherever it comes from
@@ -42,6 +43,7 @@ void normalise(qtn_options &o) {
   o.tc_fp16 = o.tc_fp16 != 0;
   o.tc_gather = o.tc_gather < 0 ? 0 : (o.tc_gather > 2 ? 2 : o.tc_gather);
   o.tc_prepack_a = o.tc_prepack_a < 0 ? 0 : (o.tc_prepack_a > 2 ? 2 : o.tc_prepack_a);
+  o.tc_gather_min_run = o.tc_gather_min_run < 6 ? 6 : (o.tc_gather_min_run > 11 ? 11 : o.tc_gather_min_run);
   o.svd_wide = o.svd_wide != 0;
   o.svd_group_mb = o.svd_group_mb < 0 ? 0 : o.svd_group_mb;
   o.svd_reg = o.svd_reg < 0 ? 0 : (o.svd_reg > 5 ? 5 : o.svd_reg);

@@ -79,7 +79,7 @@ class Options(C.Structure):
     """``qtn_options``: per-call switches of the planner and the SVD driver (include/qibotn_b200.h)."""
     _fields_ = [(n, C.c_int32) for n in ("tc_enable", "tc_min_log2", "tc_persistent", "tc_terms", "tc_accum_split",
                                          "tc_prepack", "tc_pair", "tc_stagger", "tc_fp16", "svd_wide",
-                                         "svd_group_mb", "svd_reg", "tc_gather", "tc_prepack_a")] + [("reserved", C.c_int32 * 2)]
+                                         "svd_group_mb", "svd_reg", "tc_gather", "tc_prepack_a", "tc_gather_min_run")] + [("reserved", C.c_int32 * 1)]
 
 
 class GemmItem(C.Structure):

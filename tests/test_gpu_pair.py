@@ -264,10 +264,12 @@ def test_bulk_copied_raw_chunks_of_the_staggered_kernel(shape):
         try:
             lib.set_option("tc_min_log2", 0)
             lib.set_option("tc_gather", g)
+            lib.set_option("tc_gather_min_run", 6)    # default 9 (4 KB runs): here every run length is exercised
             got[g], lc_used, plan = run_pair("complex64", la, pa_list, lb, pb, lc, None, a, b, slice_a=sa, slice_id=1)
         finally:
             lib.set_option("tc_min_log2", 18)
             lib.set_option("tc_gather", 2)
+            lib.set_option("tc_gather_min_run", 9)
         assert plan.kernel == lib.KERNEL_TC and plan.tc_pair == 2
         if g == 2:
             assert plan.tc_gather == 2 and plan.tc_run_bits == {0: 7, 1: 9, 2: 6}[variant] + (0 if variant else 0), \

@@ -208,7 +208,7 @@ def test_cta_pair_plans_are_well_formed(shape):
         assert plan.tc_gather in (0, 2) and (plan.tc_gather == 0 or not plan.tc_prepack_a)
         if plan.tc_gather == 2:
             rb = plan.tc_run_bits
-            assert rb >= 6 and plan.na_lo - rb <= 5 and list(plan.tc_a_gbit[:rb]) == list(range(rb))
+            assert rb >= 9 and plan.na_lo - rb <= 5 and list(plan.tc_a_gbit[:rb]) == list(range(rb))
             assert rb == plan.na_lo or plan.tc_a_gbit[rb] != rb
         lib.set_option("tc_min_log2", 0)
         lib.set_option("tc_gather", 1)
