@@ -1397,6 +1397,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
       if (bulk) {
         if (warp == 0) {
           const uint32_t bar = smem_u32(raw_bars + slot);
+          fence_proxy_async_smem();                   // the slot's earlier (generic-proxy) reads precede the TMA writes
           if (t == 0) mbar_arrive_expect_tx(bar, (uint32_t)RAW);
           __syncwarp();
           if (t < n_runs)
@@ -1423,6 +1424,16 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
         const float2 *src = reinterpret_cast<const float2 *>(raw_ring + (size_t)slot * RAW) + r_t;
 #pragma unroll
         for (int i = 0; i < NA; ++i) va[i] = src[P.tc_a_it_raw[i]];
+        // The loads must have RETURNED before this thread reports the slot free: a shared-memory load that is merely
+        // issued can still be overtaken by another thread's copy into the slot (seen on the full C4 contraction with
+        // bulk copies: relative error 2.7e-4).  A value that depends on every loaded element, pinned before the
+        // barrier, makes the barrier wait for the data.
+        {
+          float chk = 0.f;
+#pragma unroll
+          for (int i = 0; i < NA; ++i) chk += va[i].x;
+          asm volatile("" ::"f"(chk) : "memory");
+        }
         // every producer has taken its elements out of the slot: it may be refilled (by other threads' copies)
         asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
         if (u < nsuper) { load(slot); advance(); }

@@ -203,13 +203,23 @@ def test_cta_pair_plans_are_well_formed(shape):
         # address-ordered gather ("tc_gather", default): bit r of the gathered element index walks the tile label
         # of rank r in address order, and the element a thread converts -- enumeration (t, i) of a_lo_pos -- sits
         # in the raw ring at the index built from the ranks of its bits: both must name the same address
-        # default: bulk-copied raw chunks (tc_gather = 2) when the tile owns the >= 6 lowest address bits of A and A
-        # is not pre-packed; one cp.async.bulk per contiguous run, at most 32 runs per chunk
-        assert plan.tc_gather in (0, 2) and (plan.tc_gather == 0 or not plan.tc_prepack_a)
-        if plan.tc_gather == 2:
-            rb = plan.tc_run_bits
-            assert rb >= 9 and plan.na_lo - rb <= 5 and list(plan.tc_a_gbit[:rb]) == list(range(rb))
-            assert rb == plan.na_lo or plan.tc_a_gbit[rb] != rb
+        assert plan.tc_gather == 0                          # default: every producer gathers what it converts
+        # tc_gather = 2: bulk-copied raw chunks when the tile owns the lowest address bits of A and A is not
+        # pre-packed; one cp.async.bulk per contiguous run
+        lib.set_option("tc_min_log2", 0)
+        lib.set_option("tc_gather", 2)
+        lib.set_option("tc_gather_min_run", 6)
+        try:
+            bplan = lib.pair_plan(lib.make_pair_desc("complex64", la, lb))
+        finally:
+            lib.set_option("tc_min_log2", 18)
+            lib.set_option("tc_gather", 0)
+            lib.set_option("tc_gather_min_run", 9)
+        assert bplan.tc_gather in (0, 2) and (bplan.tc_gather == 0 or not bplan.tc_prepack_a)
+        if bplan.tc_gather == 2:
+            rb = bplan.tc_run_bits
+            assert rb >= 6 and bplan.na_lo - rb <= 5 and list(bplan.tc_a_gbit[:rb]) == list(range(rb))
+            assert rb == bplan.na_lo or bplan.tc_a_gbit[rb] != rb
         lib.set_option("tc_min_log2", 0)
         lib.set_option("tc_gather", 1)
         lib.set_option("tc_prepack_a", 0)                   # a pre-packed A is not gathered by the main kernel at all
@@ -217,7 +227,7 @@ def test_cta_pair_plans_are_well_formed(shape):
             gplan = lib.pair_plan(lib.make_pair_desc("complex64", la, lb))
         finally:
             lib.set_option("tc_min_log2", 18)
-            lib.set_option("tc_gather", 2)
+            lib.set_option("tc_gather", 0)
             lib.set_option("tc_prepack_a", 1)
         assert gplan.tc_gather == 1 and list(gplan.a_lo_pos) == list(plan.a_lo_pos)
         plan_own, plan = plan, gplan
