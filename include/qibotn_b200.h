@@ -186,7 +186,7 @@ typedef struct {
   int32_t svd_wide, svd_group_mb, svd_reg;
   int32_t tc_gather;
   int32_t tc_prepack_a;
-  int32_t tc_gather_min_run;     /* tc_gather = 2: smallest run (log2 elements) fetched by bulk copies; default 9 = 4 KB */
+  int32_t tc_gather_min_run;     /* tc_gather = 2: smallest run (log2 elements) fetched by bulk copies; default 10 = 8 KB */
   int32_t reserved[1];
 } qtn_options;
 void qtn_options_default(qtn_options *opt);     /* the built-in defaults */
@@ -207,12 +207,12 @@ void qtn_options_current(qtn_options *opt);     /* the process-wide copy (defaul
  *                  MMAs of the other; 0: the round-1 pair kernel (tile and accumulators as one unit);
  *   "tc_fp16"      1 (default): staggered tiles split their operands into scaled fp16 pieces (tc_kind = 1,
  *                  half the tensor-pipe work of the TF32 split; run through qtn_pair_run_scaled); 0: TF32 split;
- *   "tc_gather"    0 (default): every producer thread gathers the elements it converts;
- *                  2: when the labels of a tile own at least the "tc_gather_min_run" (default 9) lowest
- *                  address bits of A (runs of >= 4 KB: A is often the output tile layout of an earlier node), a
+ *   "tc_gather"    0: every producer thread gathers the elements it converts;
+ *                  2 (default): when the labels of a tile own at least the "tc_gather_min_run" (default 10) lowest
+ *                  address bits of A (runs of >= 8 KB: A is often the output tile layout of an earlier node), a
  *                  chunk is fetched into the raw ring by one cp.async.bulk per run (no LSU gather) and converted
- *                  across threads -- a gain on long runs (m25 n6 k6: 9.0 -> 8.1 ms), a loss on short ones, about
- *                  neutral over the C4 plan (profiles/r02_gather_bulk_ab.jsonl), so it stays a switch;
+ *                  across threads -- a gain on long runs (m25 n6 k6: 9.0 -> 8.1 ms), neutral at 2-4 KB, a loss on
+ *                  shorter ones (profiles/r02_gather_bulk_ab.jsonl), hence the threshold;
  *                  1: A is gathered in ascending address order (contiguous runs per warp) and the raw elements
  *                  change hands across threads through shared memory (an mbarrier per raw chunk + one named
  *                  barrier per chunk).  Measured 5-20 % slower (profiles/r02_gather_ab.jsonl): fewer LSU

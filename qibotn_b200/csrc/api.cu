@@ -16,7 +16,7 @@ extern "C" int qtn_fail(int code, const char *msg) {
 extern "C" const char *qtn_last_error(void) { return g_last_error.c_str(); }
 
 namespace {
-constexpr qtn_options kDefaults = {1, 18, 1, 3, 1, 1, 5, 1, 1, 1, 0, 4, 0, 1, 9, {0}};
+constexpr qtn_options kDefaults = {1, 18, 1, 3, 1, 1, 5, 1, 1, 1, 0, 4, 2, 1, 10, {0}};
 qtn_options g_opt = kDefaults;
 
 struct Field { const char *name; int32_t qtn_options::*member; };

@@ -477,9 +477,9 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
       p->tc_gather = 1;
       if (opt.tc_gather == 2) {
         // bulk mode: the run of address bits 0, 1, 2, ... owned by the tile.  Measured on the C4 plan
-        // (profiles/r02_gather_bulk_ab.jsonl): runs of 4 KB and more (<= 4 copies per 16 KB chunk) win (m25 n6 k6: 9.0 ->
-        // 8.1 ms, m23 n5 k7: 3.5 -> 3.15 ms), 2 KB is neutral, 512 B - 1 KB (16-32 copies per chunk) lose up to 40 %:
-        // those tiles keep the per-thread gather
+        // (profiles/r02_gather_bulk_ab.jsonl): runs of 8 KB (2 copies per 16 KB chunk) win (m25 n6 k6: 9.0 -> 8.1 ms),
+        // 2-4 KB are neutral, 512 B - 1 KB (16-32 copies per chunk) lose up to 40 %: tiles below the threshold
+        // ("tc_gather_min_run", default 10 bits) keep the per-thread gather
         int r = 0;
         while (r < n && p->tc_a_gbit[r] == r) ++r;
         if (r >= opt.tc_gather_min_run && n - r <= 5) { p->tc_gather = 2; p->tc_run_bits = r; }

@@ -1,7 +1,7 @@
-"""BASELINE config 5 at the depths this round can plan: 40-qubit QAOA MaxCut on a 3-regular graph,
-sum of the 60 ZZ expectations, one light-cone-reduced contraction per term (complex64).
-    python scripts/run_c5.py [--p 3]
-p = 4 needs diagonal gates as hyper-indices to be tractable and is not run."""
+"""BASELINE config 5's workload at small depth: 40-qubit QAOA MaxCut on a 3-regular graph, sum of the 60 ZZ
+expectations, one light-cone-reduced contraction per term, complex64 and complex128, first call and cached call.
+    python scripts/run_c5.py [--p 3] [--plan-store plans/c5_p3]
+Config 5 as named (p = 4, 10^15.7 flops) is scripts/run_c5_p4.py with the plans of scripts/plan_c5.py --p 4."""
 import argparse
 import json
 import os

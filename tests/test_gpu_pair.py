@@ -157,7 +157,7 @@ def test_tensor_core_variants_agree_with_einsum(shape):
                 dict(tc_stagger=0), dict(tc_fp16=0), dict(tc_gather=1), dict(tc_gather=1, tc_fp16=0), dict(tc_prepack_a=0),
                 dict(tc_gather=0), dict(tc_gather=0, tc_prepack_a=0), dict(tc_gather=2, tc_fp16=0), dict(tc_prepack_a=2)]
     defaults = dict(tc_persistent=1, tc_prepack=1, tc_accum_split=1, tc_terms=3, tc_min_log2=18, tc_pair=5, tc_stagger=1,
-                    tc_fp16=1, tc_gather=0, tc_prepack_a=1)
+                    tc_fp16=1, tc_gather=2, tc_prepack_a=1)
     wants = {}
     for opts in variants:
         try:
@@ -180,7 +180,7 @@ def test_tensor_core_variants_agree_with_einsum(shape):
         want_pa = opts.get("tc_prepack_a", 1)                                         # >= 4 n tiles per A tile, or forced
         prepack_a = plan.tc_kind == 1 and want_pa and (n >= 9 or want_pa == 2)
         assert plan.tc_prepack_a == (1 if prepack_a else 0), (shape, opts)
-        want_g = opts.get("tc_gather", 0)
+        want_g = opts.get("tc_gather", 2)
         if not staggered or prepack_a or want_g == 0:
             assert plan.tc_gather == 0, (shape, opts)
         elif want_g == 1:
@@ -268,8 +268,8 @@ def test_bulk_copied_raw_chunks_of_the_staggered_kernel(shape):
             got[g], lc_used, plan = run_pair("complex64", la, pa_list, lb, pb, lc, None, a, b, slice_a=sa, slice_id=1)
         finally:
             lib.set_option("tc_min_log2", 18)
-            lib.set_option("tc_gather", 0)
-            lib.set_option("tc_gather_min_run", 9)
+            lib.set_option("tc_gather", 2)
+            lib.set_option("tc_gather_min_run", 10)
         assert plan.kernel == lib.KERNEL_TC and plan.tc_pair == 2
         if g == 2:
             assert plan.tc_gather == 2 and plan.tc_run_bits == {0: 7, 1: 9, 2: 6}[variant] + (0 if variant else 0), \

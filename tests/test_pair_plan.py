@@ -203,7 +203,7 @@ def test_cta_pair_plans_are_well_formed(shape):
         # address-ordered gather ("tc_gather", default): bit r of the gathered element index walks the tile label
         # of rank r in address order, and the element a thread converts -- enumeration (t, i) of a_lo_pos -- sits
         # in the raw ring at the index built from the ranks of its bits: both must name the same address
-        assert plan.tc_gather == 0                          # default: every producer gathers what it converts
+        assert plan.tc_gather == 0                          # default: bulk copies only for runs of >= 8 KB (7 bits here)
         # tc_gather = 2: bulk-copied raw chunks when the tile owns the lowest address bits of A and A is not
         # pre-packed; one cp.async.bulk per contiguous run
         lib.set_option("tc_min_log2", 0)
@@ -213,8 +213,8 @@ def test_cta_pair_plans_are_well_formed(shape):
             bplan = lib.pair_plan(lib.make_pair_desc("complex64", la, lb))
         finally:
             lib.set_option("tc_min_log2", 18)
-            lib.set_option("tc_gather", 0)
-            lib.set_option("tc_gather_min_run", 9)
+            lib.set_option("tc_gather", 2)
+            lib.set_option("tc_gather_min_run", 10)
         assert bplan.tc_gather in (0, 2) and (bplan.tc_gather == 0 or not bplan.tc_prepack_a)
         if bplan.tc_gather == 2:
             rb = bplan.tc_run_bits
@@ -227,7 +227,7 @@ def test_cta_pair_plans_are_well_formed(shape):
             gplan = lib.pair_plan(lib.make_pair_desc("complex64", la, lb))
         finally:
             lib.set_option("tc_min_log2", 18)
-            lib.set_option("tc_gather", 0)
+            lib.set_option("tc_gather", 2)
             lib.set_option("tc_prepack_a", 1)
         assert gplan.tc_gather == 1 and list(gplan.a_lo_pos) == list(plan.a_lo_pos)
         plan_own, plan = plan, gplan
