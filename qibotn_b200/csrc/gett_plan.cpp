@@ -125,8 +125,9 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     if (!(opt.tc_pair && opt.tc_prepack && opt.tc_persistent && opt.tc_accum_split && opt.tc_stagger &&
           opt.tc_terms == 3))
       return false;
-    const int tnb = std::min(nbits, 7), tkb = std::min(kbits, 4);
-    if (mbits < 10 || tnb < opt.tc_pair || mbits - 7 + bbits > QTN_HI_MAX) return false;
+    // 16 columns (n = 4) run as a 32-column tile whose upper half is a phantom: zero rows in the B images, never stored
+    const int tnb = std::min(std::max(nbits, 5), 7), tkb = std::min(kbits, 4);
+    if (mbits < 10 || tnb < opt.tc_pair || opt.tc_pair > 5 || mbits - 7 + bbits > QTN_HI_MAX) return false;
     const int64_t images = (int64_t)1 << std::min(40, (nbits - tnb) + (kbits - tkb) + bbits);
     return images * (4 * (int64_t)(4 << (tnb + tkb))) <= kMaxImageBytes;
   };
@@ -231,7 +232,11 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     p->kernel = QTN_KERNEL_TC;
     // separate accumulators for the cross terms need 4 TMEM regions per tile: 128 columns at most
     const int sep = opt.tc_accum_split && opt.tc_persistent;
-    const int tmb = 7, tnb = std::min(nbits, sep ? 7 : 8), tkb = std::min(kbits, 4);
+    // batch nodes with 16 columns: a phantom fifth column bit (position 255 in B, none in C) makes the tile 32 wide,
+    // the narrowest the staggered kernel takes; its half 1 multiplies zeros and is not stored
+    const bool phantom_n = bbits > 0 && nbits == 4;
+    if (phantom_n) { Lab ph; ph.label = -1; ph.pb = kPhantom; N.push_back(ph); }
+    const int tmb = 7, tnb = std::min(nbits + (phantom_n ? 1 : 0), sep ? 7 : 8), tkb = std::min(kbits, 4);
     const int KT = 1 << tkb, TN = 1 << tnb;
     p->tmb = tmb; p->tnb = tnb; p->tkb = tkb;
     p->block = 288;
@@ -263,7 +268,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     std::sort(khi.begin(), khi.end(), [](const Lab &x, const Lab &y) {
       return std::max(x.pa, x.pb) < std::max(y.pa, y.pb);
     });
-    p->m_real = tmb; p->n_real = tnb; p->k_real = tkb;
+    p->m_real = tmb; p->n_real = tnb - (phantom_n ? 1 : 0); p->k_real = tkb;
     // batch labels: the top bits of the m-tile index for A and C (a_mhi / c_mhi), separate deposits for B
     // (b_bat, read by the image pre-pack); n_batch tells the kernel how many of the m-hi bits they are
     const int true_mhi = (int)mhi.size();
@@ -278,7 +283,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
       int next_c = 0;
       auto give = [&](Lab &l) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); };
       for (int j = 0; j < 5; ++j) give(mlo[j]);
-      for (auto &l : nlo) give(l);
+      for (auto &l : nlo) if (l.label >= 0) give(l);
       for (int j = 5; j < tmb; ++j) give(mlo[j]);
       for (auto &l : nhi) give(l);
       for (auto &l : mhi) give(l);
@@ -319,12 +324,15 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     for (int it = 0; it < 16; ++it) {
       int64_t g = 0; int32_t so = 0;
       for (int j = 8; j < p->nb_lo; ++j)
-        if ((it >> (j - 8)) & 1) { g |= (int64_t)1 << p->b_lo_pos[j]; so += p->b_lo_sstr[j]; }
+        if ((it >> (j - 8)) & 1) {
+          if (p->b_lo_pos[j] == kPhantom) g = -1; else if (g >= 0) g |= (int64_t)1 << p->b_lo_pos[j];
+          so += p->b_lo_sstr[j];
+        }
       p->tc_b_it_g[it] = g; p->tc_b_it_s[it] = so;
     }
     p->nc_lo = tmb + tnb;
     for (int j = 0; j < tmb; ++j) p->c_lo_pos[j] = (uint8_t)mlo[j].pc;          // m bits, then n bits
-    for (int j = 0; j < tnb; ++j) p->c_lo_pos[tmb + j] = (uint8_t)nlo[j].pc;
+    for (int j = 0; j < tnb; ++j) p->c_lo_pos[tmb + j] = nlo[j].label >= 0 ? (uint8_t)nlo[j].pc : (uint8_t)kPhantom;
     for (int i = 0; i < p->n_mhi; ++i) { p->a_mhi[i] = mhi[i].pa; p->c_mhi[i] = mhi[i].pc; }
     for (int i = 0; i < p->n_nhi; ++i) { p->b_nhi[i] = nhi[i].pb; p->c_nhi[i] = nhi[i].pc; }
     for (int i = 0; i < p->n_khi; ++i) { p->a_khi[i] = khi[i].pa; p->b_khi[i] = khi[i].pb; }
@@ -428,7 +436,10 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
           for (int it = 0; it < 16; ++it) {
             int64_t g = 0; int32_t so = 0;
             for (int j = 8; j < p->nb_lo; ++j)
-              if ((it >> (j - 8)) & 1) { g |= (int64_t)1 << p->b_lo_pos[j]; so += p->b_lo_sstr[j]; }
+              if ((it >> (j - 8)) & 1) {
+                if (p->b_lo_pos[j] == kPhantom) g = -1; else if (g >= 0) g |= (int64_t)1 << p->b_lo_pos[j];
+                so += p->b_lo_sstr[j];
+              }
             p->tc_b_it_g[it] = g; p->tc_b_it_s[it] = so;
           }
           p->tc_plane_a = 128 * KT * 2;

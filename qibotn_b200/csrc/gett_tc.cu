@@ -1527,7 +1527,8 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
     const int q = warp & 3;
     const int eh = (warp - 8) >> 2;                     // which rank block of every half this warp drains
     const int r = q * 32 + lane;
-    const long long row_off = (r & 31) + ((long long)(r >> 5) << (5 + TNB));
+    const long long row_off = (r & 31) + ((long long)(r >> 5) << (5 + P.n_real));   // n_real < TNB: phantom column bit
+    const bool store_h1 = P.n_real == TNB;              // the phantom half is multiplied (zeros) but never stored
     constexpr int CH = Q < 16 ? Q : 16, NCH = Q / CH;  // column chunks of one [re] block
     // fp16 split: undo the operand scales (two factors: their product may leave the fp32 range)
     const float inv_a = F16 ? exp2_int(-amax_scale_exp(amax_a)) : 1.f;
@@ -1548,7 +1549,7 @@ gett_tc_pair2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 2 * TN);
 #pragma unroll 2
-        for (int rc = eh * NCH; rc < (eh + 1) * NCH; ++rc) {
+        for (int rc = eh * NCH; rc < (eh + 1) * NCH && (h == 0 || store_h1); ++rc) {
           const int rr = rc / NCH, cc = (rc % NCH) * CH;    // rank block, first column inside it
           const uint32_t col = (uint32_t)(rr * 2 * Q + cc);
           uint32_t re[CH], im[CH], xr[CH], xi[CH];
@@ -1694,14 +1695,20 @@ tc_prepack_b2_kernel(const __grid_constant__ qtn_pair_plan_t P, const float2 *__
   long long b_t_g = 0;
   int b_t_s = 0;
 #pragma unroll
+  bool b_phantom = false;
   for (int j = 0; j < 8; ++j)
-    if (((t >> j) & 1) && j < P.nb_lo) { b_t_g |= 1ll << P.b_lo_pos[j]; b_t_s += P.b_lo_sstr[j]; }
+    if (((t >> j) & 1) && j < P.nb_lo) {
+      if (P.b_lo_pos[j] == 255) b_phantom = true; else b_t_g |= 1ll << P.b_lo_pos[j];
+      b_t_s += P.b_lo_sstr[j];
+    }
   const float sgn_b = P.conj_b ? -1.f : 1.f;
   const float sc = F16 ? exp2_int(amax_scale_exp(amax_b)) : 1.f;
   if (!(P.nb_lo >= 8 || t < (1 << P.nb_lo))) return;
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
-    const float2 v = __ldg(B + (b_k | b_t_g | P.tc_b_it_g[i]));
+    // a phantom column bit (position 255: 16-column batch nodes run as 32-column tiles) selects rows of zeros
+    const bool phantom = b_phantom || P.tc_b_it_g[i] < 0;
+    const float2 v = phantom ? make_float2(0.f, 0.f) : __ldg(B + (b_k | b_t_g | P.tc_b_it_g[i]));
     const int o = b_t_s + P.tc_b_it_s[i];                       // offset in the canonical 128 x KT plane
     int k, n, inner;
     if constexpr (F16) {

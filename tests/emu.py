@@ -183,8 +183,11 @@ def _run_tc(P, a, b, c, sa, sb):
         assert P.n_batch == 0                  # batch labels ride on the staggered CTA-pair kernel only
         assert P.smem_bytes >= P.tc_stages * 4 * (P.tc_plane_a + P.tc_plane_b) + 8 * (2 * P.tc_stages + 2)
     assert P.smem_bytes <= 227 * 1024 and 1 <= P.tc_stages <= 8
-    # the epilogue hard-codes C's tile layout: m bits 0-4 | n bits | m bits 5-6
-    want = list(range(5)) + [5 + P.tnb, 6 + P.tnb] + [5 + j for j in range(P.tnb)]
+    # the epilogue hard-codes C's tile layout: m bits 0-4 | n bits | m bits 5-6; a phantom column bit (16-column batch
+    # nodes on the 32-column staggered tile: n_real = tnb - 1) has no position in C
+    nr = P.n_real
+    assert nr in (P.tnb, P.tnb - 1) and (nr == P.tnb or (P.n_batch > 0 and P.tc_pair == 2))
+    want = list(range(5)) + [5 + nr, 6 + nr] + [5 + j for j in range(nr)] + [255] * (P.tnb - nr)
     assert [P.c_lo_pos[i] for i in range(7 + P.tnb)] == want
     nsplit = 1 << P.split_bits
     ws = np.zeros((nsplit, P.c_elems), dtype=c.dtype)
@@ -214,19 +217,23 @@ def _run_tc(P, a, b, c, sa, sb):
                 plane = np.full(size, np.nan, dtype=np.complex128)
                 for e in range(size):
                     g = s = 0
+                    ph = False
                     for j in range(n_lo):
                         if (e >> j) & 1:
-                            g |= 1 << lo_pos[j]
+                            if lo_pos[j] == 255:
+                                ph = True                # phantom column bit: rows of zeros
+                            else:
+                                g |= 1 << lo_pos[j]
                             s += lo_sstr[j]
                     assert np.isnan(plane[s])           # every slot written exactly once
-                    plane[s] = src[base | g]
+                    plane[s] = 0.0 if ph else src[base | g]
                 planes.append(plane)
             cm = _canonical_kmajor16 if f16 else _canonical_kmajor
             acc += cm(planes[0], 128, KT) @ cm(planes[1], TN, KT).T
         out = ws[split] if P.split_bits else c
         for r in range(128):
-            for n in range(TN):
-                out[c_base + (r & 31) + (n << 5) + ((r >> 5) << (5 + P.tnb))] = acc[r, n]
+            for n in range(1 << nr):                   # phantom columns are never stored
+                out[c_base + (r & 31) + (n << 5) + ((r >> 5) << (5 + nr))] = acc[r, n]
     if P.split_bits:
         c[: P.c_elems] = ws.sum(0)
     return c

@@ -197,6 +197,7 @@ def test_tensor_core_variants_agree_with_einsum(shape):
     # kind, m, n, k, batch: batch (hyper) labels -- the diagonal gates of QAOA networks (BASELINE config 5) -- on the
     # staggered tcgen05 pair kernel (one set of B images per batch value) and on the streaming K reduction (grid.y)
     ("tc", 10, 5, 4, 2), ("tc", 11, 7, 5, 3), ("tc", 10, 6, 3, 1), ("tc", 12, 7, 6, 2), ("tc", 10, 5, 8, 4),
+    ("tc", 10, 4, 4, 1), ("tc", 13, 4, 5, 3), ("tc", 11, 4, 3, 2), ("tc", 14, 4, 6, 5),       # 16 columns: phantom column bit
     ("kred", 4, 4, 12, 3), ("kred", 2, 3, 14, 6), ("kred", 0, 1, 16, 1), ("kred", 4, 3, 10, 9),
     ("kred", 5, 3, 14, 4), ("kred", 5, 5, 12, 0), ("kred", 2, 5, 13, 2),
 ])

@@ -285,7 +285,7 @@ BATCH_CASES = [
     ("tc", 10, 5, 3, 2, 0, 0), ("tc", 10, 5, 4, 1, 1, 0), ("tc", 11, 6, 5, 2, 0, 1), ("tc", 10, 7, 4, 3, 0, 0),
     ("kred", 2, 3, 10, 2, 0, 0), ("kred", 4, 4, 10, 1, 1, 1), ("kred", 0, 1, 11, 3, 0, 0),
     ("kred", 5, 3, 10, 2, 0, 0), ("kred", 5, 5, 10, 0, 1, 0), ("kred", 3, 5, 11, 1, 0, 1),
-    ("tile", 9, 5, 4, 2, 0, 0), ("tile", 10, 4, 4, 1, 0, 0),
+    ("tile", 9, 5, 4, 2, 0, 0), ("tc", 10, 4, 4, 1, 0, 0), ("tc", 11, 4, 3, 2, 1, 0), ("tile", 10, 3, 4, 1, 0, 0),
 ]
 
 
@@ -311,6 +311,7 @@ def test_batch_labels_in_tensor_core_and_kred_plans(case):
         assert plan.kernel == lib.KERNEL_TC and plan.tc_pair == 2 and plan.tc_prepack == 1
         assert plan.tc_kind == (1 if k >= 4 else 0)
         assert plan.n_mhi == m - 7 + batch and plan.grid == (1 << (plan.n_mhi + plan.n_nhi + plan.split_bits))
+        assert plan.n_real == min(n, 7) and plan.tnb == max(min(n, 7), 5)      # 16 columns: a phantom fifth column bit
     elif kind == "kred":
         assert plan.kernel == lib.KERNEL_KRED and plan.grid >= 1
     else:
