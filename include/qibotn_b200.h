@@ -171,6 +171,10 @@ typedef struct {
    * (one image per m tile and k chunk, 128 x 16 complex values = 16 KB: as large as A itself), at workspace offset
    * tc_prepack_a_off; the main kernel's producers shrink to one thread issuing two bulk copies per stage.  Chosen
    * when >= 4 n tiles read every A tile (A would otherwise be gathered and converted once per n tile). */
+  /* QTN_KERNEL_KRED: number of INNER batch labels (batch labels at low address bits, enumerated inside the CTA as
+   * a second row dimension of the shared-memory chunk instead of by grid.y) and their C positions */
+  int32_t kred_inner;
+  uint8_t kred_c_in[4];
   int32_t tc_prepack_a;
   int32_t tc_run_bits;           /* tc_gather == 2: log2 of the contiguous run the tile's labels own at the bottom of A */
   int64_t tc_prepack_a_off;

@@ -478,9 +478,11 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   using T = cx<R>;
   constexpr int NIT = sizeof(R) == 4 ? 8 : 4;                // loads per thread, operand and chunk
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int KC = 1 << P.tkb;
-  T *sA = reinterpret_cast<T *>(smem_raw);                   // [2][KC][16]
-  T *sB = sA + 2 * KC * KRED_ROW;                            // [2][KC][16]
+  const int KC = 1 << P.tkb;                                 // k values per chunk
+  const int QI = P.kred_inner, BL = 1 << QI;                 // inner batch values: chunk row = (k << QI) + bl
+  const int ROWS = KC << QI;
+  T *sA = reinterpret_cast<T *>(smem_raw);                   // [2][ROWS][16]
+  T *sB = sA + 2 * ROWS * KRED_ROW;                          // [2][ROWS][16]
   const int t = threadIdx.x;
   const long long a_base = slice_offset(slice_id, P.n_slice_a, P.slice_bit_a, P.slice_pos_a) |
                            deposit_present(blockIdx.y, P.a_bat, P.n_batch);   // grid.y = batch (hyper) value
@@ -530,7 +532,9 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
     ++inner;
   };
 
-  const int sb = t & 15, kg = t >> 4;
+  // thread = (4 x 4 output block sb, inner batch value bl, k group kg): 16 >> QI k groups share a chunk
+  const int sb = t & 15, bl = (t >> 4) & (BL - 1), kg = t >> (4 + QI);
+  const int kgroups = 16 >> QI;
   const int mi = (sb >> 2) * 4, ni = (sb & 3) * 4;
   T acc[4][4];
 #pragma unroll
@@ -549,7 +553,7 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
     }
   };
   auto stash = [&](int buf) {
-    T *da = sA + buf * KC * KRED_ROW, *db = sB + buf * KC * KRED_ROW;
+    T *da = sA + buf * ROWS * KRED_ROW, *db = sB + buf * ROWS * KRED_ROW;
 #pragma unroll
     for (int u = 0; u < NIT; ++u) {
       if (a_act && u < a_nit) {
@@ -568,10 +572,11 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
   for (int buf = 0; have; buf ^= 1) {
     const bool more = group < ngroups;            // the stream position after the current chunk
     if (more) { load(); advance(); }              // next chunk in flight while this one is used
-    const T *pa = sA + buf * KC * KRED_ROW, *pb = sB + buf * KC * KRED_ROW;
-    for (int k = kg; k < KC; k += 16) {
+    const T *pa = sA + buf * ROWS * KRED_ROW, *pb = sB + buf * ROWS * KRED_ROW;
+    for (int kq = kg; kq < KC; kq += kgroups) {
       T a[4], b[4];
-      const int sk = (k & 7) << 1;              // this k row's XOR (kred_swz)
+      const int k = (kq << QI) + bl;            // chunk row of (k value, this thread's inner batch value)
+      const int sk = (k & 7) << 1;              // this row's XOR (kred_swz)
       if constexpr (sizeof(R) == 4) {           // two complex64 per 128-bit shared-memory load
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -595,21 +600,22 @@ gett_kred_kernel(const __grid_constant__ qtn_pair_plan_t P, const cx<R> *__restr
     __syncthreads();
     have = more;
   }
-  // sum the 16 k-groups: red[kg][m * 16 + n] aliases the chunk buffers
+  // sum the k groups of every inner batch value: red[kg * BL + bl][m * 16 + n] aliases the chunk buffers
   T *red = reinterpret_cast<T *>(smem_raw);
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[kg * 256 + (mi + i) * 16 + (ni + j)] = acc[i][j];
+    for (int j = 0; j < 4; ++j) red[(t >> 4) * 256 + (mi + i) * 16 + (ni + j)] = acc[i][j];
   __syncthreads();
   {
-    T s = cx_zero<R>();
-    for (int g = 0; g < 16; ++g) { const T v = red[g * 256 + t]; s.x += v.x; s.y += v.y; }
     const int m = t >> 4, n = t & 15;
-    if (m < (1 << P.m_real) && n < (1 << P.n_real)) {
-      const long long off = deposit(m, P.c_mhi, P.m_real) | deposit(n, P.c_nhi, P.n_real) |
-                            deposit(blockIdx.y, P.c_bat, P.n_batch);
-      ws[(long long)blockIdx.x * P.c_elems + off] = s;
+    const bool live = m < (1 << P.m_real) && n < (1 << P.n_real);
+    const long long off = deposit(m, P.c_mhi, P.m_real) | deposit(n, P.c_nhi, P.n_real) |
+                          deposit(blockIdx.y, P.c_bat, P.n_batch);
+    for (int b = 0; b < BL; ++b) {
+      T s = cx_zero<R>();
+      for (int g = 0; g < kgroups; ++g) { const T v = red[(g * BL + b) * 256 + t]; s.x += v.x; s.y += v.y; }
+      if (live) ws[(long long)blockIdx.x * P.c_elems + (off | deposit(b, P.kred_c_in, QI))] = s;
     }
   }
 }

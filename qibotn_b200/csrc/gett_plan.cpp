@@ -158,11 +158,25 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     p->smem_bytes = 0;
     p->workspace_bytes = p->grid * 16 * esz;
   } else if (mbits <= 5 && nbits <= 5 && kbits >= 10 &&
-             bbits + std::max(0, mbits - 4) + std::max(0, nbits - 4) <= 15) {
+             bbits + std::max(0, mbits - 4) + std::max(0, nbits - 4) <= 15 && kbits >= 7) {
     // ---- streaming K reduction (<= 16 x 16 outputs) ----------------------------
     p->kernel = QTN_KERNEL_KRED;
-    const int tkb = std::min(kbits, d->dtype == QTN_C64 ? 7 : 6);   // chunk: 128 / 64 contracted values
+    // Batch labels that own LOW address bits of an operand would leave every CTA with runs of 8-16 bytes (one batch
+    // value per CTA): up to three of them (lowest address first, those below bit 6) become INNER labels -- a second
+    // row dimension of the shared-memory chunk, handled by different thread groups of the same CTA -- so that the
+    // CTA's gathers stay contiguous.  The chunk keeps its size: 2^q inner values x 2^(tkb) k values.
+    std::sort(Bt.begin(), Bt.end(), [](const Lab &x, const Lab &y) {
+      return std::min(x.pa, x.pb) != std::min(y.pa, y.pb) ? std::min(x.pa, x.pb) < std::min(y.pa, y.pb) : x.label < y.label;
+    });
+    std::vector<Lab> Bin;
+    while (Bin.size() < 3 && !Bt.empty() && std::min(Bt.front().pa, Bt.front().pb) < 6) {
+      Bin.push_back(Bt.front());
+      Bt.erase(Bt.begin());
+    }
+    const int q = (int)Bin.size();
+    const int tkb = std::min(kbits, (d->dtype == QTN_C64 ? 7 : 6) - q);   // chunk: 128 / 64 (k value, inner batch value) rows
     p->tmb = 4; p->tnb = 4; p->tkb = tkb;
+    p->kred_inner = q;
     std::sort(M.begin(), M.end(), [](const Lab &x, const Lab &y) { return x.pa < y.pa; });
     std::sort(N.begin(), N.end(), [](const Lab &x, const Lab &y) { return x.pb < y.pb; });
     // a fifth m (n) label -- the one with the highest address -- is enumerated by grid.y next to the batch labels:
@@ -171,7 +185,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     while ((int)M.size() > 4) { Mx.push_back(M.back()); M.pop_back(); }
     while ((int)N.size() > 4) { Nx.push_back(N.back()); N.pop_back(); }
     const int mt = (int)M.size(), nt = (int)N.size();
-    const int ybits = bbits + (int)Mx.size() + (int)Nx.size();      // labels enumerated by grid.y
+    const int ybits = (int)Bt.size() + (int)Mx.size() + (int)Nx.size();      // labels enumerated by grid.y
     p->m_real = mt; p->n_real = nt; p->k_real = tkb;
     // chunk labels = the K labels with the lowest addresses (in either operand): contiguous runs
     std::sort(K.begin(), K.end(), [](const Lab &x, const Lab &y) {
@@ -187,9 +201,10 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
       int next_c = 0;
       for (auto &l : N) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
       for (auto &l : M) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
-      for (auto *v : {&Nx, &Mx, &Bt})
+      for (auto *v : {&Bin, &Nx, &Mx, &Bt})
         for (auto &l : *v) { l.pc = next_c++; assigned.push_back({l.label, l.pc}); }
     }
+    for (int i = 0; i < q; ++i) p->kred_c_in[i] = (uint8_t)Bin[i].pc;
     for (int i = 0; i < mt; ++i) { p->a_mhi[i] = M[i].pa; p->c_mhi[i] = M[i].pc; }
     for (int i = 0; i < nt; ++i) { p->b_nhi[i] = N[i].pb; p->c_nhi[i] = N[i].pc; }
     // grid.y: batch (hyper) labels -- one independent reduction per value -- and the surplus m / n labels
@@ -203,14 +218,16 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     }
     p->n_mhi = 0; p->n_nhi = 0; p->n_khi = (int)khi.size();
     for (int i = 0; i < p->n_khi; ++i) { p->a_khi[i] = khi[i].pa; p->b_khi[i] = khi[i].pb; }
-    // shared-memory chunk: element (k, row) at k * 16 + row before the kernel's bank swizzle; enumerations in
-    // address order
+    // shared-memory chunk: element (k, inner batch value bl, row) at ((k << q) + bl) * 16 + row before the kernel's
+    // bank swizzle; enumerations in address order
     struct E { int pos; int sstr; };
     std::vector<E> ea, eb;
     for (int i = 0; i < mt; ++i) ea.push_back({M[i].pa, 1 << i});
-    for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, 16 << i});
+    for (int i = 0; i < q; ++i) ea.push_back({Bin[i].pa, 16 << i});
+    for (int i = 0; i < tkb; ++i) ea.push_back({klo[i].pa, (16 << q) << i});
     for (int i = 0; i < nt; ++i) eb.push_back({N[i].pb, 1 << i});
-    for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, 16 << i});
+    for (int i = 0; i < q; ++i) eb.push_back({Bin[i].pb, 16 << i});
+    for (int i = 0; i < tkb; ++i) eb.push_back({klo[i].pb, (16 << q) << i});
     auto by_pos = [](const E &x, const E &y) { return x.pos < y.pos; };
     std::sort(ea.begin(), ea.end(), by_pos);
     std::sort(eb.begin(), eb.end(), by_pos);
@@ -224,7 +241,7 @@ extern "C" int qtn_pair_plan_opts(qtn_pair_desc *d, int sm_count, const qtn_opti
     p->grid = std::min<int64_t>(ngroups, std::max<int64_t>(1, ((int64_t)2 * sm_count) >> ybits));
     p->workspace_bytes = ((int64_t)esz << d->rank_c) * p->grid;
     // max(2 buffers x (A + B) chunk, 16 x 256 partials)
-    p->smem_bytes = std::max(2 * 2 * (1 << tkb) * 16 * esz, 16 * 256 * esz);
+    p->smem_bytes = std::max(2 * 2 * (1 << (tkb + q)) * 16 * esz, 16 * 256 * esz);
   } else if (d->dtype == QTN_C64 && d->c_layout_free && (bbits == 0 || tc_batch_ok()) && mbits >= 7 && nbits >= 4 &&
              kbits >= 3 && mbits + nbits + kbits >= opt.tc_min_log2 && opt.tc_enable) {
     // ---- tensor-core kernel (gett_tc.cu) ----------------------------------------

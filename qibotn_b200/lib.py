@@ -70,7 +70,8 @@ class PairPlan(C.Structure):
         ("tc_kind", C.c_int32), ("tc_gather", C.c_int32),
         ("tc_a_gbit", C.c_uint8 * QTN_LO_MAX), ("tc_a_rank", C.c_uint8 * QTN_LO_MAX),
         ("tc_a_it_gg", C.c_int64 * 8), ("tc_a_it_raw", C.c_int32 * 8),
-        ("tile_stages", C.c_int32), ("tc_prepack_a", C.c_int32), ("tc_run_bits", C.c_int32),
+        ("tile_stages", C.c_int32), ("kred_inner", C.c_int32), ("kred_c_in", C.c_uint8 * 4),
+        ("tc_prepack_a", C.c_int32), ("tc_run_bits", C.c_int32),
         ("tc_prepack_a_off", C.c_int64),
     ]
 

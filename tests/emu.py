@@ -240,17 +240,19 @@ def _run_tc(P, a, b, c, sa, sb):
 
 
 def _run_kred(P, a, b, c, sa, sb):
-    """Emulate gett_kred_kernel: per CTA a range of k chunks, 16 x 16 (padded) outputs, one partial
-    per CTA summed at the end."""
+    """Emulate gett_kred_kernel: per CTA a range of k chunks, 16 x 16 (padded) outputs per inner batch value, one
+    partial per CTA summed at the end.  A chunk row is (k value, inner batch value): row = (k << q) + bl."""
     KC = 1 << P.tkb
-    assert P.tmb == 4 and P.tnb == 4 and 0 <= P.n_batch <= 15 and P.n_mhi == 0 and P.n_nhi == 0
+    QI = P.kred_inner
+    BL, ROWS = 1 << QI, KC << QI
+    assert P.tmb == 4 and P.tnb == 4 and 0 <= P.n_batch <= 15 and P.n_mhi == 0 and P.n_nhi == 0 and 0 <= QI <= 3
     ib = min(3, P.n_khi)
     ngroups = 1 << (P.n_khi - ib)
-    assert P.smem_bytes >= 2 * 2 * KC * 16 * c.itemsize and 1 <= P.grid <= ngroups and P.smem_bytes <= 80 * 1024
+    assert P.smem_bytes >= 2 * 2 * ROWS * 16 * c.itemsize and 1 <= P.grid <= ngroups and P.smem_bytes <= 80 * 1024
     assert P.na_lo <= 11 and P.nb_lo <= 11
     ws = np.zeros((P.grid, P.c_elems), dtype=np.complex128)
     for cta, bt in ((x, y) for x in range(P.grid) for y in range(1 << P.n_batch)):      # grid.y = batch value
-        acc = np.zeros((16, 16), dtype=np.complex128)
+        acc = np.zeros((BL, 16, 16), dtype=np.complex128)
         # groups of 2^ib consecutive chunks; neighbouring CTAs take neighbouring groups
         for kh in (g << ib | i for g in range(cta, ngroups, P.grid) for i in range(1 << ib)):
             a_k = sa | dep(kh, P.a_khi, P.n_khi) | dep_present(bt, P.a_bat, P.n_batch)
@@ -258,7 +260,7 @@ def _run_kred(P, a, b, c, sa, sb):
             chunks = []
             for (n_lo, lo_pos, lo_sstr, src, base) in ((P.na_lo, P.a_lo_pos, P.a_lo_sstr, a, a_k),
                                                        (P.nb_lo, P.b_lo_pos, P.b_lo_sstr, b, b_k)):
-                buf = np.zeros(KC * 16, dtype=np.complex128)
+                buf = np.zeros(ROWS * 16, dtype=np.complex128)
                 for e in range(1 << n_lo):
                     g = s = 0
                     for j in range(n_lo):
@@ -266,11 +268,15 @@ def _run_kred(P, a, b, c, sa, sb):
                             g |= 1 << lo_pos[j]
                             s += lo_sstr[j]
                     buf[s] = src[base | g]
-                chunks.append(buf.reshape(KC, 16))
-            acc += chunks[0].T @ chunks[1]
-        for m in range(1 << P.m_real):
-            for n in range(1 << P.n_real):
-                ws[cta, dep(m, P.c_mhi, P.m_real) | dep(n, P.c_nhi, P.n_real) | dep(bt, P.c_bat, P.n_batch)] = acc[m, n]
+                chunks.append(buf.reshape(ROWS, 16))
+            for bl in range(BL):
+                acc[bl] += chunks[0][bl::BL].T @ chunks[1][bl::BL]
+        for bl in range(BL):
+            for m in range(1 << P.m_real):
+                for n in range(1 << P.n_real):
+                    off = (dep(m, P.c_mhi, P.m_real) | dep(n, P.c_nhi, P.n_real) | dep(bt, P.c_bat, P.n_batch) |
+                           dep(bl, P.kred_c_in, QI))
+                    ws[cta, off] = acc[bl, m, n]
     tot = ws.sum(0)
     if P.accumulate:
         c[: P.c_elems] += tot

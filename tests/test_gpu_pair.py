@@ -223,7 +223,10 @@ def test_batch_labels_on_tensor_core_and_kred_kernels(case):
                                           slice_a=sa, slice_id=1)
         finally:
             lib.set_option("tc_min_log2", 18)
-        assert plan.n_batch == batch + (max(0, m - 4) + max(0, n - 4) if kind == "kred" else 0)
+        if kind == "kred":
+            assert plan.n_batch == batch - plan.kred_inner + max(0, m - 4) + max(0, n - 4)
+        else:
+            assert plan.n_batch == batch
         if kind == "tc":
             assert plan.kernel == lib.KERNEL_TC and plan.tc_pair == 2 and plan.tc_kind == (1 if k >= 4 else 0)
         else:

@@ -285,6 +285,7 @@ BATCH_CASES = [
     ("tc", 10, 5, 3, 2, 0, 0), ("tc", 10, 5, 4, 1, 1, 0), ("tc", 11, 6, 5, 2, 0, 1), ("tc", 10, 7, 4, 3, 0, 0),
     ("kred", 2, 3, 10, 2, 0, 0), ("kred", 4, 4, 10, 1, 1, 1), ("kred", 0, 1, 11, 3, 0, 0),
     ("kred", 5, 3, 10, 2, 0, 0), ("kred", 5, 5, 10, 0, 1, 0), ("kred", 3, 5, 11, 1, 0, 1),
+    ("kred", 4, 4, 10, 4, 0, 0), ("kred", 3, 2, 11, 5, 0, 0), ("kred", 1, 1, 12, 3, 1, 0),
     ("tile", 9, 5, 4, 2, 0, 0), ("tc", 10, 4, 4, 1, 0, 0), ("tc", 11, 4, 3, 2, 1, 0), ("tile", 10, 3, 4, 1, 0, 0),
 ]
 
@@ -305,7 +306,13 @@ def test_batch_labels_in_tensor_core_and_kred_plans(case):
         plan = lib.pair_plan(desc, 4)
     finally:
         lib.set_option("tc_min_log2", 18)
-    assert plan.n_batch == batch + (max(0, m - 4) + max(0, n - 4) if kind == "kred" else 0)
+    if kind == "kred":
+        # batch labels at low address bits (below bit 6, at most three) are INNER labels of the K reduction; the others
+        # and a fifth m / n label ride on grid.y
+        assert 0 <= plan.kred_inner <= min(3, batch)
+        assert plan.n_batch == batch - plan.kred_inner + max(0, m - 4) + max(0, n - 4)
+    else:
+        assert plan.n_batch == batch
     if kind == "tc":
         # m >= 10 (8 m tiles per B image), n >= 5: the staggered pair kernel; fp16 split when 16 k values fill a stage
         assert plan.kernel == lib.KERNEL_TC and plan.tc_pair == 2 and plan.tc_prepack == 1
