@@ -63,15 +63,16 @@ class QuimbBackend(QibotnBackend, NumpyBackend):
             svd["max_extent"] = int(self.max_bond_dimension)
         return {"qr_method": False, "svd_method": svd}
 
-    def _mps(self, circuit):
+    def _mps(self, circuit, initial_state=None):
         from ..mps import QiboCircuitToMPS
-        return QiboCircuitToMPS(circuit, self._gate_algo(), dtype=self.dtype).mps_tensors
+        return QiboCircuitToMPS(circuit, self._gate_algo(), dtype=self.dtype, initial_state=initial_state).mps_tensors
 
-    def _dense(self, circuit):
+    def _dense(self, circuit, initial_state=None):
         """Dense state over ALL qubits, qubit 0 most significant."""
         if self.ansatz == "mps":
             from ..mps import MPSContractionHelper
-            return MPSContractionHelper(circuit.nqubits).contract_state_vector(self._mps(circuit)).reshape(-1)
+            return MPSContractionHelper(circuit.nqubits).contract_state_vector(
+                self._mps(circuit, initial_state)).reshape(-1)
         import torch
 
         from .. import engine
@@ -90,16 +91,19 @@ class QuimbBackend(QibotnBackend, NumpyBackend):
 
     # ------------------------------------------------------------------ API
     def execute_circuit(self, circuit, initial_state=None, nshots=None, return_array=False):
-        if initial_state is not None and self.ansatz == "MPS":
-            raise_error(NotImplementedError, "An initial MPS from a dense state is not supported.")
-        elif initial_state is not None:
-            raise_error(ValueError, "Initial state not None supported only for MPS ansatz.")
         n = circuit.nqubits
+        if initial_state is not None and self.ansatz != "mps":
+            raise_error(ValueError, "Initial state not None supported only for MPS ansatz.")
+        if initial_state is not None:
+            # dense vector -> MPS on the GPU (the reference: MatrixProductState.from_dense, :162-165)
+            initial_state = np.asarray(initial_state).reshape(-1)
+            if initial_state.size != 1 << n:
+                raise_error(ValueError, f"Initial state has {initial_state.size} amplitudes, expected 2^{n}.")
         frequencies = measured_probabilities = None
         psi = None
         if nshots and self.ansatz == "mps":
             from ..mps import MPSContractionHelper
-            bits, probs = MPSContractionHelper(n).sample(self._mps(circuit), int(nshots),
+            bits, probs = MPSContractionHelper(n).sample(self._mps(circuit, initial_state), int(nshots),
                                                          seed=getattr(self, "sampling_seed", None))
             strings = ["".join("1" if b else "0" for b in row) for row in bits]
             frequencies = Counter(strings)
@@ -124,7 +128,7 @@ class QuimbBackend(QibotnBackend, NumpyBackend):
         statevector = None
         if return_array:
             from ..result import DeviceArray
-            statevector = DeviceArray(psi if psi is not None else self._dense(circuit))
+            statevector = DeviceArray(psi if psi is not None else self._dense(circuit, initial_state))
         return TensorNetworkResult(nqubits=n, backend=self, measures=frequencies,
                                    measured_probabilities=measured_probabilities, prob_type="default",
                                    statevector=statevector)

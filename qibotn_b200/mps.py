@@ -237,11 +237,22 @@ class MPSEngine:
             lib.check(self.lib.qtn_mps_apply_2q(self.code, l, r, theta.data_ptr(), gates[k].data_ptr(),
                                                 self._stream()))
             self.stats["launches"] += 1
-            transposed = p > q
-            w = self._transpose(theta, p, q) if transposed else theta.clone()
-            work.append((i, l, r, p, q, theta, w, transposed))
+            work.append(self._work_item(i, l, r, p, q, theta))
+        self._split(work)
+
+    def _work_item(self, i, l, r, p, q, theta):
+        """One block to split: theta (p x q, p = 2l, q = 2r) -> sites[i] (l,2,k), sites[i+1] (k,2,r)."""
+        transposed = p > q
+        w = self._transpose(theta, p, q) if transposed else theta.clone()
+        return (i, l, r, p, q, theta, w, transposed)
+
+    def _split(self, work):
         if self.qr_only:
             return self._split_qr(work)
+        return self._split_svd(work)
+
+    def _split_svd(self, work):
+        torch = self.torch
         nb = len(work)
         items = (lib.SvdItem * nb)()
         ld = 1
@@ -391,11 +402,80 @@ class MPSEngine:
         self.flush()
         return [int(t.shape[2]) for t in self.sites[:-1]]
 
+    # ------------------------------------------------------------------ dense initial state
+    def load_dense(self, state):
+        """Replace the sites by an MPS of the dense vector ``state`` (2^n amplitudes, qubit 0 most significant):
+        what ``MatrixProductState.from_dense`` does for the reference (eval_qu.py:5-18, backends/quimb.py:162-165).
+
+        The left half of the chain needs no arithmetic: an untruncated split of a (2l x R) block with 2l <= R has
+        full rank 2l, so sites 0..h-1 are identity isometries (l,2,2l) and the amplitudes stay in one centre block
+        (2^h x 2^(n-h)).  From there the sweep splits (2l x R) blocks left to right with this engine's decomposition
+        (singular values to the right, so every finished site is an isometry and truncation is optimal).  If a bond
+        cap (``max_extent``) is set and a bond of the identity half exceeds it, one right-to-left sweep of identity
+        gates with the singular values kept on the left truncates those bonds from the orthogonality centre."""
+        torch = self.torch
+        self.flush()
+        n = self.n
+        on_device = torch.is_tensor(state)                  # (numpy >= 2 arrays have a .device attribute too)
+        if not on_device:
+            state = np.ascontiguousarray(np.asarray(state).reshape(-1))
+        size = int(np.prod(tuple(state.shape)))
+        if size != 1 << n:
+            raise ValueError(f"initial state has {size} amplitudes, expected 2^{n}")
+        h = (n - 1) // 2
+        long_side = 1 << max(h + 1, n - 1 - h)
+        if long_side * (16 if self.dtype == "complex128" else 8) > 16384:
+            # the Jacobi kernels keep whole rows of a block in shared memory
+            raise NotImplementedError("dense initial states are limited to 20 qubits (complex128) / 22 (complex64); "
+                                      f"got {n}")
+        psi = (state.reshape(-1) if on_device else torch.from_numpy(state)).to(self.device).to(self.cdtype)
+        if n == 1:
+            self.sites = [psi.clone().view(1, 2, 1)]
+            return self
+        sites = []
+        for i in range(h):
+            d = 1 << i
+            sites.append(torch.eye(2 * d, dtype=self.cdtype, device=self.device).view(d, 2, 2 * d).contiguous())
+        self.sites = sites + [None] * (n - h)
+        cur = psi.clone()
+        l = 1 << h
+        keep = self.partition
+        try:
+            if not self.qr_only:
+                self.partition = _PARTITION["V"]
+            for i in range(h, n - 1):
+                big_r = cur.numel() // (2 * l)
+                self._split([self._work_item(i, l, big_r // 2, 2 * l, big_r, cur)])
+                cur = self.sites[i + 1].reshape(-1)
+                l = int(self.sites[i + 1].shape[0])
+            cap = int(self.trunc.max_extent)
+            if cap and not self.qr_only and (1 << h) > cap:
+                self.partition = _PARTITION["U"]
+                eye = np.eye(4, dtype=self.np_dtype).reshape(2, 2, 2, 2)
+                for i in range(n - 2, -1, -1):
+                    self._queue_two_site(i, eye)
+                    self.flush()
+        finally:
+            self.partition = keep
+        return self
+
 
 # ----------------------------------------------------------------------------- reference surface
 def initial(num_qubits, dtype):
     """|0...0> as ``num_qubits`` tensors of shape (1,2,1) on the GPU (mps_utils.py:6-18)."""
     return MPSEngine(num_qubits, dtype).sites
+
+
+def from_dense(state, dtype="complex128", algorithm=None):
+    """Dense vector (2^n, qubit 0 most significant) -> list of n site tensors (l,2,r) on the GPU
+    (eval_qu.py:5-18 ``init_state_tn``).  ``algorithm``: a gate_algo dict; the default is an untruncated SVD."""
+    shape = getattr(state, "shape", None)
+    size = int(np.prod(tuple(shape))) if shape is not None else len(state)
+    n = max(1, size.bit_length() - 1)
+    if size != 1 << n:
+        raise ValueError(f"initial state has {size} amplitudes, not a power of two")
+    algorithm = algorithm or {"qr_method": False, "svd_method": {"partition": "V"}}
+    return MPSEngine(n, dtype, algorithm).load_dense(state).sites
 
 
 def _engine_from(mps_tensors, algorithm):
@@ -428,13 +508,15 @@ def mps_site_right_swap(mps_tensors, i, **kwargs):
 class QiboCircuitToMPS:
     """Circuit -> MPS (circuit_to_mps.py:9-47): |0..0>, then every gate in queue order."""
 
-    def __init__(self, circ_qibo, gate_algo, dtype="complex128", rand_seed=0, tol=None):
+    def __init__(self, circ_qibo, gate_algo, dtype="complex128", rand_seed=0, tol=None, initial_state=None):
         np.random.seed(rand_seed)
         self.num_qubits = circ_qibo.nqubits
         self.dtype = dtype
         self.handle = None                      # the reference keeps a cutensornet handle here
         conv = QiboCircuitToEinsum(circ_qibo, dtype=dtype)
         self.engine = MPSEngine(self.num_qubits, dtype, gate_algo, tol=tol)
+        if initial_state is not None:           # dense vector -> MPS (backends/quimb.py:162-165)
+            self.engine.load_dense(initial_state)
         for gate, qubits in conv.gate_tensors:
             self.engine.apply_gate(gate, qubits)
         self.engine.flush()

@@ -127,9 +127,21 @@ class QiboCircuitToEinsum:
         g_t, g_m, _ = self._thread(self.gate_tensors, frontier, len(active))
         return active, frontier, tensors + g_t, modes + g_m
 
-    def state_vector_network(self) -> TensorNetwork:
-        active, frontier, tensors, modes = self._open_network()
-        return TensorNetwork(tensors, modes, [frontier[q] for q in active])
+    def state_vector_network(self, initial_state=None) -> TensorNetwork:
+        """``initial_state``: dense vector over ALL qubits (qubit 0 most significant) that replaces |0...0>
+        (the legacy quimb path, eval_qu.py:34-41).  It enters as ONE rank-n leaf -- the reference splits it into an
+        MPS first (``from_dense``), which changes the factorisation of the input, not the contracted value -- and
+        every qubit is active then."""
+        if initial_state is None:
+            active, frontier, tensors, modes = self._open_network()
+            return TensorNetwork(tensors, modes, [frontier[q] for q in active])
+        n = int(self.circuit.nqubits)
+        psi = np.ascontiguousarray(np.asarray(initial_state, dtype=self.dtype).reshape(-1))
+        if psi.size != 1 << n:
+            raise ValueError(f"initial state has {psi.size} amplitudes, expected 2^{n}")
+        frontier = {q: q for q in range(n)}
+        g_t, g_m, _ = self._thread(self.gate_tensors, frontier, n)
+        return TensorNetwork([psi.reshape((2,) * n)] + g_t, [list(range(n))] + g_m, [frontier[q] for q in range(n)])
 
     def state_vector_operands(self):
         """Dense state vector over the *active* qubits (:28-58)."""

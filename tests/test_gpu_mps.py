@@ -486,3 +486,100 @@ def test_c3_full_size_against_the_cpu_oracle_fixture():
         i = int(i)
         got = complex(helper.pauli_expectation(conv.mps_tensors, {i: "Z", i + 1: "Z"}).cpu())
         assert abs(got - complex(re, im)) <= 1e-10, (i, got, re, im)
+
+
+# ----------------------------------------------------------------------------- dense initial state (config 1)
+def _random_state(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    return v / np.linalg.norm(v)
+
+
+def _qft_qasm(n):
+    """QFT with swaps as qibo's ``QFT(n).to_qasm()`` writes it (h / cu1 / swap)."""
+    import math
+    lines = ['OPENQASM 2.0;', 'include "qelib1.inc";', f"qreg q[{n}];"]
+    for i in range(n):
+        lines.append(f"h q[{i}];")
+        for j in range(i + 1, n):
+            lines.append(f"cu1({math.pi / 2 ** (j - i)!r}) q[{j}],q[{i}];")
+    for i in range(n // 2):
+        lines.append(f"swap q[{i}],q[{n - 1 - i}];")
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 10, 13])
+def test_from_dense_round_trip(n, dtype):
+    """reference eval_qu.py:5-18: the MPS of a dense vector contracts back to the vector; shapes (l,2,r)."""
+    psi = _random_state(n, 100 + n)
+    sites = gmps.from_dense(psi, dtype)
+    assert len(sites) == n and sites[0].shape[0] == 1 and sites[-1].shape[2] == 1
+    for a, b in zip(sites[:-1], sites[1:]):
+        assert a.shape[1] == 2 and a.shape[2] == b.shape[0] <= 1 << (n // 2)
+    got = gmps.MPSContractionHelper(n).contract_state_vector(sites).reshape(-1).cpu().numpy()
+    assert np.abs(got - psi).max() < TOL[dtype]
+
+
+def test_from_dense_honours_the_bond_cap_and_cutoff():
+    """A state of Schmidt rank <= 3 across every cut (sum of three product states) plus nothing else: the cutoff
+    finds rank <= 3 on the decomposed half and the cap sweep brings the identity half down to it as well."""
+    n = 12
+    rng = np.random.default_rng(5)
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    for _ in range(3):
+        v = np.ones(1, dtype=np.complex128)
+        for _q in range(n):
+            v = np.kron(v, rng.standard_normal(2) + 1j * rng.standard_normal(2))
+        psi += v
+    psi /= np.linalg.norm(psi)
+    algo = {"qr_method": False, "svd_method": {"partition": "UV", "abs_cutoff": 1e-9, "max_extent": 4}}
+    sites = gmps.from_dense(psi, "complex128", algo)
+    bonds = [int(t.shape[2]) for t in sites[:-1]]
+    assert max(bonds) <= 4, bonds
+    assert max(bonds[n // 2:]) <= 3, bonds
+    got = gmps.MPSContractionHelper(n).contract_state_vector(sites).reshape(-1).cpu().numpy()
+    assert np.abs(got - psi).max() < 1e-9
+    with pytest.raises(ValueError):
+        gmps.from_dense(psi[:-1], "complex128")
+    with pytest.raises(NotImplementedError):
+        gmps.MPSEngine(23, "complex128").load_dense(np.zeros(1 << 23, dtype=np.complex64))   # rows too long to split
+
+@pytest.mark.parametrize("nqubits,tolerance,is_mps", [(1, 1e-6, True), (2, 1e-6, False), (5, 1e-3, True),
+                                                      (10, 1e-3, False), (10, 1e-5, True), (6, 1e-6, False)])
+def test_eval_qu_dense_vector_with_initial_state(nqubits, tolerance, is_mps):
+    """The reference's own quimb test (tests/test_quimb_backend.py:23-66): QFT with swaps on a random normalised
+    initial state, as QASM text, MPS options {"method": "svd", "cutoff": 1e-6, "cutoff_mode": "abs"} or None."""
+    from qibotn_b200 import eval_qu
+    from qibotn_b200.qasm import from_openqasm2_str
+
+    init = _random_state(nqubits, 7 * nqubits)
+    text = _qft_qasm(nqubits)
+    want = osv.simulate(from_openqasm2_str(text), initial_state=init)
+    assert np.abs(want - osv.simulate(circuits.qft(nqubits, True), initial_state=init)).max() < 1e-12
+    opts = {"method": "svd", "cutoff": 1e-6, "cutoff_mode": "abs"} if is_mps else None
+    got = eval_qu.dense_vector_tn_qu(text, init.copy(), opts, backend="numpy").flatten()
+    assert isinstance(got, np.ndarray) and got.shape == (1 << nqubits,)
+    assert np.allclose(want, got, atol=min(tolerance, 1e-5 if is_mps else 1e-10))
+    none = eval_qu.dense_vector_tn_qu(text, None, opts, backend="torch")
+    assert none.is_cuda and np.allclose(none.cpu().numpy(), osv.simulate(circuits.qft(nqubits, True)), atol=1e-5)
+    sites = eval_qu.init_state_tn(nqubits, init)
+    assert len(sites) == nqubits
+
+
+def test_quimb_platform_executes_from_a_dense_initial_state():
+    """reference backends/quimb.py:162-165: the MPS ansatz accepts a dense initial state; others refuse it."""
+    n = 7
+    init = _random_state(n, 3)
+    circ = circuits.qft(n, True)
+    b = MetaBackend.load("quimb")
+    res = b.execute_circuit(circ, initial_state=init, return_array=True)
+    got = np.asarray(res.statevector.get()).reshape(-1)
+    assert np.abs(got - osv.simulate(circ, initial_state=init)).max() < 1e-8
+    res = b.execute_circuit(circ, initial_state=init, nshots=200)
+    assert sum(res.frequencies().values()) == 200
+    with pytest.raises(ValueError):
+        b.execute_circuit(circ, initial_state=init[:-2])
+    b.configure_tn_simulation(ansatz=None)
+    with pytest.raises(ValueError):
+        b.execute_circuit(circ, initial_state=init)

@@ -58,6 +58,25 @@ def test_dense_vector_lowering_matches_statevector(n, layers, min_slices):
     assert np.allclose(got, want, atol=1e-12)
 
 
+@pytest.mark.parametrize("n,min_slices", [(2, 1), (5, 1), (10, 1), (6, 4)])
+def test_dense_initial_state_enters_as_one_leaf(n, min_slices):
+    """BASELINE config 1 (reference tests/test_quimb_backend.py:23-66): QFT with swaps on a random normalised
+    initial state; the state is one rank-n leaf of the network (reference eval_qu.py:34-41)."""
+    rng = np.random.default_rng(n)
+    init = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    init /= np.linalg.norm(init)
+    circ = circuits.qft(n, True)
+    net = QiboCircuitToEinsum(circ, "complex128").state_vector_network(init)
+    assert net.modes[0] == list(range(n)) and len(net.out) == n
+    info = find_path(net.modes, net.out, samples=2, seed=1, min_slices=min_slices)
+    low = executor.lower(net.modes, net.out, info, "complex128")
+    got = emulate(low, net.tensors, range(info.num_slices)).reshape(-1)
+    want = osv.simulate(circ, initial_state=init)
+    assert np.allclose(got, want, atol=1e-12)
+    with pytest.raises(ValueError):
+        QiboCircuitToEinsum(circ, "complex128").state_vector_network(init[:-1])
+
+
 @pytest.mark.parametrize("min_slices", [1, 4])
 def test_amplitude_and_expectation_lowering(min_slices):
     circ = circuits.brickwork(6, 3, seed=3)
