@@ -298,3 +298,33 @@ def test_gate_algo_rules():
         mps.parse_algorithm({"svd_method": {"partition": "UV", "cutoff": 1}})
     with pytest.raises(ValueError):
         mps.parse_algorithm({"svd": {}})
+
+
+def test_reference_module_names_resolve_to_this_engine():
+    """What the reference's tests and backends import (tests/test_quimb_backend.py:39, test_cuquantum_cutensor_backend.py,
+    backends/cutensornet.py:85): every name is the one qibotn_b200 module object, not a second copy."""
+    import importlib
+
+    import qibotn
+    import qibotn_b200
+    from qibotn.backends.abstract import QibotnBackend
+    from qibotn.backends.cutensornet import CuTensorNet
+    from qibotn.circuit_convertor import QiboCircuitToEinsum
+    from qibotn.circuit_to_mps import QiboCircuitToMPS
+    from qibotn.mps_contraction_helper import MPSContractionHelper
+    from qibotn.mps_utils import apply_gate, initial, mps_site_right_swap
+    from qibotn.result import TensorNetworkResult
+
+    assert importlib.import_module("qibotn.eval") is importlib.import_module("qibotn_b200.eval")
+    assert importlib.import_module("qibotn.eval_qu") is importlib.import_module("qibotn_b200.eval_qu")
+    assert importlib.import_module("qibotn.backends.quimb") is importlib.import_module("qibotn_b200.backends.quimb")
+    assert qibotn.MetaBackend is qibotn_b200.MetaBackend and issubclass(CuTensorNet, QibotnBackend)
+    import qibotn_b200.mps as m
+    import qibotn_b200.network as nw
+    assert QiboCircuitToEinsum is nw.QiboCircuitToEinsum and QiboCircuitToMPS is m.QiboCircuitToMPS
+    assert (MPSContractionHelper, apply_gate, initial, mps_site_right_swap) == (
+        m.MPSContractionHelper, m.apply_gate, m.initial, m.mps_site_right_swap)
+    assert m.__spec__.name == "qibotn_b200.mps" and TensorNetworkResult.__module__ == "qibotn_b200.result"
+    assert {"init_state_tn", "dense_vector_tn_qu"} <= set(dir(importlib.import_module("qibotn.eval_qu")))
+    with pytest.raises(ImportError):
+        importlib.import_module("qibotn.backends.qmatchatea")           # out of scope (DESIGN section 7)
