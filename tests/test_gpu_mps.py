@@ -553,7 +553,10 @@ def test_eval_qu_dense_vector_with_initial_state(nqubits, tolerance, is_mps):
     from qibotn_b200 import eval_qu
     from qibotn_b200.qasm import from_openqasm2_str
 
-    init = _random_state(nqubits, 7 * nqubits)
+    import os
+    closed = np.load(os.path.join(os.path.dirname(__file__), "golden", "closed_forms.npz"))
+    # the committed closed form (QFT = normalised inverse FFT) at the reference's own four sizes
+    init = closed[f"qft_in_{nqubits}"] if f"qft_in_{nqubits}" in closed else _random_state(nqubits, 7 * nqubits)
     text = _qft_qasm(nqubits)
     want = osv.simulate(from_openqasm2_str(text), initial_state=init)
     assert np.abs(want - osv.simulate(circuits.qft(nqubits, True), initial_state=init)).max() < 1e-12
@@ -561,6 +564,8 @@ def test_eval_qu_dense_vector_with_initial_state(nqubits, tolerance, is_mps):
     got = eval_qu.dense_vector_tn_qu(text, init.copy(), opts, backend="numpy").flatten()
     assert isinstance(got, np.ndarray) and got.shape == (1 << nqubits,)
     assert np.allclose(want, got, atol=min(tolerance, 1e-5 if is_mps else 1e-10))
+    if f"qft_out_{nqubits}" in closed:
+        assert np.allclose(closed[f"qft_out_{nqubits}"], got, atol=min(tolerance, 1e-5 if is_mps else 1e-10))
     none = eval_qu.dense_vector_tn_qu(text, None, opts, backend="torch")
     assert none.is_cuda and np.allclose(none.cpu().numpy(), osv.simulate(circuits.qft(nqubits, True)), atol=1e-5)
     sites = eval_qu.init_state_tn(nqubits, init)
