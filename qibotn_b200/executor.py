@@ -214,6 +214,36 @@ def _peak(arena):
     return arena.peak
 
 
+class ArenaPool:
+    """ONE grow-only device buffer from which successive runners carve their hoist / slice / workspace arenas.
+
+    An expectation value over many differently shaped terms (config 5: 60 light cones, arenas of up to 89 GiB)
+    otherwise pays a cudaMalloc and a cudaFree of tens of GiB per term.  Only one runner that uses the pool may be
+    live at a time: the caller drops a runner (``engine.clear_caches()``) before the next one is built.  Opt-in:
+    ``executor.ARENA_POOL = executor.ArenaPool()``."""
+
+    ALIGN = 4096
+
+    def __init__(self):
+        self.buf = None
+        self.grown = 0
+
+    def carve(self, torch, device, sizes):
+        offsets, total = [], 0
+        for nbytes in sizes:
+            offsets.append(total)
+            total += (max(int(nbytes), 256) + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if self.buf is None or self.buf.numel() < total:
+            self.buf = None
+            torch.cuda.empty_cache()                       # the old block goes back before the larger one is asked for
+            self.buf = torch.empty(total, dtype=torch.uint8, device=device)
+            self.grown += 1
+        return [self.buf[o:o + max(int(nbytes), 256)] for o, nbytes in zip(offsets, sizes)]
+
+
+ARENA_POOL = None
+
+
 class ContractionRunner:
     """Owns the device buffers of one lowered contraction and runs it."""
 
@@ -231,9 +261,13 @@ class ContractionRunner:
         u8 = torch.uint8
         self.leaf_buf = torch.empty(max(lowered.leaf_bytes, 256), dtype=u8, device=self.device)
         self.host_buf = torch.empty(max(lowered.leaf_bytes, 256), dtype=u8, pin_memory=True)
-        self.hoist_buf = torch.empty(max(lowered.hoist_bytes, 256), dtype=u8, device=self.device)
-        self.slice_buf = torch.empty(max(lowered.slice_bytes, 256), dtype=u8, device=self.device)
-        self.ws = torch.empty(max(lowered.workspace_bytes, 256), dtype=u8, device=self.device)
+        if ARENA_POOL is not None:
+            self.hoist_buf, self.slice_buf, self.ws = ARENA_POOL.carve(
+                torch, self.device, [lowered.hoist_bytes, lowered.slice_bytes, lowered.workspace_bytes])
+        else:
+            self.hoist_buf = torch.empty(max(lowered.hoist_bytes, 256), dtype=u8, device=self.device)
+            self.slice_buf = torch.empty(max(lowered.slice_bytes, 256), dtype=u8, device=self.device)
+            self.ws = torch.empty(max(lowered.workspace_bytes, 256), dtype=u8, device=self.device)
         self.out = torch.zeros(1 << self._live_out_rank(), dtype=self.cdtype, device=self.device)
         self.slice_id = torch.zeros(1, dtype=torch.int32, device=self.device)
         # Magnitude words (qtn_pair_run_scaled): one device word per tensor that an fp16-split plan reads,

@@ -30,7 +30,11 @@ ap.add_argument("--distributed", action="store_true")
 ap.add_argument("--check-terms", type=int, default=6)
 ap.add_argument("--max-seconds", type=float, default=0.0)
 ap.add_argument("--terms", default="", help="comma list: only these terms (debugging)")
+ap.add_argument("--no-pool", action="store_true", help="every term allocates and frees its own arenas (A/B of ArenaPool)")
 a = ap.parse_args()
+if not a.no_pool:
+    from qibotn_b200 import executor
+    executor.ARENA_POOL = executor.ArenaPool()         # one grow-only arena for all terms instead of malloc/free per term
 engine.PLAN_STORE = a.plan_store
 rank, world = 0, 1
 if a.distributed:
@@ -69,8 +73,9 @@ for t, slices in mine.items():
                    "log10_flops": round(math.log10(max(1.0, 8.0 * weights[t] * len(slices))), 3),
                    "launches": engine.LAST.launches}
     done_units += len(slices)
-    engine.clear_caches()                      # the next term has another shape: hand the arenas back
-    torch.cuda.empty_cache()
+    engine.clear_caches()                      # the next term has another shape: drop its runner
+    if a.no_pool:
+        torch.cuda.empty_cache()               # ... and hand the arenas back
 torch.cuda.synchronize()
 my_seconds = time.perf_counter() - t0
 partials = dist.reduce_result(partials, method="NCCL") if a.distributed else partials
@@ -97,7 +102,9 @@ if rank == 0:
            "per_rank": [{"seconds": round(x[0], 3), "log10_flops": round(math.log10(max(1.0, x[1])), 3),
                          "units": int(x[3]), "units_skipped": int(x[2])} for x in g],
            "plan_widths": sorted({i.log2_width for i in infos}), "max_slices": max(i.num_slices for i in infos),
-           "rank0_terms": per_term,
+           "rank0_terms": per_term, "arena_pool": None if a.no_pool else {"grown": executor.ARENA_POOL.grown,
+                                                                         "bytes": int(executor.ARENA_POOL.buf.numel())
+                                                                         if executor.ARENA_POOL.buf is not None else 0},
            "note": "first and only call: plan load, lowering, arena allocation and graph capture are inside wall_seconds"}
 # complex64 against complex128 on the cheapest terms, same trees (rank 0 only, after the timed region)
 if rank == 0 and a.check_terms > 0:

@@ -328,3 +328,22 @@ def test_reference_module_names_resolve_to_this_engine():
     assert {"init_state_tn", "dense_vector_tn_qu"} <= set(dir(importlib.import_module("qibotn.eval_qu")))
     with pytest.raises(ImportError):
         importlib.import_module("qibotn.backends.qmatchatea")           # out of scope
+
+
+def test_arena_pool_carves_aligned_disjoint_views_and_only_grows():
+    """executor.ArenaPool: one buffer for the hoist / slice / workspace arenas of successive runners."""
+    import torch
+
+    from qibotn_b200 import executor
+    pool = executor.ArenaPool()
+    a, b, c = pool.carve(torch, torch.device("cpu"), [1000, 0, 70000])
+    assert (a.numel(), b.numel(), c.numel()) == (1000, 256, 70000) and pool.grown == 1
+    base = pool.buf.data_ptr()
+    offs = [t.data_ptr() - base for t in (a, b, c)]
+    assert offs == [0, 4096, 8192] and all(o % executor.ArenaPool.ALIGN == 0 for o in offs)
+    first = pool.buf
+    x, y, z = pool.carve(torch, torch.device("cpu"), [4096, 4096, 4096])            # fits: same buffer
+    assert pool.buf is first and pool.grown == 1 and z.data_ptr() - base == 8192
+    pool.carve(torch, torch.device("cpu"), [1 << 20, 1 << 20, 1 << 20])             # larger: one reallocation
+    assert pool.grown == 2 and pool.buf.numel() >= 3 << 20
+    assert executor.ARENA_POOL is None                                               # opt-in
