@@ -224,9 +224,10 @@ class ArenaPool:
 
     ALIGN = 4096
 
-    def __init__(self):
+    def __init__(self, reserve_bytes=0):
         self.buf = None
         self.grown = 0
+        self.reserve_bytes = int(reserve_bytes)            # size of the first allocation: growing costs a free + a malloc
 
     def carve(self, torch, device, sizes):
         offsets, total = [], 0
@@ -236,7 +237,7 @@ class ArenaPool:
         if self.buf is None or self.buf.numel() < total:
             self.buf = None
             torch.cuda.empty_cache()                       # the old block goes back before the larger one is asked for
-            self.buf = torch.empty(total, dtype=torch.uint8, device=device)
+            self.buf = torch.empty(max(total, self.reserve_bytes), dtype=torch.uint8, device=device)
             self.grown += 1
         return [self.buf[o:o + max(int(nbytes), 256)] for o, nbytes in zip(offsets, sizes)]
 

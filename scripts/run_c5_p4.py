@@ -31,10 +31,12 @@ ap.add_argument("--check-terms", type=int, default=6)
 ap.add_argument("--max-seconds", type=float, default=0.0)
 ap.add_argument("--terms", default="", help="comma list: only these terms (debugging)")
 ap.add_argument("--no-pool", action="store_true", help="every term allocates and frees its own arenas (A/B of ArenaPool)")
+ap.add_argument("--pool-gib", type=float, default=64.0, help="first allocation of the arena pool (it grows if a term needs more)")
 a = ap.parse_args()
 if not a.no_pool:
     from qibotn_b200 import executor
-    executor.ARENA_POOL = executor.ArenaPool()         # one grow-only arena for all terms instead of malloc/free per term
+    # one grow-only arena for all terms instead of a malloc and a free of tens of GiB per term
+    executor.ARENA_POOL = executor.ArenaPool(reserve_bytes=int(a.pool_gib * 2 ** 30))
 engine.PLAN_STORE = a.plan_store
 rank, world = 0, 1
 if a.distributed:

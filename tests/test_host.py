@@ -347,3 +347,6 @@ def test_arena_pool_carves_aligned_disjoint_views_and_only_grows():
     pool.carve(torch, torch.device("cpu"), [1 << 20, 1 << 20, 1 << 20])             # larger: one reallocation
     assert pool.grown == 2 and pool.buf.numel() >= 3 << 20
     assert executor.ARENA_POOL is None                                               # opt-in
+    big = executor.ArenaPool(reserve_bytes=1 << 16)
+    big.carve(torch, torch.device("cpu"), [100, 100, 100])
+    assert big.buf.numel() == 1 << 16 and big.grown == 1                             # first allocation = the reserve
