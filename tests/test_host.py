@@ -350,3 +350,31 @@ def test_arena_pool_carves_aligned_disjoint_views_and_only_grows():
     big = executor.ArenaPool(reserve_bytes=1 << 16)
     big.carve(torch, torch.device("cpu"), [100, 100, 100])
     assert big.buf.numel() == 1 << 16 and big.grown == 1                             # first allocation = the reserve
+
+
+def test_eval_qu_gate_opts_translation_and_input_checks():
+    """quimb gate_opts (reference tests/test_quimb_backend.py:54-57) -> this engine's gate_algo; input validation of
+    dense_vector_tn_qu happens before any device work."""
+    from qibotn_b200 import eval_qu
+    f = eval_qu._gate_algo
+    assert f({"method": "svd", "cutoff": 1e-6, "cutoff_mode": "abs"}) == {
+        "qr_method": False, "svd_method": {"partition": "UV", "abs_cutoff": 1e-6}}
+    assert f({"cutoff": 1e-8, "max_bond": 32}) == {
+        "qr_method": False, "svd_method": {"partition": "UV", "rel_cutoff": 1e-8, "max_extent": 32}}   # quimb's default mode
+    assert f({"method": "qr"}) == {"qr_method": {}, "svd_method": False}
+    assert f({"method": "svd", "absorb": "both"})["svd_method"]["rel_cutoff"] == 1e-10
+    with pytest.raises(NotImplementedError):
+        f({"method": "eig"})
+    with pytest.raises(NotImplementedError):
+        f({"cutoff_mode": "rsum2"})
+    with pytest.raises(ValueError):
+        f({"renorm": True})
+    text = 'OPENQASM 2.0; include "qelib1.inc"; qreg q[3]; h q[0]; cx q[0],q[1];'
+    with pytest.raises(ValueError):
+        eval_qu.dense_vector_tn_qu(text, np.ones(4), None)                 # 2^3 amplitudes expected
+    with pytest.raises(ValueError):
+        eval_qu.init_state_tn(3, np.ones(4))
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(lib.QtnError):
+            eval_qu.dense_vector_tn_qu(text, None, {"method": "svd"})      # no device here: no CPU fallback
