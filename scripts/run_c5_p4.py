@@ -30,6 +30,9 @@ ap.add_argument("--distributed", action="store_true")
 ap.add_argument("--check-terms", type=int, default=6)
 ap.add_argument("--max-seconds", type=float, default=0.0)
 ap.add_argument("--terms", default="", help="comma list: only these terms (debugging)")
+ap.add_argument("--unit-seconds-from", default="", help="a one-GPU record of this script (rank0_terms): cut the units by "
+                "the MEASURED seconds per slice of every term whose plan is still the one that was measured, instead of "
+                "the time model's estimate")
 ap.add_argument("--no-pool", action="store_true", help="every term allocates and frees its own arenas (A/B of ArenaPool)")
 ap.add_argument("--pool-gib", type=float, default=64.0, help="first allocation of the arena pool (it grows if a term needs more)")
 a = ap.parse_args()
@@ -55,7 +58,16 @@ for k, net in enumerate(nets):
     infos.append(info)
 counts = [infos[k].num_slices if k in only else 0 for k in range(len(nets))]
 weights = [infos[k].opt_cost / max(1, infos[k].num_slices) for k in range(len(nets))]          # MACs per unit
-mine = dist.partition_units(counts, rank, world, ev.unit_seconds(nets, infos, dtype))          # cut by est. time
+unit = ev.unit_seconds(nets, infos, dtype)                                                     # time model
+if a.unit_seconds_from:
+    with open(a.unit_seconds_from) as f:
+        measured = json.loads([ln for ln in f.read().splitlines() if ln.startswith("{")][-1])["rank0_terms"]
+    for k, row in measured.items():
+        k = int(k)
+        same_plan = abs(row["log10_flops"] - math.log10(max(1.0, 8.0 * infos[k].opt_cost))) < 2e-3
+        if row["slices"] == row["of"] == infos[k].num_slices and same_plan:
+            unit[k] = row["seconds"] / row["of"]
+mine = dist.partition_units(counts, rank, world, unit)                                         # cut by time
 my_flops = sum(8.0 * weights[t] * len(rg) for t, rg in mine.items())
 torch.cuda.synchronize()
 dist.barrier()
