@@ -275,6 +275,35 @@ class Circuit:
             inv.queue.append(g.dagger())
         return inv
 
+    def to_qasm(self) -> str:
+        """OpenQASM 2.0 text as qibo's ``Circuit.to_qasm()`` writes it (one ``qreg q``, qelib1 names, parameters as
+        ``repr(float)``, qubits in ``control, target`` order): the wire format of the reference's CPU paths
+        (eval_qu.py:39-41, backends/quimb.py:169-171).  Gates without a qelib1 name raise."""
+        names = {"i": "id", "cnot": "cx"}
+        plain = {"id", "h", "x", "y", "z", "s", "sdg", "t", "tdg", "sx", "cx", "cz", "swap"}
+        rotations = {"rx", "ry", "rz", "u1", "cu1", "crz", "rzz", "rxx"}
+        lines = ["// Generated by qibotn_b200.qibo_compat", "OPENQASM 2.0;", 'include "qelib1.inc";',
+                 f"qreg q[{self.nqubits}];"]
+        measured = [q for g in self.queue if isinstance(g, M) for q in g.target_qubits]
+        if measured:
+            lines.append(f"creg c[{len(measured)}];")
+        slot = 0
+        for g in self.queue:
+            if isinstance(g, M):
+                for q in g.target_qubits:
+                    lines.append(f"measure q[{q}] -> c[{slot}];")
+                    slot += 1
+                continue
+            name = names.get(g.name, g.name)
+            args = ",".join(f"q[{q}]" for q in g.qubits)
+            if name in plain and not g.parameters:
+                lines.append(f"{name} {args};")
+            elif name in rotations and len(g.parameters) == 1:
+                lines.append(f"{name}({float(g.parameters[0])!r}) {args};")
+            else:
+                raise_error(NotImplementedError, f"gate {g.name} has no OpenQASM 2 (qelib1) form here")
+        return "\n".join(lines) + "\n"
+
     @property
     def ngates(self):
         return len(self.queue)
