@@ -437,6 +437,7 @@ class MPSEngine:
             d = 1 << i
             sites.append(torch.eye(2 * d, dtype=self.cdtype, device=self.device).view(d, 2, 2 * d).contiguous())
         self.sites = sites + [None] * (n - h)
+        self.stats["max_bond"] = max(self.stats["max_bond"], 1 << h)
         cur = psi.clone()
         l = 1 << h
         keep = self.partition
