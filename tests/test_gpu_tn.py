@@ -416,6 +416,41 @@ def test_quimb_platform_api(ansatz):
     assert abs(res.frequencies()[top] / 4000 - probs[int(top, 2)]) < 5 * np.sqrt(probs[int(top, 2)] / 4000)
 
 
+def test_arena_pool_changes_no_value():
+    """executor.ArenaPool (one grow-only device buffer for the arenas of successive terms, scripts/run_c5_p4.py):
+    the terms of an observable contracted one after the other give the same values with and without it, and match
+    the dense simulator."""
+    from qibotn_b200 import executor
+    from qibotn_b200.observables import get_ham_gates
+    n, dtype = 12, "complex64"
+    circ = circuits.brickwork(n, 4, seed=9)
+    psi = osv.simulate(circ)
+    conv = QiboCircuitToEinsum(circ, dtype)
+    terms = ([(5, "Z", 1.0)], [(0, "X", 1.0), (11, "Y", 1.0)], [(6, "Z", 1.0), (7, "Z", 1.0)], [(2, "Y", 1.0)])
+    nets = [conv.expectation_network(get_ham_gates(t, dtype)) for t in terms]
+
+    def run_all():
+        vals = []
+        for net in nets:
+            vals.append(complex(engine.contract(net, dtype, samples=4).cpu().numpy().reshape(-1)[0]))
+            engine.clear_caches()                      # one live runner at a time, as the pool requires
+        return vals
+
+    engine.clear_caches()
+    plain = run_all()
+    assert executor.ARENA_POOL is None
+    executor.ARENA_POOL = executor.ArenaPool(reserve_bytes=1 << 20)
+    try:
+        pooled = run_all()
+        assert executor.ARENA_POOL.buf is not None and executor.ARENA_POOL.grown >= 1
+    finally:
+        executor.ARENA_POOL = None
+        engine.clear_caches()
+    for t, a, b in zip(terms, plain, pooled):
+        want = osv.pauli_expectation(psi, [(1.0, [(l, q) for q, l, _ in t])], n)
+        assert abs(a - b) <= 1e-6 and abs(b - want) <= TOL[dtype]
+
+
 @pytest.mark.parametrize("dtype", ["complex128", "complex64"])
 def test_light_cone_cancellation_changes_no_value(dtype):
     """Dropping the gate / inverse-gate pairs outside the observable's reverse light cone is exact:
